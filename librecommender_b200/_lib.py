@@ -1,0 +1,79 @@
+"""ctypes binding of the C-ABI declared in ``include/b200reco.h``.
+
+There is NO fallback: if the shared library is missing or fails to load the
+import raises.  Device memory and streams come from torch (plumbing only).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_ulonglong, c_void_p, POINTER
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libb200reco.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -m librecommender_b200.build` "
+        "(nvcc, sm_100a).  librecommender_b200 has no CPU fallback."
+    )
+
+lib = ctypes.CDLL(LIB_PATH)
+
+# name -> (restype, argtypes); must list every symbol of include/b200reco.h
+_P = c_void_p
+SIGNATURES = {
+    "b200_version": (c_int, []),
+    "b200_last_error": (c_char_p, []),
+    "b200_launch_count": (c_ulonglong, []),
+    "b200_build_consumed_csr_host": (c_int, [_P, _P, c_int64, c_int64, _P, _P, POINTER(c_int64)]),
+    "b200_mask_consumed": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int32, _P, _P, c_int64, _P]),
+    "b200_topk_rows_workspace_bytes": (c_int, [c_int64, c_int64, c_int32, POINTER(c_size_t)]),
+    "b200_topk_rows": (c_int, [_P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, c_size_t, _P]),
+    "b200_score_rows_f32": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int32, _P, c_int64, _P]),
+    "b200_gather_dot": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int64, c_int32, c_int32, c_float, c_float, _P, _P]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here == header/library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib.b200_last_error().decode("utf-8", "replace")
+        if "exceeds num of items" in msg:
+            raise ValueError(msg)
+        raise B200Error(f"[b200reco rc={rc}] {msg}")
+
+
+def ptr(t) -> c_void_p:
+    """Raw data pointer of a torch tensor / numpy array (None -> NULL)."""
+    if t is None:
+        return c_void_p(0)
+    if hasattr(t, "data_ptr"):
+        return c_void_p(t.data_ptr())
+    return c_void_p(t.ctypes.data)
+
+
+def current_stream() -> c_void_p:
+    import torch
+
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(lib.b200_launch_count())
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise B200Error("librecommender_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())

@@ -1,0 +1,143 @@
+"""Device-resident state for the embed scoring path.
+
+``EmbedScorer`` keeps the user / item embedding tables and the consumed-CSR in
+HBM and answers ``recommend`` calls: H2D of the user ids, score → mask → top-K on
+the GPU, D2H of the ``[B, n_rec]`` ids.  It is what
+``recommend_from_embedding`` (reference: ``libreco/recommendation/recommend.py:57-78``)
+runs on; tables are uploaded once per (array object) and cached.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .consumed import ConsumedCSR, as_csr
+
+_SCORE_WS_BYTES = 1 << 30  # materialised-score workspace of the exact path
+
+
+def _as_device_f32(x, device):
+    import torch
+
+    if isinstance(x, torch.Tensor):
+        t = x.to(device=device, dtype=torch.float32)
+    else:
+        a = np.asarray(x)
+        if a.dtype != np.float32:
+            a = a.astype(np.float32)
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    if t.dim() == 1:
+        t = t[:, None]
+    return t.contiguous()
+
+
+class EmbedScorer:
+    """Score-all-items + consumed filter + top-K for embedding models (a1 + a2)."""
+
+    def __init__(self, user_embeddings, item_embeddings, n_items, user_consumed=None,
+                 n_users=None, device=None):
+        import torch
+
+        self.device = device if device is not None else _lib.require_cuda()
+        self.U = _as_device_f32(user_embeddings, self.device)
+        self.I = _as_device_f32(item_embeddings, self.device)
+        if self.U.shape[1] != self.I.shape[1]:
+            raise ValueError("user and item embeddings differ in width")
+        self.d = int(self.U.shape[1])
+        self.n_items = int(n_items)
+        if self.n_items > self.I.shape[0]:
+            raise ValueError("n_items exceeds rows of item_embeddings")
+        self.n_users = int(n_users) if n_users is not None else int(self.U.shape[0])
+        self.set_consumed(user_consumed)
+        self._torch = torch
+
+    def set_consumed(self, user_consumed):
+        if user_consumed is None:
+            user_consumed = ConsumedCSR(np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32))
+        self.csr = as_csr(user_consumed, self.n_users)
+        self.indptr_d, self.idx_d = self.csr.device(self.device)
+
+    # ------------------------------------------------------------------------------------
+    def topk_scores_inplace(self, scores, user_ids_d, n_rec, filter_consumed, out_ids, out_scores):
+        """scores: device fp32 [b, ld] (clobbered by the mask)."""
+        torch = self._torch
+        b, ld = scores.shape[0], scores.stride(0)
+        N = self.n_items
+        stream = _lib.current_stream()
+        if filter_consumed and self.csr.nnz > 0:
+            _lib.check(_lib.lib.b200_mask_consumed(
+                _lib.ptr(scores), ld, _lib.ptr(user_ids_d), b, N, n_rec,
+                _lib.ptr(self.indptr_d), _lib.ptr(self.idx_d), self.csr.n_users, stream))
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(_lib.lib.b200_topk_rows_workspace_bytes(b, N, n_rec, ctypes.byref(nbytes)))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        _lib.check(_lib.lib.b200_topk_rows(
+            _lib.ptr(scores), ld, b, N, n_rec, _lib.ptr(out_ids),
+            _lib.ptr(out_scores) if out_scores is not None else None,
+            _lib.ptr(ws), nbytes.value, stream))
+
+    def recommend_exact(self, user_ids_d, n_rec, filter_consumed=True, return_scores=False):
+        """Exact fp32 path: materialise score row-batches, mask, radix top-K."""
+        torch = self._torch
+        B = int(user_ids_d.numel())
+        N = self.n_items
+        if n_rec > N:
+            raise ValueError(f"`n_rec` {n_rec} exceeds num of items {N}")
+        ld = (N + 3) // 4 * 4
+        rows = max(1, min(B, _SCORE_WS_BYTES // (ld * 4), 32768))
+        scores = torch.empty((rows, ld), dtype=torch.float32, device=self.device)
+        out_ids = torch.empty((B, n_rec), dtype=torch.int64, device=self.device)
+        out_scores = torch.empty((B, n_rec), dtype=torch.float32, device=self.device) if return_scores else None
+        stream = _lib.current_stream()
+        for r0 in range(0, B, rows):
+            b = min(rows, B - r0)
+            uid = user_ids_d[r0:r0 + b]
+            _lib.check(_lib.lib.b200_score_rows_f32(
+                _lib.ptr(self.U), self.U.stride(0), _lib.ptr(uid), b,
+                _lib.ptr(self.I), self.I.stride(0), N, self.d,
+                _lib.ptr(scores), ld, stream))
+            self.topk_scores_inplace(
+                scores[:b], uid, n_rec, filter_consumed, out_ids[r0:r0 + b],
+                out_scores[r0:r0 + b] if return_scores else None)
+        return (out_ids, out_scores) if return_scores else out_ids
+
+    def recommend(self, user_ids, n_rec, filter_consumed=True, return_scores=False):
+        """Host ids in, host ``int64[B, n_rec]`` out (the reference-facing call)."""
+        torch = self._torch
+        uid_h = torch.as_tensor(np.asarray(user_ids, dtype=np.int64))
+        uid_d = uid_h.to(self.device, non_blocking=True)
+        res = self.recommend_exact(uid_d, int(n_rec), filter_consumed, return_scores)
+        if return_scores:
+            return res[0].cpu().numpy(), res[1].cpu().numpy()
+        return res.cpu().numpy()
+
+    def predict(self, users, items, mode=0, lo=0.0, hi=0.0):
+        """predict_from_embedding (``libreco/prediction/predict.py:36-40``)."""
+        torch = self._torch
+        u = torch.as_tensor(np.asarray(users, dtype=np.int64)).to(self.device)
+        i = torch.as_tensor(np.asarray(items, dtype=np.int64)).to(self.device)
+        out = torch.empty(u.numel(), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.b200_gather_dot(
+            _lib.ptr(self.U), self.U.stride(0), _lib.ptr(u), _lib.ptr(self.I), self.I.stride(0),
+            _lib.ptr(i), u.numel(), self.d, mode, lo, hi, _lib.ptr(out), _lib.current_stream()))
+        return out.cpu().numpy()
+
+
+# ---- cache of scorers keyed by the identity of the host arrays --------------------------------
+_scorers: dict = {}
+
+
+def scorer_for(model, user_embeddings, item_embeddings) -> EmbedScorer:
+    key = (id(user_embeddings), id(item_embeddings), id(model.user_consumed), int(model.n_items))
+    hit = _scorers.get(key)
+    if hit is not None and hit[0] is user_embeddings and hit[1] is item_embeddings:
+        return hit[2]
+    n_users = getattr(model, "n_users", None)
+    sc = EmbedScorer(user_embeddings, item_embeddings, model.n_items, model.user_consumed,
+                     n_users=n_users)
+    if len(_scorers) > 4:
+        _scorers.clear()
+    _scorers[key] = (user_embeddings, item_embeddings, sc)
+    return sc

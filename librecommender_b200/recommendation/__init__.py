@@ -1,0 +1,12 @@
+"""Drop-in replacements for ``libreco.recommendation`` (same names, same signatures)."""
+from .cold_start import cold_start_rec, popular_recommendations
+from .ranking import rank_recommendations
+from .recommend import construct_rec, recommend_from_embedding
+
+__all__ = [
+    "cold_start_rec",
+    "construct_rec",
+    "popular_recommendations",
+    "rank_recommendations",
+    "recommend_from_embedding",
+]
