@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — recommend_user users/sec (all-items top-K) on synthetic C2:
+TwoTower-style retrieval, 10 M users x 1 M items, embed 64, top-100, consumed filter on.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # this repo's CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1     # reference algorithm on host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU (users sharded)
+
+One JSON line on rank 0 (see the driver contract).  A "step" = one recommend call for a batch of
+`--batch` distinct users per rank.  `value` is device-resident (user ids already in HBM, result
+left in HBM); `e2e` goes through the reference-facing call with HOST ids in and HOST ids out.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED_U, SEED_I, SEED_C, SEED_Q = 1, 2, 3, 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--users", type=int, default=10_000_000)
+    ap.add_argument("--items", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--topk", type=int, default=100)
+    ap.add_argument("--mean-consumed", type=float, default=50.0)
+    ap.add_argument("--cpu-users", type=int, default=64, help="users per CPU-baseline call")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default="auto", choices=["auto", "exact"])
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic catalogue — generated on the device, seeds fixed
+# --------------------------------------------------------------------------------------------
+def make_tables(args, device):
+    import torch
+
+    def table(rows, seed):
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+        t = torch.empty((rows, args.dim), dtype=torch.float32, device=device)
+        step = 1 << 20
+        for r0 in range(0, rows, step):
+            r1 = min(rows, r0 + step)
+            x = torch.randn((r1 - r0, args.dim), generator=g, device=device, dtype=torch.float32)
+            t[r0:r1] = x / x.norm(dim=1, keepdim=True)       # TwoTower norm_embed=True
+        return t
+
+    U = table(args.users + 1, SEED_U)
+    I = table(args.items + 1, SEED_I)
+    return U, I
+
+
+def make_consumed_csr(args, device):
+    """c_u ~ min(Poisson(mean), 500) items per user, Zipf(1.0) over a fixed random permutation of
+    the items, duplicates inside a user removed (=> sorted unique lists)."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(SEED_C)
+    n_users, N = args.users, args.items
+    counts = torch.poisson(torch.full((n_users,), float(args.mean_consumed), device=device), generator=g)
+    counts = counts.clamp_(max=min(500, N // 4)).to(torch.int64)
+    w = 1.0 / torch.arange(1, N + 1, device=device, dtype=torch.float64)
+    cdf = torch.cumsum(w, 0)
+    cdf = (cdf / cdf[-1]).to(torch.float32)
+    perm = torch.randperm(N, generator=g, device=device)
+    shift = max(1, (N - 1).bit_length())
+    keys = []
+    chunk_users = 1 << 20
+    for u0 in range(0, n_users, chunk_users):
+        u1 = min(n_users, u0 + chunk_users)
+        c = counts[u0:u1]
+        tot = int(c.sum())
+        owner = torch.repeat_interleave(torch.arange(u0, u1, device=device), c)
+        r = torch.rand(tot, generator=g, device=device)
+        rank = torch.searchsorted(cdf, r).clamp_(max=N - 1)
+        item = perm[rank]
+        keys.append(torch.unique((owner << shift) | item))    # sorted, de-duplicated
+    key = torch.cat(keys)
+    owner = key >> shift
+    idx = (key & ((1 << shift) - 1)).to(torch.int32)
+    cnt = torch.bincount(owner, minlength=n_users)
+    indptr = torch.zeros(n_users + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(cnt, 0)
+    return indptr, idx
+
+
+def make_batches(args, rank, n):
+    rng = np.random.default_rng(SEED_Q + 1000 * rank)
+    return [rng.choice(args.users, size=args.batch, replace=False).astype(np.int64) for _ in range(n)]
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi fields through NVML)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+        0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.stop_flag, self.ok = [], set(), False, False
+        self.sm_max = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            pass
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag:
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def start(self):
+        if self.ok:
+            self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.ok:
+            self.th.join(timeout=1.0)
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline: the reference's algorithm (oracle port, same numpy primitives) on host cores
+# --------------------------------------------------------------------------------------------
+def cpu_baseline_run(args, U_rows_fn, I_host, consumed_fn, seconds, users_per_call, max_calls=None):
+    from oracle.ranking import recommend_from_embedding_numpy_path
+
+    rng = np.random.default_rng(SEED_Q + 77)
+    done_users, t_total, calls = 0, 0.0, 0
+    per_call = []
+    while True:
+        users = rng.choice(args.users, size=users_per_call, replace=False).astype(np.int64)
+        rows = U_rows_fn(users)
+        consumed = consumed_fn(users)
+        t0 = time.perf_counter()
+        ids = recommend_from_embedding_numpy_path(users.tolist(), args.topk, rows, I_host, args.items,
+                                                  consumed, True)
+        dt = time.perf_counter() - t0
+        assert ids.shape == (users_per_call, args.topk)
+        calls += 1
+        if calls > 1 or max_calls == 1:   # first call is the warm-up unless only one is allowed
+            t_total += dt
+            done_users += users_per_call
+            per_call.append(dt)
+        if (max_calls and calls >= max_calls + (0 if max_calls == 1 else 1)) or t_total >= seconds:
+            break
+    return done_users / max(t_total, 1e-9), per_call
+
+
+def host_views(U, I, indptr, idx):
+    """Callables that fetch the host-side data the CPU arm needs for a user sample."""
+    import torch
+
+    I_host = I.cpu().numpy()
+
+    def rows(users):
+        return U[torch.as_tensor(users, device=U.device)].cpu().numpy()
+
+    def consumed(users):
+        ut = torch.as_tensor(users, device=indptr.device)
+        b, e = indptr[ut].cpu().numpy(), indptr[ut + 1].cpu().numpy()
+        out = {}
+        for u, bb, ee in zip(users.tolist(), b.tolist(), e.tolist()):
+            if ee > bb:
+                out[u] = idx[bb:ee].cpu().numpy().tolist()
+        return out
+
+    return I_host, rows, consumed
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+
+    distributed = world > 1
+    if args.impl == "reference" and rank != 0:
+        return 0                                   # rank 0 alone runs the CPU arm
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if distributed and args.impl == "b200":
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+
+    workload = (f"C2 TwoTower retrieval: {args.users} users x {args.items} items, embed {args.dim}, "
+                f"top-{args.topk}, filter_consumed, batch {args.batch} users/step/GPU")
+    config = {"workload": workload, "users": args.users, "items": args.items, "embed": args.dim,
+              "n_rec": args.topk, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+              "parallelism": f"users sharded x{world}, item table replicated, no data-path collective",
+              "l2": "inputs larger than L2 (item table 256 MB fp32 + 128 MB bf16, user table 2.56 GB)"}
+
+    U, I = make_tables(args, device)
+    indptr, idx = make_consumed_csr(args, device)
+    torch.cuda.synchronize()
+
+    if args.impl == "reference":
+        I_host, rows_fn, cons_fn = host_views(U, I, indptr, idx)
+        ncalls = max(1, args.steps)
+        for _ in range(max(0, args.warmup)):
+            cpu_baseline_run(args, rows_fn, I_host, cons_fn, 0.0, args.cpu_users, max_calls=1)
+        t0 = time.perf_counter()
+        ups, per_call = cpu_baseline_run(args, rows_fn, I_host, cons_fn, 1e9, args.cpu_users,
+                                         max_calls=ncalls if ncalls > 1 else 1)
+        ms = 1e3 * float(np.mean(per_call))
+        cores = os.cpu_count()
+        line = {
+            "impl": "reference", "metric": "recommend_user users/sec (all-items top-K)", "value": ups,
+            "unit": "users/s", "n_gpus": args.gpus, "steps": len(per_call), "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": ups, "unit": "users/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.cpu_users} users per call x {len(per_call)} calls, full "
+                                       f"{args.items}-item catalogue (oracle port of recommend.py:57-78 + "
+                                       "ranking.py:10-78, numpy/OpenBLAS on all host threads)"},
+            "e2e": {"value": ups, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ this repo's CUDA path
+    from librecommender_b200 import _lib
+    from librecommender_b200.consumed import ConsumedCSR
+    from librecommender_b200.engine import EmbedScorer
+
+    csr = ConsumedCSR.from_device_tensors(indptr, idx)
+    scorer = EmbedScorer(U, I, args.items, csr, n_users=args.users, device=device)
+    n_batches = args.warmup + args.steps
+    batches_h = [torch.from_numpy(b).pin_memory() for b in make_batches(args, rank, n_batches)]
+    batches_d = [b.to(device) for b in batches_h]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if distributed:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if not distributed:
+            return ms
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg ------------------------------------------------------------
+    for i in range(args.warmup):
+        scorer.recommend_device(batches_d[i], args.topk, True, False, args.path)
+    barrier()
+    scorer.events = []
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = None
+    for i in range(args.warmup, n_batches):
+        out = scorer.recommend_device(batches_d[i], args.topk, True, False, args.path)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = _lib.launch_count() - launches0
+    dev_ms = max_over_ranks(e0.elapsed_time(e1))
+    sweep_ms = [a.elapsed_time(b) for a, b in scorer.events]
+    scorer.events = None
+    value = world * args.batch * args.steps / (dev_ms * 1e-3)
+
+    # ---- end-to-end leg: host ids in, host ids out ---------------------------------------
+    for i in range(min(args.warmup, 2)):
+        scorer.recommend(batches_h[i], args.topk, True, False, args.path)
+    barrier()
+    e0.record()
+    res = None
+    for i in range(args.warmup, n_batches):
+        res = scorer.recommend(batches_h[i], args.topk, True, False, args.path)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * args.batch * args.steps / (e2e_ms * 1e-3)
+    assert res.shape == (args.batch, args.topk) and res.dtype == np.int64 and (res >= 0).all()
+
+    if rank != 0:
+        return 0
+
+    # ---- roofline of the dominant kernel (tcgen05 sweep) ----------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roofline = None
+    if sweep_ms:
+        flops = 2.0 * args.dim * args.items * args.batch               # per launch (2*d*N per user)
+        avg_ms = float(np.mean(sweep_ms))
+        achieved = flops / (avg_ms * 1e-3) / 1e12
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "sweep_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roofline = {"bound": "tensor", "kernel": "b200::tc::sweep_kernel", "achieved": achieved,
+                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks
+                    else "fallback 1400 (of fallback)",
+                    "traffic": traffic, "avg_launch_ms": avg_ms, "launches_timed": len(sweep_ms),
+                    "share_of_step": avg_ms * len(sweep_ms) / max(dev_ms, 1e-9) if not distributed else None}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        I_host, rows_fn, cons_fn = host_views(U, I, indptr, idx)
+        ups, per_call = cpu_baseline_run(args, rows_fn, I_host, cons_fn, args.cpu_seconds, args.cpu_users)
+        cpu = {"value": ups, "unit": "users/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"{args.cpu_users} users per call x {len(per_call)} calls against the full "
+                         f"{args.items}-item catalogue (oracle port of the reference's numpy path)"}
+
+    line = {
+        "metric": "recommend_user users/sec (all-items top-K)", "value": value, "unit": "users/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 scores (bf16 tensor-core candidate pass + exact fp32 re-score)",
+        "data": "synthetic", "config": config, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": args.batch * 8,
+                "d2h_bytes_per_step": args.batch * args.topk * 8, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "path": args.path,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -63,6 +63,26 @@ int b200_score_rows_f32(const float* U, int64_t ldu, const int64_t* user_ids, in
                         const float* I, int64_t ldi, int64_t N, int32_t d, float* scores,
                         int64_t lds, void* stream);
 
+/* ---- a1+a2 fused: recommend_from_embedding + rank_recommendations on the tensor cores -----
+ * (recommend.py:57-78 + ranking.py:10-78, never materialising [B,N]).
+ * catalog: device buffer prepared ONCE per item table (bf16 K-major copy + max row norm).
+ * Result per row: the K best non-consumed items by EXACT fp32 score (same definition as
+ * b200_score_rows_f32), sorted (score desc, id asc).  row_status[r] (device int32[B]) = 1 marks a
+ * row the fused path could not bound (K + consumed > 448, or too many near-ties): its out_ids are
+ * -1 and the caller re-runs it through b200_score_rows_f32 + b200_mask_consumed + b200_topk_rows.
+ * Limits: d <= 256, K <= 448. */
+int b200_embed_catalog_bytes(int64_t N, int32_t d, size_t* bytes);
+int b200_embed_catalog_prepare(const float* I, int64_t ldi, int64_t N, int32_t d, void* catalog,
+                               size_t bytes, void* stream);
+int b200_recommend_embed_workspace_bytes(int64_t B, int64_t N, int32_t d, int32_t K, size_t* bytes);
+int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* user_ids, int64_t B,
+                         const float* I, int64_t ldi, int64_t N, int32_t d, const void* catalog,
+                         const int64_t* indptr, const int32_t* idx, int64_t n_users, int32_t filter,
+                         int32_t K, int64_t* out_ids, float* out_scores, int32_t* row_status,
+                         void* workspace, size_t workspace_bytes, void* stream,
+                         void* ev_sweep_start /* cudaEvent_t or NULL: recorded on `stream` */,
+                         void* ev_sweep_stop  /* just before / after the tcgen05 sweep kernel */);
+
 /* ---- a14: predict_from_embedding (libreco/prediction/predict.py:36-40) -----------------
  * out[r] = sum_k U[users[r],k] * I[items[r],k]; mode 0: raw, 1: expit (ranking),
  * 2: clip to [lo, hi] (rating) — normalize_prediction (:18-23). */

@@ -31,6 +31,11 @@ SIGNATURES = {
     "b200_topk_rows_workspace_bytes": (c_int, [c_int64, c_int64, c_int32, POINTER(c_size_t)]),
     "b200_topk_rows": (c_int, [_P, c_int64, c_int64, c_int64, c_int32, _P, _P, _P, c_size_t, _P]),
     "b200_score_rows_f32": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int32, _P, c_int64, _P]),
+    "b200_embed_catalog_bytes": (c_int, [c_int64, c_int32, POINTER(c_size_t)]),
+    "b200_embed_catalog_prepare": (c_int, [_P, c_int64, c_int64, c_int32, _P, c_size_t, _P]),
+    "b200_recommend_embed_workspace_bytes": (c_int, [c_int64, c_int64, c_int32, c_int32, POINTER(c_size_t)]),
+    "b200_recommend_embed": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int64, c_int32, _P, _P, _P,
+                                     c_int64, c_int32, c_int32, _P, _P, _P, _P, c_size_t, _P, _P, _P]),
     "b200_gather_dot": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int64, c_int32, c_int32, c_float, c_float, _P, _P]),
 }
 

@@ -1,0 +1,767 @@
+// K4 — fused user x all-items scoring + consumed filter + top-K on the 5th-gen tensor cores.
+//
+// Replaces recommend_from_embedding + rank_recommendations
+// (libreco/recommendation/recommend.py:57-78, ranking.py:10-78) without ever materialising
+// the [B, N] score matrix.
+//
+// Pipeline (all on one stream, no host sync):
+//   prep_items   (once per item table)  fp32 [N,d] -> bf16 [N_pad, d_pad] (K-major, zero padded)
+//                                        + max item L2 norm
+//   prep_users   gather U[user_ids] -> bf16 [B_pad, d_pad]; per-row error bound eps and k_row
+//   sweep        persistent tcgen05 kernel: TMA -> smem (SWIZZLE_128B) -> tcgen05.mma (bf16,
+//                fp32 accumulate in TMEM, 128x256 tile, double-buffered accumulator) ->
+//                epilogue warps read TMEM (tcgen05.ld) and keep, per user row, every item whose
+//                COARSE score can still be in the exact top-k_row: score >= tau,
+//                tau = (k_row-th best coarse score so far) - 2*eps, tightened by warp-cooperative
+//                radix compactions and shared across item splits through a global per-row max.
+//   finalize     per row: exact k_row-th coarse score over the union of the split lists, cut at
+//                -2*eps, drop consumed items, EXACT fp32 re-score (sequential fma, the library's
+//                exact-score definition), sort by (score desc, id asc), emit K ids.
+//
+// Exactness argument: |coarse - exact| <= eps for every (user, item) (bf16 rounding of both
+// operands, |delta| <= 2^-8 each, plus a generous accumulation term).  Let c_k be the k-th
+// largest coarse score.  Every item of the exact top-k has coarse >= c_k - 2 eps, hence is in
+// the candidate set; the final order is decided on exact fp32 scores only.  k_row = K + c_u
+// (c_u = consumed count, duplicates included) when the reference's filter rule applies
+// (ranking.py:38), so removing consumed candidates still leaves the exact top-K.
+// Rows the fast path cannot bound (k_row too large, or too many near-ties to hold) are flagged
+// in row_status and re-run by the caller on the exact materialised path (score_f32.cu+topk.cu).
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "../../include/b200reco.h"
+#include <cuda_bf16.h>
+
+namespace b200 {
+namespace tc {
+
+constexpr int TM = 128;        // users per tile (UMMA M)
+constexpr int TN = 256;        // items per tile (UMMA N)
+constexpr int KBLK = 64;       // bf16 per 128-byte swizzled row
+constexpr int CAP = 1024;      // candidate slots per (row, split)
+constexpr int KROW_MAX = 448;  // fast-path limit for k_row = K + c_u
+constexpr int MAX_KB = 4;      // d_pad <= 256
+constexpr int A_KB_BYTES = TM * KBLK * 2;   // 16 KB
+constexpr int B_KB_BYTES = TN * KBLK * 2;   // 32 KB
+constexpr int SWEEP_THREADS = 192;          // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int MAXC = 2048;                  // finalize: candidates per row
+constexpr int FIN_THREADS = 256;
+constexpr float ERR_COEF = 0.0082f;  // 2^-7*(1+2^-9) for bf16 x bf16 products + accumulation slack
+
+struct CatalogHeader {   // first 256 bytes of the catalog buffer (device)
+  uint32_t max_norm_bits;  // max_i ||I_i||_2 (fp32 bits; non-negative so uint order == float order)
+  int32_t d, d_pad;
+  int64_t N, N_pad;
+};
+
+struct RowMeta {
+  float eps2;       // 2 * eps
+  int32_t k_row;    // K (+ consumed count when the filter applies)
+  int32_t active;   // 0: pad row / fallback row (never collects)
+  int32_t apply;    // consumed filter applies
+};
+
+struct SweepParams {
+  int64_t N;
+  int32_t B_pad, m_tiles, n_splits, tiles_per_split, total_tiles, KB, nstage;
+  const RowMeta* meta;        // [B_pad]
+  uint32_t* row_tau_key;      // [B_pad]  running max of tau (order-preserving key)
+  int32_t* row_status;        // [B_pad]  1 = needs the exact path
+  float* cand_score;          // [n_splits][B_pad][CAP]
+  int32_t* cand_id;           // [n_splits][B_pad][CAP]
+  int32_t* cand_cnt;          // [n_splits][B_pad]
+};
+
+// ------------------------------------------------------------------------------------------
+// prep kernels
+// ------------------------------------------------------------------------------------------
+__global__ void prep_items_kernel(const float* __restrict__ I, int64_t ldi, int64_t N, int d,
+                                  int d_pad, int64_t N_pad, __nv_bfloat16* __restrict__ out,
+                                  CatalogHeader* hdr) {
+  // one warp per item row
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= N_pad) return;
+  float ss = 0.f;
+  for (int k = lane; k < d_pad; k += 32) {
+    float v = 0.f;
+    if (row < N && k < d) v = __ldg(I + row * ldi + k);
+    ss = fmaf(v, v, ss);
+    out[row * d_pad + k] = __float2bfloat16_rn(v);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0 && row < N) {
+    const float nrm = sqrtf(ss) * 1.0001f;  // round up a little
+    atomicMax(&hdr->max_norm_bits, __float_as_uint(nrm));
+  }
+}
+
+__global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
+                                  const int64_t* __restrict__ user_ids, int64_t B, int B_pad, int d,
+                                  int d_pad, int K, int64_t N, int filter,
+                                  const int64_t* __restrict__ indptr, int64_t n_users,
+                                  const CatalogHeader* __restrict__ hdr,
+                                  __nv_bfloat16* __restrict__ A, RowMeta* __restrict__ meta,
+                                  uint32_t* __restrict__ row_tau_key, int32_t* __restrict__ row_status) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B_pad) return;
+  const bool real = row < B;
+  const int64_t u = real ? user_ids[row] : 0;
+  float ss = 0.f;
+  for (int k = lane; k < d_pad; k += 32) {
+    float v = 0.f;
+    if (real && k < d) v = __ldg(U + u * ldu + k);
+    ss = fmaf(v, v, ss);
+    A[row * d_pad + k] = __float2bfloat16_rn(v);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) {
+    RowMeta m;
+    const float max_norm = __uint_as_float(hdr->max_norm_bits);
+    const float coef = ERR_COEF + (float)d_pad * 2.4e-7f;
+    m.eps2 = 2.f * coef * (sqrtf(ss) * 1.0001f) * max_norm + 1e-30f;
+    int64_t c = 0;
+    if (real && filter && indptr && u >= 0 && u < n_users) c = indptr[u + 1] - indptr[u];
+    const bool apply = c > 0 && (int64_t)K + c <= N;
+    const int64_t k_row = (int64_t)K + (apply ? c : 0);
+    m.apply = apply;
+    m.k_row = (int32_t)min(k_row, (int64_t)(1 << 30));
+    const bool fast = real && k_row <= KROW_MAX;
+    m.active = fast;
+    meta[row] = m;
+    row_tau_key[row] = 0u;  // below every finite float
+    row_status[row] = (real && !fast) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// sweep kernel
+// ------------------------------------------------------------------------------------------
+struct SweepSmem {
+  uint64_t full[8];
+  uint64_t empty[8];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint64_t a_full;
+  uint64_t a_empty;
+  uint32_t tmem_base;
+  uint32_t pad_[3];
+  uint32_t hist[4][256];
+};
+
+// Warp-cooperative compaction of one row's candidate list: find a lower bound of the k-th
+// largest coarse score (24-bit radix select on the order-preserving key), set
+// tau = bound - eps2, keep entries >= tau.  Returns the new count; *tau_out gets the new tau.
+__device__ __forceinline__ int compact_row(float* __restrict__ sc, int32_t* __restrict__ id, int n,
+                                           int k, float eps2, uint32_t* hist, int lane,
+                                           float* tau_out) {
+  uint32_t keys[CAP / 32];
+#pragma unroll
+  for (int j = 0; j < CAP / 32; ++j) {
+    const int i = j * 32 + lane;
+    keys[j] = (i < n) ? float_to_key(sc[i]) : 0u;
+  }
+  uint32_t prefix = 0;
+  uint32_t krem = (uint32_t)k;
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = 24 - 8 * pass;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < CAP / 32; ++j) {
+      const int i = j * 32 + lane;
+      const bool match = (pass == 0) || ((keys[j] >> (shift + 8)) == prefix);
+      if (i < n && match) atomicAdd(&hist[(keys[j] >> shift) & 255u], 1u);
+    }
+    __syncwarp();
+    uint32_t mine[8], v = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { mine[b] = hist[lane * 8 + b]; v += mine[b]; }
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += t;
+    }
+    const uint32_t excl = incl - v;
+    uint32_t found_digit = 0, found_krem = 0;
+    const bool owner = excl < krem && krem <= incl;
+    if (owner) {
+      uint32_t c = excl;
+#pragma unroll
+      for (int b = 7; b >= 0; --b) {
+        if (c + mine[b] >= krem) { found_digit = lane * 8 + b; found_krem = krem - c; break; }
+        c += mine[b];
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, owner);
+    const int src = __ffs(bal) - 1;  // exactly one owner when n >= k
+    found_digit = __shfl_sync(0xffffffffu, found_digit, src < 0 ? 0 : src);
+    found_krem = __shfl_sync(0xffffffffu, found_krem, src < 0 ? 0 : src);
+    prefix = (prefix << 8) | found_digit;
+    krem = found_krem;
+    __syncwarp();
+  }
+  const float bound = key_to_float(prefix << 8);  // <= k-th largest coarse score
+  const float tau = bound - eps2;
+  *tau_out = tau;
+  int w = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    float s = 0.f;
+    int32_t it = 0;
+    if (i < n) { s = sc[i]; it = id[i]; }
+    const bool keep = (i < n) && (s >= tau);
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) {
+      const int pos = w + __popc(bal & ((1u << lane) - 1u));
+      sc[pos] = s;
+      id[pos] = it;
+    }
+    w += __popc(bal);
+  }
+  __syncwarp();
+  return w;
+}
+
+__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const SweepParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for SWIZZLE_128B tiles
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smemA = smem;                                  // KB * 16 KB
+  uint8_t* smemB = smem + (size_t)p.KB * A_KB_BYTES;      // nstage * KB * 32 KB
+  SweepSmem* ss = (SweepSmem*)(smemB + (size_t)p.nstage * p.KB * B_KB_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_units = p.m_tiles * p.n_splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstage; ++s) { ptx::mbar_init(&ss->full[s], 1); ptx::mbar_init(&ss->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&ss->tmem_full[a], 1); ptx::mbar_init(&ss->tmem_empty[a], 4); }
+    ptx::mbar_init(&ss->a_full, 1);
+    ptx::mbar_init(&ss->a_empty, 1);
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&ss->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ss->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t uiter = 0;
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++uiter) {
+        const int split = unit / p.m_tiles, m = unit % p.m_tiles;
+        const int t0 = split * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
+        ptx::mbar_wait(&ss->a_empty, (uiter & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&ss->a_full, (uint32_t)(p.KB * A_KB_BYTES));
+        for (int kb = 0; kb < p.KB; ++kb)
+          ptx::tma_load_2d(smemA + (size_t)kb * A_KB_BYTES, &tmA, &ss->a_full, kb * KBLK, m * TM);
+        for (int t = t0; t < t1; ++t) {
+          ptx::mbar_wait(&ss->empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&ss->full[stage], (uint32_t)(p.KB * B_KB_BYTES));
+          uint8_t* dst = smemB + (size_t)stage * p.KB * B_KB_BYTES;
+          for (int kb = 0; kb < p.KB; ++kb)
+            ptx::tma_load_2d(dst + (size_t)kb * B_KB_BYTES, &tmB, &ss->full[stage], kb * KBLK, t * TN);
+          if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(TM, TN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      uint32_t uiter = 0;
+      const uint32_t a_addr = ptx::smem_u32(smemA);
+      const uint32_t b_addr = ptx::smem_u32(smemB);
+      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++uiter) {
+        const int split = unit / p.m_tiles;
+        const int t0 = split * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
+        ptx::mbar_wait(&ss->a_full, uiter & 1);
+        for (int t = t0; t < t1; ++t) {
+          ptx::mbar_wait(&ss->tmem_empty[acc], acc_phase ^ 1);
+          ptx::mbar_wait(&ss->full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
+          for (int kb = 0; kb < p.KB; ++kb) {
+            const uint64_t da = ptx::umma_desc_sw128_kmajor(a_addr + (uint32_t)(kb * A_KB_BYTES));
+            const uint64_t db = ptx::umma_desc_sw128_kmajor(
+                b_addr + (uint32_t)((stage * p.KB + kb) * B_KB_BYTES));
+#pragma unroll
+            for (int k4 = 0; k4 < KBLK / 16; ++k4) {
+              // advance 16 bf16 = 32 bytes inside the 128-byte swizzled row: +2 in the >>4 field
+              ptx::umma_f16(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
+                            (uint32_t)((kb | k4) != 0));
+            }
+          }
+          ptx::umma_commit(&ss->empty[stage]);      // smem stage reusable when these MMAs finish
+          ptx::umma_commit(&ss->tmem_full[acc]);    // accumulator ready for the epilogue
+          if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+        ptx::umma_commit(&ss->a_empty);             // A tile reusable after the unit's last MMA
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
+    const int q = warp & 3;                 // TMEM lanes [32q, 32q+32)
+    const int trow = q * 32 + lane;         // row inside the tile
+    uint32_t* hist = ss->hist[q];
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const float pinf = __int_as_float(0x7f800000);
+    const float ninf = __int_as_float(0xff800000);
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int split = unit / p.m_tiles, m = unit % p.m_tiles;
+      const int t0 = split * p.tiles_per_split;
+      const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
+      const int grow = m * TM + trow;
+      const RowMeta meta = p.meta[grow];
+      const int64_t slot = (int64_t)split * p.B_pad + grow;
+      float* my_sc = p.cand_score + slot * CAP;
+      int32_t* my_id = p.cand_id + slot * CAP;
+      bool active = meta.active != 0;
+      float tau = active ? ninf : pinf;
+      int cnt = 0;
+      for (int t = t0; t < t1; ++t) {
+        if (active) {  // another split of this row may have tightened the bound
+          const uint32_t gk = __ldcg(p.row_tau_key + grow);
+          if (gk != 0u) tau = fmaxf(tau, key_to_float(gk));
+        }
+        ptx::mbar_wait(&ss->tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN);
+        const int n_base = t * TN;
+#pragma unroll 1
+        for (int ch = 0; ch < TN / 32; ++ch) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(ch * 32), r);
+          ptx::tmem_ld_wait();
+          float mx = __uint_as_float(r[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          if (mx >= tau) {
+            const int nb = n_base + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(r[j]);
+              if (v >= tau && (int64_t)(nb + j) < p.N) {
+                my_sc[cnt] = v;
+                my_id[cnt] = nb + j;
+                ++cnt;
+              }
+            }
+          }
+          uint32_t need = __ballot_sync(0xffffffffu, cnt > CAP - 32);
+          while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const int64_t s_slot = (int64_t)split * p.B_pad + (m * TM + q * 32 + src);
+            const int s_cnt = __shfl_sync(0xffffffffu, cnt, src);
+            const int s_k = __shfl_sync(0xffffffffu, meta.k_row, src);
+            const float s_e = __shfl_sync(0xffffffffu, meta.eps2, src);
+            float new_tau;
+            const int w = compact_row(p.cand_score + s_slot * CAP, p.cand_id + s_slot * CAP, s_cnt,
+                                      s_k, s_e, hist, lane, &new_tau);
+            if (lane == src) {
+              cnt = w;
+              tau = fmaxf(tau, new_tau);
+              atomicMax(p.row_tau_key + grow, float_to_key(new_tau));
+              if (w > CAP - 64) {  // too many near-ties to bound: hand the row to the exact path
+                active = false;
+                tau = pinf;
+                cnt = 0;
+                p.row_status[grow] = 1;
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      p.cand_cnt[slot] = cnt;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize kernel: one CTA per user row
+// ------------------------------------------------------------------------------------------
+struct FinalizeParams {
+  int64_t B, N;
+  int32_t B_pad, n_splits, K, d;
+  const RowMeta* meta;
+  int32_t* row_status;
+  const float* cand_score;
+  const int32_t* cand_id;
+  const int32_t* cand_cnt;
+  const float* U; int64_t ldu;
+  const float* I; int64_t ldi;
+  const int64_t* user_ids;
+  const int64_t* indptr; const int32_t* idx;
+  int64_t* out_ids;    // [B, K]
+  float* out_scores;   // [B, K] or null
+};
+
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_kernel(const FinalizeParams p) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_krem;
+  __shared__ int s_nc;
+  __shared__ int32_t c_id[MAXC];
+  __shared__ unsigned long long c_sort[MAXC];
+  __shared__ int32_t htab[2 * MAXC];
+  __shared__ float urow[MAX_KB * KBLK];
+  const int tid = threadIdx.x;
+  const int64_t row = blockIdx.x;
+  int64_t* oid = p.out_ids + row * p.K;
+  float* osc = p.out_scores ? p.out_scores + row * p.K : nullptr;
+  const RowMeta meta = p.meta[row];
+  if (p.row_status[row] != 0) {
+    for (int i = tid; i < p.K; i += FIN_THREADS) { oid[i] = -1; if (osc) osc[i] = 0.f; }
+    return;
+  }
+  // ---- exact k_row-th largest coarse score over the union of the split lists (4 x 8-bit radix)
+  uint32_t prefix = 0, krem = (uint32_t)meta.k_row;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    hist[tid] = 0;
+    __syncthreads();
+    for (int s = 0; s < p.n_splits; ++s) {
+      const int64_t slot = (int64_t)s * p.B_pad + row;
+      const int n = p.cand_cnt[slot];
+      const float* sc = p.cand_score + slot * CAP;
+      for (int i = tid; i < n; i += FIN_THREADS) {
+        const uint32_t key = float_to_key(sc[i]);
+        if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t c = 0;
+      int b = 255;
+      for (; b > 0; --b) {
+        if (c + hist[b] >= krem) break;
+        c += hist[b];
+      }
+      s_prefix = (prefix << 8) | (uint32_t)b;
+      s_krem = krem - c;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    krem = s_krem;
+    __syncthreads();
+  }
+  const float thr = key_to_float(prefix) - meta.eps2;
+  // ---- collect candidates
+  if (tid == 0) s_nc = 0;
+  for (int i = tid; i < 2 * MAXC; i += FIN_THREADS) htab[i] = -1;
+  __syncthreads();
+  for (int s = 0; s < p.n_splits; ++s) {
+    const int64_t slot = (int64_t)s * p.B_pad + row;
+    const int n = p.cand_cnt[slot];
+    const float* sc = p.cand_score + slot * CAP;
+    const int32_t* id = p.cand_id + slot * CAP;
+    for (int i = tid; i < n; i += FIN_THREADS) {
+      if (sc[i] >= thr) {
+        const int pos = atomicAdd(&s_nc, 1);
+        if (pos < MAXC) c_id[pos] = id[i];
+      }
+    }
+  }
+  __syncthreads();
+  const int nc = s_nc;
+  if (nc > MAXC || nc < p.K) {  // cannot bound (dense near-ties) -> exact path
+    if (tid == 0) p.row_status[row] = 1;
+    for (int i = tid; i < p.K; i += FIN_THREADS) { oid[i] = -1; if (osc) osc[i] = 0.f; }
+    return;
+  }
+  const int64_t u = p.user_ids[row];
+  // ---- consumed filter through a hash set of candidate ids
+  if (meta.apply) {
+    for (int i = tid; i < nc; i += FIN_THREADS) {
+      uint32_t h = ((uint32_t)c_id[i] * 2654435761u) & (2 * MAXC - 1);
+      while (atomicCAS(&htab[h], -1, i) != -1) h = (h + 1) & (2 * MAXC - 1);
+    }
+    __syncthreads();
+    const int64_t beg = p.indptr[u], end = p.indptr[u + 1];
+    for (int64_t j = beg + tid; j < end; j += FIN_THREADS) {
+      const int32_t it = p.idx[j];
+      uint32_t h = ((uint32_t)it * 2654435761u) & (2 * MAXC - 1);
+      while (true) {
+        const int32_t e = htab[h];
+        if (e < 0) break;
+        if (c_id[e] == it || c_id[e] == ~it) { c_id[e] = ~it; break; }  // mark removed (negative)
+        h = (h + 1) & (2 * MAXC - 1);
+      }
+    }
+  }
+  for (int k = tid; k < p.d; k += FIN_THREADS) urow[k] = __ldg(p.U + u * p.ldu + k);
+  __syncthreads();
+  // ---- exact fp32 re-score: acc = fma(u[k], i[k], acc), k ascending
+  int P = 1;
+  while (P < nc) P <<= 1;
+  for (int i = tid; i < P; i += FIN_THREADS) {
+    unsigned long long comp = 0ull;
+    if (i < nc && c_id[i] >= 0) {
+      const float* it = p.I + (int64_t)c_id[i] * p.ldi;
+      float acc = 0.f;
+      for (int k = 0; k < p.d; ++k) acc = fmaf(urow[k], __ldg(it + k), acc);
+      comp = ((unsigned long long)float_to_key(acc) << 32) | (unsigned long long)(~(uint32_t)c_id[i]);
+    }
+    c_sort[i] = comp;
+  }
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < P; i += FIN_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = c_sort[i], b = c_sort[ixj];
+          const bool desc = ((i & k) == 0);
+          if (desc ? (a < b) : (a > b)) { c_sort[i] = b; c_sort[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < p.K; i += FIN_THREADS) {
+    const unsigned long long c = c_sort[i];
+    oid[i] = (int64_t)(~(uint32_t)(c & 0xffffffffull));
+    if (osc) osc[i] = key_to_float((uint32_t)(c >> 32));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+// bf16 [rows, d_pad] row-major, box = [KBLK, box_rows], SWIZZLE_128B
+static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int d_pad, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  B200_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+static inline int pad_to(int64_t x, int m) { return (int)((x + m - 1) / m * m); }
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Plan {
+  int B_pad, d_pad, KB, m_tiles, total_tiles, n_splits, tiles_per_split, nstage;
+  int64_t N_pad;
+  size_t smem_bytes;
+  // workspace offsets
+  size_t off_A, off_meta, off_tau, off_status, off_cnt, off_sc, off_id, total;
+};
+
+static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
+  pl->d_pad = pad_to(d, KBLK);
+  pl->KB = pl->d_pad / KBLK;
+  B200_REQUIRE(pl->KB >= 1 && pl->KB <= MAX_KB, "fused scorer supports embed width <= %d (got %d)",
+               MAX_KB * KBLK, d);
+  pl->B_pad = pad_to(B, TM);
+  pl->N_pad = (N + TN - 1) / TN * TN;
+  pl->m_tiles = pl->B_pad / TM;
+  pl->total_tiles = (int)(pl->N_pad / TN);
+  // item splits: minimise makespan = waves * (tiles per split + per-unit overhead)
+  const int ovh = 12;
+  long best = -1;
+  int bestS = 1;
+  const int maxS = pl->total_tiles < 2 * kNumSMs ? pl->total_tiles : 2 * kNumSMs;
+  for (int S = 1; S <= maxS; ++S) {
+    const long units = (long)pl->m_tiles * S;
+    const long waves = (units + kNumSMs - 1) / kNumSMs;
+    const long tps = (pl->total_tiles + S - 1) / S;
+    const long cost = waves * (tps + ovh);
+    if (best < 0 || cost < best) { best = cost; bestS = S; }
+  }
+  pl->tiles_per_split = (pl->total_tiles + bestS - 1) / bestS;
+  pl->n_splits = (pl->total_tiles + pl->tiles_per_split - 1) / pl->tiles_per_split;
+  const size_t budget = 227 * 1024 - 1024 /*align*/ - sizeof(SweepSmem) - (size_t)pl->KB * A_KB_BYTES;
+  int ns = (int)(budget / ((size_t)pl->KB * B_KB_BYTES));
+  if (ns > 6) ns = 6;
+  B200_REQUIRE(ns >= 2, "not enough shared memory for the item pipeline");
+  pl->nstage = ns;
+  pl->smem_bytes = 1024 + (size_t)pl->KB * A_KB_BYTES + (size_t)ns * pl->KB * B_KB_BYTES + sizeof(SweepSmem);
+  size_t off = 0;
+  pl->off_A = off; off += al256((size_t)pl->B_pad * pl->d_pad * 2);
+  pl->off_meta = off; off += al256((size_t)pl->B_pad * sizeof(RowMeta));
+  pl->off_tau = off; off += al256((size_t)pl->B_pad * 4);
+  pl->off_status = off; off += al256((size_t)pl->B_pad * 4);
+  pl->off_cnt = off; off += al256((size_t)pl->n_splits * pl->B_pad * 4);
+  pl->off_sc = off; off += al256((size_t)pl->n_splits * pl->B_pad * CAP * 4);
+  pl->off_id = off; off += al256((size_t)pl->n_splits * pl->B_pad * CAP * 4);
+  pl->total = off + 256;
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace b200
+
+using namespace b200;
+using namespace b200::tc;
+
+extern "C" int b200_embed_catalog_bytes(int64_t N, int32_t d, size_t* bytes) {
+  B200_REQUIRE(bytes && N >= 1 && d >= 1, "b200_embed_catalog_bytes: bad arguments");
+  const int d_pad = pad_to(d, KBLK);
+  const int64_t N_pad = (N + TN - 1) / TN * TN;
+  *bytes = 256 + (size_t)N_pad * d_pad * 2 + 1024;
+  return 0;
+}
+
+extern "C" int b200_embed_catalog_prepare(const float* I, int64_t ldi, int64_t N, int32_t d,
+                                          void* catalog, size_t bytes, void* stream_) {
+  B200_REQUIRE(I && catalog, "b200_embed_catalog_prepare: null pointer");
+  size_t need;
+  if (int rc = b200_embed_catalog_bytes(N, d, &need)) return rc;
+  B200_REQUIRE(bytes >= need, "catalog buffer too small (%zu < %zu)", bytes, need);
+  B200_REQUIRE(((uintptr_t)catalog & 255) == 0, "catalog buffer must be 256-byte aligned");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int d_pad = pad_to(d, KBLK);
+  const int64_t N_pad = (N + TN - 1) / TN * TN;
+  CatalogHeader h;
+  h.max_norm_bits = 0; h.d = d; h.d_pad = d_pad; h.N = N; h.N_pad = N_pad;
+  B200_CUDA_OK(cudaMemcpyAsync(catalog, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
+  __nv_bfloat16* tab = (__nv_bfloat16*)((char*)catalog + 256);
+  const int64_t threads = N_pad * 32;
+  prep_items_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
+      I, ldi, N, d, d_pad, N_pad, tab, (CatalogHeader*)catalog);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200_recommend_embed_workspace_bytes(int64_t B, int64_t N, int32_t d, int32_t K,
+                                                    size_t* bytes) {
+  B200_REQUIRE(bytes && B >= 1 && N >= 1 && d >= 1 && K >= 1, "bad arguments");
+  Plan pl;
+  if (int rc = make_plan(B, N, d, &pl)) return rc;
+  *bytes = pl.total;
+  return 0;
+}
+
+extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* user_ids, int64_t B,
+                                    const float* I, int64_t ldi, int64_t N, int32_t d,
+                                    const void* catalog, const int64_t* indptr, const int32_t* idx,
+                                    int64_t n_users, int32_t filter, int32_t K, int64_t* out_ids,
+                                    float* out_scores, int32_t* row_status, void* workspace,
+                                    size_t workspace_bytes, void* stream_, void* ev_sweep_start,
+                                    void* ev_sweep_stop) {
+  B200_REQUIRE(U && user_ids && I && catalog && out_ids && row_status && workspace,
+               "b200_recommend_embed: null pointer");
+  B200_REQUIRE((int64_t)K <= N, "`n_rec` %d exceeds num of items %lld", K, (long long)N);
+  B200_REQUIRE(K <= KROW_MAX, "b200_recommend_embed: n_rec %d above the fused-path limit %d", K, KROW_MAX);
+  B200_REQUIRE(N < (1ll << 31) - TN, "N too large");
+  if (B == 0) return 0;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Plan pl;
+  if (int rc = make_plan(B, N, d, &pl)) return rc;
+  B200_REQUIRE(workspace_bytes >= pl.total, "workspace too small (%zu < %zu)", workspace_bytes, pl.total);
+  char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+  __nv_bfloat16* A = (__nv_bfloat16*)(ws + pl.off_A);
+  RowMeta* meta = (RowMeta*)(ws + pl.off_meta);
+  uint32_t* tau = (uint32_t*)(ws + pl.off_tau);
+  int32_t* status = (int32_t*)(ws + pl.off_status);
+  int32_t* cnt = (int32_t*)(ws + pl.off_cnt);
+  float* csc = (float*)(ws + pl.off_sc);
+  int32_t* cid = (int32_t*)(ws + pl.off_id);
+  const CatalogHeader* hdr = (const CatalogHeader*)catalog;
+  const __nv_bfloat16* Ibf = (const __nv_bfloat16*)((const char*)catalog + 256);
+
+  prep_users_kernel<<<(unsigned)ceil_div64((int64_t)pl.B_pad * 32, 256), 256, 0, stream>>>(
+      U, ldu, user_ids, B, pl.B_pad, d, pl.d_pad, K, N, filter, indptr, n_users, hdr, A, meta, tau,
+      status);
+  B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)pl.n_splits * pl.B_pad * 4, stream));
+
+  CUtensorMap tmA, tmB;
+  if (int rc = make_tmap(&tmA, A, pl.B_pad, pl.d_pad, TM)) return rc;
+  if (int rc = make_tmap(&tmB, Ibf, pl.N_pad, pl.d_pad, TN)) return rc;
+
+  SweepParams sp;
+  sp.N = N; sp.B_pad = pl.B_pad; sp.m_tiles = pl.m_tiles; sp.n_splits = pl.n_splits;
+  sp.tiles_per_split = pl.tiles_per_split; sp.total_tiles = pl.total_tiles; sp.KB = pl.KB;
+  sp.nstage = pl.nstage; sp.meta = meta; sp.row_tau_key = tau; sp.row_status = status;
+  sp.cand_score = csc; sp.cand_id = cid; sp.cand_cnt = cnt;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024));
+    attr_set = true;
+  }
+  const int n_units = pl.m_tiles * pl.n_splits;
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    B200_CUDA_OK(cudaGetDevice(&dev));
+    B200_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = n_units < sm_count ? n_units : sm_count;
+  if (ev_sweep_start) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_start, stream));
+  sweep_kernel<<<grid, SWEEP_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, sp);
+  if (ev_sweep_stop) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_stop, stream));
+
+  FinalizeParams fp;
+  fp.B = B; fp.N = N; fp.B_pad = pl.B_pad; fp.n_splits = pl.n_splits; fp.K = K; fp.d = d;
+  fp.meta = meta; fp.row_status = status; fp.cand_score = csc; fp.cand_id = cid; fp.cand_cnt = cnt;
+  fp.U = U; fp.ldu = ldu; fp.I = I; fp.ldi = ldi; fp.user_ids = user_ids; fp.indptr = indptr;
+  fp.idx = idx; fp.out_ids = out_ids; fp.out_scores = out_scores;
+  finalize_kernel<<<(unsigned)B, FIN_THREADS, 0, stream>>>(fp);
+  B200_CUDA_OK(cudaMemcpyAsync(row_status, status, (size_t)B * 4, cudaMemcpyDeviceToDevice, stream));
+  count_launch(3);
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}

@@ -16,6 +16,9 @@ from . import _lib
 from .consumed import ConsumedCSR, as_csr
 
 _SCORE_WS_BYTES = 1 << 30  # materialised-score workspace of the exact path
+FUSED_MAX_D = 256           # limits of b200_recommend_embed (include/b200reco.h)
+FUSED_MAX_K = 448
+FUSED_ROWS_PER_CALL = 16384
 
 
 def _as_device_f32(x, device):
@@ -52,6 +55,20 @@ class EmbedScorer:
         self.n_users = int(n_users) if n_users is not None else int(self.U.shape[0])
         self.set_consumed(user_consumed)
         self._torch = torch
+        self.events = None  # optional list collecting (start, stop) CUDA events of the sweep kernel
+        self.catalog = None
+        if self.d <= FUSED_MAX_D:
+            self._prepare_catalog()
+
+    def _prepare_catalog(self):
+        """bf16 K-major copy of the item table + max row norm (once per table)."""
+        torch = self._torch if hasattr(self, "_torch") else __import__("torch")
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(_lib.lib.b200_embed_catalog_bytes(self.n_items, self.d, ctypes.byref(nbytes)))
+        self.catalog = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        _lib.check(_lib.lib.b200_embed_catalog_prepare(
+            _lib.ptr(self.I), self.I.stride(0), self.n_items, self.d, _lib.ptr(self.catalog),
+            nbytes.value, _lib.current_stream()))
 
     def set_consumed(self, user_consumed):
         if user_consumed is None:
@@ -103,12 +120,91 @@ class EmbedScorer:
                 out_scores[r0:r0 + b] if return_scores else None)
         return (out_ids, out_scores) if return_scores else out_ids
 
-    def recommend(self, user_ids, n_rec, filter_consumed=True, return_scores=False):
+    def fused_ok(self, n_rec) -> bool:
+        return self.catalog is not None and n_rec <= FUSED_MAX_K
+
+    def recommend_fused(self, user_ids_d, n_rec, filter_consumed=True, return_scores=False):
+        """Tensor-core path (b200_recommend_embed).  Returns (ids, scores|None, status):
+        rows with status != 0 hold -1 ids and must be re-run on the exact path."""
+        torch = self._torch
+        B = int(user_ids_d.numel())
+        N = self.n_items
+        if n_rec > N:
+            raise ValueError(f"`n_rec` {n_rec} exceeds num of items {N}")
+        out_ids = torch.empty((B, n_rec), dtype=torch.int64, device=self.device)
+        out_scores = torch.empty((B, n_rec), dtype=torch.float32, device=self.device) if return_scores else None
+        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        stream = _lib.current_stream()
+        use_filter = 1 if (filter_consumed and self.csr.nnz > 0) else 0
+        for r0 in range(0, B, FUSED_ROWS_PER_CALL):
+            b = min(FUSED_ROWS_PER_CALL, B - r0)
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(_lib.lib.b200_recommend_embed_workspace_bytes(b, N, self.d, n_rec, ctypes.byref(nbytes)))
+            ws = self._workspace(nbytes.value)
+            ev0 = ev1 = None
+            if self.events is not None:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()   # creates the cudaEvent_t; re-recorded inside the C-ABI call
+                e1.record()
+                ev0, ev1 = ctypes.c_void_p(e0.cuda_event), ctypes.c_void_p(e1.cuda_event)
+            _lib.check(_lib.lib.b200_recommend_embed(
+                _lib.ptr(self.U), self.U.stride(0), _lib.ptr(user_ids_d[r0:r0 + b]), b,
+                _lib.ptr(self.I), self.I.stride(0), N, self.d, _lib.ptr(self.catalog),
+                _lib.ptr(self.indptr_d), _lib.ptr(self.idx_d), self.csr.n_users, use_filter, n_rec,
+                _lib.ptr(out_ids[r0:r0 + b]),
+                _lib.ptr(out_scores[r0:r0 + b]) if return_scores else None,
+                _lib.ptr(status[r0:r0 + b]), _lib.ptr(ws), nbytes.value, stream, ev0, ev1))
+            if self.events is not None:
+                self.events.append((e0, e1))
+        return out_ids, out_scores, status
+
+    def _workspace(self, nbytes):
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < nbytes:
+            self._ws = None
+            ws = self._torch.empty(int(nbytes), dtype=self._torch.uint8, device=self.device)
+            self._ws = ws
+        return ws
+
+    def recommend_device(self, user_ids_d, n_rec, filter_consumed=True, return_scores=False,
+                         path="auto"):
+        """Device ids in, device results out; flagged rows are re-run on the exact path."""
+        torch = self._torch
+        n_rec = int(n_rec)
+        if path == "exact" or (path == "auto" and not self.fused_ok(n_rec)):
+            return self.recommend_exact(user_ids_d, n_rec, filter_consumed, return_scores)
+        ids, scores, status = self.recommend_fused(user_ids_d, n_rec, filter_consumed, return_scores)
+        bad = torch.nonzero(status).flatten()          # one sync; empty in the common case
+        if bad.numel():
+            res = self.recommend_exact(user_ids_d[bad], n_rec, filter_consumed, return_scores)
+            if return_scores:
+                ids[bad], scores[bad] = res[0], res[1]
+            else:
+                ids[bad] = res
+        return (ids, scores) if return_scores else ids
+
+    def score_rows(self, user_ids_d):
+        """Materialised exact fp32 scores [B, n_items] (used by the random_rec branch)."""
+        torch = self._torch
+        B = int(user_ids_d.numel())
+        N = self.n_items
+        ld = (N + 3) // 4 * 4
+        scores = torch.empty((B, ld), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.b200_score_rows_f32(
+            _lib.ptr(self.U), self.U.stride(0), _lib.ptr(user_ids_d), B,
+            _lib.ptr(self.I), self.I.stride(0), N, self.d, _lib.ptr(scores), ld,
+            _lib.current_stream()))
+        return scores[:, :N]
+
+    def recommend(self, user_ids, n_rec, filter_consumed=True, return_scores=False, path="auto"):
         """Host ids in, host ``int64[B, n_rec]`` out (the reference-facing call)."""
         torch = self._torch
         uid_h = torch.as_tensor(np.asarray(user_ids, dtype=np.int64))
+        if uid_h.numel() >= 4096:
+            uid_h = uid_h.pin_memory()
         uid_d = uid_h.to(self.device, non_blocking=True)
-        res = self.recommend_exact(uid_d, int(n_rec), filter_consumed, return_scores)
+        res = self.recommend_device(uid_d, int(n_rec), filter_consumed, return_scores, path)
         if return_scores:
             return res[0].cpu().numpy(), res[1].cpu().numpy()
         return res.cpu().numpy()

@@ -156,3 +156,38 @@ def near_tie_mask(ref_ids, got_ids, full_scores, rel_tol=1e-6):
         b = full_scores[r, got_ids[r, diff]].astype(np.float64)
         ok[r, diff] = np.abs(a - b) <= rel_tol * scale
     return ok
+
+
+# ---------------------------------------------------------------------------------------------
+# Cost-faithful variant for the CPU-baseline leg of bench.py: the same numpy primitives, in the
+# same order, as the reference (tile of int64 ids, per-user isin filter, argpartition, then a
+# reversed argsort) — ranking.py:30-49,59-61,76-78.  Tie order is whatever numpy gives, like the
+# reference; `rank_recommendations` above is the deterministic checker.
+# ---------------------------------------------------------------------------------------------
+def rank_recommendations_numpy_path(user_ids, preds, n_rec, n_items, user_consumed, filter_consumed=True):
+    if n_rec > n_items:
+        raise ValueError(f"`n_rec` {n_rec} exceeds num of items {n_items}")
+    preds = np.asarray(preds)
+    if preds.ndim == 1:
+        preds = preds.reshape(len(preds) // n_items, n_items)
+    id_matrix = np.tile(np.arange(n_items), (len(preds), 1))           # ranking.py:30
+    picked_ids, picked_scores = [], []
+    for r, user in enumerate(user_ids):                                 # ranking.py:33-45
+        ids, row = id_matrix[r], preds[r]
+        consumed = user_consumed[user] if user in user_consumed else []
+        if filter_consumed and consumed and n_rec + len(consumed) <= n_items:
+            keep = np.isin(ids, consumed, assume_unique=True, invert=True)   # ranking.py:60
+            ids, row = ids[keep], row[keep]
+        top = np.argpartition(row, -n_rec)[-n_rec:]                     # ranking.py:77
+        picked_ids.append(ids[top])
+        picked_scores.append(row[top])
+    picked_ids, picked_scores = np.array(picked_ids), np.array(picked_scores)
+    order = np.argsort(picked_scores, axis=1)[:, ::-1]                  # ranking.py:48
+    return np.take_along_axis(picked_ids, order, axis=1)
+
+
+def recommend_from_embedding_numpy_path(user_ids, n_rec, user_rows, item_embeddings, n_items,
+                                        user_consumed, filter_consumed=True):
+    """recommend.py:66-77 with ``user_rows = user_embeddings[user_ids]`` already gathered."""
+    preds = user_rows @ item_embeddings[:n_items].T
+    return rank_recommendations_numpy_path(user_ids, preds, n_rec, n_items, user_consumed, filter_consumed)

@@ -102,3 +102,13 @@ def test_assign_oov_and_predict():
     np.testing.assert_allclose(out[-1], E.mean(axis=0))
     p = orc.predict_from_embedding(E, E, [0, 1], [2, 3])
     assert ((p > 0) & (p < 1)).all()
+
+
+def test_numpy_path_variant_equals_deterministic_oracle():
+    rng = np.random.default_rng(8)
+    B, N, K = 6, 900, 25
+    preds = rng.standard_normal((B, N)).astype(np.float32)
+    consumed = {u: rng.choice(N, size=40, replace=False).tolist() for u in range(B - 1)}
+    a = orc.rank_recommendations_numpy_path(list(range(B)), preds, K, N, consumed, True)
+    b = orc.rank_recommendations("ranking", list(range(B)), preds, K, N, consumed, True)
+    np.testing.assert_array_equal(a, b)
