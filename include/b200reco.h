@@ -68,9 +68,9 @@ int b200_score_rows_f32(const float* U, int64_t ldu, const int64_t* user_ids, in
  * catalog: device buffer prepared ONCE per item table (bf16 K-major copy + max row norm).
  * Result per row: the K best non-consumed items by EXACT fp32 score (same definition as
  * b200_score_rows_f32), sorted (score desc, id asc).  row_status[r] (device int32[B]) = 1 marks a
- * row the fused path could not bound (K + consumed > 448, or too many near-ties): its out_ids are
+ * row the fused path could not bound (K + consumed > 288, or too many near-ties): its out_ids are
  * -1 and the caller re-runs it through b200_score_rows_f32 + b200_mask_consumed + b200_topk_rows.
- * Limits: d <= 256, K <= 448. */
+ * Limits: d <= 256, K <= 288. */
 int b200_embed_catalog_bytes(int64_t N, int32_t d, size_t* bytes);
 int b200_embed_catalog_prepare(const float* I, int64_t ldi, int64_t N, int32_t d, void* catalog,
                                size_t bytes, void* stream);
@@ -82,6 +82,21 @@ int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* user_ids, i
                          void* workspace, size_t workspace_bytes, void* stream,
                          void* ev_sweep_start /* cudaEvent_t or NULL: recorded on `stream` */,
                          void* ev_sweep_stop  /* just before / after the tcgen05 sweep kernel */);
+
+/* ---- a10: LightGCN propagation (libreco/algorithms/torch_modules/lightgcn_module.py:66-88) -
+ * out[r,:] = sum_j val[j] * E[col[j],:] over the CSR row r (fma in CSR order), optionally fused with
+ * the layer-mean: acc = (acc_init ? E[r,:] : acc[r,:]) + out[r,:], then acc /= final_div if > 0.
+ * Rows longer than b200_spmm_long_row_threshold() nnz must be listed in long_rows and split into
+ * chunks of b200_spmm_chunk() nnz: chunk c covers nnz [indptr[row] + chunk_k[c]*chunk, ...) of
+ * row chunk_row[c]; long_chunk_ptr[n_long+1] delimits each long row's chunks; partials is a
+ * caller-provided float [n_chunks, d] scratch.  Deterministic (no float atomics).  d <= 256. */
+int b200_spmm_long_row_threshold(void);
+int b200_spmm_chunk(void);
+int b200_spmm_csr(const int64_t* indptr, const int32_t* col, const float* val, int64_t n_rows,
+                  const float* E, int64_t ld_e, int32_t d, float* out, int64_t ld_out, float* acc,
+                  int64_t ld_acc, int32_t acc_init, float final_div, const int32_t* long_rows,
+                  const int64_t* long_chunk_ptr, int64_t n_long, const int32_t* chunk_row,
+                  const int32_t* chunk_k, int64_t n_chunks, float* partials, void* stream);
 
 /* ---- a14: predict_from_embedding (libreco/prediction/predict.py:36-40) -----------------
  * out[r] = sum_k U[users[r],k] * I[items[r],k]; mode 0: raw, 1: expit (ranking),

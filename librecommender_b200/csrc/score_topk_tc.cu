@@ -37,12 +37,15 @@ namespace tc {
 constexpr int TM = 128;        // users per tile (UMMA M)
 constexpr int TN = 256;        // items per tile (UMMA N)
 constexpr int KBLK = 64;       // bf16 per 128-byte swizzled row
-constexpr int CAP = 1024;      // candidate slots per (row, split)
-constexpr int KROW_MAX = 448;  // fast-path limit for k_row = K + c_u
+constexpr int CAP = 512;       // candidate slots per (row, list); list = (item split, column half)
+constexpr int NB = 1024;       // bins of the per-row global coarse-score histogram
+constexpr int TRIG = 192;      // uncounted entries that trigger a compaction
+constexpr int EPI_WARPS = 8;   // two epilogue warps per TMEM lane quadrant (column halves)
+constexpr int KROW_MAX = 288;  // fast-path limit for k_row = K + c_u (a list must hold k_row + margin + TRIG)
 constexpr int MAX_KB = 4;      // d_pad <= 256
 constexpr int A_KB_BYTES = TM * KBLK * 2;   // 16 KB
 constexpr int B_KB_BYTES = TN * KBLK * 2;   // 32 KB
-constexpr int SWEEP_THREADS = 192;          // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int SWEEP_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int MAXC = 2048;                  // finalize: candidates per row
 constexpr int FIN_THREADS = 256;
 constexpr float ERR_COEF = 0.0082f;  // 2^-7*(1+2^-9) for bf16 x bf16 products + accumulation slack
@@ -55,6 +58,7 @@ struct CatalogHeader {   // first 256 bytes of the catalog buffer (device)
 
 struct RowMeta {
   float eps2;       // 2 * eps
+  float R;          // |coarse score| <= R for every item (Cauchy-Schwarz on the row norms)
   int32_t k_row;    // K (+ consumed count when the filter applies)
   int32_t active;   // 0: pad row / fallback row (never collects)
   int32_t apply;    // consumed filter applies
@@ -66,9 +70,10 @@ struct SweepParams {
   const RowMeta* meta;        // [B_pad]
   uint32_t* row_tau_key;      // [B_pad]  running max of tau (order-preserving key)
   int32_t* row_status;        // [B_pad]  1 = needs the exact path
-  float* cand_score;          // [n_splits][B_pad][CAP]
-  int32_t* cand_id;           // [n_splits][B_pad][CAP]
-  int32_t* cand_cnt;          // [n_splits][B_pad]
+  uint32_t* ghist;            // [B_pad][NB]  coarse-score histogram of every counted candidate
+  float* cand_score;          // [2*n_splits][B_pad][CAP]
+  int32_t* cand_id;           // [2*n_splits][B_pad][CAP]
+  int32_t* cand_cnt;          // [2*n_splits][B_pad]
 };
 
 // ------------------------------------------------------------------------------------------
@@ -120,6 +125,7 @@ __global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
     const float max_norm = __uint_as_float(hdr->max_norm_bits);
     const float coef = ERR_COEF + (float)d_pad * 2.4e-7f;
     m.eps2 = 2.f * coef * (sqrtf(ss) * 1.0001f) * max_norm + 1e-30f;
+    m.R = 1.02f * (sqrtf(ss) * 1.0001f) * max_norm + 1e-30f;
     int64_t c = 0;
     if (real && filter && indptr && u >= 0 && u < n_users) c = indptr[u + 1] - indptr[u];
     const bool apply = c > 0 && (int64_t)K + c <= N;
@@ -146,86 +152,92 @@ struct SweepSmem {
   uint64_t a_empty;
   uint32_t tmem_base;
   uint32_t pad_[3];
-  uint32_t hist[4][256];
 };
 
-// Warp-cooperative compaction of one row's candidate list: find a lower bound of the k-th
-// largest coarse score (24-bit radix select on the order-preserving key), set
-// tau = bound - eps2, keep entries >= tau.  Returns the new count; *tau_out gets the new tau.
+__device__ __forceinline__ int score_bin(float s, float R, float inv_w) {
+  const float t = (s + R) * inv_w;
+  return (int)fminf(fmaxf(t, 0.f), (float)(NB - 1));
+}
+
+// Warp-cooperative compaction of one candidate list of one row.
+//  1. every entry pushed since the previous compaction is counted ONCE into the row's global
+//     coarse-score histogram (shared by all lists / CTAs working on that row);
+//  2. the histogram is read back: the highest bin whose suffix count reaches k gives a rigorous
+//     lower bound of the k-th largest coarse score over everything seen so far by ANY list
+//     (counts are a subset of the items at or above each edge), tau = edge - eps2;
+//  3. the list is rewritten keeping entries >= tau.
+// Entries live in registers (CAP/32 per lane).  Returns the new count; *tau_out = new tau.
 __device__ __forceinline__ int compact_row(float* __restrict__ sc, int32_t* __restrict__ id, int n,
-                                           int k, float eps2, uint32_t* hist, int lane,
-                                           float* tau_out) {
-  uint32_t keys[CAP / 32];
+                                           int n_counted, int k, float eps2, float R, float tau_old,
+                                           uint32_t* __restrict__ gh, int lane, float* tau_out) {
+  const float inv_w = (float)NB / (2.f * R);
+  float v[CAP / 32];
+  int32_t it[CAP / 32];
 #pragma unroll
   for (int j = 0; j < CAP / 32; ++j) {
     const int i = j * 32 + lane;
-    keys[j] = (i < n) ? float_to_key(sc[i]) : 0u;
+    v[j] = 0.f;
+    it[j] = 0;
+    if (i < n) { v[j] = sc[i]; it[j] = id[i]; }
   }
-  uint32_t prefix = 0;
-  uint32_t krem = (uint32_t)k;
 #pragma unroll
-  for (int pass = 0; pass < 3; ++pass) {
-    const int shift = 24 - 8 * pass;
-#pragma unroll
-    for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < CAP / 32; ++j) {
-      const int i = j * 32 + lane;
-      const bool match = (pass == 0) || ((keys[j] >> (shift + 8)) == prefix);
-      if (i < n && match) atomicAdd(&hist[(keys[j] >> shift) & 255u], 1u);
-    }
-    __syncwarp();
-    uint32_t mine[8], v = 0;
-#pragma unroll
-    for (int b = 0; b < 8; ++b) { mine[b] = hist[lane * 8 + b]; v += mine[b]; }
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o);
-      if (lane + o < 32) incl += t;
-    }
-    const uint32_t excl = incl - v;
-    uint32_t found_digit = 0, found_krem = 0;
-    const bool owner = excl < krem && krem <= incl;
-    if (owner) {
-      uint32_t c = excl;
-#pragma unroll
-      for (int b = 7; b >= 0; --b) {
-        if (c + mine[b] >= krem) { found_digit = lane * 8 + b; found_krem = krem - c; break; }
-        c += mine[b];
-      }
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, owner);
-    const int src = __ffs(bal) - 1;  // exactly one owner when n >= k
-    found_digit = __shfl_sync(0xffffffffu, found_digit, src < 0 ? 0 : src);
-    found_krem = __shfl_sync(0xffffffffu, found_krem, src < 0 ? 0 : src);
-    prefix = (prefix << 8) | found_digit;
-    krem = found_krem;
-    __syncwarp();
+  for (int j = 0; j < CAP / 32; ++j) {
+    const int i = j * 32 + lane;
+    if (i >= n_counted && i < n) atomicAdd(gh + score_bin(v[j], R, inv_w), 1u);
   }
-  const float bound = key_to_float(prefix << 8);  // <= k-th largest coarse score
-  const float tau = bound - eps2;
+  __threadfence();
+  __syncwarp();
+  // lane l owns bins [32 l, 32 l + 32); lane 31 holds the top of the range
+  uint32_t mine[32], tot = 0;
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const uint4 h = __ldcg(reinterpret_cast<const uint4*>(gh + lane * 32) + q4);
+    mine[q4 * 4 + 0] = h.x; mine[q4 * 4 + 1] = h.y; mine[q4 * 4 + 2] = h.z; mine[q4 * 4 + 3] = h.w;
+    tot += h.x + h.y + h.z + h.w;
+  }
+  uint32_t incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += t;
+  }
+  const uint32_t excl = incl - tot;
+  const bool owner = excl < (uint32_t)k && (uint32_t)k <= incl;
+  int f_bin = -1;
+  if (owner) {
+    uint32_t c = excl;
+#pragma unroll
+    for (int b = 31; b >= 0; --b) {
+      c += mine[b];
+      if (c >= (uint32_t)k) { f_bin = lane * 32 + b; break; }
+    }
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, owner);
+  float tau = tau_old;
+  if (bal) {
+    f_bin = __shfl_sync(0xffffffffu, f_bin, __ffs(bal) - 1);
+    const float edge = -R + (float)f_bin * (2.f * R / (float)NB) - 1e-6f * R;
+    tau = fmaxf(tau, edge - eps2);
+  }
   *tau_out = tau;
   int w = 0;
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    float s = 0.f;
-    int32_t it = 0;
-    if (i < n) { s = sc[i]; it = id[i]; }
-    const bool keep = (i < n) && (s >= tau);
-    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-    __syncwarp();
+#pragma unroll
+  for (int j = 0; j < CAP / 32; ++j) {
+    const int i = j * 32 + lane;
+    const bool keep = (i < n) && (v[j] >= tau);
+    const uint32_t kb = __ballot_sync(0xffffffffu, keep);
     if (keep) {
-      const int pos = w + __popc(bal & ((1u << lane) - 1u));
-      sc[pos] = s;
-      id[pos] = it;
+      const int p = w + __popc(kb & ((1u << lane) - 1u));
+      sc[p] = v[j];
+      id[p] = it[j];
     }
-    w += __popc(bal);
+    w += __popc(kb);
   }
   __syncwarp();
   return w;
 }
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -243,7 +255,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstage; ++s) { ptx::mbar_init(&ss->full[s], 1); ptx::mbar_init(&ss->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&ss->tmem_full[a], 1); ptx::mbar_init(&ss->tmem_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&ss->tmem_full[a], 1); ptx::mbar_init(&ss->tmem_empty[a], EPI_WARPS); }
     ptx::mbar_init(&ss->a_full, 1);
     ptx::mbar_init(&ss->a_empty, 1);
     ptx::fence_barrier_init();
@@ -325,10 +337,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else {
-    // ===================== epilogue (4 warps, one TMEM lane quadrant each) =====================
-    const int q = warp & 3;                 // TMEM lanes [32q, 32q+32)
+    // ===================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves ==========
+    const int q = warp & 3;                 // TMEM lanes [32q, 32q+32) (hardware: warp id % 4)
+    const int half = (warp - 2) >> 2;       // columns [128*half, 128*half + 128) of every tile
     const int trow = q * 32 + lane;         // row inside the tile
-    uint32_t* hist = ss->hist[q];
     int acc = 0;
     uint32_t acc_phase = 0;
     const float pinf = __int_as_float(0x7f800000);
@@ -339,63 +351,88 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
       const int grow = m * TM + trow;
       const RowMeta meta = p.meta[grow];
-      const int64_t slot = (int64_t)split * p.B_pad + grow;
+      const int64_t list0 = (int64_t)(split * 2 + half) * p.B_pad + (m * TM + q * 32);  // lane 0's slot
+      const int64_t slot = list0 + lane;
       float* my_sc = p.cand_score + slot * CAP;
       int32_t* my_id = p.cand_id + slot * CAP;
       bool active = meta.active != 0;
       float tau = active ? ninf : pinf;
-      int cnt = 0;
+      int cnt = 0, n_counted = 0;
+
+      // compaction of the lists flagged in `need` (warp-uniform mask)
+      auto compact_flagged = [&](uint32_t need) {
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          const int64_t s_slot = list0 + src;
+          const int s_cnt = __shfl_sync(0xffffffffu, cnt, src);
+          const int s_cntd = __shfl_sync(0xffffffffu, n_counted, src);
+          const int s_k = __shfl_sync(0xffffffffu, meta.k_row, src);
+          const float s_e = __shfl_sync(0xffffffffu, meta.eps2, src);
+          const float s_R = __shfl_sync(0xffffffffu, meta.R, src);
+          const float s_tau = __shfl_sync(0xffffffffu, tau, src);
+          float new_tau;
+          const int w = compact_row(p.cand_score + s_slot * CAP, p.cand_id + s_slot * CAP, s_cnt,
+                                    s_cntd, s_k, s_e, s_R, s_tau,
+                                    p.ghist + (int64_t)(m * TM + q * 32 + src) * NB, lane, &new_tau);
+          if (lane == src) {
+            cnt = w;
+            n_counted = w;
+            tau = new_tau;
+            atomicMax(p.row_tau_key + grow, float_to_key(new_tau));
+            if (w > CAP - 64) {  // too many near-ties to bound: hand the row to the exact path
+              active = false;
+              tau = pinf;
+              cnt = 0;
+              n_counted = 0;
+              p.row_status[grow] = 1;
+            }
+          }
+        }
+      };
+
       for (int t = t0; t < t1; ++t) {
-        if (active) {  // another split of this row may have tightened the bound
+        if (active) {  // another list of this row may have tightened the bound
           const uint32_t gk = __ldcg(p.row_tau_key + grow);
           if (gk != 0u) tau = fmaxf(tau, key_to_float(gk));
         }
         ptx::mbar_wait(&ss->tmem_full[acc], acc_phase);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN);
-        const int n_base = t * TN;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * (TN / 2));
+        const int n_base = t * TN + half * (TN / 2);
 #pragma unroll 1
-        for (int ch = 0; ch < TN / 32; ++ch) {
+        for (int ch = 0; ch < TN / 64; ++ch) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(ch * 32), r);
-          ptx::tmem_ld_wait();
-          float mx = __uint_as_float(r[0]);
+          ptx::tmem_ld_wait_regs(r);
+          float g[4];
 #pragma unroll
-          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
-          if (mx >= tau) {
-            const int nb = n_base + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = __uint_as_float(r[j]);
-              if (v >= tau && (int64_t)(nb + j) < p.N) {
-                my_sc[cnt] = v;
-                my_id[cnt] = nb + j;
-                ++cnt;
-              }
-            }
+          for (int gq = 0; gq < 4; ++gq) {
+            const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
+            const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+            g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
           }
-          uint32_t need = __ballot_sync(0xffffffffu, cnt > CAP - 32);
-          while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            const int64_t s_slot = (int64_t)split * p.B_pad + (m * TM + q * 32 + src);
-            const int s_cnt = __shfl_sync(0xffffffffu, cnt, src);
-            const int s_k = __shfl_sync(0xffffffffu, meta.k_row, src);
-            const float s_e = __shfl_sync(0xffffffffu, meta.eps2, src);
-            float new_tau;
-            const int w = compact_row(p.cand_score + s_slot * CAP, p.cand_id + s_slot * CAP, s_cnt,
-                                      s_k, s_e, hist, lane, &new_tau);
-            if (lane == src) {
-              cnt = w;
-              tau = fmaxf(tau, new_tau);
-              atomicMax(p.row_tau_key + grow, float_to_key(new_tau));
-              if (w > CAP - 64) {  // too many near-ties to bound: hand the row to the exact path
-                active = false;
-                tau = pinf;
-                cnt = 0;
-                p.row_status[grow] = 1;
+          const float mx = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+          const bool hit = mx >= tau;
+          if (__any_sync(0xffffffffu, hit)) {
+            if (hit) {
+              const int nb = n_base + ch * 32;
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                if (g[gq] >= tau) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float v = __uint_as_float(r[gq * 8 + j]);
+                    if (v >= tau && (int64_t)(nb + gq * 8 + j) < p.N) {
+                      my_sc[cnt] = v;
+                      my_id[cnt] = nb + gq * 8 + j;
+                      ++cnt;
+                    }
+                  }
+                }
               }
             }
+            compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > TRIG) || (cnt > CAP - 32)));
           }
         }
         ptx::tc_fence_before();
@@ -404,6 +441,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+      // count what is still uncounted and trim the list to the final bound
+      compact_flagged(__ballot_sync(0xffffffffu, cnt > n_counted));
       p.cand_cnt[slot] = cnt;
     }
   }
@@ -419,7 +458,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // ------------------------------------------------------------------------------------------
 struct FinalizeParams {
   int64_t B, N;
-  int32_t B_pad, n_splits, K, d;
+  int32_t B_pad, n_lists, K, d;
   const RowMeta* meta;
   int32_t* row_status;
   const float* cand_score;
@@ -457,7 +496,7 @@ finalize_kernel(const FinalizeParams p) {
     const int shift = 24 - 8 * pass;
     hist[tid] = 0;
     __syncthreads();
-    for (int s = 0; s < p.n_splits; ++s) {
+    for (int s = 0; s < p.n_lists; ++s) {
       const int64_t slot = (int64_t)s * p.B_pad + row;
       const int n = p.cand_cnt[slot];
       const float* sc = p.cand_score + slot * CAP;
@@ -487,7 +526,7 @@ finalize_kernel(const FinalizeParams p) {
   if (tid == 0) s_nc = 0;
   for (int i = tid; i < 2 * MAXC; i += FIN_THREADS) htab[i] = -1;
   __syncthreads();
-  for (int s = 0; s < p.n_splits; ++s) {
+  for (int s = 0; s < p.n_lists; ++s) {
     const int64_t slot = (int64_t)s * p.B_pad + row;
     const int n = p.cand_cnt[slot];
     const float* sc = p.cand_score + slot * CAP;
@@ -605,7 +644,7 @@ struct Plan {
   int64_t N_pad;
   size_t smem_bytes;
   // workspace offsets
-  size_t off_A, off_meta, off_tau, off_status, off_cnt, off_sc, off_id, total;
+  size_t off_A, off_meta, off_tau, off_status, off_cnt, off_hist, off_sc, off_id, total;
 };
 
 static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
@@ -642,9 +681,10 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->off_meta = off; off += al256((size_t)pl->B_pad * sizeof(RowMeta));
   pl->off_tau = off; off += al256((size_t)pl->B_pad * 4);
   pl->off_status = off; off += al256((size_t)pl->B_pad * 4);
-  pl->off_cnt = off; off += al256((size_t)pl->n_splits * pl->B_pad * 4);
-  pl->off_sc = off; off += al256((size_t)pl->n_splits * pl->B_pad * CAP * 4);
-  pl->off_id = off; off += al256((size_t)pl->n_splits * pl->B_pad * CAP * 4);
+  pl->off_cnt = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * 4);
+  pl->off_hist = off; off += al256((size_t)pl->B_pad * NB * 4);
+  pl->off_sc = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * CAP * 4);
+  pl->off_id = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * CAP * 4);
   pl->total = off + 256;
   return 0;
 }
@@ -717,6 +757,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   uint32_t* tau = (uint32_t*)(ws + pl.off_tau);
   int32_t* status = (int32_t*)(ws + pl.off_status);
   int32_t* cnt = (int32_t*)(ws + pl.off_cnt);
+  uint32_t* ghist = (uint32_t*)(ws + pl.off_hist);
   float* csc = (float*)(ws + pl.off_sc);
   int32_t* cid = (int32_t*)(ws + pl.off_id);
   const CatalogHeader* hdr = (const CatalogHeader*)catalog;
@@ -725,7 +766,8 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   prep_users_kernel<<<(unsigned)ceil_div64((int64_t)pl.B_pad * 32, 256), 256, 0, stream>>>(
       U, ldu, user_ids, B, pl.B_pad, d, pl.d_pad, K, N, filter, indptr, n_users, hdr, A, meta, tau,
       status);
-  B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (size_t)pl.n_splits * pl.B_pad * 4, stream));
+  // cnt and ghist are adjacent in the workspace: one memset
+  B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (pl.off_sc - pl.off_cnt), stream));
 
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap(&tmA, A, pl.B_pad, pl.d_pad, TM)) return rc;
@@ -735,7 +777,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   sp.N = N; sp.B_pad = pl.B_pad; sp.m_tiles = pl.m_tiles; sp.n_splits = pl.n_splits;
   sp.tiles_per_split = pl.tiles_per_split; sp.total_tiles = pl.total_tiles; sp.KB = pl.KB;
   sp.nstage = pl.nstage; sp.meta = meta; sp.row_tau_key = tau; sp.row_status = status;
-  sp.cand_score = csc; sp.cand_id = cid; sp.cand_cnt = cnt;
+  sp.ghist = ghist; sp.cand_score = csc; sp.cand_id = cid; sp.cand_cnt = cnt;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -755,7 +797,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   if (ev_sweep_stop) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_stop, stream));
 
   FinalizeParams fp;
-  fp.B = B; fp.N = N; fp.B_pad = pl.B_pad; fp.n_splits = pl.n_splits; fp.K = K; fp.d = d;
+  fp.B = B; fp.N = N; fp.B_pad = pl.B_pad; fp.n_lists = 2 * pl.n_splits; fp.K = K; fp.d = d;
   fp.meta = meta; fp.row_status = status; fp.cand_score = csc; fp.cand_id = cid; fp.cand_cnt = cnt;
   fp.U = U; fp.ldu = ldu; fp.I = I; fp.ldi = ldi; fp.user_ids = user_ids; fp.indptr = indptr;
   fp.idx = idx; fp.out_ids = out_ids; fp.out_scores = out_scores;

@@ -17,7 +17,7 @@ from .consumed import ConsumedCSR, as_csr
 
 _SCORE_WS_BYTES = 1 << 30  # materialised-score workspace of the exact path
 FUSED_MAX_D = 256           # limits of b200_recommend_embed (include/b200reco.h)
-FUSED_MAX_K = 448
+FUSED_MAX_K = 288
 FUSED_ROWS_PER_CALL = 16384
 
 
