@@ -98,6 +98,18 @@ int b200_spmm_csr(const int64_t* indptr, const int32_t* col, const float* val, i
                   const int64_t* long_chunk_ptr, int64_t n_long, const int32_t* chunk_row,
                   const int32_t* chunk_k, int64_t n_chunks, float* partials, void* stream);
 
+/* ---- a12: negative sampling (libreco/sampling/negatives.py:17-82; collators.py:138-166) ---
+ * Counter-based (Philox4x32-10) device sampler; result = f(seed, step, index) only.
+ * mode 0 random, 1 unconsumed (needs users + per-user SORTED consumed CSR), 2 popular (needs the
+ * cdf of p ~ freq^0.75).  out[j*num_neg + t] = t-th negative of positive j.  The bit-exact
+ * reproduction of the reference's numpy / Mersenne streams is the host parity mode
+ * (librecommender_b200/sampling.py). */
+int b200_sample_negatives(const int64_t* users, const int64_t* items_pos, int64_t n_pos,
+                          int32_t num_neg, int64_t n_items, int32_t mode, int32_t tolerance,
+                          uint64_t seed, uint64_t step, const int64_t* indptr,
+                          const int32_t* idx_sorted, int64_t n_users, const float* cdf, int64_t* out,
+                          void* stream);
+
 /* ---- a14: predict_from_embedding (libreco/prediction/predict.py:36-40) -----------------
  * out[r] = sum_k U[users[r],k] * I[items[r],k]; mode 0: raw, 1: expit (ranking),
  * 2: clip to [lo, hi] (rating) — normalize_prediction (:18-23). */

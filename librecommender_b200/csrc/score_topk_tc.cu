@@ -60,6 +60,7 @@ struct RowMeta {
   float eps2;       // 2 * eps
   float R;          // |coarse score| <= R for every item (Cauchy-Schwarz on the row norms)
   int32_t k_row;    // K (+ consumed count when the filter applies)
+  int32_t pre_k;    // rank tracked by the sampling pre-pass (speculative threshold)
   int32_t active;   // 0: pad row / fallback row (never collects)
   int32_t apply;    // consumed filter applies
 };
@@ -67,6 +68,8 @@ struct RowMeta {
 struct SweepParams {
   int64_t N;
   int32_t B_pad, m_tiles, n_splits, tiles_per_split, total_tiles, KB, nstage;
+  int32_t pre;                // 1: sampling pre-pass (every `stride`-th item tile, rank pre_k, eps = 0)
+  int32_t stride;             // item-tile stride inside a split (1 in the main pass)
   const RowMeta* meta;        // [B_pad]
   uint32_t* row_tau_key;      // [B_pad]  running max of tau (order-preserving key)
   int32_t* row_status;        // [B_pad]  1 = needs the exact path
@@ -132,6 +135,7 @@ __global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
     const int64_t k_row = (int64_t)K + (apply ? c : 0);
     m.apply = apply;
     m.k_row = (int32_t)min(k_row, (int64_t)(1 << 30));
+    m.pre_k = 16 + m.k_row / 6;
     const bool fast = real && k_row <= KROW_MAX;
     m.active = fast;
     meta[row] = m;
@@ -281,12 +285,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int split = unit / p.m_tiles, m = unit % p.m_tiles;
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
-        ptx::mbar_wait(&ss->a_empty, (uiter & 1) ^ 1);
+        ptx::mbar_wait_backoff(&ss->a_empty, (uiter & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&ss->a_full, (uint32_t)(p.KB * A_KB_BYTES));
         for (int kb = 0; kb < p.KB; ++kb)
           ptx::tma_load_2d(smemA + (size_t)kb * A_KB_BYTES, &tmA, &ss->a_full, kb * KBLK, m * TM);
-        for (int t = t0; t < t1; ++t) {
-          ptx::mbar_wait(&ss->empty[stage], phase ^ 1);
+        for (int t = t0; t < t1; t += p.stride) {
+          ptx::mbar_wait_backoff(&ss->empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&ss->full[stage], (uint32_t)(p.KB * B_KB_BYTES));
           uint8_t* dst = smemB + (size_t)stage * p.KB * B_KB_BYTES;
           for (int kb = 0; kb < p.KB; ++kb)
@@ -311,8 +315,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
         ptx::mbar_wait(&ss->a_full, uiter & 1);
-        for (int t = t0; t < t1; ++t) {
-          ptx::mbar_wait(&ss->tmem_empty[acc], acc_phase ^ 1);
+        for (int t = t0; t < t1; t += p.stride) {
+          ptx::mbar_wait_backoff(&ss->tmem_empty[acc], acc_phase ^ 1);
           ptx::mbar_wait(&ss->full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
@@ -367,8 +371,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int64_t s_slot = list0 + src;
           const int s_cnt = __shfl_sync(0xffffffffu, cnt, src);
           const int s_cntd = __shfl_sync(0xffffffffu, n_counted, src);
-          const int s_k = __shfl_sync(0xffffffffu, meta.k_row, src);
-          const float s_e = __shfl_sync(0xffffffffu, meta.eps2, src);
+          const int s_k = __shfl_sync(0xffffffffu, p.pre ? meta.pre_k : meta.k_row, src);
+          const float s_e = p.pre ? 0.f : __shfl_sync(0xffffffffu, meta.eps2, src);
           const float s_R = __shfl_sync(0xffffffffu, meta.R, src);
           const float s_tau = __shfl_sync(0xffffffffu, tau, src);
           float new_tau;
@@ -385,14 +389,16 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               tau = pinf;
               cnt = 0;
               n_counted = 0;
-              p.row_status[grow] = 1;
+              if (!p.pre) p.row_status[grow] = 1;
             }
           }
         }
       };
 
-      for (int t = t0; t < t1; ++t) {
-        if (active) {  // another list of this row may have tightened the bound
+      int refresh = 0;
+      for (int t = t0; t < t1; t += p.stride) {
+        if (active && (refresh++ & 15) == 0) {
+          // speculative start value from the pre-pass / bounds tightened by other lists of the row
           const uint32_t gk = __ldcg(p.row_tau_key + grow);
           if (gk != 0u) tau = fmaxf(tau, key_to_float(gk));
         }
@@ -417,17 +423,18 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (__any_sync(0xffffffffu, hit)) {
             if (hit) {
               const int nb = n_base + ch * 32;
+              // padded item rows (>= N) score exactly 0: only the last tile can contain them
+              const int lim = (int)min((int64_t)32, p.N - (int64_t)nb);   // valid columns in this chunk
 #pragma unroll
               for (int gq = 0; gq < 4; ++gq) {
                 if (g[gq] >= tau) {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {
+                  for (int j = 0; j < 8; ++j) {   // predicated stores, no per-element branch
                     const float v = __uint_as_float(r[gq * 8 + j]);
-                    if (v >= tau && (int64_t)(nb + gq * 8 + j) < p.N) {
-                      my_sc[cnt] = v;
-                      my_id[cnt] = nb + gq * 8 + j;
-                      ++cnt;
-                    }
+                    const bool ph = (v >= tau) && (gq * 8 + j < lim);
+                    if (ph) my_sc[cnt] = v;
+                    if (ph) my_id[cnt] = nb + gq * 8 + j;
+                    cnt += ph ? 1 : 0;
                   }
                 }
               }
@@ -441,8 +448,9 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      // count what is still uncounted and trim the list to the final bound
-      compact_flagged(__ballot_sync(0xffffffffu, cnt > n_counted));
+      // pre-pass: count what is still uncounted so that the published bound uses every sample;
+      // main pass: finalize_kernel reads the lists as they are
+      if (p.pre) compact_flagged(__ballot_sync(0xffffffffu, cnt > n_counted));
       p.cand_cnt[slot] = cnt;
     }
   }
@@ -461,6 +469,7 @@ struct FinalizeParams {
   int32_t B_pad, n_lists, K, d;
   const RowMeta* meta;
   int32_t* row_status;
+  const uint32_t* tau_guess_key;   // [B_pad] speculative threshold used by the main pass (0 = none)
   const float* cand_score;
   const int32_t* cand_id;
   const int32_t* cand_cnt;
@@ -522,6 +531,16 @@ finalize_kernel(const FinalizeParams p) {
     __syncthreads();
   }
   const float thr = key_to_float(prefix) - meta.eps2;
+  {
+    // The main pass started from a speculative threshold: the lists are complete only above it.
+    // Every exact top-k_row item has coarse >= thr, so the guess must not exceed thr.
+    const uint32_t gk = p.tau_guess_key[row];
+    if (gk != 0u && key_to_float(gk) > thr) {
+      if (tid == 0) p.row_status[row] = 1;
+      for (int i = tid; i < p.K; i += FIN_THREADS) { oid[i] = -1; if (osc) osc[i] = 0.f; }
+      return;
+    }
+  }
   // ---- collect candidates
   if (tid == 0) s_nc = 0;
   for (int i = tid; i < 2 * MAXC; i += FIN_THREADS) htab[i] = -1;
@@ -644,7 +663,7 @@ struct Plan {
   int64_t N_pad;
   size_t smem_bytes;
   // workspace offsets
-  size_t off_A, off_meta, off_tau, off_status, off_cnt, off_hist, off_sc, off_id, total;
+  size_t off_A, off_meta, off_tau, off_guess, off_status, off_cnt, off_hist, off_sc, off_id, total;
 };
 
 static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
@@ -680,6 +699,7 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->off_A = off; off += al256((size_t)pl->B_pad * pl->d_pad * 2);
   pl->off_meta = off; off += al256((size_t)pl->B_pad * sizeof(RowMeta));
   pl->off_tau = off; off += al256((size_t)pl->B_pad * 4);
+  pl->off_guess = off; off += al256((size_t)pl->B_pad * 4);
   pl->off_status = off; off += al256((size_t)pl->B_pad * 4);
   pl->off_cnt = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * 4);
   pl->off_hist = off; off += al256((size_t)pl->B_pad * NB * 4);
@@ -755,6 +775,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   __nv_bfloat16* A = (__nv_bfloat16*)(ws + pl.off_A);
   RowMeta* meta = (RowMeta*)(ws + pl.off_meta);
   uint32_t* tau = (uint32_t*)(ws + pl.off_tau);
+  uint32_t* guess = (uint32_t*)(ws + pl.off_guess);
   int32_t* status = (int32_t*)(ws + pl.off_status);
   int32_t* cnt = (int32_t*)(ws + pl.off_cnt);
   uint32_t* ghist = (uint32_t*)(ws + pl.off_hist);
@@ -792,13 +813,27 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
     B200_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = n_units < sm_count ? n_units : sm_count;
+  // --- sampling pre-pass: every PRE_STRIDE-th item tile, tracks a small rank (pre_k) without the
+  // error margin; its result only SEEDS the main pass and is verified in finalize_kernel.
+  constexpr int PRE_STRIDE = 16;
+  const bool use_pre = pl.tiles_per_split >= 4 * PRE_STRIDE;
   if (ev_sweep_start) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_start, stream));
+  if (use_pre) {
+    sp.pre = 1; sp.stride = PRE_STRIDE;
+    sweep_kernel<<<grid, SWEEP_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, sp);
+    B200_CUDA_OK(cudaMemcpyAsync(guess, tau, (size_t)pl.B_pad * 4, cudaMemcpyDeviceToDevice, stream));
+    B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (pl.off_sc - pl.off_cnt), stream));
+    count_launch();
+  } else {
+    B200_CUDA_OK(cudaMemsetAsync(guess, 0, (size_t)pl.B_pad * 4, stream));
+  }
+  sp.pre = 0; sp.stride = 1;
   sweep_kernel<<<grid, SWEEP_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, sp);
   if (ev_sweep_stop) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_stop, stream));
 
   FinalizeParams fp;
   fp.B = B; fp.N = N; fp.B_pad = pl.B_pad; fp.n_lists = 2 * pl.n_splits; fp.K = K; fp.d = d;
-  fp.meta = meta; fp.row_status = status; fp.cand_score = csc; fp.cand_id = cid; fp.cand_cnt = cnt;
+  fp.meta = meta; fp.row_status = status; fp.tau_guess_key = guess; fp.cand_score = csc; fp.cand_id = cid; fp.cand_cnt = cnt;
   fp.U = U; fp.ldu = ldu; fp.I = I; fp.ldi = ldi; fp.user_ids = user_ids; fp.indptr = indptr;
   fp.idx = idx; fp.out_ids = out_ids; fp.out_scores = out_scores;
   finalize_kernel<<<(unsigned)B, FIN_THREADS, 0, stream>>>(fp);
