@@ -98,6 +98,92 @@ int b200_spmm_csr(const int64_t* indptr, const int32_t* col, const float* val, i
                   const int64_t* long_chunk_ptr, int64_t n_long, const int32_t* chunk_row,
                   const int32_t* chunk_k, int64_t n_chunks, float* partials, void* stream);
 
+/* ---- a4/a5/a6: feature models (FM, DeepFM, towers) -------------------------------------
+ * Layout of the per-row features, as the reference's DataInfo provides them
+ * (libreco/data/data_info.py:107-158, libreco/prediction/preprocess.py:15-57):
+ * sparse field f of a row comes either from an explicit matrix sparse_rows[r, f] or — when
+ * sparse_rows is NULL — from the unique table of its side: user_sparse_unique[user, col] /
+ * item_sparse_unique[item, col].  Same for dense fields.  All indices are global offsets into the
+ * ONE shared sparse table (libreco/feature/sparse.py:106-119,165-168). */
+#define B200_MAX_FIELDS 128
+typedef struct {
+  int32_t embed_size, n_sparse, n_dense;
+  int32_t id_mask;                      /* bit0: user-id embedding is a field, bit1: item-id embedding
+                                           (3 for FM/DeepFM/DIN rows, 1 / 2 for the TwoTower towers) */
+  int32_t dense_embed_row[B200_MAX_FIELDS]; /* row of dense_embeds / dense_linear used by dense field f */
+  int32_t sparse_side[B200_MAX_FIELDS]; /* 0 = user side, 1 = item side */
+  int32_t sparse_col[B200_MAX_FIELDS];  /* column inside that side's unique table */
+  int32_t dense_side[B200_MAX_FIELDS];
+  int32_t dense_col[B200_MAX_FIELDS];
+  const int32_t* user_sparse_unique; int64_t ld_us;  /* [n_users+1, F_us] */
+  const int32_t* item_sparse_unique; int64_t ld_is;  /* [n_items+1, F_is] */
+  const float* user_dense_unique; int64_t ld_ud;
+  const float* item_dense_unique; int64_t ld_id;
+  const int32_t* sparse_rows; int64_t ld_sparse_rows; /* explicit [R, n_sparse] or NULL */
+  const float* dense_rows; int64_t ld_dense_rows;     /* explicit [R, n_dense] or NULL */
+} b200_feat_layout;
+
+typedef struct {       /* TF scope "embedding" (SURVEY.md Appendix C), fp32, row-major */
+  const float* user_embeds;   /* [n_users+1, K] */
+  const float* item_embeds;   /* [n_items+1, K] */
+  const float* sparse_embeds; /* [V_s, K] */
+  const float* dense_embeds;  /* [F_d, K] */
+  const float* user_linear;   /* [n_users+1] (FM / DeepFM only, else NULL) */
+  const float* item_linear;   /* [n_items+1] */
+  const float* sparse_linear; /* [V_s] */
+  const float* dense_linear;  /* [F_d] */
+} b200_feat_tables;
+
+/* One pass over R rows: row r = (users[r], items[r]), or with grid_items > 0 the implicit grid
+ * (users[(r + row_offset) / grid_items], item (r + row_offset) % grid_items) used by all-items
+ * scoring (outputs are indexed by the local r).  Any output may be NULL:
+ *   concat [R, (2+F_s+F_d)*K]  concatenated field embeddings (deep / tower input)
+ *   pw     [R, K]              0.5((sum_f e)^2 - sum_f e^2)            (fm.py:158-161)
+ *   lin    [R]                 Dense1(concat of linear features) + bias (fm.py:156)
+ *   fm_out [R]                 lin + elu(Dense1(BN(pw)))               (fm.py:165-170); BN folded
+ *                              to scale/shift (inference), bn_scale NULL = use_bn False */
+int b200_feat_forward(const b200_feat_layout* layout, const b200_feat_tables* tables,
+                      const int64_t* users, const int64_t* items, int64_t R, int64_t grid_items,
+                      int64_t row_offset, float* concat, int64_t ld_concat, float* pw, int64_t ld_pw, float* lin,
+                      float* fm_out, const float* lin_kernel, float lin_bias, const float* bn_scale,
+                      const float* bn_shift, const float* pw_kernel, float pw_bias, void* stream);
+
+/* Y = act(X Wt^T + b): tf_dense (libreco/layers/dense.py:52-80) with BN folded by the caller.
+ * Wt is the TRANSPOSED kernel [dout, din]; fp32 SIMT (exact fma chain in k). */
+int b200_linear_f32(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
+                    const float* bias, int32_t din, int32_t dout, int32_t relu, float* Y,
+                    int64_t ldy, void* stream);
+
+/* out[r] = bias + <[a[r,:na], b[r,:nb], c[r,:nc]], w>: Dense(1) on a concatenation
+ * (deepfm.py:172-173; the final Dense(1) of DIN / YouTubeRanking). */
+int b200_concat_dense(const float* a, int64_t lda, int32_t na, const float* b, int64_t ldb, int32_t nb,
+                      const float* c, int64_t ldc, int32_t nc, const float* w, float bias, int64_t R,
+                      float* out, void* stream);
+
+/* x[r,:] /= sqrt(max(sum x^2, 1e-12)) — normalize_embeds (libreco/layers/normalization.py:32-44) */
+int b200_l2_normalize_rows(float* x, int64_t ld, int64_t R, int32_t d, void* stream);
+
+/* ---- a7/a8: behaviour sequences (DIN attention, YouTubeRanking pooling) -------------------
+ * Sequences live in a per-user table seqs[n_users+1, T] (pad index = n_items) with lens[n_users+1]
+ * (libreco/batch/sequence.py:75-91); row r reads the row of users[r], or with grid_items > 0 of
+ * users[(r + row_offset) / grid_items] (item = (r + row_offset) % grid_items) — the reference's
+ * np.repeat(seqs, n_items) (prediction/preprocess.py:109-118) is never built.
+ * b200_seq_pool:      out[r,:d] = sum_t E[seq_t,:] / sqrt(len), entries equal to pad_index read as 0
+ *                     (libreco/layers/embedding.py:54-85).
+ * b200_din_attention: G = item feature table [n_items+1, Kp] (combine_seq_features, concat mode,
+ *                     libreco/tfops/features.py:165-218); out[r,:Kp] = softmax_t(Dense1(sigmoid(
+ *                     Dense16([q,k,q-k,q*k]))) * rsqrt(Kp), t < len) weighted sum of the keys
+ *                     (libreco/layers/attention.py:45-64).  k1 [4Kp,16], b1 [16], k2 [16], b2.
+ *                     Kp <= 128, T <= 256. */
+int b200_seq_pool(const float* E, int64_t lde, int32_t d, int64_t pad_index, const int32_t* seqs,
+                  int64_t ld_seq, const int32_t* lens, int32_t T, const int64_t* users, int64_t R,
+                  int64_t grid_items, int64_t row_offset, float* out, int64_t ld_out, void* stream);
+int b200_din_attention(const float* G, int64_t ldg, int32_t Kp, const int64_t* items,
+                       const int32_t* seqs, int64_t ld_seq, const int32_t* lens, int32_t T,
+                       const int64_t* users, int64_t R, int64_t grid_items, int64_t row_offset,
+                       const float* k1, const float* b1, const float* k2, float b2, float* out,
+                       int64_t ld_out, void* stream);
+
 /* ---- a12: negative sampling (libreco/sampling/negatives.py:17-82; collators.py:138-166) ---
  * Counter-based (Philox4x32-10) device sampler; result = f(seed, step, index) only.
  * mode 0 random, 1 unconsumed (needs users + per-user SORTED consumed CSR), 2 popular (needs the

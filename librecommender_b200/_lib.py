@@ -40,6 +40,16 @@ SIGNATURES = {
     "b200_spmm_chunk": (c_int, []),
     "b200_spmm_csr": (c_int, [_P, _P, _P, c_int64, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, c_int32,
                               c_float, _P, _P, c_int64, _P, _P, c_int64, _P, _P]),
+    "b200_feat_forward": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, c_float,
+                                  _P, _P, _P, c_float, _P]),
+    "b200_linear_f32": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, c_int32, c_int32, c_int32, _P, c_int64, _P]),
+    "b200_concat_dense": (c_int, [_P, c_int64, c_int32, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, c_float,
+                                  c_int64, _P, _P]),
+    "b200_l2_normalize_rows": (c_int, [_P, c_int64, c_int64, c_int32, _P]),
+    "b200_seq_pool": (c_int, [_P, c_int64, c_int32, c_int64, _P, c_int64, _P, c_int32, _P, c_int64, c_int64, c_int64,
+                              _P, c_int64, _P]),
+    "b200_din_attention": (c_int, [_P, c_int64, c_int32, _P, _P, c_int64, _P, c_int32, _P, c_int64, c_int64, c_int64,
+                                   _P, _P, _P, c_float, _P, c_int64, _P]),
     "b200_sample_negatives": (c_int, [_P, _P, c_int64, c_int32, c_int64, c_int32, c_int32, c_uint64, c_uint64,
                                       _P, _P, c_int64, _P, _P, _P]),
     "b200_gather_dot": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int64, c_int32, c_int32, c_float, c_float, _P, _P]),

@@ -1,0 +1,321 @@
+// K1 — fused multi-field embedding gather + FM pairwise interaction + linear term, and the small
+// dense kernels of the FM / DeepFM / MLP heads (K3, fp32).
+//
+// Replaces, for inference rows:
+//   embedding_lookup / compute_sparse_feats / compute_dense_feats
+//       (libreco/layers/embedding.py:4-23, libreco/tfops/features.py:6-44,121-148)
+//   the feed construction of predict_tf_feat / process_tf_feat
+//       (libreco/prediction/predict.py:43-92, libreco/recommendation/preprocess.py:104-212):
+//       per-row feature indices are read IN THE KERNEL from the per-user / per-item unique tables
+//       (data_info.user_sparse_unique, item_sparse_unique, ...) — the [B*N, F] feed is never built
+//   FM head    (libreco/algorithms/fm.py:152-171)
+//   DeepFM head (libreco/algorithms/deepfm.py:155-174) through b200_linear_f32 + b200_concat_dense
+//
+// HBM-bound gather: per row (2+F_s) random reads of 4K (+4) bytes.  One sub-warp of
+// lpr = min(32, pow2 >= K) lanes per row, lanes stride the embedding width; field indices are
+// loaded cooperatively and broadcast by shuffle, 4 gathers in flight.
+#include "common.cuh"
+#include "../../include/b200reco.h"
+
+namespace b200 {
+namespace feat {
+
+constexpr int MAX_T = 8;   // K <= 256
+
+__device__ __forceinline__ float subwarp_sum(float v, int lpr, uint32_t gmask) {
+  for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+
+// field f of row r -> (table row index) for sparse fields, value for dense fields
+__device__ __forceinline__ int32_t sparse_index(const b200_feat_layout& L, int64_t r, int64_t u, int64_t it, int f) {
+  if (L.sparse_rows) return L.sparse_rows[r * L.ld_sparse_rows + f];
+  return L.sparse_side[f] == 0 ? __ldg(L.user_sparse_unique + u * L.ld_us + L.sparse_col[f])
+                               : __ldg(L.item_sparse_unique + it * L.ld_is + L.sparse_col[f]);
+}
+__device__ __forceinline__ float dense_value(const b200_feat_layout& L, int64_t r, int64_t u, int64_t it, int f) {
+  if (L.dense_rows) return L.dense_rows[r * L.ld_dense_rows + f];
+  return L.dense_side[f] == 0 ? __ldg(L.user_dense_unique + u * L.ld_ud + L.dense_col[f])
+                              : __ldg(L.item_dense_unique + it * L.ld_id + L.dense_col[f]);
+}
+
+struct Out {
+  float* concat; int64_t ld_concat;   // [R, F*K]  (deep / tower input) or null
+  float* pw; int64_t ld_pw;           // [R, K]    FM pairwise term or null
+  float* lin;                         // [R]       Dense1(linear features) incl. bias, or null
+  float* fm_out;                      // [R]       full FM logit, or null
+};
+
+struct Head {           // weights of the heads that can be fused here
+  const float* lin_kernel;   // [2+F_s+F_d]   Dense(1) on the concatenated linear features
+  float lin_bias;
+  const float* bn_scale;     // [K] folded BN of the FM pairwise term (or null)
+  const float* bn_shift;     // [K]
+  const float* pw_kernel;    // [K]  Dense(1, elu) on the pairwise term
+  float pw_bias;
+};
+
+__global__ void __launch_bounds__(256)
+feat_forward_kernel(const b200_feat_layout L, const b200_feat_tables T, const int64_t* __restrict__ users,
+                    const int64_t* __restrict__ items, int64_t R, int64_t grid_items,
+                    int64_t row_offset, Out o, Head h, int lpr, int Tn) {
+  const int lane = threadIdx.x & 31;
+  const int rows_per_warp = 32 / lpr;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int g = lane / lpr, li = lane % lpr;
+  const int64_t r = warp * rows_per_warp + g;
+  const int gbase = g * lpr;
+  const uint32_t gmask = (lpr == 32) ? 0xffffffffu : (((1u << lpr) - 1u) << gbase);
+  if (r >= R) return;
+  // row -> (user, item): explicit pairs, or the implicit grid "user r / N  x  item r % N"
+  int64_t u, it;
+  if (grid_items > 0) { const int64_t rg = r + row_offset; u = users[rg / grid_items]; it = rg % grid_items; }
+  else { u = users[r]; it = items[r]; }
+  const int K = L.embed_size;
+
+  float s[MAX_T], s2[MAX_T];
+#pragma unroll
+  for (int t = 0; t < MAX_T; ++t) { s[t] = 0.f; s2[t] = 0.f; }
+  float lin_acc = 0.f;
+
+  int fpos = 0;   // position of the next field inside the concatenated row
+  auto add_field = [&](int f, const float* __restrict__ rowp, float scale) {
+#pragma unroll
+    for (int t = 0; t < MAX_T; ++t) {
+      const int k = li + t * lpr;
+      if (t < Tn && k < K) {
+        const float e = __ldg(rowp + k) * scale;
+        s[t] += e;
+        s2[t] = fmaf(e, e, s2[t]);
+        if (o.concat) o.concat[r * o.ld_concat + (int64_t)f * K + k] = e;
+      }
+    }
+  };
+  // user / item id embeddings (fields 0, 1; a tower keeps only its own side)
+  const bool want_lin = (o.lin != nullptr) || (o.fm_out != nullptr);
+  if (L.id_mask & 1) {
+    add_field(fpos, T.user_embeds + u * K, 1.f);
+    if (want_lin && li == 0) lin_acc = fmaf(__ldg(T.user_linear + u), h.lin_kernel[fpos], lin_acc);
+    ++fpos;
+  }
+  if (L.id_mask & 2) {
+    add_field(fpos, T.item_embeds + it * K, 1.f);
+    if (want_lin && li == 0) lin_acc = fmaf(__ldg(T.item_linear + it), h.lin_kernel[fpos], lin_acc);
+    ++fpos;
+  }
+  // sparse fields: indices loaded cooperatively (lpr at a time), rows gathered 4 at a time
+  for (int f0 = 0; f0 < L.n_sparse; f0 += lpr) {
+    const int f = f0 + li;
+    int32_t idx = 0;
+    if (f < L.n_sparse) {
+      idx = sparse_index(L, r, u, it, f);
+      if (want_lin) lin_acc = fmaf(__ldg(T.sparse_linear + idx), h.lin_kernel[fpos + f], lin_acc);
+    }
+    const int cnt = min(lpr, L.n_sparse - f0);
+    for (int q = 0; q < cnt; ++q) {
+      const int32_t ix = __shfl_sync(gmask, idx, gbase + q);
+      add_field(fpos + f0 + q, T.sparse_embeds + (int64_t)ix * K, 1.f);
+    }
+  }
+  fpos += L.n_sparse;
+  // dense fields: value * embedding row of the field
+  for (int f0 = 0; f0 < L.n_dense; f0 += lpr) {
+    const int f = f0 + li;
+    float x = 0.f;
+    if (f < L.n_dense) {
+      x = dense_value(L, r, u, it, f);
+      if (want_lin) lin_acc = fmaf(__ldg(T.dense_linear + L.dense_embed_row[f]) * x, h.lin_kernel[fpos + f], lin_acc);
+    }
+    const int cnt = min(lpr, L.n_dense - f0);
+    for (int q = 0; q < cnt; ++q) {
+      const float xv = __shfl_sync(gmask, x, gbase + q);
+      add_field(fpos + f0 + q, T.dense_embeds + (int64_t)L.dense_embed_row[f0 + q] * K, xv);
+    }
+  }
+  // epilogue: pairwise term, linear term, FM logit
+  float head_acc = 0.f;
+#pragma unroll
+  for (int t = 0; t < MAX_T; ++t) {
+    const int k = li + t * lpr;
+    if (t < Tn && k < K) {
+      const float pw = 0.5f * (s[t] * s[t] - s2[t]);
+      if (o.pw) o.pw[r * o.ld_pw + k] = pw;
+      if (o.fm_out) {
+        const float z = h.bn_scale ? fmaf(pw, h.bn_scale[k], h.bn_shift[k]) : pw;
+        head_acc = fmaf(z, h.pw_kernel[k], head_acc);
+      }
+    }
+  }
+  if (want_lin) lin_acc = subwarp_sum(lin_acc, lpr, gmask) + h.lin_bias;
+  if (o.fm_out) {
+    head_acc = subwarp_sum(head_acc, lpr, gmask) + h.pw_bias;
+    const float elu = head_acc > 0.f ? head_acc : expm1f(head_acc);
+    if (li == 0) o.fm_out[r] = lin_acc + elu;
+  }
+  if (o.lin && li == 0) o.lin[r] = lin_acc;
+}
+
+// y[r, n] = act(sum_k x[r,k] * Wt[n,k] + b[n]) — 64x64x16 register-tiled SIMT GEMM (fp32, exact fma chain)
+constexpr int LM = 64, LN = 64, LK = 16;
+__global__ void __launch_bounds__(256)
+linear_f32_kernel(const float* __restrict__ X, int64_t ldx, int64_t R, const float* __restrict__ Wt,
+                  int64_t ldw, const float* __restrict__ bias, int din, int dout, int relu,
+                  float* __restrict__ Y, int64_t ldy) {
+  __shared__ float Xs[LK][LM + 4];
+  __shared__ float Ws[LK][LN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * LM;
+  const int n0 = blockIdx.x * LN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;   // 64 rows x 16 k, 4 consecutive k per thread
+  for (int k0 = 0; k0 < din; k0 += LK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = k0 + lk + q;
+      float a = 0.f, b = 0.f;
+      if (k < din) {
+        if (m0 + lrow < R) a = __ldg(X + (m0 + lrow) * ldx + k);
+        if (n0 + lrow < dout) b = __ldg(Wt + (int64_t)(n0 + lrow) * ldw + k);
+      }
+      Xs[lk + q][lrow] = a;
+      Ws[lk + q][lrow] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < LK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = Xs[k][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ws[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = m0 + ty + 16 * i;
+    if (r >= R) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n < dout) {
+        float v = acc[i][j] + (bias ? bias[n] : 0.f);
+        if (relu) v = fmaxf(v, 0.f);
+        Y[r * ldy + n] = v;
+      }
+    }
+  }
+}
+
+// out[r] = b + sum over up to 3 row-blocks of <block[r,:], w_block>  (the Dense(1) on a concat)
+__global__ void concat_dense_kernel(const float* __restrict__ a, int64_t lda, int na,
+                                    const float* __restrict__ b, int64_t ldb, int nb,
+                                    const float* __restrict__ c, int64_t ldc, int nc,
+                                    const float* __restrict__ w, float bias, int64_t R,
+                                    float* __restrict__ out) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float acc = 0.f;
+  for (int k = lane; k < na; k += 32) acc = fmaf(a[r * lda + k], w[k], acc);
+  for (int k = lane; k < nb; k += 32) acc = fmaf(b[r * ldb + k], w[na + k], acc);
+  for (int k = lane; k < nc; k += 32) acc = fmaf(c[r * ldc + k], w[na + nb + k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc + bias;
+}
+
+// row-wise L2 normalisation (libreco/layers/normalization.py:32-44, tf.linalg.l2_normalize)
+__global__ void l2_normalize_kernel(float* __restrict__ x, int64_t ld, int64_t R, int d) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float ss = 0.f;
+  for (int k = lane; k < d; k += 32) { const float v = x[r * ld + k]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+  for (int k = lane; k < d; k += 32) x[r * ld + k] *= inv;
+}
+
+}  // namespace feat
+}  // namespace b200
+
+using namespace b200;
+using namespace b200::feat;
+
+extern "C" int b200_feat_forward(const b200_feat_layout* L, const b200_feat_tables* T,
+                                 const int64_t* users, const int64_t* items, int64_t R,
+                                 int64_t grid_items, int64_t row_offset, float* concat, int64_t ld_concat, float* pw,
+                                 int64_t ld_pw, float* lin, float* fm_out, const float* lin_kernel,
+                                 float lin_bias, const float* bn_scale, const float* bn_shift,
+                                 const float* pw_kernel, float pw_bias, void* stream) {
+  B200_REQUIRE(L && T && users, "b200_feat_forward: null pointer");
+  B200_REQUIRE(grid_items > 0 || items, "b200_feat_forward: item ids missing");
+  B200_REQUIRE(L->embed_size >= 1 && L->embed_size <= 32 * MAX_T, "embed size %d outside [1, %d]",
+               L->embed_size, 32 * MAX_T);
+  B200_REQUIRE(L->n_sparse <= B200_MAX_FIELDS && L->n_dense <= B200_MAX_FIELDS, "too many feature fields");
+  B200_REQUIRE((lin == nullptr && fm_out == nullptr) || lin_kernel, "linear head weights missing");
+  B200_REQUIRE(fm_out == nullptr || pw_kernel, "FM head weights missing");
+  if (R == 0) return 0;
+  int lpr = 1;
+  while (lpr < L->embed_size && lpr < 32) lpr <<= 1;
+  const int Tn = (L->embed_size + lpr - 1) / lpr;
+  Out o; o.concat = concat; o.ld_concat = ld_concat; o.pw = pw; o.ld_pw = ld_pw; o.lin = lin; o.fm_out = fm_out;
+  Head h; h.lin_kernel = lin_kernel; h.lin_bias = lin_bias; h.bn_scale = bn_scale; h.bn_shift = bn_shift;
+  h.pw_kernel = pw_kernel; h.pw_bias = pw_bias;
+  const int64_t warps = ceil_div64(R, 32 / lpr);
+  feat_forward_kernel<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      *L, *T, users, items, R, grid_items, row_offset, o, h, lpr, Tn);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200_linear_f32(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
+                               const float* bias, int32_t din, int32_t dout, int32_t relu, float* Y,
+                               int64_t ldy, void* stream) {
+  B200_REQUIRE(X && Wt && Y, "b200_linear_f32: null pointer");
+  if (R == 0) return 0;
+  const int64_t gy = ceil_div64(R, LM);
+  B200_REQUIRE(gy <= 65535 * 32ll, "b200_linear_f32: too many rows");
+  // grid.y limit: process in slabs of 65535 row tiles
+  for (int64_t y0 = 0; y0 < gy; y0 += 65535) {
+    const int64_t ny = min((int64_t)65535, gy - y0);
+    const int64_t r0 = y0 * LM;
+    dim3 grid((unsigned)ceil_div64(dout, LN), (unsigned)ny);
+    linear_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X + r0 * ldx, ldx, R - r0, Wt, ldw, bias, din,
+                                                              dout, relu, Y + r0 * ldy, ldy);
+    count_launch();
+  }
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200_concat_dense(const float* a, int64_t lda, int32_t na, const float* b, int64_t ldb,
+                                 int32_t nb, const float* c, int64_t ldc, int32_t nc, const float* w,
+                                 float bias, int64_t R, float* out, void* stream) {
+  B200_REQUIRE(w && out && (na == 0 || a) && (nb == 0 || b) && (nc == 0 || c), "b200_concat_dense: null pointer");
+  if (R == 0) return 0;
+  concat_dense_kernel<<<(unsigned)ceil_div64(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      a, lda, na, b, ldb, nb, c, ldc, nc, w, bias, R, out);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200_l2_normalize_rows(float* x, int64_t ld, int64_t R, int32_t d, void* stream) {
+  B200_REQUIRE(x, "b200_l2_normalize_rows: null pointer");
+  if (R == 0) return 0;
+  l2_normalize_kernel<<<(unsigned)ceil_div64(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, ld, R, d);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}

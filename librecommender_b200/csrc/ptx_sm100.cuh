@@ -48,7 +48,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // for the single-lane producer / issuer roles: back off between probes so that the spinning lane
 // does not take issue slots from the epilogue warps sharing its scheduler
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+  while (!mbar_try_wait(bar, parity)) __nanosleep(256);
 }
 
 // ---------------------------------------------------------------- TMA

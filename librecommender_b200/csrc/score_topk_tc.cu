@@ -7,25 +7,33 @@
 // Pipeline (all on one stream, no host sync):
 //   prep_items   (once per item table)  fp32 [N,d] -> bf16 [N_pad, d_pad] (K-major, zero padded)
 //                                        + max item L2 norm
-//   prep_users   gather U[user_ids] -> bf16 [B_pad, d_pad]; per-row error bound eps and k_row
-//   sweep        persistent tcgen05 kernel: TMA -> smem (SWIZZLE_128B) -> tcgen05.mma (bf16,
-//                fp32 accumulate in TMEM, 128x256 tile, double-buffered accumulator) ->
-//                epilogue warps read TMEM (tcgen05.ld) and keep, per user row, every item whose
-//                COARSE score can still be in the exact top-k_row: score >= tau,
-//                tau = (k_row-th best coarse score so far) - 2*eps, tightened by warp-cooperative
-//                radix compactions and shared across item splits through a global per-row max.
-//   finalize     per row: exact k_row-th coarse score over the union of the split lists, cut at
-//                -2*eps, drop consumed items, EXACT fp32 re-score (sequential fma, the library's
-//                exact-score definition), sort by (score desc, id asc), emit K ids.
+//   prep_users   gather U[user_ids] -> bf16 [B_pad, d_pad]; per-row error bound eps, k_row
+//   sweep<PRE>   tensor-core pass over every 16th item tile that only records, per user row, the
+//                maximum coarse score of each sampled 128-item block (one coalesced store per
+//                tile, no divergence); guess_kernel turns the block maxima into a SPECULATIVE
+//                per-row threshold (the pre_k-th largest block maximum).
+//   sweep<MAIN>  persistent tcgen05 kernel over all item tiles: TMA -> smem (SWIZZLE_128B) ->
+//                tcgen05.mma (bf16 in, fp32 accumulate in TMEM, 128x256 tile, double-buffered
+//                accumulator) -> 8 epilogue warps read TMEM (tcgen05.ld) and keep, per user row,
+//                every item whose COARSE score is >= tau.  tau starts at the speculative value and
+//                is only ever raised by a rigorous bound: (k_row-th best coarse score counted so
+//                far in the row's global histogram) - 2*eps.
+//   finalize     per row: exact k_row-th coarse score c_k over the union of the lists; checks that
+//                the speculative threshold did not exceed c_k - 2*eps (otherwise the row is
+//                flagged); cuts at c_k - 2*eps, drops consumed items, EXACT fp32 re-score
+//                (sequential fma = the library's exact-score definition), sorts by
+//                (score desc, id asc), emits K ids.
 //
 // Exactness argument: |coarse - exact| <= eps for every (user, item) (bf16 rounding of both
 // operands, |delta| <= 2^-8 each, plus a generous accumulation term).  Let c_k be the k-th
-// largest coarse score.  Every item of the exact top-k has coarse >= c_k - 2 eps, hence is in
-// the candidate set; the final order is decided on exact fp32 scores only.  k_row = K + c_u
-// (c_u = consumed count, duplicates included) when the reference's filter rule applies
-// (ranking.py:38), so removing consumed candidates still leaves the exact top-K.
-// Rows the fast path cannot bound (k_row too large, or too many near-ties to hold) are flagged
-// in row_status and re-run by the caller on the exact materialised path (score_f32.cu+topk.cu).
+// largest coarse score.  Every item of the exact top-k has coarse >= c_k - 2 eps.  The lists hold
+// every item with coarse >= T, T = the largest threshold ever used for the row; finalize proves
+// T <= c_k - 2 eps (rigorous raises satisfy it by construction, the speculative start value is
+// checked explicitly), so the candidate set contains the exact top-k; the order is decided on
+// exact fp32 scores only.  k_row = K + c_u (c_u = consumed count, duplicates included) when the
+// reference's filter rule applies (ranking.py:38), so removing consumed candidates still leaves
+// the exact top-K.  Rows that cannot be bounded (k_row too large, failed speculation, too many
+// near-ties) are flagged in row_status and re-run by the caller on the exact materialised path.
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "../../include/b200reco.h"
@@ -43,6 +51,7 @@ constexpr int TRIG = 192;      // uncounted entries that trigger a compaction
 constexpr int EPI_WARPS = 8;   // two epilogue warps per TMEM lane quadrant (column halves)
 constexpr int KROW_MAX = 288;  // fast-path limit for k_row = K + c_u (a list must hold k_row + margin + TRIG)
 constexpr int MAX_KB = 4;      // d_pad <= 256
+constexpr int PRE_STRIDE = 16; // the pre-pass visits every 16th item tile of a split
 constexpr int A_KB_BYTES = TM * KBLK * 2;   // 16 KB
 constexpr int B_KB_BYTES = TN * KBLK * 2;   // 32 KB
 constexpr int SWEEP_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
@@ -60,23 +69,27 @@ struct RowMeta {
   float eps2;       // 2 * eps
   float R;          // |coarse score| <= R for every item (Cauchy-Schwarz on the row norms)
   int32_t k_row;    // K (+ consumed count when the filter applies)
-  int32_t pre_k;    // rank tracked by the sampling pre-pass (speculative threshold)
+  int32_t pre_k;    // rank of the block maximum used as speculative threshold
   int32_t active;   // 0: pad row / fallback row (never collects)
   int32_t apply;    // consumed filter applies
+};
+
+struct __align__(8) Cand {   // one candidate: coarse score + item id (8 bytes, written with one store)
+  float s;
+  int32_t id;
 };
 
 struct SweepParams {
   int64_t N;
   int32_t B_pad, m_tiles, n_splits, tiles_per_split, total_tiles, KB, nstage;
-  int32_t pre;                // 1: sampling pre-pass (every `stride`-th item tile, rank pre_k, eps = 0)
-  int32_t stride;             // item-tile stride inside a split (1 in the main pass)
+  int32_t n_pre_tiles;        // sampled tiles per split in the pre-pass
   const RowMeta* meta;        // [B_pad]
   uint32_t* row_tau_key;      // [B_pad]  running max of tau (order-preserving key)
   int32_t* row_status;        // [B_pad]  1 = needs the exact path
   uint32_t* ghist;            // [B_pad][NB]  coarse-score histogram of every counted candidate
-  float* cand_score;          // [2*n_splits][B_pad][CAP]
-  int32_t* cand_id;           // [2*n_splits][B_pad][CAP]
+  Cand* cand;                 // [2*n_splits][B_pad][CAP]
   int32_t* cand_cnt;          // [2*n_splits][B_pad]
+  float* blockmax;            // [2*n_splits][n_pre_tiles][B_pad]   (pre-pass output)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -163,31 +176,31 @@ __device__ __forceinline__ int score_bin(float s, float R, float inv_w) {
   return (int)fminf(fmaxf(t, 0.f), (float)(NB - 1));
 }
 
-// Warp-cooperative compaction of one candidate list of one row.
+// Warp-cooperative compaction of one candidate list of one row (rare in the main pass: the
+// speculative threshold keeps the lists short; this is the rigorous safety net).
 //  1. every entry pushed since the previous compaction is counted ONCE into the row's global
 //     coarse-score histogram (shared by all lists / CTAs working on that row);
 //  2. the histogram is read back: the highest bin whose suffix count reaches k gives a rigorous
-//     lower bound of the k-th largest coarse score over everything seen so far by ANY list
+//     lower bound of the k-th largest coarse score over everything counted so far
 //     (counts are a subset of the items at or above each edge), tau = edge - eps2;
 //  3. the list is rewritten keeping entries >= tau.
 // Entries live in registers (CAP/32 per lane).  Returns the new count; *tau_out = new tau.
-__device__ __forceinline__ int compact_row(float* __restrict__ sc, int32_t* __restrict__ id, int n,
-                                           int n_counted, int k, float eps2, float R, float tau_old,
+__device__ __forceinline__ int compact_row(Cand* __restrict__ list, int n, int n_counted, int k,
+                                           float eps2, float R, float tau_old,
                                            uint32_t* __restrict__ gh, int lane, float* tau_out) {
   const float inv_w = (float)NB / (2.f * R);
-  float v[CAP / 32];
-  int32_t it[CAP / 32];
+  Cand e[CAP / 32];
 #pragma unroll
   for (int j = 0; j < CAP / 32; ++j) {
     const int i = j * 32 + lane;
-    v[j] = 0.f;
-    it[j] = 0;
-    if (i < n) { v[j] = sc[i]; it[j] = id[i]; }
+    e[j].s = 0.f;
+    e[j].id = 0;
+    if (i < n) e[j] = list[i];
   }
 #pragma unroll
   for (int j = 0; j < CAP / 32; ++j) {
     const int i = j * 32 + lane;
-    if (i >= n_counted && i < n) atomicAdd(gh + score_bin(v[j], R, inv_w), 1u);
+    if (i >= n_counted && i < n) atomicAdd(gh + score_bin(e[j].s, R, inv_w), 1u);
   }
   __threadfence();
   __syncwarp();
@@ -228,13 +241,9 @@ __device__ __forceinline__ int compact_row(float* __restrict__ sc, int32_t* __re
 #pragma unroll
   for (int j = 0; j < CAP / 32; ++j) {
     const int i = j * 32 + lane;
-    const bool keep = (i < n) && (v[j] >= tau);
+    const bool keep = (i < n) && (e[j].s >= tau);
     const uint32_t kb = __ballot_sync(0xffffffffu, keep);
-    if (keep) {
-      const int p = w + __popc(kb & ((1u << lane) - 1u));
-      sc[p] = v[j];
-      id[p] = it[j];
-    }
+    if (keep) list[w + __popc(kb & ((1u << lane) - 1u))] = e[j];
     w += __popc(kb);
   }
   __syncwarp();
@@ -243,6 +252,18 @@ __device__ __forceinline__ int compact_row(float* __restrict__ sc, int32_t* __re
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
+// group maxima (8 columns each) and the chunk maximum of 32 accumulator columns
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], float (&g)[4]) {
+#pragma unroll
+  for (int gq = 0; gq < 4; ++gq) {
+    const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
+    const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+    g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
+  }
+  return fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+}
+
+template <bool PRE>
 __global__ void __launch_bounds__(SWEEP_THREADS, 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const SweepParams p) {
@@ -256,6 +277,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_units = p.m_tiles * p.n_splits;
+  constexpr int STRIDE = PRE ? PRE_STRIDE : 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstage; ++s) { ptx::mbar_init(&ss->full[s], 1); ptx::mbar_init(&ss->empty[s], 1); }
@@ -289,7 +311,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         ptx::mbar_arrive_expect_tx(&ss->a_full, (uint32_t)(p.KB * A_KB_BYTES));
         for (int kb = 0; kb < p.KB; ++kb)
           ptx::tma_load_2d(smemA + (size_t)kb * A_KB_BYTES, &tmA, &ss->a_full, kb * KBLK, m * TM);
-        for (int t = t0; t < t1; t += p.stride) {
+        for (int t = t0; t < t1; t += STRIDE) {
           ptx::mbar_wait_backoff(&ss->empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&ss->full[stage], (uint32_t)(p.KB * B_KB_BYTES));
           uint8_t* dst = smemB + (size_t)stage * p.KB * B_KB_BYTES;
@@ -315,8 +337,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
         ptx::mbar_wait(&ss->a_full, uiter & 1);
-        for (int t = t0; t < t1; t += p.stride) {
-          ptx::mbar_wait_backoff(&ss->tmem_empty[acc], acc_phase ^ 1);
+        for (int t = t0; t < t1; t += STRIDE) {
+          ptx::mbar_wait(&ss->tmem_empty[acc], acc_phase ^ 1);   // latency critical: no back-off
           ptx::mbar_wait(&ss->full[stage], phase);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
@@ -354,90 +376,121 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int t0 = split * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
       const int grow = m * TM + trow;
+      const int list_id = split * 2 + half;
+
+      if (PRE) {
+        // ---- pre-pass: per sampled tile the maximum coarse score of this warp's 128 columns ----
+        float* bm = p.blockmax + (int64_t)list_id * p.n_pre_tiles * p.B_pad + grow;
+        int ti = 0;
+        for (int t = t0; t < t1; t += STRIDE, ++ti) {
+          ptx::mbar_wait(&ss->tmem_full[acc], acc_phase);
+          ptx::tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * (TN / 2));
+          float tm = ninf;
+#pragma unroll 1
+          for (int ch = 0; ch < TN / 64; ++ch) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(ch * 32), r);
+            ptx::tmem_ld_wait_regs(r);
+            float g[4];
+            tm = fmaxf(tm, chunk_max(r, g));
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc]);
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+          // tiles that contain zero-padded item rows would bias the estimate: drop them
+          if ((int64_t)(t + 1) * TN > p.N) tm = ninf;
+          bm[(int64_t)ti * p.B_pad] = tm;
+        }
+        for (; ti < p.n_pre_tiles; ++ti) bm[(int64_t)ti * p.B_pad] = ninf;   // short last split
+        continue;
+      }
+
+      // ---- main pass ----
       const RowMeta meta = p.meta[grow];
-      const int64_t list0 = (int64_t)(split * 2 + half) * p.B_pad + (m * TM + q * 32);  // lane 0's slot
-      const int64_t slot = list0 + lane;
-      float* my_sc = p.cand_score + slot * CAP;
-      int32_t* my_id = p.cand_id + slot * CAP;
+      const int64_t list0 = (int64_t)list_id * p.B_pad + (m * TM + q * 32);  // lane 0's slot
+      Cand* my_list = p.cand + (list0 + lane) * CAP;
       bool active = meta.active != 0;
       float tau = active ? ninf : pinf;
       int cnt = 0, n_counted = 0;
+      if (active) {  // speculative start value (guess_kernel) / bounds published by other lists
+        const uint32_t gk = __ldcg(p.row_tau_key + grow);
+        if (gk != 0u) tau = key_to_float(gk);
+      }
 
       // compaction of the lists flagged in `need` (warp-uniform mask)
       auto compact_flagged = [&](uint32_t need) {
         while (need) {
           const int src = __ffs(need) - 1;
           need &= need - 1;
-          const int64_t s_slot = list0 + src;
           const int s_cnt = __shfl_sync(0xffffffffu, cnt, src);
           const int s_cntd = __shfl_sync(0xffffffffu, n_counted, src);
-          const int s_k = __shfl_sync(0xffffffffu, p.pre ? meta.pre_k : meta.k_row, src);
-          const float s_e = p.pre ? 0.f : __shfl_sync(0xffffffffu, meta.eps2, src);
+          const int s_k = __shfl_sync(0xffffffffu, meta.k_row, src);
+          const float s_e = __shfl_sync(0xffffffffu, meta.eps2, src);
           const float s_R = __shfl_sync(0xffffffffu, meta.R, src);
           const float s_tau = __shfl_sync(0xffffffffu, tau, src);
           float new_tau;
-          const int w = compact_row(p.cand_score + s_slot * CAP, p.cand_id + s_slot * CAP, s_cnt,
-                                    s_cntd, s_k, s_e, s_R, s_tau,
+          const int w = compact_row(p.cand + (list0 + src) * CAP, s_cnt, s_cntd, s_k, s_e, s_R, s_tau,
                                     p.ghist + (int64_t)(m * TM + q * 32 + src) * NB, lane, &new_tau);
           if (lane == src) {
             cnt = w;
             n_counted = w;
-            tau = new_tau;
+            // also pick up what other lists of this row published meanwhile
+            tau = fmaxf(new_tau, key_to_float(max(__ldcg(p.row_tau_key + grow), 1u)));
             atomicMax(p.row_tau_key + grow, float_to_key(new_tau));
             if (w > CAP - 64) {  // too many near-ties to bound: hand the row to the exact path
               active = false;
               tau = pinf;
               cnt = 0;
               n_counted = 0;
-              if (!p.pre) p.row_status[grow] = 1;
+              p.row_status[grow] = 1;
             }
           }
         }
       };
 
-      int refresh = 0;
-      for (int t = t0; t < t1; t += p.stride) {
-        if (active && (refresh++ & 15) == 0) {
-          // speculative start value from the pre-pass / bounds tightened by other lists of the row
-          const uint32_t gk = __ldcg(p.row_tau_key + grow);
-          if (gk != 0u) tau = fmaxf(tau, key_to_float(gk));
-        }
+      const int last_full = (int)(p.N / TN);   // tiles >= last_full contain padded item rows
+      for (int t = t0; t < t1; ++t) {
         ptx::mbar_wait(&ss->tmem_full[acc], acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * (TN / 2));
         const int n_base = t * TN + half * (TN / 2);
+        const bool tail = t >= last_full;
 #pragma unroll 1
         for (int ch = 0; ch < TN / 64; ++ch) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(ch * 32), r);
           ptx::tmem_ld_wait_regs(r);
-          float g[4];
+          if (tail) {   // zero-padded item rows (>= N) must never be collected: only the last tile
+            const int lim = (int)max((int64_t)0, min((int64_t)32, p.N - (int64_t)(n_base + ch * 32)));
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
-            const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
-            const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
-            g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
+            for (int j = 0; j < 32; ++j) if (j >= lim) r[j] = 0xff800000u;
           }
-          const float mx = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+          float g[4];
+          const float mx = chunk_max(r, g);
           const bool hit = mx >= tau;
           if (__any_sync(0xffffffffu, hit)) {
             if (hit) {
               const int nb = n_base + ch * 32;
-              // padded item rows (>= N) score exactly 0: only the last tile can contain them
-              const int lim = (int)min((int64_t)32, p.N - (int64_t)nb);   // valid columns in this chunk
+              Cand* wp = my_list + cnt;
 #pragma unroll
               for (int gq = 0; gq < 4; ++gq) {
-                if (g[gq] >= tau) {
+                // warp vote => a real (uniform) branch: only groups that are hot in some lane are scanned
+                if (__any_sync(__activemask(), g[gq] >= tau)) {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) {   // predicated stores, no per-element branch
-                    const float v = __uint_as_float(r[gq * 8 + j]);
-                    const bool ph = (v >= tau) && (gq * 8 + j < lim);
-                    if (ph) my_sc[cnt] = v;
-                    if (ph) my_id[cnt] = nb + gq * 8 + j;
-                    cnt += ph ? 1 : 0;
+                  for (int j = 0; j < 8; ++j) {   // one predicated 8-byte store per element
+                    Cand c;
+                    c.s = __uint_as_float(r[gq * 8 + j]);
+                    c.id = nb + gq * 8 + j;
+                    const bool ph = c.s >= tau;
+                    if (ph) *wp = c;
+                    wp += ph ? 1 : 0;
                   }
                 }
               }
+              cnt = (int)(wp - my_list);
             }
             compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > TRIG) || (cnt > CAP - 32)));
           }
@@ -448,16 +501,63 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      // pre-pass: count what is still uncounted so that the published bound uses every sample;
-      // main pass: finalize_kernel reads the lists as they are
-      if (p.pre) compact_flagged(__ballot_sync(0xffffffffu, cnt > n_counted));
-      p.cand_cnt[slot] = cnt;
+      p.cand_cnt[list0 + lane] = cnt;
     }
   }
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// guess kernel: speculative threshold = pre_k-th largest sampled block maximum of the row
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+guess_kernel(const float* __restrict__ blockmax, int n_vals /* lists * n_pre_tiles */, int B_pad,
+             const RowMeta* __restrict__ meta, uint32_t* __restrict__ row_tau_key,
+             uint32_t* __restrict__ guess_key) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_krem, s_found;
+  const int tid = threadIdx.x;
+  const int row = blockIdx.x;
+  const RowMeta m = meta[row];
+  uint32_t prefix = 0, krem = (uint32_t)m.pre_k;
+  bool ok = m.active != 0;
+  for (int pass = 0; pass < 4 && ok; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int b = tid; b < 256; b += 128) hist[b] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_vals; i += 128) {
+      const float v = blockmax[(int64_t)i * B_pad + row];
+      const uint32_t key = float_to_key(v);
+      if (v > -3.0e38f && (pass == 0 || (key >> (shift + 8)) == prefix))
+        atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t c = 0;
+      int b = 255;
+      bool found = false;
+      for (; b >= 0; --b) {
+        if (c + hist[b] >= krem) { found = true; break; }
+        c += hist[b];
+      }
+      s_found = found;
+      s_prefix = (prefix << 8) | (uint32_t)(b < 0 ? 0 : b);
+      s_krem = krem - c;
+    }
+    __syncthreads();
+    ok = s_found != 0;
+    prefix = s_prefix;
+    krem = s_krem;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const uint32_t key = ok ? prefix : 0u;   // 0 = no speculation for this row
+    row_tau_key[row] = key;
+    guess_key[row] = key;
   }
 }
 
@@ -470,8 +570,7 @@ struct FinalizeParams {
   const RowMeta* meta;
   int32_t* row_status;
   const uint32_t* tau_guess_key;   // [B_pad] speculative threshold used by the main pass (0 = none)
-  const float* cand_score;
-  const int32_t* cand_id;
+  const Cand* cand;
   const int32_t* cand_cnt;
   const float* U; int64_t ldu;
   const float* I; int64_t ldi;
@@ -485,6 +584,7 @@ __global__ void __launch_bounds__(FIN_THREADS)
 finalize_kernel(const FinalizeParams p) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_prefix, s_krem;
+  __shared__ uint32_t s_wtot[FIN_THREADS / 32];
   __shared__ int s_nc;
   __shared__ int32_t c_id[MAXC];
   __shared__ unsigned long long c_sort[MAXC];
@@ -495,11 +595,12 @@ finalize_kernel(const FinalizeParams p) {
   int64_t* oid = p.out_ids + row * p.K;
   float* osc = p.out_scores ? p.out_scores + row * p.K : nullptr;
   const RowMeta meta = p.meta[row];
-  if (p.row_status[row] != 0) {
+  auto give_up = [&](bool flag) {
+    if (flag && tid == 0) p.row_status[row] = 1;
     for (int i = tid; i < p.K; i += FIN_THREADS) { oid[i] = -1; if (osc) osc[i] = 0.f; }
-    return;
-  }
-  // ---- exact k_row-th largest coarse score over the union of the split lists (4 x 8-bit radix)
+  };
+  if (p.row_status[row] != 0) { give_up(false); return; }
+  // ---- exact k_row-th largest coarse score over the union of the lists (4 x 8-bit radix)
   uint32_t prefix = 0, krem = (uint32_t)meta.k_row;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
@@ -508,22 +609,33 @@ finalize_kernel(const FinalizeParams p) {
     for (int s = 0; s < p.n_lists; ++s) {
       const int64_t slot = (int64_t)s * p.B_pad + row;
       const int n = p.cand_cnt[slot];
-      const float* sc = p.cand_score + slot * CAP;
+      const Cand* l = p.cand + slot * CAP;
       for (int i = tid; i < n; i += FIN_THREADS) {
-        const uint32_t key = float_to_key(sc[i]);
+        const uint32_t key = float_to_key(l[i].s);
         if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t c = 0;
-      int b = 255;
-      for (; b > 0; --b) {
-        if (c + hist[b] >= krem) break;
-        c += hist[b];
+    {
+      // parallel resolution of the digit: thread t owns bin t, suffix sums by warp scan + warp totals
+      const int lane = tid & 31, wid = tid >> 5;
+      const uint32_t v = hist[tid];
+      uint32_t incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += t;
       }
-      s_prefix = (prefix << 8) | (uint32_t)b;
-      s_krem = krem - c;
+      if (lane == 0) s_wtot[wid] = incl;
+      __syncthreads();
+      uint32_t above = 0;
+      for (int w2 = wid + 1; w2 < FIN_THREADS / 32; ++w2) above += s_wtot[w2];
+      incl += above;                       // count in bins >= tid
+      const uint32_t excl = incl - v;      // count in bins >  tid
+      if ((excl < krem && krem <= incl) || (tid == 0 && incl < krem)) {
+        s_prefix = (prefix << 8) | (uint32_t)tid;
+        s_krem = krem - min(excl, krem);
+      }
     }
     __syncthreads();
     prefix = s_prefix;
@@ -535,11 +647,7 @@ finalize_kernel(const FinalizeParams p) {
     // The main pass started from a speculative threshold: the lists are complete only above it.
     // Every exact top-k_row item has coarse >= thr, so the guess must not exceed thr.
     const uint32_t gk = p.tau_guess_key[row];
-    if (gk != 0u && key_to_float(gk) > thr) {
-      if (tid == 0) p.row_status[row] = 1;
-      for (int i = tid; i < p.K; i += FIN_THREADS) { oid[i] = -1; if (osc) osc[i] = 0.f; }
-      return;
-    }
+    if (gk != 0u && key_to_float(gk) > thr) { give_up(true); return; }
   }
   // ---- collect candidates
   if (tid == 0) s_nc = 0;
@@ -548,22 +656,18 @@ finalize_kernel(const FinalizeParams p) {
   for (int s = 0; s < p.n_lists; ++s) {
     const int64_t slot = (int64_t)s * p.B_pad + row;
     const int n = p.cand_cnt[slot];
-    const float* sc = p.cand_score + slot * CAP;
-    const int32_t* id = p.cand_id + slot * CAP;
+    const Cand* l = p.cand + slot * CAP;
     for (int i = tid; i < n; i += FIN_THREADS) {
-      if (sc[i] >= thr) {
+      const Cand c = l[i];
+      if (c.s >= thr) {
         const int pos = atomicAdd(&s_nc, 1);
-        if (pos < MAXC) c_id[pos] = id[i];
+        if (pos < MAXC) c_id[pos] = c.id;
       }
     }
   }
   __syncthreads();
   const int nc = s_nc;
-  if (nc > MAXC || nc < p.K) {  // cannot bound (dense near-ties) -> exact path
-    if (tid == 0) p.row_status[row] = 1;
-    for (int i = tid; i < p.K; i += FIN_THREADS) { oid[i] = -1; if (osc) osc[i] = 0.f; }
-    return;
-  }
+  if (nc > MAXC || nc < p.K) { give_up(true); return; }  // cannot bound (dense near-ties) -> exact path
   const int64_t u = p.user_ids[row];
   // ---- consumed filter through a hash set of candidate ids
   if (meta.apply) {
@@ -587,6 +691,7 @@ finalize_kernel(const FinalizeParams p) {
   for (int k = tid; k < p.d; k += FIN_THREADS) urow[k] = __ldg(p.U + u * p.ldu + k);
   __syncthreads();
   // ---- exact fp32 re-score: acc = fma(u[k], i[k], acc), k ascending
+  const bool vec4 = (p.d % 4 == 0) && (p.ldi % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.I) & 15) == 0);
   int P = 1;
   while (P < nc) P <<= 1;
   for (int i = tid; i < P; i += FIN_THREADS) {
@@ -594,7 +699,18 @@ finalize_kernel(const FinalizeParams p) {
     if (i < nc && c_id[i] >= 0) {
       const float* it = p.I + (int64_t)c_id[i] * p.ldi;
       float acc = 0.f;
-      for (int k = 0; k < p.d; ++k) acc = fmaf(urow[k], __ldg(it + k), acc);
+      if (vec4) {   // 16-byte loads; the fma chain stays sequential in k (exact-score definition)
+        const float4* it4 = reinterpret_cast<const float4*>(it);
+        for (int k4 = 0; k4 < p.d / 4; ++k4) {
+          const float4 x = __ldg(it4 + k4);
+          acc = fmaf(urow[4 * k4 + 0], x.x, acc);
+          acc = fmaf(urow[4 * k4 + 1], x.y, acc);
+          acc = fmaf(urow[4 * k4 + 2], x.z, acc);
+          acc = fmaf(urow[4 * k4 + 3], x.w, acc);
+        }
+      } else {
+        for (int k = 0; k < p.d; ++k) acc = fmaf(urow[k], __ldg(it + k), acc);
+      }
       comp = ((unsigned long long)float_to_key(acc) << 32) | (unsigned long long)(~(uint32_t)c_id[i]);
     }
     c_sort[i] = comp;
@@ -659,11 +775,12 @@ static inline int pad_to(int64_t x, int m) { return (int)((x + m - 1) / m * m); 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Plan {
-  int B_pad, d_pad, KB, m_tiles, total_tiles, n_splits, tiles_per_split, nstage;
+  int B_pad, d_pad, KB, m_tiles, total_tiles, n_splits, tiles_per_split, nstage, n_pre_tiles;
+  bool use_pre;
   int64_t N_pad;
   size_t smem_bytes;
   // workspace offsets
-  size_t off_A, off_meta, off_tau, off_guess, off_status, off_cnt, off_hist, off_sc, off_id, total;
+  size_t off_A, off_meta, off_tau, off_guess, off_status, off_cnt, off_hist, off_cand, off_bm, total;
 };
 
 static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
@@ -689,6 +806,9 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   }
   pl->tiles_per_split = (pl->total_tiles + bestS - 1) / bestS;
   pl->n_splits = (pl->total_tiles + pl->tiles_per_split - 1) / pl->tiles_per_split;
+  pl->n_pre_tiles = (pl->tiles_per_split + PRE_STRIDE - 1) / PRE_STRIDE;
+  // speculation needs enough sampled blocks per row to take a stable order statistic
+  pl->use_pre = (long)2 * pl->n_splits * pl->n_pre_tiles >= 256;
   const size_t budget = 227 * 1024 - 1024 /*align*/ - sizeof(SweepSmem) - (size_t)pl->KB * A_KB_BYTES;
   int ns = (int)(budget / ((size_t)pl->KB * B_KB_BYTES));
   if (ns > 6) ns = 6;
@@ -703,8 +823,8 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->off_status = off; off += al256((size_t)pl->B_pad * 4);
   pl->off_cnt = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * 4);
   pl->off_hist = off; off += al256((size_t)pl->B_pad * NB * 4);
-  pl->off_sc = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * CAP * 4);
-  pl->off_id = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * CAP * 4);
+  pl->off_cand = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * CAP * sizeof(Cand));
+  pl->off_bm = off; off += al256((size_t)2 * pl->n_splits * pl->n_pre_tiles * pl->B_pad * 4);
   pl->total = off + 256;
   return 0;
 }
@@ -779,8 +899,8 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   int32_t* status = (int32_t*)(ws + pl.off_status);
   int32_t* cnt = (int32_t*)(ws + pl.off_cnt);
   uint32_t* ghist = (uint32_t*)(ws + pl.off_hist);
-  float* csc = (float*)(ws + pl.off_sc);
-  int32_t* cid = (int32_t*)(ws + pl.off_id);
+  Cand* cand = (Cand*)(ws + pl.off_cand);
+  float* bm = (float*)(ws + pl.off_bm);
   const CatalogHeader* hdr = (const CatalogHeader*)catalog;
   const __nv_bfloat16* Ibf = (const __nv_bfloat16*)((const char*)catalog + 256);
 
@@ -788,7 +908,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
       U, ldu, user_ids, B, pl.B_pad, d, pl.d_pad, K, N, filter, indptr, n_users, hdr, A, meta, tau,
       status);
   // cnt and ghist are adjacent in the workspace: one memset
-  B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (pl.off_sc - pl.off_cnt), stream));
+  B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (pl.off_cand - pl.off_cnt), stream));
 
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap(&tmA, A, pl.B_pad, pl.d_pad, TM)) return rc;
@@ -797,11 +917,13 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   SweepParams sp;
   sp.N = N; sp.B_pad = pl.B_pad; sp.m_tiles = pl.m_tiles; sp.n_splits = pl.n_splits;
   sp.tiles_per_split = pl.tiles_per_split; sp.total_tiles = pl.total_tiles; sp.KB = pl.KB;
-  sp.nstage = pl.nstage; sp.meta = meta; sp.row_tau_key = tau; sp.row_status = status;
-  sp.ghist = ghist; sp.cand_score = csc; sp.cand_id = cid; sp.cand_cnt = cnt;
+  sp.nstage = pl.nstage; sp.n_pre_tiles = pl.n_pre_tiles; sp.meta = meta; sp.row_tau_key = tau;
+  sp.row_status = status; sp.ghist = ghist; sp.cand = cand; sp.cand_cnt = cnt; sp.blockmax = bm;
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024));
+    B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));
     attr_set = true;
   }
@@ -813,27 +935,22 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
     B200_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = n_units < sm_count ? n_units : sm_count;
-  // --- sampling pre-pass: every PRE_STRIDE-th item tile, tracks a small rank (pre_k) without the
-  // error margin; its result only SEEDS the main pass and is verified in finalize_kernel.
-  constexpr int PRE_STRIDE = 16;
-  const bool use_pre = pl.tiles_per_split >= 4 * PRE_STRIDE;
+
   if (ev_sweep_start) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_start, stream));
-  if (use_pre) {
-    sp.pre = 1; sp.stride = PRE_STRIDE;
-    sweep_kernel<<<grid, SWEEP_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, sp);
-    B200_CUDA_OK(cudaMemcpyAsync(guess, tau, (size_t)pl.B_pad * 4, cudaMemcpyDeviceToDevice, stream));
-    B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (pl.off_sc - pl.off_cnt), stream));
-    count_launch();
+  if (pl.use_pre) {
+    sweep_kernel<true><<<grid, SWEEP_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, sp);
+    guess_kernel<<<(unsigned)pl.B_pad, 128, 0, stream>>>(bm, 2 * pl.n_splits * pl.n_pre_tiles, pl.B_pad,
+                                                          meta, tau, guess);
+    count_launch(2);
   } else {
     B200_CUDA_OK(cudaMemsetAsync(guess, 0, (size_t)pl.B_pad * 4, stream));
   }
-  sp.pre = 0; sp.stride = 1;
-  sweep_kernel<<<grid, SWEEP_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, sp);
+  sweep_kernel<false><<<grid, SWEEP_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, sp);
   if (ev_sweep_stop) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_stop, stream));
 
   FinalizeParams fp;
   fp.B = B; fp.N = N; fp.B_pad = pl.B_pad; fp.n_lists = 2 * pl.n_splits; fp.K = K; fp.d = d;
-  fp.meta = meta; fp.row_status = status; fp.tau_guess_key = guess; fp.cand_score = csc; fp.cand_id = cid; fp.cand_cnt = cnt;
+  fp.meta = meta; fp.row_status = status; fp.tau_guess_key = guess; fp.cand = cand; fp.cand_cnt = cnt;
   fp.U = U; fp.ldu = ldu; fp.I = I; fp.ldi = ldi; fp.user_ids = user_ids; fp.indptr = indptr;
   fp.idx = idx; fp.out_ids = out_ids; fp.out_scores = out_scores;
   finalize_kernel<<<(unsigned)B, FIN_THREADS, 0, stream>>>(fp);

@@ -1,0 +1,217 @@
+// K2 — behaviour-sequence kernels: DIN attention and YouTubeRanking sequence pooling.
+//
+// Replaces
+//   din_attention        libreco/layers/attention.py:28-64   (+ the lookups of din.py:236-250)
+//   seq_embeds_pooling   libreco/layers/embedding.py:54-85   (youtube_ranking.py:188-199)
+// Sequences come from the per-user cache the reference keeps on the host
+// (recent_seqs / recent_seq_lens, libreco/batch/sequence.py:75-91, prediction/preprocess.py:109-118):
+// row r uses the sequence of user users[r] or — all-items scoring — users[(r + off) / grid].
+// The [B*N, T] repeat of the reference is never materialised.
+//
+// One warp per row.  DIN: the attention MLP input [q, k, q-k, q*k] W1 is re-associated per row as
+//   h_j(t) = c_j + sum_c k_c(t) * M[c][j],   M[c][j] = (W1k - W1d)[c][j] + q_c * W1p[c][j],
+//   c_j    = b1_j + sum_c q_c * (W1q + W1d)[c][j]
+// (W1q/W1k/W1d/W1p = the four K'-row blocks of the Dense(16) kernel), so the per-key work is one
+// K' x 16 mat-vec held in registers; a 16-value butterfly reduction needs 16 shuffles.
+#include "common.cuh"
+#include "../../include/b200reco.h"
+
+namespace b200 {
+namespace seq {
+
+constexpr int HID = 16;      // attention.py:47  Dense(16)
+constexpr int MAX_TK = 4;    // K' <= 128
+constexpr int MAX_T = 256;   // sequence length limit
+
+__device__ __forceinline__ int64_t seq_row_of(const int64_t* users, int64_t r, int64_t grid, int64_t off) {
+  return grid > 0 ? users[(r + off) / grid] : users[r];
+}
+
+__global__ void __launch_bounds__(256)
+seq_pool_kernel(const float* __restrict__ E, int64_t lde, int d, int64_t pad_index,
+                const int32_t* __restrict__ seqs, int64_t ld_seq, const int32_t* __restrict__ lens, int T,
+                const int64_t* __restrict__ users, int64_t R, int64_t grid, int64_t off,
+                float* __restrict__ out, int64_t ld_out) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int64_t sr = seq_row_of(users, r, grid, off);
+  const int32_t* s = seqs + sr * ld_seq;
+  const float len = (float)lens[sr];
+  const float inv = len > 0.f ? 1.0f / sqrtf(len) : 0.f;          // tf.div_no_nan
+  for (int k0 = 0; k0 < d; k0 += 32) {
+    const int k = k0 + lane;
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int32_t it = __ldg(s + t);
+      if (it != pad_index && k < d) acc += __ldg(E + (int64_t)it * lde + k);   // pad row reads as zero
+    }
+    if (k < d) out[r * ld_out + k] = acc * inv;
+  }
+}
+
+struct AttW {
+  const float* k1;   // [4K', 16] row-major (Dense(16) kernel; rows: q | k | q-k | q*k)
+  const float* b1;   // [16]
+  const float* k2;   // [16]      Dense(1) kernel
+  float b2;
+};
+
+__global__ void __launch_bounds__(128)
+din_attention_kernel(const float* __restrict__ G, int64_t ldg, int Kp, const int64_t* __restrict__ items,
+                     const int32_t* __restrict__ seqs, int64_t ld_seq, const int32_t* __restrict__ lens, int T,
+                     const int64_t* __restrict__ users, int64_t R, int64_t grid, int64_t off, AttW w,
+                     float* __restrict__ out, int64_t ld_out) {
+  __shared__ float s_att[4][MAX_T];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 4 + wid;
+  if (r >= R) return;
+  const int64_t sr = seq_row_of(users, r, grid, off);
+  const int64_t item = grid > 0 ? (r + off) % grid : items[r];
+  const int32_t* s = seqs + sr * ld_seq;
+  const int len = min(max(lens[sr], 0), T);
+  const int TK = (Kp + 31) / 32;
+  // query row and the per-row matrix M (registers)
+  float q[MAX_TK];
+  float M[MAX_TK][HID];
+  float cpart[HID];
+#pragma unroll
+  for (int j = 0; j < HID; ++j) cpart[j] = 0.f;
+#pragma unroll
+  for (int t = 0; t < MAX_TK; ++t) {
+    const int c = lane + t * 32;
+    q[t] = 0.f;
+    if (t < TK && c < Kp) {
+      q[t] = __ldg(G + item * ldg + c);
+#pragma unroll
+      for (int j = 0; j < HID; ++j) {
+        const float wq = __ldg(w.k1 + (int64_t)c * HID + j);
+        const float wk = __ldg(w.k1 + (int64_t)(Kp + c) * HID + j);
+        const float wd = __ldg(w.k1 + (int64_t)(2 * Kp + c) * HID + j);
+        const float wp = __ldg(w.k1 + (int64_t)(3 * Kp + c) * HID + j);
+        M[t][j] = (wk - wd) + q[t] * wp;
+        cpart[j] = fmaf(q[t], wq + wd, cpart[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < HID; ++j) M[t][j] = 0.f;
+    }
+  }
+  // c_j: full warp sums (once per row)
+#pragma unroll
+  for (int j = 0; j < HID; ++j) cpart[j] = warp_sum(cpart[j]) + __ldg(w.b1 + j);
+  const float scale = rsqrtf((float)Kp);
+  float amax = -3.0e38f;
+  for (int t = 0; t < len; ++t) {
+    const int64_t key = __ldg(s + t);
+    float part[HID];
+#pragma unroll
+    for (int j = 0; j < HID; ++j) part[j] = 0.f;
+#pragma unroll
+    for (int tt = 0; tt < MAX_TK; ++tt) {
+      const int c = lane + tt * 32;
+      if (tt < TK && c < Kp) {
+        const float kv = __ldg(G + key * ldg + c);
+#pragma unroll
+        for (int j = 0; j < HID; ++j) part[j] = fmaf(kv, M[tt][j], part[j]);
+      }
+    }
+    // butterfly: after the stage with offset o each lane keeps half of its values
+    // 16 -> 8 -> 4 -> 2 -> 1 values, 15 shuffles, then one more across the last pair
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool up = lane & 16;
+      const float send = up ? part[j] : part[j + 8];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+      part[j] = (up ? part[j + 8] : part[j]) + recv;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool up = lane & 8;
+      const float send = up ? part[j] : part[j + 4];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+      part[j] = (up ? part[j + 4] : part[j]) + recv;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const bool up = lane & 4;
+      const float send = up ? part[j] : part[j + 2];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+      part[j] = (up ? part[j + 2] : part[j]) + recv;
+    }
+    {
+      const bool up = lane & 2;
+      const float send = up ? part[0] : part[1];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+      part[0] = (up ? part[1] : part[0]) + recv;
+    }
+    part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
+    // lane now holds the full sum of hidden unit j(lane)
+    const int j = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const float hj = 1.0f / (1.0f + expf(-(part[0] + cpart[j])));
+    float a = hj * __ldg(w.k2 + j);
+    a = warp_sum(a) * 0.5f;                       // every j is held by two lanes
+    a = (a + w.b2) * scale;
+    if (lane == 0) s_att[wid][t] = a;
+    amax = fmaxf(amax, a);
+  }
+  __syncwarp();
+  // softmax over the unmasked positions (masked logits are -2^32+1: exp underflows to exactly 0)
+  float den = 0.f;
+  for (int t = lane; t < len; t += 32) den += expf(s_att[wid][t] - amax);
+  den = warp_sum(den);
+  float acc[MAX_TK];
+#pragma unroll
+  for (int tt = 0; tt < MAX_TK; ++tt) acc[tt] = 0.f;
+  for (int t = 0; t < len; ++t) {
+    const int64_t key = __ldg(s + t);
+    const float p = expf(s_att[wid][t] - amax) / den;
+#pragma unroll
+    for (int tt = 0; tt < MAX_TK; ++tt) {
+      const int c = lane + tt * 32;
+      if (tt < TK && c < Kp) acc[tt] = fmaf(p, __ldg(G + key * ldg + c), acc[tt]);
+    }
+  }
+#pragma unroll
+  for (int tt = 0; tt < MAX_TK; ++tt) {
+    const int c = lane + tt * 32;
+    if (tt < TK && c < Kp) out[r * ld_out + c] = acc[tt];
+  }
+}
+
+}  // namespace seq
+}  // namespace b200
+
+using namespace b200;
+using namespace b200::seq;
+
+extern "C" int b200_seq_pool(const float* E, int64_t lde, int32_t d, int64_t pad_index,
+                             const int32_t* seqs, int64_t ld_seq, const int32_t* lens, int32_t T,
+                             const int64_t* users, int64_t R, int64_t grid_items, int64_t row_offset,
+                             float* out, int64_t ld_out, void* stream) {
+  B200_REQUIRE(E && seqs && lens && users && out, "b200_seq_pool: null pointer");
+  if (R == 0) return 0;
+  seq_pool_kernel<<<(unsigned)ceil_div64(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      E, lde, d, pad_index, seqs, ld_seq, lens, T, users, R, grid_items, row_offset, out, ld_out);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200_din_attention(const float* G, int64_t ldg, int32_t Kp, const int64_t* items,
+                                  const int32_t* seqs, int64_t ld_seq, const int32_t* lens, int32_t T,
+                                  const int64_t* users, int64_t R, int64_t grid_items,
+                                  int64_t row_offset, const float* k1, const float* b1,
+                                  const float* k2, float b2, float* out, int64_t ld_out, void* stream) {
+  B200_REQUIRE(G && seqs && lens && users && out && k1 && b1 && k2, "b200_din_attention: null pointer");
+  B200_REQUIRE(grid_items > 0 || items, "b200_din_attention: item ids missing");
+  B200_REQUIRE(Kp >= 1 && Kp <= 32 * MAX_TK, "b200_din_attention: feature width %d outside [1, %d]", Kp, 32 * MAX_TK);
+  B200_REQUIRE(T >= 1 && T <= MAX_T, "b200_din_attention: sequence length %d outside [1, %d]", T, MAX_T);
+  if (R == 0) return 0;
+  AttW w; w.k1 = k1; w.b1 = b1; w.k2 = k2; w.b2 = b2;
+  din_attention_kernel<<<(unsigned)ceil_div64(R, 4), 128, 0, (cudaStream_t)stream>>>(
+      G, ldg, Kp, items, seqs, ld_seq, lens, T, users, R, grid_items, row_offset, w, out, ld_out);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,544 @@
+"""Inference engines for the reference's feature ("TfBase") models on the GPU: FM, DeepFM
+(``libreco/algorithms/fm.py``, ``deepfm.py``) — forward (``predict``) and all-items scoring
+(``recommend_user`` = ``recommend_tf_feat``, ``libreco/recommendation/recommend.py:81-105``).
+
+* The per-row feed the reference materialises on the host (``process_tf_feat`` /
+  ``get_original_feats``) is never built: ``b200_feat_forward`` reads the per-user / per-item
+  unique feature tables in the kernel, and for all-items scoring rows are the implicit grid
+  (user, item 0..N-1).
+* BatchNorm layers are folded into scale/shift (inference = moving statistics, TF defaults
+  epsilon 1e-3) and, inside ``dense_nn``, into the following Dense layer.
+* Weights arrive as a dict with the keys of ``WEIGHT_KEYS`` (numpy arrays) — see
+  ``from_tf_variables`` for the mapping from a reference ``*_tf_variables.npz``.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, Structure, c_float, c_int32, c_int64, c_void_p
+
+import numpy as np
+
+from . import _lib
+from .consumed import ConsumedCSR, as_csr
+
+MAX_FIELDS = 128
+BN_EPS = 1e-3
+
+WEIGHT_KEYS = (
+    "user_embeds", "item_embeds", "sparse_embeds", "dense_embeds",
+    "user_linear", "item_linear", "sparse_linear", "dense_linear",
+    "lin_kernel", "lin_bias", "pw_kernel", "pw_bias", "fm_bn", "mlp", "out_kernel", "out_bias",
+)
+
+
+class FeatLayoutStruct(Structure):
+    _fields_ = [
+        ("embed_size", c_int32), ("n_sparse", c_int32), ("n_dense", c_int32),
+        ("id_mask", c_int32), ("dense_embed_row", c_int32 * MAX_FIELDS),
+        ("sparse_side", c_int32 * MAX_FIELDS), ("sparse_col", c_int32 * MAX_FIELDS),
+        ("dense_side", c_int32 * MAX_FIELDS), ("dense_col", c_int32 * MAX_FIELDS),
+        ("user_sparse_unique", c_void_p), ("ld_us", c_int64),
+        ("item_sparse_unique", c_void_p), ("ld_is", c_int64),
+        ("user_dense_unique", c_void_p), ("ld_ud", c_int64),
+        ("item_dense_unique", c_void_p), ("ld_id", c_int64),
+        ("sparse_rows", c_void_p), ("ld_sparse_rows", c_int64),
+        ("dense_rows", c_void_p), ("ld_dense_rows", c_int64),
+    ]
+
+
+class FeatTablesStruct(Structure):
+    _fields_ = [(n, c_void_p) for n in ("user_embeds", "item_embeds", "sparse_embeds", "dense_embeds",
+                                        "user_linear", "item_linear", "sparse_linear", "dense_linear")]
+
+
+def _dev(x, device, dtype):
+    import torch
+
+    if x is None:
+        return None
+    return torch.as_tensor(np.ascontiguousarray(x)).to(device=device, dtype=dtype).contiguous()
+
+
+def _side_cols(user_cols, item_cols):
+    n = len(user_cols) + len(item_cols)
+    side, col = [0] * n, [0] * n
+    for f in range(n):
+        if f in user_cols:
+            side[f], col[f] = 0, list(user_cols).index(f)
+        else:
+            side[f], col[f] = 1, list(item_cols).index(f)
+    return side, col
+
+
+def fold_bn(bn):
+    """BN(x) = x * scale + shift at inference."""
+    if bn is None:
+        return None, None
+    scale = (bn["gamma"] / np.sqrt(bn["var"] + np.float32(BN_EPS))).astype(np.float32)
+    shift = (bn["beta"] - bn["mean"] * scale).astype(np.float32)
+    return scale, shift
+
+
+def fold_mlp(mlp):
+    """dense_nn (libreco/layers/dense.py:12-49) -> [(Wt [dout, din], bias, relu)], BN folded into
+    the Dense that FOLLOWS it: Dense(BN(a)) = a (diag(s) W) + (t W + b)."""
+    layers = []
+    scale, shift = fold_bn(mlp.get("bn_in"))
+    n = len(mlp["kernels"])
+    for i in range(n):
+        W = np.asarray(mlp["kernels"][i], dtype=np.float32)
+        b = np.asarray(mlp["biases"][i], dtype=np.float32)
+        if scale is not None:
+            b = (shift @ W + b).astype(np.float32)
+            W = (scale[:, None] * W).astype(np.float32)
+        layers.append((np.ascontiguousarray(W.T), b, i != n - 1))
+        scale, shift = (None, None)
+        if i != n - 1 and mlp.get("bns"):
+            scale, shift = fold_bn(mlp["bns"][i])
+    return layers
+
+
+class FeatSpec:
+    """Device-resident feature layout (from the reference's DataInfo or an equivalent dict)."""
+
+    def __init__(self, spec, embed_size, device=None):
+        import torch
+
+        self.device = device if device is not None else _lib.require_cuda()
+        g = spec.get if isinstance(spec, dict) else (lambda k, d=None: getattr(spec, k, d))
+        self.n_users, self.n_items = int(g("n_users")), int(g("n_items"))
+        ucol, icol = list(g("user_sparse_col_index") or []), list(g("item_sparse_col_index") or [])
+        udc, idc = list(g("user_dense_col_index") or []), list(g("item_dense_col_index") or [])
+        self.n_sparse, self.n_dense = len(ucol) + len(icol), len(udc) + len(idc)
+        if self.n_sparse > MAX_FIELDS or self.n_dense > MAX_FIELDS:
+            raise ValueError("too many feature fields")
+        self.us = _dev(g("user_sparse_unique"), self.device, torch.int32) if ucol else None
+        self.is_ = _dev(g("item_sparse_unique"), self.device, torch.int32) if icol else None
+        self.ud = _dev(g("user_dense_unique"), self.device, torch.float32) if udc else None
+        self.id_ = _dev(g("item_dense_unique"), self.device, torch.float32) if idc else None
+        L = FeatLayoutStruct()
+        L.embed_size, L.n_sparse, L.n_dense = int(embed_size), self.n_sparse, self.n_dense
+        L.id_mask = 3
+        for f in range(self.n_dense):
+            L.dense_embed_row[f] = f
+        side, col = _side_cols(ucol, icol)
+        for f in range(self.n_sparse):
+            L.sparse_side[f], L.sparse_col[f] = side[f], col[f]
+        side, col = _side_cols(udc, idc)
+        for f in range(self.n_dense):
+            L.dense_side[f], L.dense_col[f] = side[f], col[f]
+        for name, t in (("user_sparse_unique", self.us), ("item_sparse_unique", self.is_),
+                        ("user_dense_unique", self.ud), ("item_dense_unique", self.id_)):
+            setattr(L, name, t.data_ptr() if t is not None else None)
+        L.ld_us = self.us.stride(0) if self.us is not None else 0
+        L.ld_is = self.is_.stride(0) if self.is_ is not None else 0
+        L.ld_ud = self.ud.stride(0) if self.ud is not None else 0
+        L.ld_id = self.id_.stride(0) if self.id_ is not None else 0
+        L.sparse_rows, L.dense_rows = None, None
+        self.layout = L
+        self.item_sparse_cols, self.item_dense_cols = icol, idc
+        self.user_sparse_cols, self.user_dense_cols = ucol, udc
+
+    def with_rows(self, sparse_rows, dense_rows):
+        """Layout copy that reads explicit per-row features (predict with given feature rows)."""
+        L = FeatLayoutStruct.from_buffer_copy(self.layout)
+        if sparse_rows is not None:
+            L.sparse_rows, L.ld_sparse_rows = sparse_rows.data_ptr(), sparse_rows.stride(0)
+        if dense_rows is not None:
+            L.dense_rows, L.ld_dense_rows = dense_rows.data_ptr(), dense_rows.stride(0)
+        return L
+
+
+class _FeatModelBase:
+    """Shared machinery: device tables, row forward, all-items scoring + masked top-K."""
+
+    needs_linear = True
+
+    def __init__(self, spec, weights, user_consumed=None, task="ranking", device=None):
+        import torch
+
+        self._torch = torch
+        K = int(np.asarray(weights["user_embeds"]).shape[1])
+        self.spec = spec if isinstance(spec, FeatSpec) else FeatSpec(spec, K, device)
+        self.device = self.spec.device
+        self.K = K
+        self.task = task
+        self.n_users, self.n_items = self.spec.n_users, self.spec.n_items
+        self.F = 2 + self.spec.n_sparse + self.spec.n_dense
+        f32 = torch.float32
+        self.t = {k: _dev(weights.get(k), self.device, f32) for k in
+                  ("user_embeds", "item_embeds", "sparse_embeds", "dense_embeds",
+                   "user_linear", "item_linear", "sparse_linear", "dense_linear")}
+        T = FeatTablesStruct()
+        for k, v in self.t.items():
+            setattr(T, k, v.data_ptr() if v is not None else None)
+        self.tables = T
+        if self.needs_linear:
+            self.lin_kernel = _dev(np.asarray(weights["lin_kernel"]).reshape(-1), self.device, f32)
+            self.lin_bias = float(np.asarray(weights["lin_bias"]).reshape(-1)[0])
+        csr = user_consumed if user_consumed is not None else ConsumedCSR(
+            np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32))
+        self.csr = as_csr(csr, self.n_users)
+        self.indptr_d, self.idx_d = self.csr.device(self.device)
+
+    # -- to be provided by subclasses ---------------------------------------------------------
+    def _forward(self, layout, users_d, items_d, R, grid_items):
+        raise NotImplementedError
+
+    # -- public ------------------------------------------------------------------------------------
+    def logits(self, users, items, sparse_rows=None, dense_rows=None):
+        torch = self._torch
+        u = torch.as_tensor(np.asarray(users, dtype=np.int64)).to(self.device)
+        i = torch.as_tensor(np.asarray(items, dtype=np.int64)).to(self.device)
+        layout = self.spec.layout
+        if sparse_rows is not None or dense_rows is not None:
+            sr = _dev(sparse_rows, self.device, torch.int32)
+            dr = _dev(dense_rows, self.device, torch.float32)
+            layout = self.spec.with_rows(sr, dr)
+            self._keep = (sr, dr)
+        return self._forward(layout, u, i, u.numel(), 0)
+
+    def predict(self, users, items):
+        """predict_tf_feat + normalize_prediction (prediction/predict.py:18-33,43-92), known ids."""
+        z = self.logits(users, items)
+        if self.task == "ranking":
+            z = self._torch.sigmoid(z)
+        return z.cpu().numpy()
+
+    def score_all_items(self, user_ids_d):
+        """[b, n_items] logits of every (user, item) pair — rows are the implicit grid."""
+        b = int(user_ids_d.numel())
+        out = self._forward(self.spec.layout, user_ids_d, None, b * self.n_items, self.n_items)
+        return out.view(b, self.n_items)
+
+    def recommend(self, user_ids, n_rec, filter_consumed=True, return_scores=False, rows_per_chunk=None):
+        """recommend_tf_feat (recommend.py:81-105): all-items scoring, consumed filter, top-K."""
+        torch = self._torch
+        if n_rec > self.n_items:
+            raise ValueError(f"`n_rec` {n_rec} exceeds num of items {self.n_items}")
+        uid = torch.as_tensor(np.asarray(user_ids, dtype=np.int64)).to(self.device)
+        B = uid.numel()
+        if rows_per_chunk is None:
+            rows_per_chunk = max(1, min(B, self.max_grid_rows() // max(self.n_items, 1)))
+        out_ids = torch.empty((B, n_rec), dtype=torch.int64, device=self.device)
+        out_sc = torch.empty((B, n_rec), dtype=torch.float32, device=self.device)
+        lib, stream = _lib.lib, _lib.current_stream()
+        for r0 in range(0, B, rows_per_chunk):
+            u = uid[r0:r0 + rows_per_chunk]
+            b = u.numel()
+            scores = self.score_all_items(u).contiguous()
+            if filter_consumed and self.csr.nnz > 0:
+                _lib.check(lib.b200_mask_consumed(_lib.ptr(scores), scores.stride(0), _lib.ptr(u), b,
+                                                  self.n_items, n_rec, _lib.ptr(self.indptr_d),
+                                                  _lib.ptr(self.idx_d), self.csr.n_users, stream))
+            nbytes = ctypes.c_size_t(0)
+            _lib.check(lib.b200_topk_rows_workspace_bytes(b, self.n_items, n_rec, ctypes.byref(nbytes)))
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            _lib.check(lib.b200_topk_rows(_lib.ptr(scores), scores.stride(0), b, self.n_items, n_rec,
+                                          _lib.ptr(out_ids[r0:r0 + b]), _lib.ptr(out_sc[r0:r0 + b]),
+                                          _lib.ptr(ws), nbytes.value, stream))
+        ids = out_ids.cpu().numpy()
+        if return_scores:
+            sc = out_sc.cpu().numpy()
+            return ids, (1.0 / (1.0 + np.exp(-sc)) if self.task == "ranking" else sc)
+        return ids
+
+    def max_grid_rows(self):
+        return 1 << 22
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _feat_forward(self, layout, users_d, items_d, R, grid_items, concat=None, pw=None, lin=None,
+                      fm_out=None, head=None, row_offset=0):
+        head = head or {}
+        _lib.check(_lib.lib.b200_feat_forward(
+            ctypes.byref(layout), ctypes.byref(self.tables), _lib.ptr(users_d), _lib.ptr(items_d), R,
+            grid_items, row_offset, _lib.ptr(concat), concat.stride(0) if concat is not None else 0,
+            _lib.ptr(pw), pw.stride(0) if pw is not None else 0, _lib.ptr(lin), _lib.ptr(fm_out),
+            _lib.ptr(self.lin_kernel) if self.needs_linear else None,
+            self.lin_bias if self.needs_linear else 0.0,
+            _lib.ptr(head.get("bn_scale")), _lib.ptr(head.get("bn_shift")), _lib.ptr(head.get("pw_kernel")),
+            float(head.get("pw_bias", 0.0)), _lib.current_stream()))
+
+    def _mlp(self, x, layers):
+        torch = self._torch
+        for Wt, b, relu in layers:
+            y = torch.empty((x.shape[0], Wt.shape[0]), dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib.b200_linear_f32(_lib.ptr(x), x.stride(0), x.shape[0], _lib.ptr(Wt), Wt.stride(0),
+                                                _lib.ptr(b), Wt.shape[1], Wt.shape[0], 1 if relu else 0,
+                                                _lib.ptr(y), y.stride(0), _lib.current_stream()))
+            x = y
+        return x
+
+    def _upload_mlp(self, mlp):
+        torch = self._torch
+        return [(_dev(Wt, self.device, torch.float32), _dev(b, self.device, torch.float32), relu)
+                for Wt, b, relu in fold_mlp(mlp)]
+
+
+class FM(_FeatModelBase):
+    """libreco/algorithms/fm.py:140-172 (inference)."""
+
+    def __init__(self, spec, weights, user_consumed=None, task="ranking", device=None):
+        super().__init__(spec, weights, user_consumed, task, device)
+        torch = self._torch
+        scale, shift = fold_bn(weights.get("fm_bn"))
+        self.head = dict(bn_scale=_dev(scale, self.device, torch.float32),
+                         bn_shift=_dev(shift, self.device, torch.float32),
+                         pw_kernel=_dev(np.asarray(weights["pw_kernel"]).reshape(-1), self.device, torch.float32),
+                         pw_bias=float(np.asarray(weights["pw_bias"]).reshape(-1)[0]))
+
+    def _forward(self, layout, users_d, items_d, R, grid_items):
+        out = self._torch.empty(R, dtype=self._torch.float32, device=self.device)
+        self._feat_forward(layout, users_d, items_d, R, grid_items, fm_out=out, head=self.head)
+        return out
+
+    def max_grid_rows(self):
+        return 1 << 28
+
+
+class DeepFM(_FeatModelBase):
+    """libreco/algorithms/deepfm.py:143-175 (inference)."""
+
+    def __init__(self, spec, weights, user_consumed=None, task="ranking", device=None):
+        super().__init__(spec, weights, user_consumed, task, device)
+        torch = self._torch
+        self.mlp = self._upload_mlp(weights["mlp"])
+        self.hidden_last = self.mlp[-1][0].shape[0]
+        self.out_kernel = _dev(np.asarray(weights["out_kernel"]).reshape(-1), self.device, torch.float32)
+        self.out_bias = float(np.asarray(weights["out_bias"]).reshape(-1)[0])
+
+    def _forward(self, layout, users_d, items_d, R, grid_items):
+        torch = self._torch
+        out = torch.empty(R, dtype=torch.float32, device=self.device)
+        step = self.max_grid_rows()
+        for r0 in range(0, R, step):                  # bound the [rows, F*K] deep input
+            r1 = min(R, r0 + step)
+            n = r1 - r0
+            concat = torch.empty((n, self.F * self.K), dtype=torch.float32, device=self.device)
+            pw = torch.empty((n, self.K), dtype=torch.float32, device=self.device)
+            lin = torch.empty(n, dtype=torch.float32, device=self.device)
+            if grid_items > 0:
+                self._feat_forward(layout, users_d, None, n, grid_items, concat=concat, pw=pw, lin=lin,
+                                   row_offset=r0)
+            else:
+                self._feat_forward(layout, users_d[r0:r1], items_d[r0:r1], n, 0, concat=concat, pw=pw, lin=lin)
+            deep = self._mlp(concat, self.mlp)
+            lin2 = lin.view(n, 1)
+            _lib.check(_lib.lib.b200_concat_dense(
+                _lib.ptr(lin2), 1, 1, _lib.ptr(pw), pw.stride(0), self.K, _lib.ptr(deep), deep.stride(0),
+                self.hidden_last, _lib.ptr(self.out_kernel), self.out_bias, n, _lib.ptr(out[r0:r1]),
+                _lib.current_stream()))
+        return out
+
+    def max_grid_rows(self):
+        # deep input bytes per row = F*K*4; keep a chunk under ~1 GiB and a whole number of users
+        return max(1, (1 << 30) // (self.F * self.K * 4))
+
+
+def from_tf_variables(npz, names=None):
+    """Map a reference ``<name>_tf_variables.npz`` (utils/save_load.py:70-80) to WEIGHT_KEYS.
+    Embedding names are fixed by the reference code; the un-named
+    ``tf_dense`` heads get TF-version-dependent auto names, so `names` may override the defaults."""
+    names = names or {}
+    g = lambda k, d: npz[names.get(k, d)] if names.get(k, d) in npz else None
+    w = {}
+    for k in ("user_embeds", "item_embeds", "sparse_embeds", "dense_embeds"):
+        v = g(k, f"embedding/{k}_var:0")
+        if v is not None:
+            w[k] = v
+    for k in ("user_linear", "item_linear", "sparse_linear", "dense_linear"):
+        v = g(k, f"embedding/{k}_var:0")
+        if v is not None:
+            w[k] = np.asarray(v).reshape(-1)
+    return w
+
+
+# ==============================================================================================
+# sequence models (DIN, YouTubeRanking) and TwoTower
+# ==============================================================================================
+def recent_sequences(user_consumed, n_users, n_items, max_seq_len):
+    """get_recent_seqs (libreco/batch/sequence.py:75-91): last `max_seq_len` consumed items per
+    user, padded with n_items; an extra all-pad OOV row with length 1."""
+    seqs = np.full((n_users + 1, max_seq_len), n_items, dtype=np.int32)
+    lens = np.ones(n_users + 1, dtype=np.int32)
+    for u in range(n_users):
+        items = user_consumed[u] if u in user_consumed else []
+        n = min(len(items), max_seq_len)
+        if n:
+            seqs[u, :n] = items[-n:] if len(items) >= max_seq_len else items
+        lens[u] = n if len(items) < max_seq_len else max_seq_len
+    return seqs, lens
+
+
+def permute_mlp_input(mlp, perm):
+    """Re-order the input features of a dense_nn (first kernel rows + input BN) by `perm`."""
+    out = dict(mlp)
+    out["kernels"] = [np.asarray(mlp["kernels"][0])[perm]] + list(mlp["kernels"][1:])
+    if mlp.get("bn_in") is not None:
+        out["bn_in"] = {k: np.asarray(v)[perm] for k, v in mlp["bn_in"].items()}
+    return out
+
+
+class _SeqModelBase(_FeatModelBase):
+    needs_linear = False
+
+    def __init__(self, spec, weights, recent_seqs, recent_seq_lens, user_consumed=None, task="ranking",
+                 device=None):
+        super().__init__(spec, weights, user_consumed, task, device)
+        torch = self._torch
+        self.seqs = _dev(recent_seqs, self.device, torch.int32)
+        self.lens = _dev(recent_seq_lens, self.device, torch.int32)
+        self.T = int(self.seqs.shape[1])
+        self.out_kernel = _dev(np.asarray(weights["out_kernel"]).reshape(-1), self.device, torch.float32)
+        self.out_bias = float(np.asarray(weights["out_bias"]).reshape(-1)[0])
+        self.extra = 0          # width of the sequence block appended to the concatenated row
+
+    def _seq_block(self, layout, users_d, items_d, n, grid_items, row_offset, out_view):
+        raise NotImplementedError
+
+    def _forward(self, layout, users_d, items_d, R, grid_items):
+        torch = self._torch
+        out = torch.empty(R, dtype=torch.float32, device=self.device)
+        width = self.F * self.K + self.extra
+        step = max(1, (1 << 30) // (width * 4))
+        for r0 in range(0, R, step):
+            r1 = min(R, r0 + step)
+            n = r1 - r0
+            x = torch.empty((n, width), dtype=torch.float32, device=self.device)
+            if grid_items > 0:
+                self._feat_forward(layout, users_d, None, n, grid_items, concat=x, row_offset=r0)
+                self._seq_block(users_d, None, n, grid_items, r0, x[:, self.F * self.K:])
+            else:
+                self._feat_forward(layout, users_d[r0:r1], items_d[r0:r1], n, 0, concat=x)
+                self._seq_block(users_d[r0:r1], items_d[r0:r1], n, 0, 0, x[:, self.F * self.K:])
+            h = self._mlp(x, self.mlp)
+            _lib.check(_lib.lib.b200_concat_dense(
+                _lib.ptr(h), h.stride(0), h.shape[1], None, 0, 0, None, 0, 0, _lib.ptr(self.out_kernel),
+                self.out_bias, n, _lib.ptr(out[r0:r1]), _lib.current_stream()))
+        return out
+
+    def max_grid_rows(self):
+        return max(1, (1 << 30) // ((self.F * self.K + self.extra) * 4))
+
+
+class YouTubeRanking(_SeqModelBase):
+    """libreco/algorithms/youtube_ranking.py:167-218 (inference)."""
+
+    def __init__(self, spec, weights, recent_seqs, recent_seq_lens, user_consumed=None, task="ranking",
+                 device=None):
+        super().__init__(spec, weights, recent_seqs, recent_seq_lens, user_consumed, task, device)
+        K, F = self.K, self.F
+        self.extra = K
+        # reference order [user, item, pooled, sparse.., dense..] -> ours [user, item, sparse.., dense.., pooled]
+        perm = np.concatenate([np.arange(0, 2 * K), np.arange(3 * K, (F + 1) * K), np.arange(2 * K, 3 * K)])
+        self.mlp = self._upload_mlp(permute_mlp_input(weights["mlp"], perm))
+
+    def _seq_block(self, users_d, items_d, n, grid_items, row_offset, out_view):
+        E = self.t["item_embeds"]
+        _lib.check(_lib.lib.b200_seq_pool(
+            _lib.ptr(E), E.stride(0), self.K, self.n_items, _lib.ptr(self.seqs), self.seqs.stride(0),
+            _lib.ptr(self.lens), self.T, _lib.ptr(users_d), n, grid_items, row_offset,
+            _lib.ptr(out_view), out_view.stride(0), _lib.current_stream()))
+
+
+class DIN(_SeqModelBase):
+    """libreco/algorithms/din.py:165-250 (inference, use_tf_attention=False)."""
+
+    def __init__(self, spec, weights, recent_seqs, recent_seq_lens, user_consumed=None, task="ranking",
+                 device=None):
+        super().__init__(spec, weights, recent_seqs, recent_seq_lens, user_consumed, task, device)
+        torch = self._torch
+        # item feature table G (combine_seq_features, concat mode; tfops/features.py:165-218), built once
+        parts = [self.t["item_embeds"]]
+        if self.spec.is_ is not None:
+            parts.append(self.t["sparse_embeds"][self.spec.is_.long()].reshape(self.n_items + 1, -1))
+        if self.spec.id_ is not None:
+            cols = torch.as_tensor(self.spec.item_dense_cols, device=self.device)
+            parts.append((self.spec.id_[:, :, None] * self.t["dense_embeds"][cols][None]).reshape(self.n_items + 1, -1))
+        self.G = torch.cat(parts, dim=1).contiguous()
+        self.Kp = int(self.G.shape[1])
+        self.extra = self.Kp
+        att = weights["attention"]
+        self.att = dict(k1=_dev(att["k1"], self.device, torch.float32), b1=_dev(att["b1"], self.device, torch.float32),
+                        k2=_dev(np.asarray(att["k2"]).reshape(-1), self.device, torch.float32),
+                        b2=float(np.asarray(att["b2"]).reshape(-1)[0]))
+        self.mlp = self._upload_mlp(weights["mlp"])
+
+    def _seq_block(self, users_d, items_d, n, grid_items, row_offset, out_view):
+        _lib.check(_lib.lib.b200_din_attention(
+            _lib.ptr(self.G), self.G.stride(0), self.Kp, _lib.ptr(items_d), _lib.ptr(self.seqs),
+            self.seqs.stride(0), _lib.ptr(self.lens), self.T, _lib.ptr(users_d), n, grid_items, row_offset,
+            _lib.ptr(self.att["k1"]), _lib.ptr(self.att["b1"]), _lib.ptr(self.att["k2"]), self.att["b2"],
+            _lib.ptr(out_view), out_view.stride(0), _lib.current_stream()))
+
+
+class TwoTower:
+    """libreco/algorithms/two_tower.py:306-346,400-410 + DynEmbedBase.set_embeddings
+    (libreco/bases/dyn_embed_base.py:240-269): both towers over ALL users / items on the GPU; the
+    results (plus the mean OOV rows of embed_base.py:257-265) feed the embed scorer directly."""
+
+    def __init__(self, spec, weights, norm_embed=False, device=None):
+        import torch
+
+        self._torch = torch
+        K = int(np.asarray(weights["user_embeds"]).shape[1])
+        self.base = FeatSpec(spec, K, device)
+        self.device = self.base.device
+        self.K = K
+        self.norm_embed = norm_embed
+        self.n_users, self.n_items = self.base.n_users, self.base.n_items
+        f32 = torch.float32
+        self.t = {k: _dev(weights.get(k), self.device, f32) for k in
+                  ("user_embeds", "item_embeds", "sparse_embeds", "dense_embeds")}
+        T = FeatTablesStruct()
+        for k, v in self.t.items():
+            setattr(T, k, v.data_ptr() if v is not None else None)
+        self.tables = T
+        self.layouts, self.mlps, self.widths = {}, {}, {}
+        for which, mask in (("user", 1), ("item", 2)):
+            L = FeatLayoutStruct.from_buffer_copy(self.base.layout)
+            L.id_mask = mask
+            scols = self.base.user_sparse_cols if which == "user" else self.base.item_sparse_cols
+            dcols = self.base.user_dense_cols if which == "user" else self.base.item_dense_cols
+            L.n_sparse, L.n_dense = len(scols), len(dcols)
+            for f in range(len(scols)):
+                L.sparse_side[f], L.sparse_col[f] = (0 if which == "user" else 1), f
+            for f in range(len(dcols)):
+                L.dense_side[f], L.dense_col[f] = (0 if which == "user" else 1), f
+                L.dense_embed_row[f] = dcols[f]
+            self.layouts[which] = L
+            self.widths[which] = (1 + len(scols) + len(dcols)) * K
+            self.mlps[which] = [(_dev(Wt, self.device, f32), _dev(b, self.device, f32), relu)
+                                for Wt, b, relu in fold_mlp(weights[f"{which}_tower"])]
+
+    def tower(self, which, ids):
+        torch = self._torch
+        ids_d = torch.as_tensor(np.asarray(ids, dtype=np.int64)).to(self.device)
+        n = ids_d.numel()
+        x = torch.empty((n, self.widths[which]), dtype=torch.float32, device=self.device)
+        L = self.layouts[which]
+        _lib.check(_lib.lib.b200_feat_forward(
+            ctypes.byref(L), ctypes.byref(self.tables), _lib.ptr(ids_d), _lib.ptr(ids_d), n, 0, 0,
+            _lib.ptr(x), x.stride(0), None, 0, None, None, None, 0.0, None, None, None, 0.0,
+            _lib.current_stream()))
+        for Wt, b, relu in self.mlps[which]:
+            y = torch.empty((n, Wt.shape[0]), dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib.b200_linear_f32(_lib.ptr(x), x.stride(0), n, _lib.ptr(Wt), Wt.stride(0), _lib.ptr(b),
+                                                Wt.shape[1], Wt.shape[0], 1 if relu else 0, _lib.ptr(y),
+                                                y.stride(0), _lib.current_stream()))
+            x = y
+        if self.norm_embed:
+            _lib.check(_lib.lib.b200_l2_normalize_rows(_lib.ptr(x), x.stride(0), n, x.shape[1],
+                                                       _lib.current_stream()))
+        return x
+
+    def set_embeddings(self, chunk=1 << 20):
+        """User / item vectors of every id + the mean OOV row; returns device tensors
+        [n_users+1, d], [n_items+1, d]."""
+        torch = self._torch
+        outs = []
+        for which, n in (("user", self.n_users), ("item", self.n_items)):
+            rows = [self.tower(which, np.arange(i, min(n, i + chunk))) for i in range(0, n, chunk)]
+            E = torch.cat(rows, dim=0)
+            outs.append(torch.cat([E, E.mean(dim=0, keepdim=True)], dim=0))
+        return outs[0], outs[1]

@@ -1,0 +1,212 @@
+"""GPU parity of the FM / DeepFM inference engines against the numpy restatement of the
+reference graphs (oracle/tf_models.py — parity unpinned, see its header): logits within 1e-5
+relative (the tolerance BASELINE.json's north_star states), top-K ids equal to the oracle's
+ranking of the oracle's own scores outside near-ties."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed, n_users=300, n_items=500, K=16, us=(7, 30), its=(11, 5, 40), ud=1, idn=2):
+    from oracle import tf_models as tm
+
+    rng = np.random.default_rng(seed)
+    spec = tm.make_spec(rng, n_users, n_items, list(us), list(its), ud, idn)
+    return rng, spec
+
+
+def _close(got, ref, tol=1e-5):
+    scale = np.maximum(np.abs(ref), np.abs(ref).mean())
+    assert (np.abs(got - ref) <= tol * scale + 1e-6).all(), float(np.abs(got - ref).max())
+
+
+@pytest.mark.parametrize("use_bn", [True, False])
+@pytest.mark.parametrize("K", [16, 8, 64, 20])
+def test_fm_logits_and_predict(use_bn, K):
+    from librecommender_b200.feat_models import FM
+    from oracle import tf_models as tm
+
+    rng, spec = _case(K + int(use_bn), K=K)
+    w = tm.make_fm_weights(rng, spec, K, use_bn)
+    model = FM(spec, w)
+    users = rng.integers(0, spec["n_users"] + 1, size=777)      # includes the OOV row
+    items = rng.integers(0, spec["n_items"] + 1, size=777)
+    sparse, dense = tm.row_features(spec, users, items)
+    ref = tm.fm_forward(w, users, items, sparse, dense)
+    ref64 = tm.fm_forward(w, users, items, sparse, dense, dtype=np.float64)
+    got = model.logits(users, items).cpu().numpy()
+    _close(got, ref64, 1e-5)
+    _close(ref, ref64, 1e-5)
+    # explicit feature rows (predict with a feed) give the same numbers
+    got2 = model.logits(users, items, sparse_rows=sparse, dense_rows=dense).cpu().numpy()
+    np.testing.assert_array_equal(got, got2)
+    p = model.predict(users, items)
+    np.testing.assert_allclose(p, 1 / (1 + np.exp(-ref64)), rtol=1e-5, atol=1e-6)
+
+
+def test_fm_only_ids_no_features():
+    from librecommender_b200.feat_models import FM
+    from oracle import tf_models as tm
+
+    rng = np.random.default_rng(0)
+    spec = tm.make_spec(rng, 100, 80, [], [], 0, 0)          # DatasetPure: user / item ids only
+    w = tm.make_fm_weights(rng, spec, 16, True)
+    model = FM(spec, w)
+    users, items = rng.integers(0, 100, 300), rng.integers(0, 80, 300)
+    _close(model.logits(users, items).cpu().numpy(), tm.fm_forward(w, users, items, dtype=np.float64))
+
+
+@pytest.mark.parametrize("use_bn", [True, False])
+def test_deepfm_logits(use_bn):
+    from librecommender_b200.feat_models import DeepFM
+    from oracle import tf_models as tm
+
+    rng, spec = _case(5 + int(use_bn), K=16)
+    w = tm.make_deepfm_weights(rng, spec, 16, (128, 64, 32), use_bn)
+    model = DeepFM(spec, w)
+    users = rng.integers(0, spec["n_users"], size=1000)
+    items = rng.integers(0, spec["n_items"], size=1000)
+    sparse, dense = tm.row_features(spec, users, items)
+    ref64 = tm.deepfm_forward(w, users, items, sparse, dense, dtype=np.float64)
+    _close(model.logits(users, items).cpu().numpy(), ref64, 1e-5)
+
+
+@pytest.mark.parametrize("cls_name", ["FM", "DeepFM"])
+def test_recommend_all_items_matches_oracle(cls_name):
+    from librecommender_b200 import feat_models as fmods
+    from oracle import ranking as orc
+    from oracle import tf_models as tm
+
+    rng, spec = _case(11, n_users=120, n_items=700, K=16)
+    N = spec["n_items"]
+    if cls_name == "FM":
+        w = tm.make_fm_weights(rng, spec, 16, True)
+        fwd = tm.fm_forward
+    else:
+        w = tm.make_deepfm_weights(rng, spec, 16, (64, 32), True)
+        fwd = tm.deepfm_forward
+    consumed = {u: rng.choice(N, size=int(rng.integers(1, 40)), replace=False).tolist() for u in range(120)}
+    model = getattr(fmods, cls_name)(spec, w, consumed)
+    user_ids = rng.choice(120, size=37, replace=False)
+    got = model.recommend(user_ids, 10, True)
+    # oracle: the reference's own B*N-row feed (process_tf_feat), then rank_recommendations
+    uu = np.repeat(user_ids, N)
+    ii = np.tile(np.arange(N), len(user_ids))
+    sparse, dense = tm.row_features(spec, uu, ii)
+    preds = fwd(w, uu, ii, sparse, dense, dtype=np.float64).astype(np.float32)
+    ref = orc.rank_recommendations("ranking", user_ids.tolist(), preds, 10, N, consumed, True)
+    full = preds.reshape(len(user_ids), N)
+    assert orc.near_tie_mask(ref, got, full, 1e-5).all()
+    assert (got == ref).mean() > 0.98
+    for r, u in enumerate(user_ids.tolist()):
+        assert not set(got[r].tolist()) & set(consumed[u])
+
+
+def _seq_case(seed, T=12):
+    from librecommender_b200.feat_models import recent_sequences
+    from oracle import tf_models as tm
+
+    rng = np.random.default_rng(seed)
+    spec = tm.make_spec(rng, 150, 400, [9], [6, 13, 21], 1, 1)
+    consumed = {u: rng.choice(400, size=int(rng.integers(1, 30)), replace=False).tolist() for u in range(149)}
+    seqs, lens = recent_sequences(consumed, 150, 400, T)       # user 149 has no history
+    return rng, spec, consumed, seqs, lens
+
+
+def test_recent_sequences_matches_reference_rule():
+    from librecommender_b200.feat_models import recent_sequences
+
+    consumed = {0: [5, 6, 7, 8, 9], 1: [3], 2: []}
+    seqs, lens = recent_sequences(consumed, 3, 50, 3)
+    np.testing.assert_array_equal(seqs, [[7, 8, 9], [3, 50, 50], [50, 50, 50], [50, 50, 50]])
+    np.testing.assert_array_equal(lens, [3, 1, 0, 1])
+
+
+@pytest.mark.parametrize("use_bn", [True, False])
+def test_din_logits(use_bn):
+    from librecommender_b200.feat_models import DIN
+    from oracle import tf_models as tm
+
+    rng, spec, consumed, seqs, lens = _seq_case(21)
+    w = tm.make_seq_weights(rng, spec, 16, (64, 32), use_bn, din=True)
+    model = DIN(spec, w, seqs, lens)
+    users = rng.integers(0, 151, size=600)
+    items = rng.integers(0, 400, size=600)
+    sparse, dense = tm.row_features(spec, users, items)
+    ref64 = tm.din_forward(w, spec, users, items, seqs[users], np.maximum(lens[users], 0), sparse, dense,
+                           dtype=np.float64)
+    ok = lens[users] > 0                                     # len 0 rows: reference divides 0/0 (never built)
+    _close(model.logits(users, items).cpu().numpy()[ok], ref64[ok], 1e-5)
+
+
+def test_youtube_ranking_logits_and_recommend():
+    from librecommender_b200.feat_models import YouTubeRanking
+    from oracle import ranking as orc
+    from oracle import tf_models as tm
+
+    rng, spec, consumed, seqs, lens = _seq_case(22)
+    w = tm.make_seq_weights(rng, spec, 16, (64, 32), True, din=False)
+    model = YouTubeRanking(spec, w, seqs, lens, consumed)
+    users = rng.integers(0, 151, size=500)
+    items = rng.integers(0, 400, size=500)
+    sparse, dense = tm.row_features(spec, users, items)
+    ref64 = tm.youtube_ranking_forward(w, users, items, seqs[users], lens[users], 400, sparse, dense,
+                                       dtype=np.float64)
+    _close(model.logits(users, items).cpu().numpy(), ref64, 1e-5)
+    uid = np.arange(0, 40)
+    got = model.recommend(uid, 7, True)
+    uu, ii = np.repeat(uid, 400), np.tile(np.arange(400), len(uid))
+    sp, de = tm.row_features(spec, uu, ii)
+    preds = tm.youtube_ranking_forward(w, uu, ii, seqs[uu], lens[uu], 400, sp, de, dtype=np.float64).astype(np.float32)
+    ref = orc.rank_recommendations("ranking", uid.tolist(), preds, 7, 400, consumed, True)
+    assert orc.near_tie_mask(ref, got, preds.reshape(len(uid), 400), 1e-5).all()
+
+
+def test_din_recommend_all_items():
+    from librecommender_b200.feat_models import DIN
+    from oracle import ranking as orc
+    from oracle import tf_models as tm
+
+    rng, spec, consumed, seqs, lens = _seq_case(23, T=20)
+    w = tm.make_seq_weights(rng, spec, 16, (32, 16), True, din=True)
+    model = DIN(spec, w, seqs, lens, consumed)
+    uid = np.arange(3, 25)
+    got = model.recommend(uid, 10, True)
+    uu, ii = np.repeat(uid, 400), np.tile(np.arange(400), len(uid))
+    sp, de = tm.row_features(spec, uu, ii)
+    preds = tm.din_forward(w, spec, uu, ii, seqs[uu], lens[uu], sp, de, dtype=np.float64).astype(np.float32)
+    ref = orc.rank_recommendations("ranking", uid.tolist(), preds, 10, 400, consumed, True)
+    assert orc.near_tie_mask(ref, got, preds.reshape(len(uid), 400), 1e-5).all()
+    assert (got == ref).mean() > 0.97
+
+
+@pytest.mark.parametrize("norm", [True, False])
+def test_two_tower_embeddings_and_retrieval(norm):
+    from librecommender_b200.engine import EmbedScorer
+    from librecommender_b200.feat_models import TwoTower
+    from oracle import ranking as orc
+    from oracle import tf_models as tm
+
+    rng = np.random.default_rng(31)
+    spec = tm.make_spec(rng, 200, 300, [8, 17], [5, 9], 1, 2)
+    w = tm.make_two_tower_weights(rng, spec, 16, (64, 32), True)
+    tt = TwoTower(spec, w, norm_embed=norm)
+    U, I = tt.set_embeddings()
+    uids, iids = np.arange(200), np.arange(300)
+    us = spec["user_sparse_unique"][uids]
+    ud = spec["user_dense_unique"][uids]
+    is_ = spec["item_sparse_unique"][iids]
+    idn = spec["item_dense_unique"][iids]
+    ru = tm.tower_forward(w, uids, us, ud, "user", norm, dtype=np.float64)
+    ri = tm.tower_forward(w, iids, is_, idn, "item", norm, dtype=np.float64)
+    _close(U[:200].cpu().numpy(), ru, 2e-5)
+    _close(I[:300].cpu().numpy(), ri, 2e-5)
+    np.testing.assert_allclose(U[200].cpu().numpy(), ru.mean(axis=0), rtol=1e-4, atol=1e-6)   # OOV row
+    # the tower outputs feed the embed scorer directly (no host round trip)
+    consumed = {u: rng.choice(300, size=5, replace=False).tolist() for u in range(200)}
+    sc = EmbedScorer(U, I, 300, consumed, n_users=200)
+    got = sc.recommend(np.arange(50), 10, True)
+    Uh, Ih = U.cpu().numpy(), I.cpu().numpy()
+    ref = orc.recommend_from_embedding("ranking", list(range(50)), 10, Uh, Ih, 300, consumed, True)
+    assert orc.near_tie_mask(ref, got, orc.embed_scores(Uh, Ih, list(range(50)), 300), 1e-6).all()
