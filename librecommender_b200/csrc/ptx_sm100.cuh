@@ -30,14 +30,16 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the thread is parked by the hardware (no issue slots) until
+// the phase completes or ~hint_ns elapse, so waiting roles do not steal cycles from the epilogue
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 20000u) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
       : "memory");
   return ok != 0;
 }
@@ -48,7 +50,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // for the single-lane producer / issuer roles: back off between probes so that the spinning lane
 // does not take issue slots from the epilogue warps sharing its scheduler
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) __nanosleep(256);
+  while (!mbar_try_wait(bar, parity)) {
+  }
 }
 
 // ---------------------------------------------------------------- TMA

@@ -163,8 +163,8 @@ __global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
 struct SweepSmem {
   uint64_t full[8];
   uint64_t empty[8];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
+  uint64_t tmem_full[2][2];    // [accumulator stage][column half]
+  uint64_t tmem_empty[2][2];
   uint64_t a_full;
   uint64_t a_empty;
   uint32_t tmem_base;
@@ -281,7 +281,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstage; ++s) { ptx::mbar_init(&ss->full[s], 1); ptx::mbar_init(&ss->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&ss->tmem_full[a], 1); ptx::mbar_init(&ss->tmem_empty[a], EPI_WARPS); }
+    for (int a = 0; a < 2; ++a)
+      for (int hh = 0; hh < 2; ++hh) {
+        ptx::mbar_init(&ss->tmem_full[a][hh], 1);
+        ptx::mbar_init(&ss->tmem_empty[a][hh], EPI_WARPS / 2);
+      }
     ptx::mbar_init(&ss->a_full, 1);
     ptx::mbar_init(&ss->a_empty, 1);
     ptx::fence_barrier_init();
@@ -324,7 +328,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(TM, TN);
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(TM, TN / 2);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -338,23 +342,28 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
         ptx::mbar_wait(&ss->a_full, uiter & 1);
         for (int t = t0; t < t1; t += STRIDE) {
-          ptx::mbar_wait(&ss->tmem_empty[acc], acc_phase ^ 1);   // latency critical: no back-off
           ptx::mbar_wait(&ss->full[stage], phase);
-          ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
-          for (int kb = 0; kb < p.KB; ++kb) {
-            const uint64_t da = ptx::umma_desc_sw128_kmajor(a_addr + (uint32_t)(kb * A_KB_BYTES));
-            const uint64_t db = ptx::umma_desc_sw128_kmajor(
-                b_addr + (uint32_t)((stage * p.KB + kb) * B_KB_BYTES));
+          // one N=128 MMA group per column half: the two halves of the accumulator are released by
+          // (and handed to) their own four epilogue warps, so a slow warp only stalls its half
 #pragma unroll
-            for (int k4 = 0; k4 < KBLK / 16; ++k4) {
-              // advance 16 bf16 = 32 bytes inside the 128-byte swizzled row: +2 in the >>4 field
-              ptx::umma_f16(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
-                            (uint32_t)((kb | k4) != 0));
+          for (int hh = 0; hh < 2; ++hh) {
+            ptx::mbar_wait(&ss->tmem_empty[acc][hh], acc_phase ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN + hh * (TN / 2));
+            for (int kb = 0; kb < p.KB; ++kb) {
+              const uint64_t da = ptx::umma_desc_sw128_kmajor(a_addr + (uint32_t)(kb * A_KB_BYTES));
+              const uint64_t db = ptx::umma_desc_sw128_kmajor(
+                  b_addr + (uint32_t)((stage * p.KB + kb) * B_KB_BYTES + hh * (TN / 2) * KBLK * 2));
+#pragma unroll
+              for (int k4 = 0; k4 < KBLK / 16; ++k4) {
+                // advance 16 bf16 = 32 bytes inside the 128-byte swizzled row: +2 in the >>4 field
+                ptx::umma_f16(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
+                              (uint32_t)((kb | k4) != 0));
+              }
             }
+            ptx::umma_commit(&ss->tmem_full[acc][hh]);   // this half is ready for its epilogue warps
           }
-          ptx::umma_commit(&ss->empty[stage]);      // smem stage reusable when these MMAs finish
-          ptx::umma_commit(&ss->tmem_full[acc]);    // accumulator ready for the epilogue
+          ptx::umma_commit(&ss->empty[stage]);           // smem stage reusable when these MMAs finish
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
@@ -383,7 +392,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         float* bm = p.blockmax + (int64_t)list_id * p.n_pre_tiles * p.B_pad + grow;
         int ti = 0;
         for (int t = t0; t < t1; t += STRIDE, ++ti) {
-          ptx::mbar_wait(&ss->tmem_full[acc], acc_phase);
+          ptx::mbar_wait(&ss->tmem_full[acc][half], acc_phase);
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * (TN / 2));
           float tm = ninf;
@@ -397,7 +406,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc]);
+          if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
           // tiles that contain zero-padded item rows would bias the estimate: drop them
@@ -453,7 +462,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
       const int last_full = (int)(p.N / TN);   // tiles >= last_full contain padded item rows
       for (int t = t0; t < t1; ++t) {
-        ptx::mbar_wait(&ss->tmem_full[acc], acc_phase);
+        ptx::mbar_wait(&ss->tmem_full[acc][half], acc_phase);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * (TN / 2));
         const int n_base = t * TN + half * (TN / 2);
@@ -471,33 +480,32 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           float g[4];
           const float mx = chunk_max(r, g);
           const bool hit = mx >= tau;
-          if (__any_sync(0xffffffffu, hit)) {
+          const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+          if (hm) {
             if (hit) {
               const int nb = n_base + ch * 32;
-              Cand* wp = my_list + cnt;
 #pragma unroll
               for (int gq = 0; gq < 4; ++gq) {
-                // warp vote => a real (uniform) branch: only groups that are hot in some lane are scanned
-                if (__any_sync(__activemask(), g[gq] >= tau)) {
+                // vote over the hit lanes => a real, uniform branch: cold groups are skipped
+                if (__any_sync(hm, g[gq] >= tau)) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {   // one predicated 8-byte store per element
                     Cand c;
                     c.s = __uint_as_float(r[gq * 8 + j]);
                     c.id = nb + gq * 8 + j;
                     const bool ph = c.s >= tau;
-                    if (ph) *wp = c;
-                    wp += ph ? 1 : 0;
+                    if (ph) my_list[cnt] = c;
+                    cnt += ph ? 1 : 0;
                   }
                 }
               }
-              cnt = (int)(wp - my_list);
             }
             compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > TRIG) || (cnt > CAP - 32)));
           }
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc]);
+        if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

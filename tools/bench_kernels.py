@@ -1,0 +1,141 @@
+"""Secondary kernel measurements (HBM-bound rows of SURVEY.md §8d): achieved GB/s against the
+measured copy bandwidth.  CUDA-event timing, 3 warm-ups, inputs larger than L2.
+    python tools/bench_kernels.py > gpurun_out/kernels.jsonl
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+PEAK = 6572.2
+try:
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def emit(name, ms, bytes_, extra=None):
+    gbs = bytes_ / (ms * 1e-3) / 1e9
+    d = {"kernel": name, "ms": ms, "algorithmic_bytes": bytes_, "achieved_gbs": gbs, "peak_gbs": PEAK,
+         "frac": gbs / PEAK}
+    d.update(extra or {})
+    print(json.dumps(d), flush=True)
+
+
+def bench_spmm():
+    from librecommender_b200.lightgcn import SpmmGraph, propagate
+
+    dev = torch.device("cuda")
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    n_users, n_items, d = 2_000_000, 200_000, 64
+    counts = torch.poisson(torch.full((n_users,), 50.0, device=dev), generator=g).clamp_(min=1, max=2000).long()
+    w = 1.0 / torch.arange(1, n_items + 1, device=dev, dtype=torch.float64)
+    cdf = (torch.cumsum(w, 0) / w.sum()).float()
+    perm = torch.randperm(n_items, generator=g, device=dev)
+    owner = torch.repeat_interleave(torch.arange(n_users, device=dev), counts)
+    item = perm[torch.searchsorted(cdf, torch.rand(owner.numel(), generator=g, device=dev)).clamp_(max=n_items - 1)]
+    n = n_users + n_items
+    shift = (n - 1).bit_length()
+    und = torch.unique((owner << shift) | (item + n_users))
+    r, c = und >> shift, und & ((1 << shift) - 1)
+    key = torch.sort(torch.cat([und, (c << shift) | r])).values
+    rows, cols = key >> shift, (key & ((1 << shift) - 1)).to(torch.int32)
+    deg = torch.bincount(rows, minlength=n)
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(deg, 0)
+    dinv = deg.float().pow(-0.5)
+    dinv[torch.isinf(dinv)] = 0
+    val = dinv[rows] * dinv[cols.long()]
+    graph = SpmmGraph(indptr, cols.contiguous(), val.contiguous())
+    E = torch.randn(n, d, device=dev) * 0.1
+    out = torch.empty_like(E)
+    nnz = graph.nnz
+    ms = timeit(lambda: graph.spmm(E, out=out))
+    bytes_ = nnz * (4 + 4 + 4 * d) + n * (4 * d + 8)
+    emit("spmm_csr (LightGCN layer)", ms, bytes_, {"nnz": nnz, "rows": n, "d": d, "long_rows": graph.n_long,
+                                                  "max_degree": int(deg.max())})
+    ms3 = timeit(lambda: propagate(graph, E, 3), iters=5)
+    emit("lightgcn propagate 3 layers (fused mean)", ms3, 3 * bytes_ + 3 * n * 4 * d, {"nnz": nnz})
+
+
+def bench_feat():
+    from librecommender_b200.feat_models import DeepFM, FM
+    from oracle import tf_models as tm
+
+    rng = np.random.default_rng(0)
+    us = [int(x) for x in np.exp(rng.uniform(np.log(10), np.log(2e5), 50))]
+    its = [int(x) for x in np.exp(rng.uniform(np.log(10), np.log(2e5), 50))]
+    spec = tm.make_spec(rng, 1_000_000, 100_000, us, its, 5, 5, interleave=False)
+    K = 16
+    w = tm.make_deepfm_weights(rng, spec, K, (128, 64, 32), True)
+    model = DeepFM(spec, w)
+    R = 1 << 20
+    users = torch.as_tensor(rng.integers(0, 1_000_000, R)).cuda()
+    items = torch.as_tensor(rng.integers(0, 100_000, R)).cuda()
+    F = 2 + spec["n_sparse"] + spec["n_dense"]
+    concat = torch.empty((R, F * K), dtype=torch.float32, device="cuda")
+    pw = torch.empty((R, K), dtype=torch.float32, device="cuda")
+    lin = torch.empty(R, dtype=torch.float32, device="cuda")
+    ms = timeit(lambda: model._feat_forward(model.spec.layout, users, items, R, 0, concat=concat, pw=pw, lin=lin))
+    Fs, Fd = spec["n_sparse"], spec["n_dense"]
+    read = R * ((2 + Fs) * (4 * K + 4) + 4 * Fs + 4 * Fd + 16)
+    emit("feat_forward gather+FM (DeepFM C3 row shape, writes deep input)", ms, read + R * (F * K + K + 1) * 4,
+         {"rows": R, "F_sparse": Fs, "F_dense": Fd, "K": K, "gather_only_bytes": read})
+    wfm = tm.make_fm_weights(rng, spec, K, True)
+    fm = FM(spec, wfm)
+    out = torch.empty(R, dtype=torch.float32, device="cuda")
+    ms = timeit(lambda: fm._feat_forward(fm.spec.layout, users, items, R, 0, fm_out=out, head=fm.head))
+    emit("feat_forward FM fused head (no intermediate)", ms, read + R * 4, {"rows": R})
+    ms = timeit(lambda: model.logits(users[:1 << 18].cpu().numpy(), items[:1 << 18].cpu().numpy()), iters=3)
+    print(json.dumps({"kernel": "DeepFM predict rows/s (gather + fp32 MLP 1792-128-64-32)", "rows_per_s": (1 << 18) / (ms * 1e-3)}))
+
+
+def bench_topk_and_sampler():
+    import ctypes
+    from librecommender_b200 import _lib
+    from librecommender_b200.sampling import DeviceNegativeSampler
+
+    B, N, K = 256, 1_000_000, 100
+    scores = torch.randn(B, N, device="cuda")
+    ids = torch.empty(B, K, dtype=torch.int64, device="cuda")
+    nb = ctypes.c_size_t()
+    _lib.lib.b200_topk_rows_workspace_bytes(B, N, K, ctypes.byref(nb))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device="cuda")
+    ms = timeit(lambda: _lib.check(_lib.lib.b200_topk_rows(_lib.ptr(scores), N, B, N, K, _lib.ptr(ids), None,
+                                                           _lib.ptr(ws), nb.value, _lib.current_stream())))
+    emit("topk_rows radix select (256 x 1M, K=100)", ms, 5 * B * N * 4, {"passes": 5})
+    smp = DeviceNegativeSampler(1_000_000, seed=42)
+    pos = torch.randint(0, 1_000_000, (1 << 22,), device="cuda")
+    ms = timeit(lambda: smp.sample(None, pos, 5, "random"))
+    print(json.dumps({"kernel": "sample_negatives random (4M positives x 5)", "ms": ms,
+                      "negatives_per_s": (1 << 22) * 5 / (ms * 1e-3)}))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["spmm", "feat", "topk"]
+    if "spmm" in which:
+        bench_spmm()
+    if "feat" in which:
+        bench_feat()
+    if "topk" in which:
+        bench_topk_and_sampler()
