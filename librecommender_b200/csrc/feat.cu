@@ -112,9 +112,30 @@ feat_forward_kernel(const b200_feat_layout L, const b200_feat_tables T, const in
       if (want_lin) lin_acc = fmaf(__ldg(T.sparse_linear + idx), h.lin_kernel[fpos + f], lin_acc);
     }
     const int cnt = min(lpr, L.n_sparse - f0);
-    for (int q = 0; q < cnt; ++q) {
-      const int32_t ix = __shfl_sync(gmask, idx, gbase + q);
-      add_field(fpos + f0 + q, T.sparse_embeds + (int64_t)ix * K, 1.f);
+    if (Tn == 1) {
+      // common case K <= 32: one element per lane and field -> issue 8 row gathers before using them
+      const bool kok = li < K;
+      for (int q0 = 0; q0 < cnt; q0 += 8) {
+        float e[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int32_t ix = __shfl_sync(gmask, idx, gbase + min(q0 + u, cnt - 1));
+          e[u] = (kok && q0 + u < cnt) ? __ldg(T.sparse_embeds + (int64_t)ix * K + li) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (q0 + u < cnt) {
+            s[0] += e[u];
+            s2[0] = fmaf(e[u], e[u], s2[0]);
+            if (o.concat && kok) o.concat[r * o.ld_concat + (int64_t)(fpos + f0 + q0 + u) * K + li] = e[u];
+          }
+        }
+      }
+    } else {
+      for (int q = 0; q < cnt; ++q) {
+        const int32_t ix = __shfl_sync(gmask, idx, gbase + q);
+        add_field(fpos + f0 + q, T.sparse_embeds + (int64_t)ix * K, 1.f);
+      }
     }
   }
   fpos += L.n_sparse;
@@ -153,6 +174,109 @@ feat_forward_kernel(const b200_feat_layout L, const b200_feat_tables T, const in
     if (li == 0) o.fm_out[r] = lin_acc + elu;
   }
   if (o.lin && li == 0) o.lin[r] = lin_acc;
+}
+
+// ---- fast path for K % 4 == 0, K <= 32: one warp per row, ONE LANE PER FIELD.
+// Every lane gathers whole embedding rows of its fields (K/4 16-byte loads, several fields in
+// flight), accumulates its private sum / sum of squares over its fields and writes its slice of the
+// concatenated row (consecutive lanes = consecutive fields = fully coalesced stores); the cross-lane
+// reduction over fields happens once per row.
+template <int K4>
+__global__ void __launch_bounds__(256)
+feat_forward_lanefield_kernel(const b200_feat_layout L, const b200_feat_tables T,
+                              const int64_t* __restrict__ users, const int64_t* __restrict__ items,
+                              int64_t R, int64_t grid_items, int64_t row_offset, Out o, Head h) {
+  constexpr int K = K4 * 4;
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= R) return;
+  int64_t u, it;
+  if (grid_items > 0) { const int64_t rg = r + row_offset; u = users[rg / grid_items]; it = rg % grid_items; }
+  else { u = users[r]; it = items[r]; }
+  const int n_id = ((L.id_mask & 1) ? 1 : 0) + ((L.id_mask & 2) ? 1 : 0);
+  const int F = n_id + L.n_sparse + L.n_dense;
+  const bool want_lin = (o.lin != nullptr) || (o.fm_out != nullptr);
+  float4 s[K4], s2[K4];
+#pragma unroll
+  for (int q = 0; q < K4; ++q) { s[q] = make_float4(0.f, 0.f, 0.f, 0.f); s2[q] = s[q]; }
+  float lin_acc = 0.f;
+  for (int f0 = 0; f0 < F; f0 += 64) {          // two fields per lane and iteration in flight
+    const float4* src[2];
+    float scale[2];
+    bool valid[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int f = f0 + j * 32 + lane;
+      valid[j] = f < F;
+      scale[j] = 1.f;
+      const float* rowp = T.user_embeds;       // placeholder for invalid lanes
+      float lw = 0.f;
+      if (valid[j]) {
+        if (f < n_id) {
+          const bool is_user = (L.id_mask & 1) && f == 0;
+          rowp = is_user ? T.user_embeds + u * K : T.item_embeds + it * K;
+          if (want_lin) lw = is_user ? __ldg(T.user_linear + u) : __ldg(T.item_linear + it);
+        } else if (f < n_id + L.n_sparse) {
+          const int32_t idx = sparse_index(L, r, u, it, f - n_id);
+          rowp = T.sparse_embeds + (int64_t)idx * K;
+          if (want_lin) lw = __ldg(T.sparse_linear + idx);
+        } else {
+          const int fd = f - n_id - L.n_sparse;
+          const float x = dense_value(L, r, u, it, fd);
+          rowp = T.dense_embeds + (int64_t)L.dense_embed_row[fd] * K;
+          scale[j] = x;
+          if (want_lin) lw = __ldg(T.dense_linear + L.dense_embed_row[fd]) * x;
+        }
+        if (want_lin) lin_acc = fmaf(lw, h.lin_kernel[f], lin_acc);
+      }
+      src[j] = reinterpret_cast<const float4*>(rowp);
+    }
+    float4 e[2][K4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < K4; ++q) e[j][q] = valid[j] ? __ldg(src[j] + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (!valid[j]) continue;
+      const int f = f0 + j * 32 + lane;
+#pragma unroll
+      for (int q = 0; q < K4; ++q) {
+        float4 v = e[j][q];
+        v.x *= scale[j]; v.y *= scale[j]; v.z *= scale[j]; v.w *= scale[j];
+        s[q].x += v.x; s[q].y += v.y; s[q].z += v.z; s[q].w += v.w;
+        s2[q].x = fmaf(v.x, v.x, s2[q].x); s2[q].y = fmaf(v.y, v.y, s2[q].y);
+        s2[q].z = fmaf(v.z, v.z, s2[q].z); s2[q].w = fmaf(v.w, v.w, s2[q].w);
+        if (o.concat) *(reinterpret_cast<float4*>(o.concat + r * o.ld_concat + (int64_t)f * K) + q) = v;
+      }
+    }
+  }
+  if (!o.pw && !o.fm_out && !o.lin) return;
+  // one reduction over the 32 lanes (= over the fields) per row
+  float head_acc = 0.f;
+#pragma unroll
+  for (int q = 0; q < K4; ++q) {
+    float sv[4] = {s[q].x, s[q].y, s[q].z, s[q].w};
+    float s2v[4] = {s2[q].x, s2[q].y, s2[q].z, s2[q].w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float a = warp_sum(sv[c]);
+      const float b = warp_sum(s2v[c]);
+      const float pw = 0.5f * (a * a - b);
+      const int k = q * 4 + c;
+      if (o.pw && lane == 0) o.pw[r * o.ld_pw + k] = pw;
+      if (o.fm_out) {
+        const float z = h.bn_scale ? fmaf(pw, h.bn_scale[k], h.bn_shift[k]) : pw;
+        head_acc = fmaf(z, h.pw_kernel[k], head_acc);
+      }
+    }
+  }
+  if (want_lin) lin_acc = warp_sum(lin_acc) + h.lin_bias;
+  if (o.fm_out && lane == 0) {
+    head_acc += h.pw_bias;
+    o.fm_out[r] = lin_acc + (head_acc > 0.f ? head_acc : expm1f(head_acc));
+  }
+  if (o.lin && lane == 0) o.lin[r] = lin_acc;
 }
 
 // y[r, n] = act(sum_k x[r,k] * Wt[n,k] + b[n]) — 64x64x16 register-tiled SIMT GEMM (fp32, exact fma chain)
@@ -271,9 +395,28 @@ extern "C" int b200_feat_forward(const b200_feat_layout* L, const b200_feat_tabl
   Out o; o.concat = concat; o.ld_concat = ld_concat; o.pw = pw; o.ld_pw = ld_pw; o.lin = lin; o.fm_out = fm_out;
   Head h; h.lin_kernel = lin_kernel; h.lin_bias = lin_bias; h.bn_scale = bn_scale; h.bn_shift = bn_shift;
   h.pw_kernel = pw_kernel; h.pw_bias = pw_bias;
-  const int64_t warps = ceil_div64(R, 32 / lpr);
-  feat_forward_kernel<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      *L, *T, users, items, R, grid_items, row_offset, o, h, lpr, Tn);
+  auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const int K = L->embed_size;
+  const bool fast = K % 4 == 0 && K <= 32 && al16(T->user_embeds) && al16(T->item_embeds) &&
+                    al16(T->sparse_embeds) && al16(T->dense_embeds) && al16(concat) && (ld_concat % 4 == 0);
+  if (fast) {
+    const unsigned blocks = (unsigned)ceil_div64(R * 32, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (K / 4) {
+      case 1: feat_forward_lanefield_kernel<1><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+      case 2: feat_forward_lanefield_kernel<2><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+      case 3: feat_forward_lanefield_kernel<3><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+      case 4: feat_forward_lanefield_kernel<4><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+      case 5: feat_forward_lanefield_kernel<5><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+      case 6: feat_forward_lanefield_kernel<6><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+      case 7: feat_forward_lanefield_kernel<7><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+      default: feat_forward_lanefield_kernel<8><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+    }
+  } else {
+    const int64_t warps = ceil_div64(R, 32 / lpr);
+    feat_forward_kernel<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        *L, *T, users, items, R, grid_items, row_offset, o, h, lpr, Tn);
+  }
   count_launch();
   B200_CUDA_OK(cudaGetLastError());
   return 0;

@@ -45,17 +45,19 @@ namespace tc {
 constexpr int TM = 128;        // users per tile (UMMA M)
 constexpr int TN = 256;        // items per tile (UMMA N)
 constexpr int KBLK = 64;       // bf16 per 128-byte swizzled row
-constexpr int CAP = 512;       // candidate slots per (row, list); list = (item split, column half)
+constexpr int CAPG = 256;      // candidate GROUP records per (row, list); list = (item split, column half)
+constexpr int GW = 8;          // a record = the 8 coarse scores of one 8-column group + its first item id
 constexpr int NB = 1024;       // bins of the per-row global coarse-score histogram
-constexpr int TRIG = 192;      // uncounted entries that trigger a compaction
+constexpr int TRIG = 96;       // uncounted records that trigger a compaction
 constexpr int EPI_WARPS = 8;   // two epilogue warps per TMEM lane quadrant (column halves)
-constexpr int KROW_MAX = 288;  // fast-path limit for k_row = K + c_u (a list must hold k_row + margin + TRIG)
+constexpr int KROW_MAX = 288;  // fast-path limit for k_row = K + c_u
 constexpr int MAX_KB = 4;      // d_pad <= 256
 constexpr int PRE_STRIDE = 16; // the pre-pass visits every 16th item tile of a split
 constexpr int A_KB_BYTES = TM * KBLK * 2;   // 16 KB
 constexpr int B_KB_BYTES = TN * KBLK * 2;   // 32 KB
 constexpr int SWEEP_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-constexpr int MAXC = 2048;                  // finalize: candidates per row
+constexpr int MAXU = 3072;                  // finalize: collected elements per row (union of the lists)
+constexpr int MAXC = 2048;                  // finalize: candidates per row after the c_k - 2 eps cut
 constexpr int FIN_THREADS = 256;
 constexpr float ERR_COEF = 0.0082f;  // 2^-7*(1+2^-9) for bf16 x bf16 products + accumulation slack
 
@@ -74,10 +76,6 @@ struct RowMeta {
   int32_t apply;    // consumed filter applies
 };
 
-struct __align__(8) Cand {   // one candidate: coarse score + item id (8 bytes, written with one store)
-  float s;
-  int32_t id;
-};
 
 struct SweepParams {
   int64_t N;
@@ -87,8 +85,9 @@ struct SweepParams {
   uint32_t* row_tau_key;      // [B_pad]  running max of tau (order-preserving key)
   int32_t* row_status;        // [B_pad]  1 = needs the exact path
   uint32_t* ghist;            // [B_pad][NB]  coarse-score histogram of every counted candidate
-  Cand* cand;                 // [2*n_splits][B_pad][CAP]
-  int32_t* cand_cnt;          // [2*n_splits][B_pad]
+  float* cand_s;              // [2*n_splits][B_pad][CAPG][GW]  group records: 8 coarse scores ...
+  int32_t* cand_b;            // [2*n_splits][B_pad][CAPG]      ... and the item id of the first column
+  int32_t* cand_cnt;          // [2*n_splits][B_pad]            records per list
   float* blockmax;            // [2*n_splits][n_pre_tiles][B_pad]   (pre-pass output)
 };
 
@@ -177,30 +176,42 @@ __device__ __forceinline__ int score_bin(float s, float R, float inv_w) {
 }
 
 // Warp-cooperative compaction of one candidate list of one row (rare in the main pass: the
-// speculative threshold keeps the lists short; this is the rigorous safety net).
-//  1. every entry pushed since the previous compaction is counted ONCE into the row's global
-//     coarse-score histogram (shared by all lists / CTAs working on that row);
+// speculative threshold keeps the lists short; this is the rigorous safety net and the normal
+// mode when no pre-pass ran).  A list holds GROUP records (8 scores + first item id).
+//  1. every element >= tau_old of every record pushed since the previous compaction is counted
+//     ONCE into the row's global coarse-score histogram (shared by all lists / CTAs of the row);
 //  2. the histogram is read back: the highest bin whose suffix count reaches k gives a rigorous
 //     lower bound of the k-th largest coarse score over everything counted so far
 //     (counts are a subset of the items at or above each edge), tau = edge - eps2;
-//  3. the list is rewritten keeping entries >= tau.
-// Entries live in registers (CAP/32 per lane).  Returns the new count; *tau_out = new tau.
-__device__ __forceinline__ int compact_row(Cand* __restrict__ list, int n, int n_counted, int k,
-                                           float eps2, float R, float tau_old,
+//  3. the list is rewritten keeping the records whose maximum is >= tau.
+// Records live in registers (CAPG/32 per lane).  Returns the new count; *tau_out = new tau.
+__device__ __noinline__ int compact_row(float* __restrict__ ls, int32_t* __restrict__ lb, int n,
+                                           int n_counted, int k, float eps2, float R, float tau_old,
                                            uint32_t* __restrict__ gh, int lane, float* tau_out) {
   const float inv_w = (float)NB / (2.f * R);
-  Cand e[CAP / 32];
+  constexpr int PER = CAPG / 32;
+  float4 e0[PER], e1[PER];
+  int32_t bs[PER];
 #pragma unroll
-  for (int j = 0; j < CAP / 32; ++j) {
+  for (int j = 0; j < PER; ++j) {
     const int i = j * 32 + lane;
-    e[j].s = 0.f;
-    e[j].id = 0;
-    if (i < n) e[j] = list[i];
+    e0[j] = e1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bs[j] = 0;
+    if (i < n) {
+      e0[j] = *reinterpret_cast<const float4*>(ls + (size_t)i * GW);
+      e1[j] = *reinterpret_cast<const float4*>(ls + (size_t)i * GW + 4);
+      bs[j] = lb[i];
+    }
   }
 #pragma unroll
-  for (int j = 0; j < CAP / 32; ++j) {
+  for (int j = 0; j < PER; ++j) {
     const int i = j * 32 + lane;
-    if (i >= n_counted && i < n) atomicAdd(gh + score_bin(e[j].s, R, inv_w), 1u);
+    if (i >= n_counted && i < n) {
+      const float v[GW] = {e0[j].x, e0[j].y, e0[j].z, e0[j].w, e1[j].x, e1[j].y, e1[j].z, e1[j].w};
+#pragma unroll
+      for (int q = 0; q < GW; ++q)
+        if (v[q] >= tau_old) atomicAdd(gh + score_bin(v[q], R, inv_w), 1u);
+    }
   }
   __threadfence();
   __syncwarp();
@@ -239,11 +250,18 @@ __device__ __forceinline__ int compact_row(Cand* __restrict__ list, int n, int n
   *tau_out = tau;
   int w = 0;
 #pragma unroll
-  for (int j = 0; j < CAP / 32; ++j) {
+  for (int j = 0; j < PER; ++j) {
     const int i = j * 32 + lane;
-    const bool keep = (i < n) && (e[j].s >= tau);
+    const float m = fmaxf(fmaxf(fmaxf(e0[j].x, e0[j].y), fmaxf(e0[j].z, e0[j].w)),
+                          fmaxf(fmaxf(e1[j].x, e1[j].y), fmaxf(e1[j].z, e1[j].w)));
+    const bool keep = (i < n) && (m >= tau);
     const uint32_t kb = __ballot_sync(0xffffffffu, keep);
-    if (keep) list[w + __popc(kb & ((1u << lane) - 1u))] = e[j];
+    if (keep) {
+      const int pos = w + __popc(kb & ((1u << lane) - 1u));
+      *reinterpret_cast<float4*>(ls + (size_t)pos * GW) = e0[j];
+      *reinterpret_cast<float4*>(ls + (size_t)pos * GW + 4) = e1[j];
+      lb[pos] = bs[j];
+    }
     w += __popc(kb);
   }
   __syncwarp();
@@ -420,7 +438,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // ---- main pass ----
       const RowMeta meta = p.meta[grow];
       const int64_t list0 = (int64_t)list_id * p.B_pad + (m * TM + q * 32);  // lane 0's slot
-      Cand* my_list = p.cand + (list0 + lane) * CAP;
+      float* my_s = p.cand_s + (list0 + lane) * (int64_t)(CAPG * GW);
+      int32_t* my_b = p.cand_b + (list0 + lane) * (int64_t)CAPG;
       bool active = meta.active != 0;
       float tau = active ? ninf : pinf;
       int cnt = 0, n_counted = 0;
@@ -441,15 +460,16 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const float s_R = __shfl_sync(0xffffffffu, meta.R, src);
           const float s_tau = __shfl_sync(0xffffffffu, tau, src);
           float new_tau;
-          const int w = compact_row(p.cand + (list0 + src) * CAP, s_cnt, s_cntd, s_k, s_e, s_R, s_tau,
-                                    p.ghist + (int64_t)(m * TM + q * 32 + src) * NB, lane, &new_tau);
+          const int w = compact_row(p.cand_s + (list0 + src) * (int64_t)(CAPG * GW),
+                                    p.cand_b + (list0 + src) * (int64_t)CAPG, s_cnt, s_cntd, s_k, s_e, s_R,
+                                    s_tau, p.ghist + (int64_t)(m * TM + q * 32 + src) * NB, lane, &new_tau);
           if (lane == src) {
             cnt = w;
             n_counted = w;
             // also pick up what other lists of this row published meanwhile
             tau = fmaxf(new_tau, key_to_float(max(__ldcg(p.row_tau_key + grow), 1u)));
             atomicMax(p.row_tau_key + grow, float_to_key(new_tau));
-            if (w > CAP - 64) {  // too many near-ties to bound: hand the row to the exact path
+            if (w > CAPG - 16) {  // too many near-ties to bound: hand the row to the exact path
               active = false;
               tau = pinf;
               cnt = 0;
@@ -479,29 +499,28 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           float g[4];
           const float mx = chunk_max(r, g);
-          const bool hit = mx >= tau;
-          const uint32_t hm = __ballot_sync(0xffffffffu, hit);
-          if (hm) {
-            if (hit) {
-              const int nb = n_base + ch * 32;
+          (void)mx;
+          // Four warp-uniform tests (one per 8-column group): a group that is hot in some lane is
+          // pushed WHOLE by that lane (two 16-byte stores + its first item id); finalize_kernel
+          // sorts out which of its 8 scores are candidates.  Cold groups cost 4 instructions.
+          bool pushed = false;
 #pragma unroll
-              for (int gq = 0; gq < 4; ++gq) {
-                // vote over the hit lanes => a real, uniform branch: cold groups are skipped
-                if (__any_sync(hm, g[gq] >= tau)) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) {   // one predicated 8-byte store per element
-                    Cand c;
-                    c.s = __uint_as_float(r[gq * 8 + j]);
-                    c.id = nb + gq * 8 + j;
-                    const bool ph = c.s >= tau;
-                    if (ph) my_list[cnt] = c;
-                    cnt += ph ? 1 : 0;
-                  }
-                }
+          for (int gq = 0; gq < 4; ++gq) {
+            if (__any_sync(0xffffffffu, g[gq] >= tau)) {
+              if (g[gq] >= tau) {
+                float4* dst = reinterpret_cast<float4*>(my_s + (size_t)cnt * GW);
+                dst[0] = make_float4(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]),
+                                     __uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
+                dst[1] = make_float4(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]),
+                                     __uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
+                my_b[cnt] = n_base + ch * 32 + gq * 8;
+                ++cnt;
               }
+              pushed = true;
             }
-            compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > TRIG) || (cnt > CAP - 32)));
           }
+          if (pushed)   // warp-uniform
+            compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > TRIG) || (cnt > CAPG - 4)));
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -577,8 +596,10 @@ struct FinalizeParams {
   int32_t B_pad, n_lists, K, d;
   const RowMeta* meta;
   int32_t* row_status;
+  const uint32_t* row_tau_key;     // [B_pad] final threshold of the row (speculative start or rigorous raises)
   const uint32_t* tau_guess_key;   // [B_pad] speculative threshold used by the main pass (0 = none)
-  const Cand* cand;
+  const float* cand_s;
+  const int32_t* cand_b;
   const int32_t* cand_cnt;
   const float* U; int64_t ldu;
   const float* I; int64_t ldi;
@@ -593,11 +614,12 @@ finalize_kernel(const FinalizeParams p) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_prefix, s_krem;
   __shared__ uint32_t s_wtot[FIN_THREADS / 32];
-  __shared__ int s_nc;
-  __shared__ int32_t c_id[MAXC];
-  __shared__ unsigned long long c_sort[MAXC];
-  __shared__ int32_t htab[2 * MAXC];
+  __shared__ int s_nu, s_nc;
+  __shared__ float u_s[MAXU];                      // union of the lists: coarse scores ...
+  __shared__ int32_t u_id[MAXU];                   // ... and item ids (later: the candidate ids)
+  __shared__ unsigned long long c_sort[MAXC];      // first the consumed hash set (int32 x 4096), then sort keys
   __shared__ float urow[MAX_KB * KBLK];
+  int32_t* htab = reinterpret_cast<int32_t*>(c_sort);
   const int tid = threadIdx.x;
   const int64_t row = blockIdx.x;
   int64_t* oid = p.out_ids + row * p.K;
@@ -608,21 +630,56 @@ finalize_kernel(const FinalizeParams p) {
     for (int i = tid; i < p.K; i += FIN_THREADS) { oid[i] = -1; if (osc) osc[i] = 0.f; }
   };
   if (p.row_status[row] != 0) { give_up(false); return; }
-  // ---- exact k_row-th largest coarse score over the union of the lists (4 x 8-bit radix)
+  // ---- gather: every element of every group record that is >= the row's final threshold.
+  // (every exact top-k_row item has coarse >= c_k - 2 eps >= that threshold, see the header)
+  const uint32_t tk = p.row_tau_key[row];
+  const float low = tk ? key_to_float(tk) : __int_as_float(0xff800000);
+  if (tid == 0) { s_nu = 0; s_nc = 0; }
+  __syncthreads();
+  for (int s = 0; s < p.n_lists; ++s) {
+    const int64_t slot = (int64_t)s * p.B_pad + row;
+    const int n = p.cand_cnt[slot];
+    const float* ls = p.cand_s + slot * (int64_t)(CAPG * GW);
+    const int32_t* lb = p.cand_b + slot * (int64_t)CAPG;
+    for (int i = tid; i < n * GW; i += FIN_THREADS) {
+      const float v = ls[i];
+      if (v >= low) {
+        const int pos = atomicAdd(&s_nu, 1);
+        if (pos < MAXU) { u_s[pos] = v; u_id[pos] = lb[i / GW] + (i % GW); }
+      }
+    }
+  }
+  __syncthreads();
+  const int nu = s_nu;
+  if (nu < meta.k_row) { give_up(true); return; }
+  const bool in_smem = nu <= MAXU;   // common case; otherwise (no speculation, small catalogue) stream from HBM
+  // visit every collected element (score, id): from shared memory, or again from the lists
+  auto for_each = [&](auto&& f) {
+    if (in_smem) {
+      for (int i = tid; i < nu; i += FIN_THREADS) f(u_s[i], u_id[i]);
+    } else {
+      for (int s = 0; s < p.n_lists; ++s) {
+        const int64_t slot = (int64_t)s * p.B_pad + row;
+        const int n = p.cand_cnt[slot];
+        const float* ls = p.cand_s + slot * (int64_t)(CAPG * GW);
+        const int32_t* lb = p.cand_b + slot * (int64_t)CAPG;
+        for (int i = tid; i < n * GW; i += FIN_THREADS) {
+          const float v = ls[i];
+          if (v >= low) f(v, lb[i / GW] + (i % GW));
+        }
+      }
+    }
+  };
+  // ---- exact k_row-th largest coarse score of the union (4 x 8-bit radix select)
   uint32_t prefix = 0, krem = (uint32_t)meta.k_row;
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
     hist[tid] = 0;
     __syncthreads();
-    for (int s = 0; s < p.n_lists; ++s) {
-      const int64_t slot = (int64_t)s * p.B_pad + row;
-      const int n = p.cand_cnt[slot];
-      const Cand* l = p.cand + slot * CAP;
-      for (int i = tid; i < n; i += FIN_THREADS) {
-        const uint32_t key = float_to_key(l[i].s);
-        if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-      }
-    }
+    for_each([&](float v, int32_t) {
+      const uint32_t key = float_to_key(v);
+      if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    });
     __syncthreads();
     {
       // parallel resolution of the digit: thread t owns bin t, suffix sums by warp scan + warp totals
@@ -640,9 +697,9 @@ finalize_kernel(const FinalizeParams p) {
       for (int w2 = wid + 1; w2 < FIN_THREADS / 32; ++w2) above += s_wtot[w2];
       incl += above;                       // count in bins >= tid
       const uint32_t excl = incl - v;      // count in bins >  tid
-      if ((excl < krem && krem <= incl) || (tid == 0 && incl < krem)) {
+      if (excl < krem && krem <= incl) {
         s_prefix = (prefix << 8) | (uint32_t)tid;
-        s_krem = krem - min(excl, krem);
+        s_krem = krem - excl;
       }
     }
     __syncthreads();
@@ -657,24 +714,35 @@ finalize_kernel(const FinalizeParams p) {
     const uint32_t gk = p.tau_guess_key[row];
     if (gk != 0u && key_to_float(gk) > thr) { give_up(true); return; }
   }
-  // ---- collect candidates
-  if (tid == 0) s_nc = 0;
-  for (int i = tid; i < 2 * MAXC; i += FIN_THREADS) htab[i] = -1;
-  __syncthreads();
-  for (int s = 0; s < p.n_lists; ++s) {
-    const int64_t slot = (int64_t)s * p.B_pad + row;
-    const int n = p.cand_cnt[slot];
-    const Cand* l = p.cand + slot * CAP;
-    for (int i = tid; i < n; i += FIN_THREADS) {
-      const Cand c = l[i];
-      if (c.s >= thr) {
+  // ---- candidates: elements >= thr (ids only from here on)
+  if (in_smem) {   // compact in place: read everything first, then write
+    int my_keep[MAXU / FIN_THREADS];
+#pragma unroll
+    for (int t = 0; t < MAXU / FIN_THREADS; ++t) {
+      const int i = tid + t * FIN_THREADS;
+      my_keep[t] = (i < nu && u_s[i] >= thr) ? u_id[i] : -1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < MAXU / FIN_THREADS; ++t) {
+      if (my_keep[t] >= 0) {
         const int pos = atomicAdd(&s_nc, 1);
-        if (pos < MAXC) c_id[pos] = c.id;
+        if (pos < MAXC) u_id[pos] = my_keep[t];
       }
     }
+  } else {
+    __syncthreads();
+    for_each([&](float v, int32_t id) {
+      if (v >= thr) {
+        const int pos = atomicAdd(&s_nc, 1);
+        if (pos < MAXC) u_id[pos] = id;
+      }
+    });
   }
+  for (int i = tid; i < 2 * MAXC; i += FIN_THREADS) htab[i] = -1;
   __syncthreads();
   const int nc = s_nc;
+  int32_t* c_id = u_id;
   if (nc > MAXC || nc < p.K) { give_up(true); return; }  // cannot bound (dense near-ties) -> exact path
   const int64_t u = p.user_ids[row];
   // ---- consumed filter through a hash set of candidate ids
@@ -697,12 +765,15 @@ finalize_kernel(const FinalizeParams p) {
     }
   }
   for (int k = tid; k < p.d; k += FIN_THREADS) urow[k] = __ldg(p.U + u * p.ldu + k);
-  __syncthreads();
+  __syncthreads();   // the hash set is dead from here on: its storage becomes the sort buffer
   // ---- exact fp32 re-score: acc = fma(u[k], i[k], acc), k ascending
   const bool vec4 = (p.d % 4 == 0) && (p.ldi % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.I) & 15) == 0);
   int P = 1;
   while (P < nc) P <<= 1;
-  for (int i = tid; i < P; i += FIN_THREADS) {
+  unsigned long long mine[MAXC / FIN_THREADS];
+#pragma unroll
+  for (int t = 0; t < MAXC / FIN_THREADS; ++t) {
+    const int i = tid + t * FIN_THREADS;
     unsigned long long comp = 0ull;
     if (i < nc && c_id[i] >= 0) {
       const float* it = p.I + (int64_t)c_id[i] * p.ldi;
@@ -721,7 +792,13 @@ finalize_kernel(const FinalizeParams p) {
       }
       comp = ((unsigned long long)float_to_key(acc) << 32) | (unsigned long long)(~(uint32_t)c_id[i]);
     }
-    c_sort[i] = comp;
+    mine[t] = comp;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < MAXC / FIN_THREADS; ++t) {
+    const int i = tid + t * FIN_THREADS;
+    if (i < P) c_sort[i] = mine[t];
   }
   __syncthreads();
   for (int k = 2; k <= P; k <<= 1) {
@@ -788,7 +865,7 @@ struct Plan {
   int64_t N_pad;
   size_t smem_bytes;
   // workspace offsets
-  size_t off_A, off_meta, off_tau, off_guess, off_status, off_cnt, off_hist, off_cand, off_bm, total;
+  size_t off_A, off_meta, off_tau, off_guess, off_status, off_cnt, off_hist, off_cs, off_cb, off_bm, total;
 };
 
 static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
@@ -831,7 +908,8 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->off_status = off; off += al256((size_t)pl->B_pad * 4);
   pl->off_cnt = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * 4);
   pl->off_hist = off; off += al256((size_t)pl->B_pad * NB * 4);
-  pl->off_cand = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * CAP * sizeof(Cand));
+  pl->off_cs = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * CAPG * GW * 4);
+  pl->off_cb = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * CAPG * 4);
   pl->off_bm = off; off += al256((size_t)2 * pl->n_splits * pl->n_pre_tiles * pl->B_pad * 4);
   pl->total = off + 256;
   return 0;
@@ -907,7 +985,8 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   int32_t* status = (int32_t*)(ws + pl.off_status);
   int32_t* cnt = (int32_t*)(ws + pl.off_cnt);
   uint32_t* ghist = (uint32_t*)(ws + pl.off_hist);
-  Cand* cand = (Cand*)(ws + pl.off_cand);
+  float* cand_s = (float*)(ws + pl.off_cs);
+  int32_t* cand_b = (int32_t*)(ws + pl.off_cb);
   float* bm = (float*)(ws + pl.off_bm);
   const CatalogHeader* hdr = (const CatalogHeader*)catalog;
   const __nv_bfloat16* Ibf = (const __nv_bfloat16*)((const char*)catalog + 256);
@@ -916,7 +995,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
       U, ldu, user_ids, B, pl.B_pad, d, pl.d_pad, K, N, filter, indptr, n_users, hdr, A, meta, tau,
       status);
   // cnt and ghist are adjacent in the workspace: one memset
-  B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (pl.off_cand - pl.off_cnt), stream));
+  B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (pl.off_cs - pl.off_cnt), stream));
 
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap(&tmA, A, pl.B_pad, pl.d_pad, TM)) return rc;
@@ -926,7 +1005,8 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   sp.N = N; sp.B_pad = pl.B_pad; sp.m_tiles = pl.m_tiles; sp.n_splits = pl.n_splits;
   sp.tiles_per_split = pl.tiles_per_split; sp.total_tiles = pl.total_tiles; sp.KB = pl.KB;
   sp.nstage = pl.nstage; sp.n_pre_tiles = pl.n_pre_tiles; sp.meta = meta; sp.row_tau_key = tau;
-  sp.row_status = status; sp.ghist = ghist; sp.cand = cand; sp.cand_cnt = cnt; sp.blockmax = bm;
+  sp.row_status = status; sp.ghist = ghist; sp.cand_s = cand_s; sp.cand_b = cand_b; sp.cand_cnt = cnt;
+  sp.blockmax = bm;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -958,7 +1038,8 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
 
   FinalizeParams fp;
   fp.B = B; fp.N = N; fp.B_pad = pl.B_pad; fp.n_lists = 2 * pl.n_splits; fp.K = K; fp.d = d;
-  fp.meta = meta; fp.row_status = status; fp.tau_guess_key = guess; fp.cand = cand; fp.cand_cnt = cnt;
+  fp.meta = meta; fp.row_status = status; fp.row_tau_key = tau; fp.tau_guess_key = guess;
+  fp.cand_s = cand_s; fp.cand_b = cand_b; fp.cand_cnt = cnt;
   fp.U = U; fp.ldu = ldu; fp.I = I; fp.ldi = ldi; fp.user_ids = user_ids; fp.indptr = indptr;
   fp.idx = idx; fp.out_ids = out_ids; fp.out_scores = out_scores;
   finalize_kernel<<<(unsigned)B, FIN_THREADS, 0, stream>>>(fp);

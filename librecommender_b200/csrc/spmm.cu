@@ -107,6 +107,104 @@ spmm_rows_kernel(const Args a) {
   row_epilogue(a, r, li, sum);
 }
 
+// ---- fast path: d % 4 == 0, 16-byte aligned rows: LPR lanes x float4 per row, 8 gathers in flight
+template <int LPR>
+__device__ __forceinline__ float4 accumulate_vec4(const Args& a, int64_t beg, int64_t end, int li,
+                                                  uint32_t gmask, int gbase) {
+  constexpr int U = 8;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool col_ok = li * 4 < a.d;
+  for (int64_t j0 = beg; j0 < end; j0 += LPR) {
+    const int64_t j = j0 + li;
+    int32_t c = 0;
+    float v = 0.f;
+    if (j < end) { c = __ldg(a.col + j); v = __ldg(a.val + j); }
+    const int cnt = (int)min((int64_t)LPR, end - j0);
+    for (int q0 = 0; q0 < cnt; q0 += U) {
+      int32_t cc[U];
+      float vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int src = gbase + min(q0 + u, cnt - 1);
+        cc[u] = __shfl_sync(gmask, c, src);
+        vv[u] = __shfl_sync(gmask, v, src);
+        if (q0 + u >= cnt) vv[u] = 0.f;
+      }
+      float4 e[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        e[u] = col_ok ? __ldg(reinterpret_cast<const float4*>(a.E + (int64_t)cc[u] * a.ld_e) + li)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc.x = fmaf(vv[u], e[u].x, acc.x);
+        acc.y = fmaf(vv[u], e[u].y, acc.y);
+        acc.z = fmaf(vv[u], e[u].z, acc.z);
+        acc.w = fmaf(vv[u], e[u].w, acc.w);
+      }
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ void row_epilogue_vec4(const Args& a, int64_t r, int li, float4 sum) {
+  if (li * 4 >= a.d) return;
+  if (a.out) *(reinterpret_cast<float4*>(a.out + r * a.ld_out) + li) = sum;
+  if (a.acc) {
+    float4 base = a.acc_init ? __ldg(reinterpret_cast<const float4*>(a.E + r * a.ld_e) + li)
+                             : *(reinterpret_cast<const float4*>(a.acc + r * a.ld_acc) + li);
+    float4 v = make_float4(base.x + sum.x, base.y + sum.y, base.z + sum.z, base.w + sum.w);
+    if (a.final_div > 0.f) { v.x /= a.final_div; v.y /= a.final_div; v.z /= a.final_div; v.w /= a.final_div; }
+    *(reinterpret_cast<float4*>(a.acc + r * a.ld_acc) + li) = v;
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+spmm_rows_vec4_kernel(const Args a) {
+  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int g = lane / LPR, li = lane % LPR;
+  const int64_t r = warp * RPW + g;
+  const int gbase = g * LPR;
+  const uint32_t gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << gbase);
+  if (r >= a.n_rows) return;
+  const int64_t beg = a.indptr[r], end = a.indptr[r + 1];
+  if (end - beg > LONG_ROW) return;   // chunked path
+  row_epilogue_vec4(a, r, li, accumulate_vec4<LPR>(a, beg, end, li, gmask, gbase));
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+spmm_long_chunks_vec4_kernel(const Args a, const int32_t* __restrict__ chunk_row,
+                             const int32_t* __restrict__ chunk_k, int64_t n_chunks,
+                             float* __restrict__ partials) {
+  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int g = lane / LPR, li = lane % LPR;
+  const int64_t chunk = warp * RPW + g;
+  const int gbase = g * LPR;
+  const uint32_t gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << gbase);
+  if (chunk >= n_chunks) return;
+  const int64_t r = chunk_row[chunk];
+  const int64_t beg = a.indptr[r] + (int64_t)chunk_k[chunk] * CHUNK;
+  const int64_t end = min(beg + (int64_t)CHUNK, a.indptr[r + 1]);
+  const float4 s = accumulate_vec4<LPR>(a, beg, end, li, gmask, gbase);
+  if (li * 4 < a.d) *(reinterpret_cast<float4*>(partials + chunk * a.d) + li) = s;
+}
+
+template <int LPR>
+static void launch_vec4(const Args& a, const int32_t* chunk_row, const int32_t* chunk_k, int64_t n_chunks,
+                        float* partials, int64_t n_long, cudaStream_t stream) {
+  constexpr int RPW = 32 / LPR;
+  spmm_rows_vec4_kernel<LPR><<<(unsigned)ceil_div64(ceil_div64(a.n_rows, RPW) * 32, 256), 256, 0, stream>>>(a);
+  if (n_long > 0)
+    spmm_long_chunks_vec4_kernel<LPR><<<(unsigned)ceil_div64(ceil_div64(n_chunks, RPW) * 32, 256), 256, 0, stream>>>(
+        a, chunk_row, chunk_k, n_chunks, partials);
+}
+
 // one warp (lpr forced to its row width) per CHUNK nnz of a long row -> partials[chunk, d]
 __global__ void __launch_bounds__(256)
 spmm_long_chunks_kernel(const Args a, const int32_t* __restrict__ chunk_row,
@@ -188,16 +286,32 @@ extern "C" int b200_spmm_csr(const int64_t* indptr, const int32_t* col, const fl
   while (lpr < d && lpr < 32) lpr <<= 1;
   a.lpr = lpr;
   a.T = (d + lpr - 1) / lpr;
-  const int rows_per_warp = 32 / lpr;
-  const int64_t warps = ceil_div64(n_rows, rows_per_warp);
-  spmm_rows_kernel<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, stream>>>(a);
-  count_launch();
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec4 = d % 4 == 0 && d <= 128 && ld_e % 4 == 0 && al16(E) &&
+                    (!out || (ld_out % 4 == 0 && al16(out))) && (!acc || (ld_acc % 4 == 0 && al16(acc))) &&
+                    (n_long == 0 || al16(partials));
+  if (vec4) {
+    const int q = d / 4;
+    if (q <= 4) launch_vec4<4>(a, chunk_row, chunk_k, n_chunks, partials, n_long, stream);
+    else if (q <= 8) launch_vec4<8>(a, chunk_row, chunk_k, n_chunks, partials, n_long, stream);
+    else if (q <= 16) launch_vec4<16>(a, chunk_row, chunk_k, n_chunks, partials, n_long, stream);
+    else launch_vec4<32>(a, chunk_row, chunk_k, n_chunks, partials, n_long, stream);
+    count_launch(n_long > 0 ? 2 : 1);
+  } else {
+    const int rows_per_warp = 32 / lpr;
+    const int64_t warps = ceil_div64(n_rows, rows_per_warp);
+    spmm_rows_kernel<<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, stream>>>(a);
+    count_launch();
+    if (n_long > 0) {
+      spmm_long_chunks_kernel<<<(unsigned)ceil_div64(n_chunks * 32, 256), 256, 0, stream>>>(
+          a, chunk_row, chunk_k, n_chunks, partials);
+      count_launch();
+    }
+  }
   if (n_long > 0) {
-    spmm_long_chunks_kernel<<<(unsigned)ceil_div64(n_chunks * 32, 256), 256, 0, stream>>>(
-        a, chunk_row, chunk_k, n_chunks, partials);
     spmm_long_reduce_kernel<<<(unsigned)ceil_div64(n_long * 32, 256), 256, 0, stream>>>(
         a, long_rows, long_chunk_ptr, n_long, partials);
-    count_launch(2);
+    count_launch();
   }
   B200_CUDA_OK(cudaGetLastError());
   return 0;

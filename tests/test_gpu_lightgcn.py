@@ -88,3 +88,35 @@ def test_module_forward_backward_matches_torch_sparse():
     (torch.cat([ue, ie]) * w).sum().backward()
     got = torch.cat([m.user_init_embeds.weight.grad, m.item_init_embeds.weight.grad])
     torch.testing.assert_close(got, E0.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_bpr_training_steps_reduce_loss():
+    """A few BPR steps exactly as TorchTrainer._compute_loss does them
+    (libreco/training/torch_trainer.py:140-161: full-graph propagation, gather, bpr_loss of
+    libreco/torchops/loss.py:22-24, Adam) through the CUDA propagation and its backward."""
+    import torch
+    from librecommender_b200.lightgcn import make_lightgcn_model_class
+    from librecommender_b200.sampling import DeviceNegativeSampler
+
+    rng = np.random.default_rng(5)
+    nu, ni, d = 400, 300, 16
+    consumed = {u: rng.choice(ni, size=int(rng.integers(3, 25)), replace=False).tolist() for u in range(nu)}
+    Model = make_lightgcn_model_class()
+    torch.manual_seed(1)
+    m = Model(nu, ni, d, 2, 0.0, consumed, "cuda")
+    opt = torch.optim.Adam(m.parameters(), lr=0.05)
+    sampler = DeviceNegativeSampler(ni, consumed, nu, seed=42)
+    users = torch.as_tensor(np.repeat(np.arange(nu), 3)).cuda()
+    pos = torch.as_tensor(np.array([consumed[u][j] for u in range(nu) for j in range(3)])).cuda()
+    losses = []
+    for step in range(8):
+        neg = sampler.sample(users, pos, 1, "unconsumed")
+        ue, ie = m(use_dropout=False)
+        s_pos = (ue[users] * ie[pos]).sum(1)
+        s_neg = (ue[users] * ie[neg]).sum(1)
+        loss = -torch.nn.functional.logsigmoid(s_pos - s_neg).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0] * 0.9, losses
