@@ -68,8 +68,9 @@ int b200_score_rows_f32(const float* U, int64_t ldu, const int64_t* user_ids, in
  * catalog: device buffer prepared ONCE per item table (bf16 K-major copy + max row norm).
  * Result per row: the K best non-consumed items by EXACT fp32 score (same definition as
  * b200_score_rows_f32), sorted (score desc, id asc).  row_status[r] (device int32[B]) = 1 marks a
- * row the fused path could not bound (K + consumed > 288, or too many near-ties): its out_ids are
- * -1 and the caller re-runs it through b200_score_rows_f32 + b200_mask_consumed + b200_topk_rows.
+ * row the fused path could not prove exact (failed threshold speculation, too many near-ties, or a
+ * heavy user whose capped candidate budget did not suffice): its out_ids are -1 and the caller
+ * re-runs it through b200_score_rows_f32 + b200_mask_consumed + b200_topk_rows.
  * Limits: d <= 256, K <= 288. */
 int b200_embed_catalog_bytes(int64_t N, int32_t d, size_t* bytes);
 int b200_embed_catalog_prepare(const float* I, int64_t ldi, int64_t N, int32_t d, void* catalog,

@@ -49,13 +49,15 @@ constexpr int CAPG = 256;      // candidate GROUP records per (row, list); list 
 constexpr int GW = 8;          // a record = the 8 coarse scores of one 8-column group + its first item id
 constexpr int NB = 1024;       // bins of the per-row global coarse-score histogram
 constexpr int TRIG = 96;       // uncounted records that trigger a compaction
-constexpr int EPI_WARPS = 8;   // two epilogue warps per TMEM lane quadrant (column halves)
+constexpr int EPI_WARPS = 8;   // LPS epilogue warps per TMEM lane quadrant (column groups of a tile); 16 measured slower
+constexpr int LPS = EPI_WARPS / 4;   // candidate lists per (row, item split) = column groups per tile
+constexpr int CW = 256 / LPS;        // accumulator columns one epilogue warp scans per tile
 constexpr int KROW_MAX = 288;  // fast-path limit for k_row = K + c_u
 constexpr int MAX_KB = 4;      // d_pad <= 256
 constexpr int PRE_STRIDE = 16; // the pre-pass visits every 16th item tile of a split
 constexpr int A_KB_BYTES = TM * KBLK * 2;   // 16 KB
 constexpr int B_KB_BYTES = TN * KBLK * 2;   // 32 KB
-constexpr int SWEEP_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int SWEEP_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA, warps 2.. epilogue
 constexpr int MAXU = 3072;                  // finalize: collected elements per row (union of the lists)
 constexpr int MAXC = 2048;                  // finalize: candidates per row after the c_k - 2 eps cut
 constexpr int FIN_THREADS = 256;
@@ -72,8 +74,9 @@ struct RowMeta {
   float R;          // |coarse score| <= R for every item (Cauchy-Schwarz on the row norms)
   int32_t k_row;    // K (+ consumed count when the filter applies)
   int32_t pre_k;    // rank of the block maximum used as speculative threshold
-  int32_t active;   // 0: pad row / fallback row (never collects)
+  int32_t active;   // 0: pad row (never collects)
   int32_t apply;    // consumed filter applies
+  int32_t capped;   // k_row was capped below K + c_u: finalize must verify the result a posteriori
 };
 
 
@@ -85,10 +88,10 @@ struct SweepParams {
   uint32_t* row_tau_key;      // [B_pad]  running max of tau (order-preserving key)
   int32_t* row_status;        // [B_pad]  1 = needs the exact path
   uint32_t* ghist;            // [B_pad][NB]  coarse-score histogram of every counted candidate
-  float* cand_s;              // [2*n_splits][B_pad][CAPG][GW]  group records: 8 coarse scores ...
-  int32_t* cand_b;            // [2*n_splits][B_pad][CAPG]      ... and the item id of the first column
-  int32_t* cand_cnt;          // [2*n_splits][B_pad]            records per list
-  float* blockmax;            // [2*n_splits][n_pre_tiles][B_pad]   (pre-pass output)
+  float* cand_s;              // [LPS*n_splits][B_pad][CAPG][GW]  group records: 8 coarse scores ...
+  int32_t* cand_b;            // [LPS*n_splits][B_pad][CAPG]      ... and the item id of the first column
+  int32_t* cand_cnt;          // [LPS*n_splits][B_pad]            records per list
+  float* blockmax;            // [LPS*n_splits][n_pre_tiles][B_pad]   (pre-pass output)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -144,15 +147,19 @@ __global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
     int64_t c = 0;
     if (real && filter && indptr && u >= 0 && u < n_users) c = indptr[u + 1] - indptr[u];
     const bool apply = c > 0 && (int64_t)K + c <= N;
-    const int64_t k_row = (int64_t)K + (apply ? c : 0);
+    // k_row = K + c_u guarantees K survivors after the consumed filter.  Heavy users would need
+    // lists longer than the kernel keeps: their k_row is capped and finalize_kernel verifies the
+    // result instead (the K-th surviving exact score must beat everything that was not collected).
+    const int64_t k_full = (int64_t)K + (apply ? c : 0);
+    const int64_t k_row = min(k_full, (int64_t)KROW_MAX);
     m.apply = apply;
-    m.k_row = (int32_t)min(k_row, (int64_t)(1 << 30));
+    m.capped = k_row < k_full;
+    m.k_row = (int32_t)k_row;
     m.pre_k = 16 + m.k_row / 6;
-    const bool fast = real && k_row <= KROW_MAX;
-    m.active = fast;
+    m.active = real;
     meta[row] = m;
     row_tau_key[row] = 0u;  // below every finite float
-    row_status[row] = (real && !fast) ? 1 : 0;
+    row_status[row] = 0;
   }
 }
 
@@ -392,7 +399,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else {
     // ===================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves ==========
     const int q = warp & 3;                 // TMEM lanes [32q, 32q+32) (hardware: warp id % 4)
-    const int half = (warp - 2) >> 2;       // columns [128*half, 128*half + 128) of every tile
+    const int cg = (warp - 2) >> 2;         // column group: columns [CW*cg, CW*cg + CW) of every tile
+    const int half = (cg * 2) / LPS;        // accumulator half (= MMA group / barrier pair) it belongs to
     const int trow = q * 32 + lane;         // row inside the tile
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -403,7 +411,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int t0 = split * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
       const int grow = m * TM + trow;
-      const int list_id = split * 2 + half;
+      const int list_id = split * LPS + cg;
 
       if (PRE) {
         // ---- pre-pass: per sampled tile the maximum coarse score of this warp's 128 columns ----
@@ -412,10 +420,10 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int t = t0; t < t1; t += STRIDE, ++ti) {
           ptx::mbar_wait(&ss->tmem_full[acc][half], acc_phase);
           ptx::tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * (TN / 2));
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cg * CW);
           float tm = ninf;
 #pragma unroll 1
-          for (int ch = 0; ch < TN / 64; ++ch) {
+          for (int ch = 0; ch < CW / 32; ++ch) {
             uint32_t r[32];
             ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(ch * 32), r);
             ptx::tmem_ld_wait_regs(r);
@@ -484,11 +492,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int t = t0; t < t1; ++t) {
         ptx::mbar_wait(&ss->tmem_full[acc][half], acc_phase);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + half * (TN / 2));
-        const int n_base = t * TN + half * (TN / 2);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cg * CW);
+        const int n_base = t * TN + cg * CW;
         const bool tail = t >= last_full;
 #pragma unroll 1
-        for (int ch = 0; ch < TN / 64; ++ch) {
+        for (int ch = 0; ch < CW / 32; ++ch) {
           uint32_t r[32];
           ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(ch * 32), r);
           ptx::tmem_ld_wait_regs(r);
@@ -625,33 +633,41 @@ finalize_kernel(const FinalizeParams p) {
   int64_t* oid = p.out_ids + row * p.K;
   float* osc = p.out_scores ? p.out_scores + row * p.K : nullptr;
   const RowMeta meta = p.meta[row];
-  auto give_up = [&](bool flag) {
-    if (flag && tid == 0) p.row_status[row] = 1;
+  // row_status codes (non-zero = re-run on the exact path): 1 sweep overflow, 2 too few collected,
+  // 3 failed speculation, 4 candidate set outside [K, MAXC], 5 capped row not provable
+  auto give_up = [&](int code) {
+    if (code && tid == 0) p.row_status[row] = code;
     for (int i = tid; i < p.K; i += FIN_THREADS) { oid[i] = -1; if (osc) osc[i] = 0.f; }
   };
-  if (p.row_status[row] != 0) { give_up(false); return; }
+  if (p.row_status[row] != 0) { give_up(0); return; }
   // ---- gather: every element of every group record that is >= the row's final threshold.
   // (every exact top-k_row item has coarse >= c_k - 2 eps >= that threshold, see the header)
   const uint32_t tk = p.row_tau_key[row];
   const float low = tk ? key_to_float(tk) : __int_as_float(0xff800000);
   if (tid == 0) { s_nu = 0; s_nc = 0; }
+  // list lengths first (one parallel round of loads), then one warp per list
+  int* s_cnt = reinterpret_cast<int*>(c_sort);          // c_sort is free until the hash set is built
+  for (int s = tid; s < p.n_lists; s += FIN_THREADS) s_cnt[s] = p.cand_cnt[(int64_t)s * p.B_pad + row];
   __syncthreads();
-  for (int s = 0; s < p.n_lists; ++s) {
-    const int64_t slot = (int64_t)s * p.B_pad + row;
-    const int n = p.cand_cnt[slot];
-    const float* ls = p.cand_s + slot * (int64_t)(CAPG * GW);
-    const int32_t* lb = p.cand_b + slot * (int64_t)CAPG;
-    for (int i = tid; i < n * GW; i += FIN_THREADS) {
-      const float v = ls[i];
-      if (v >= low) {
-        const int pos = atomicAdd(&s_nu, 1);
-        if (pos < MAXU) { u_s[pos] = v; u_id[pos] = lb[i / GW] + (i % GW); }
+  {
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int s = wid; s < p.n_lists; s += FIN_THREADS / 32) {
+      const int64_t slot = (int64_t)s * p.B_pad + row;
+      const int n = s_cnt[s];
+      const float* ls = p.cand_s + slot * (int64_t)(CAPG * GW);
+      const int32_t* lb = p.cand_b + slot * (int64_t)CAPG;
+      for (int i = lane; i < n * GW; i += 32) {
+        const float v = ls[i];
+        if (v >= low) {
+          const int pos = atomicAdd(&s_nu, 1);
+          if (pos < MAXU) { u_s[pos] = v; u_id[pos] = lb[i / GW] + (i % GW); }
+        }
       }
     }
   }
   __syncthreads();
   const int nu = s_nu;
-  if (nu < meta.k_row) { give_up(true); return; }
+  if (nu < meta.k_row) { give_up(2); return; }
   const bool in_smem = nu <= MAXU;   // common case; otherwise (no speculation, small catalogue) stream from HBM
   // visit every collected element (score, id): from shared memory, or again from the lists
   auto for_each = [&](auto&& f) {
@@ -712,7 +728,7 @@ finalize_kernel(const FinalizeParams p) {
     // The main pass started from a speculative threshold: the lists are complete only above it.
     // Every exact top-k_row item has coarse >= thr, so the guess must not exceed thr.
     const uint32_t gk = p.tau_guess_key[row];
-    if (gk != 0u && key_to_float(gk) > thr) { give_up(true); return; }
+    if (gk != 0u && key_to_float(gk) > thr) { give_up(3); return; }
   }
   // ---- candidates: elements >= thr (ids only from here on)
   if (in_smem) {   // compact in place: read everything first, then write
@@ -743,7 +759,7 @@ finalize_kernel(const FinalizeParams p) {
   __syncthreads();
   const int nc = s_nc;
   int32_t* c_id = u_id;
-  if (nc > MAXC || nc < p.K) { give_up(true); return; }  // cannot bound (dense near-ties) -> exact path
+  if (nc > MAXC || nc < p.K) { give_up(4); return; }  // cannot bound (dense near-ties) -> exact path
   const int64_t u = p.user_ids[row];
   // ---- consumed filter through a hash set of candidate ids
   if (meta.apply) {
@@ -780,7 +796,8 @@ finalize_kernel(const FinalizeParams p) {
       float acc = 0.f;
       if (vec4) {   // 16-byte loads; the fma chain stays sequential in k (exact-score definition)
         const float4* it4 = reinterpret_cast<const float4*>(it);
-        for (int k4 = 0; k4 < p.d / 4; ++k4) {
+#pragma unroll 8
+        for (int k4 = 0; k4 < p.d / 4; ++k4) {   // loads are independent of the fma chain: keep 8 in flight
           const float4 x = __ldg(it4 + k4);
           acc = fmaf(urow[4 * k4 + 0], x.x, acc);
           acc = fmaf(urow[4 * k4 + 1], x.y, acc);
@@ -813,6 +830,15 @@ finalize_kernel(const FinalizeParams p) {
       }
       __syncthreads();
     }
+  }
+  {
+    // Survivors: fewer than K (possible when k_row was capped), or — capped rows — a K-th exact
+    // score that an uncollected item could still beat.  Uncollected items have coarse < thr, hence
+    // exact < thr + eps = c_k - eps; the row is only accepted if the K-th survivor is above that.
+    const unsigned long long kth = c_sort[p.K - 1];
+    const bool short_row = kth == 0ull;
+    const bool unsafe = meta.capped && key_to_float((uint32_t)(kth >> 32)) < thr + 0.5f * meta.eps2;
+    if (short_row || unsafe) { __syncthreads(); give_up(5); return; }
   }
   for (int i = tid; i < p.K; i += FIN_THREADS) {
     const unsigned long long c = c_sort[i];
@@ -893,7 +919,7 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->n_splits = (pl->total_tiles + pl->tiles_per_split - 1) / pl->tiles_per_split;
   pl->n_pre_tiles = (pl->tiles_per_split + PRE_STRIDE - 1) / PRE_STRIDE;
   // speculation needs enough sampled blocks per row to take a stable order statistic
-  pl->use_pre = (long)2 * pl->n_splits * pl->n_pre_tiles >= 256;
+  pl->use_pre = (long)LPS * pl->n_splits * pl->n_pre_tiles >= 256;
   const size_t budget = 227 * 1024 - 1024 /*align*/ - sizeof(SweepSmem) - (size_t)pl->KB * A_KB_BYTES;
   int ns = (int)(budget / ((size_t)pl->KB * B_KB_BYTES));
   if (ns > 6) ns = 6;
@@ -906,11 +932,11 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->off_tau = off; off += al256((size_t)pl->B_pad * 4);
   pl->off_guess = off; off += al256((size_t)pl->B_pad * 4);
   pl->off_status = off; off += al256((size_t)pl->B_pad * 4);
-  pl->off_cnt = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * 4);
+  pl->off_cnt = off; off += al256((size_t)LPS * pl->n_splits * pl->B_pad * 4);
   pl->off_hist = off; off += al256((size_t)pl->B_pad * NB * 4);
-  pl->off_cs = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * CAPG * GW * 4);
-  pl->off_cb = off; off += al256((size_t)2 * pl->n_splits * pl->B_pad * CAPG * 4);
-  pl->off_bm = off; off += al256((size_t)2 * pl->n_splits * pl->n_pre_tiles * pl->B_pad * 4);
+  pl->off_cs = off; off += al256((size_t)LPS * pl->n_splits * pl->B_pad * CAPG * GW * 4);
+  pl->off_cb = off; off += al256((size_t)LPS * pl->n_splits * pl->B_pad * CAPG * 4);
+  pl->off_bm = off; off += al256((size_t)LPS * pl->n_splits * pl->n_pre_tiles * pl->B_pad * 4);
   pl->total = off + 256;
   return 0;
 }
@@ -1027,7 +1053,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   if (ev_sweep_start) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_start, stream));
   if (pl.use_pre) {
     sweep_kernel<true><<<grid, SWEEP_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, sp);
-    guess_kernel<<<(unsigned)pl.B_pad, 128, 0, stream>>>(bm, 2 * pl.n_splits * pl.n_pre_tiles, pl.B_pad,
+    guess_kernel<<<(unsigned)pl.B_pad, 128, 0, stream>>>(bm, LPS * pl.n_splits * pl.n_pre_tiles, pl.B_pad,
                                                           meta, tau, guess);
     count_launch(2);
   } else {
@@ -1037,7 +1063,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   if (ev_sweep_stop) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_stop, stream));
 
   FinalizeParams fp;
-  fp.B = B; fp.N = N; fp.B_pad = pl.B_pad; fp.n_lists = 2 * pl.n_splits; fp.K = K; fp.d = d;
+  fp.B = B; fp.N = N; fp.B_pad = pl.B_pad; fp.n_lists = LPS * pl.n_splits; fp.K = K; fp.d = d;
   fp.meta = meta; fp.row_status = status; fp.row_tau_key = tau; fp.tau_guess_key = guess;
   fp.cand_s = cand_s; fp.cand_b = cand_b; fp.cand_cnt = cnt;
   fp.U = U; fp.ldu = ldu; fp.I = I; fp.ldi = ldi; fp.user_ids = user_ids; fp.indptr = indptr;

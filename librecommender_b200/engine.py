@@ -197,17 +197,58 @@ class EmbedScorer:
             _lib.current_stream()))
         return scores[:, :N]
 
-    def recommend(self, user_ids, n_rec, filter_consumed=True, return_scores=False, path="auto"):
-        """Host ids in, host ``int64[B, n_rec]`` out (the reference-facing call)."""
+    def _pinned(self, name, shape, dtype):
+        """Small ring of pinned host staging buffers (a returned array stays valid for the next
+        three calls; it is a fresh view each time, like the reference's fresh ndarray)."""
         torch = self._torch
-        uid_h = torch.as_tensor(np.asarray(user_ids, dtype=np.int64))
-        if uid_h.numel() >= 4096:
-            uid_h = uid_h.pin_memory()
+        ring = self.__dict__.setdefault("_pin_ring", {})
+        key = (name, tuple(shape), dtype)
+        bufs, pos = ring.get(key, ([], 0))
+        if len(bufs) < 4:
+            bufs.append(torch.empty(shape, dtype=dtype, pin_memory=True))
+            buf = bufs[-1]
+        else:
+            buf = bufs[pos % 4]
+        ring[key] = (bufs, pos + 1)
+        return buf
+
+    def recommend(self, user_ids, n_rec, filter_consumed=True, return_scores=False, path="auto"):
+        """Host ids in, host ``int64[B, n_rec]`` out (the reference-facing call): one H2D of the
+        ids, the kernels, one D2H of ids (+ the per-row status) and a single synchronisation."""
+        torch = self._torch
+        n_rec = int(n_rec)
+        if isinstance(user_ids, torch.Tensor):
+            uid_h = user_ids.to(torch.int64)
+        else:
+            uid_h = torch.as_tensor(np.asarray(user_ids, dtype=np.int64))
         uid_d = uid_h.to(self.device, non_blocking=True)
-        res = self.recommend_device(uid_d, int(n_rec), filter_consumed, return_scores, path)
+        B = int(uid_d.numel())
+        if path == "exact" or (path == "auto" and not self.fused_ok(n_rec)):
+            res = self.recommend_exact(uid_d, n_rec, filter_consumed, return_scores)
+            if return_scores:
+                return res[0].cpu().numpy(), res[1].cpu().numpy()
+            return res.cpu().numpy()
+        ids_d, sc_d, status_d = self.recommend_fused(uid_d, n_rec, filter_consumed, return_scores)
+        ids_h = self._pinned("ids", (B, n_rec), torch.int64)
+        st_h = self._pinned("status", (B,), torch.int32)
+        ids_h.copy_(ids_d, non_blocking=True)
+        st_h.copy_(status_d, non_blocking=True)
+        sc_h = None
         if return_scores:
-            return res[0].cpu().numpy(), res[1].cpu().numpy()
-        return res.cpu().numpy()
+            sc_h = self._pinned("scores", (B, n_rec), torch.float32)
+            sc_h.copy_(sc_d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        ids = ids_h.numpy()
+        scores = sc_h.numpy() if return_scores else None
+        bad = np.flatnonzero(st_h.numpy())
+        if len(bad):                       # rows the fused path could not prove: exact path
+            bad_d = torch.as_tensor(bad, device=self.device)
+            fix = self.recommend_exact(uid_d[bad_d], n_rec, filter_consumed, return_scores)
+            if return_scores:
+                ids[bad], scores[bad] = fix[0].cpu().numpy(), fix[1].cpu().numpy()
+            else:
+                ids[bad] = fix.cpu().numpy()
+        return (ids, scores) if return_scores else ids
 
     def predict(self, users, items, mode=0, lo=0.0, hi=0.0):
         """predict_from_embedding (``libreco/prediction/predict.py:36-40``)."""

@@ -46,7 +46,7 @@ def test_fused_equals_exact_and_oracle(n_users, N, d, K, mean_c, B):
     ids_f, sc_f, status = sc.recommend_fused(uid, K, True, True)
     ids_e, sc_e = sc.recommend_exact(uid, K, True, True)
     torch.cuda.synchronize()
-    assert int(status.sum()) == 0
+    assert not bool((status != 0).any()), status[status != 0].tolist()   # reason codes: see finalize_kernel
     np.testing.assert_array_equal(ids_f.cpu().numpy(), ids_e.cpu().numpy())
     np.testing.assert_array_equal(sc_f.cpu().numpy(), sc_e.cpu().numpy())
     ref = orc.recommend_from_embedding("ranking", users.tolist(), K, U, I, N, consumed, True)
@@ -81,15 +81,18 @@ def test_fused_heavy_users_and_dense_ties_fall_back():
     U = rng.standard_normal((n_users + 1, d)).astype(np.float32)
     I = rng.standard_normal((N + 1, d)).astype(np.float32)
     I[: N // 2] = I[0]                      # half the catalogue ties exactly
-    consumed = {0: rng.choice(N, size=1500, replace=False).tolist(),   # K + c > 448 -> exact path
+    consumed = {0: rng.choice(N, size=1500, replace=False).tolist(),   # heavy user: capped k_row + verification
                 1: list(range(10)), 2: rng.choice(N, size=N - 10, replace=False).tolist()}  # cannot filter
     sc = EmbedScorer(U, I, N, consumed, n_users=n_users)
     uid = torch.arange(0, n_users).cuda()
     ids = sc.recommend_device(uid, K, True, False, path="auto")
     ids_e = sc.recommend_exact(uid, K, True, False)
     np.testing.assert_array_equal(ids.cpu().numpy(), ids_e.cpu().numpy())
-    _, _, status = sc.recommend_fused(uid, K, True, False)
-    assert int(status[0]) == 1              # heavy user handed to the exact path
+    ids_f, _, status = sc.recommend_fused(uid, K, True, False)
+    ok = (status == 0).cpu().numpy()
+    # rows the fused path accepted are exact (the heavy user is verified a posteriori, not refused)
+    np.testing.assert_array_equal(ids_f.cpu().numpy()[ok], ids_e.cpu().numpy()[ok])
+    assert ok[0] and ok[3:].all()
 
 
 def test_fused_adversarial_near_ties():
@@ -122,3 +125,30 @@ def test_public_api_uses_fused_path_and_matches_oracle():
     full = orc.embed_scores(U, I, users, 100000)
     assert orc.near_tie_mask(ref, got, full, 1e-6).all()
     assert (got == ref).mean() > 0.995
+
+
+def test_fused_heavy_users_with_top_ranked_history():
+    """Consumed items that ARE the user's best-scoring items (the realistic case) and exceed the
+    candidate budget: the capped rows must either be proven exact or be flagged — never wrong."""
+    import torch
+    from librecommender_b200.engine import EmbedScorer
+
+    rng = np.random.default_rng(17)
+    n_users, N, d, K = 64, 30000, 64, 50
+    U = rng.standard_normal((n_users + 1, d)).astype(np.float32)
+    I = rng.standard_normal((N + 1, d)).astype(np.float32)
+    full = U[:n_users] @ I[:N].T
+    consumed = {}
+    for u in range(n_users):
+        c = [150, 400, 1200][u % 3]
+        consumed[u] = np.argsort(-full[u])[:c].tolist()        # exactly the top-c items
+    sc = EmbedScorer(U, I, N, consumed, n_users=n_users)
+    uid = torch.arange(0, n_users).cuda()
+    ids_f, _, status = sc.recommend_fused(uid, K, True, False)
+    ids_e = sc.recommend_exact(uid, K, True, False)
+    ok = (status == 0).cpu().numpy()
+    np.testing.assert_array_equal(ids_f.cpu().numpy()[ok], ids_e.cpu().numpy()[ok])
+    assert ok[0::3].all()                    # K + 150 fits the budget
+    assert not ok[2::3].any()                # 1200 top-ranked consumed items cannot be proven -> flagged
+    got = sc.recommend_device(uid, K, True, False).cpu().numpy()
+    np.testing.assert_array_equal(got, ids_e.cpu().numpy())
