@@ -30,7 +30,7 @@ SEED_U, SEED_I, SEED_C, SEED_Q = 1, 2, 3, 4
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--users", type=int, default=10_000_000)
@@ -143,7 +143,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def start(self):
         if self.ok:
@@ -236,6 +236,12 @@ def main():
     torch.cuda.synchronize()
 
     if args.impl == "reference":
+        try:   # torchrun exports OMP_NUM_THREADS=1: the CPU arm must still use every host thread
+            from threadpoolctl import threadpool_limits
+
+            threadpool_limits(limits=os.cpu_count())
+        except Exception:
+            pass
         I_host, rows_fn, cons_fn = host_views(U, I, indptr, idx)
         ncalls = max(1, args.steps)
         for _ in range(max(0, args.warmup)):
@@ -324,6 +330,11 @@ def main():
     e2e_value = world * args.batch * args.steps / (e2e_ms * 1e-3)
     assert res.shape == (args.batch, args.topk) and res.dtype == np.int64 and (res >= 0).all()
 
+    if distributed:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return 0
 

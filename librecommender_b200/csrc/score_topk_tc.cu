@@ -496,24 +496,29 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int n_base = t * TN + cg * CW;
         const bool tail = t >= last_full;
 #pragma unroll 1
-        for (int ch = 0; ch < CW / 32; ++ch) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(ch * 32), r);
-          ptx::tmem_ld_wait_regs(r);
+        for (int ch = 0; ch < CW / 64; ++ch) {
+          // 64 accumulator columns per step: two independent max trees in flight
+          uint32_t r[64];
+          ptx::tmem_ld_32x32b_x64(taddr + (uint32_t)(ch * 64), r);
+          ptx::tmem_ld_wait_regs64(r);
           if (tail) {   // zero-padded item rows (>= N) must never be collected: only the last tile
-            const int lim = (int)max((int64_t)0, min((int64_t)32, p.N - (int64_t)(n_base + ch * 32)));
+            const int lim = (int)max((int64_t)0, min((int64_t)64, p.N - (int64_t)(n_base + ch * 64)));
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j >= lim) r[j] = 0xff800000u;
+            for (int j = 0; j < 64; ++j) if (j >= lim) r[j] = 0xff800000u;
           }
-          float g[4];
-          const float mx = chunk_max(r, g);
-          (void)mx;
-          // Four warp-uniform tests (one per 8-column group): a group that is hot in some lane is
-          // pushed WHOLE by that lane (two 16-byte stores + its first item id); finalize_kernel
-          // sorts out which of its 8 scores are candidates.  Cold groups cost 4 instructions.
+          float g[8];
+#pragma unroll
+          for (int gq = 0; gq < 8; ++gq) {
+            const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
+            const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+            g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
+          }
+          // Warp-uniform tests, one per 8-column group: a group that is hot in some lane is pushed
+          // WHOLE by that lane (two 16-byte stores + its first item id); finalize_kernel sorts out
+          // which of its 8 scores are candidates.  Cold groups cost 4 instructions.
           bool pushed = false;
 #pragma unroll
-          for (int gq = 0; gq < 4; ++gq) {
+          for (int gq = 0; gq < 8; ++gq) {
             if (__any_sync(0xffffffffu, g[gq] >= tau)) {
               if (g[gq] >= tau) {
                 float4* dst = reinterpret_cast<float4*>(my_s + (size_t)cnt * GW);
@@ -521,14 +526,14 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                      __uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
                 dst[1] = make_float4(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]),
                                      __uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
-                my_b[cnt] = n_base + ch * 32 + gq * 8;
+                my_b[cnt] = n_base + ch * 64 + gq * 8;
                 ++cnt;
               }
               pushed = true;
             }
           }
           if (pushed)   // warp-uniform
-            compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > TRIG) || (cnt > CAPG - 4)));
+            compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > TRIG) || (cnt > CAPG - 8)));
         }
         ptx::tc_fence_before();
         __syncwarp();

@@ -203,14 +203,13 @@ class EmbedScorer:
         torch = self._torch
         ring = self.__dict__.setdefault("_pin_ring", {})
         key = (name, tuple(shape), dtype)
-        bufs, pos = ring.get(key, ([], 0))
-        if len(bufs) < 4:
-            bufs.append(torch.empty(shape, dtype=dtype, pin_memory=True))
-            buf = bufs[-1]
-        else:
-            buf = bufs[pos % 4]
+        if key not in ring:            # page-locking is slow: allocate the whole ring once
+            if len(ring) > 24:
+                ring.clear()
+            ring[key] = ([torch.empty(shape, dtype=dtype, pin_memory=True) for _ in range(4)], 0)
+        bufs, pos = ring[key]
         ring[key] = (bufs, pos + 1)
-        return buf
+        return bufs[pos % 4]
 
     def recommend(self, user_ids, n_rec, filter_consumed=True, return_scores=False, path="auto"):
         """Host ids in, host ``int64[B, n_rec]`` out (the reference-facing call): one H2D of the
