@@ -661,11 +661,20 @@ finalize_kernel(const FinalizeParams p) {
       const int n = s_cnt[s];
       const float* ls = p.cand_s + slot * (int64_t)(CAPG * GW);
       const int32_t* lb = p.cand_b + slot * (int64_t)CAPG;
-      for (int i = lane; i < n * GW; i += 32) {
-        const float v = ls[i];
-        if (v >= low) {
-          const int pos = atomicAdd(&s_nu, 1);
-          if (pos < MAXU) { u_s[pos] = v; u_id[pos] = lb[i / GW] + (i % GW); }
+      for (int i0 = lane; i0 < n * GW; i0 += 32 * 8) {   // 8 independent loads in flight per lane
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = i0 + q * 32;
+          v[q] = (i < n * GW) ? __ldcs(ls + i) : __int_as_float(0xff800000);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = i0 + q * 32;
+          if (i < n * GW && v[q] >= low) {
+            const int pos = atomicAdd(&s_nu, 1);
+            if (pos < MAXU) { u_s[pos] = v[q]; u_id[pos] = lb[i / GW] + (i % GW); }
+          }
         }
       }
     }

@@ -76,6 +76,37 @@ def bench_spmm():
                                                   "max_degree": int(deg.max())})
     ms3 = timeit(lambda: propagate(graph, E, 3), iters=5)
     emit("lightgcn propagate 3 layers (fused mean)", ms3, 3 * bytes_ + 3 * n * 4 * d, {"nnz": nnz})
+    # one BPR training step exactly as TorchTrainer._compute_loss (full-graph propagation + backward + Adam)
+    from librecommender_b200.lightgcn import propagate_autograd
+
+    W = torch.nn.Parameter(E.clone())
+    opt = torch.optim.Adam([W], lr=1e-3)
+    bs = 2048
+    uu = torch.randint(0, n_users, (bs,), device=dev)
+    pp = torch.randint(0, n_items, (bs,), device=dev) + n_users
+    nn_ = torch.randint(0, n_items, (bs,), device=dev) + n_users
+
+    def step():
+        out = propagate_autograd(graph, W, 3)
+        loss = -torch.nn.functional.logsigmoid((out[uu] * out[pp]).sum(1) - (out[uu] * out[nn_]).sum(1)).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    ms_step = timeit(step, iters=5)
+    print(json.dumps({"kernel": "LightGCN BPR training step (3-layer full-graph fwd+bwd, dense Adam), batch 2048",
+                      "ms": ms_step, "interactions_per_s": bs / (ms_step * 1e-3), "nodes": n, "nnz": nnz}), flush=True)
+    # CPU side: the reference's own op (torch.sparse.mm on a COO Laplacian, lightgcn_module.py:74-88), one layer
+    t_rows = torch.repeat_interleave(torch.arange(n, device=dev), deg).cpu()
+    Lc = torch.sparse_coo_tensor(torch.stack([t_rows, cols.long().cpu()]), val.cpu(), (n, n)).coalesce()
+    Ec = E.cpu()
+    torch.set_num_threads(os.cpu_count())
+    t0 = time.perf_counter()
+    torch.sparse.mm(Lc, Ec)
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({"kernel": "cpu_baseline: torch.sparse.mm one layer (reference op)", "seconds": cpu_s,
+                      "cores": os.cpu_count(), "kind": "reference-op", "speedup_vs_gpu_layer": cpu_s / (ms * 1e-3)}),
+          flush=True)
 
 
 def bench_feat():
@@ -108,6 +139,15 @@ def bench_feat():
     emit("feat_forward FM fused head (no intermediate)", ms, read + R * 4, {"rows": R})
     ms = timeit(lambda: model.logits(users[:1 << 18].cpu().numpy(), items[:1 << 18].cpu().numpy()), iters=3)
     print(json.dumps({"kernel": "DeepFM predict rows/s (gather + fp32 MLP 1792-128-64-32)", "rows_per_s": (1 << 18) / (ms * 1e-3)}))
+    # CPU side: numpy restatement of the DeepFM graph (oracle port) on a bounded sample
+    nu = 1 << 15
+    uh, ih = users[:nu].cpu().numpy(), items[:nu].cpu().numpy()
+    sp, de = tm.row_features(spec, uh, ih)
+    t0 = time.perf_counter()
+    tm.deepfm_forward(w, uh, ih, sp, de)
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({"kernel": "cpu_baseline: DeepFM forward (oracle port, numpy)", "rows_per_s": nu / cpu_s,
+                      "cores": os.cpu_count(), "kind": "port", "sample": f"{nu} rows"}), flush=True)
 
 
 def bench_topk_and_sampler():
@@ -129,6 +169,13 @@ def bench_topk_and_sampler():
     ms = timeit(lambda: smp.sample(None, pos, 5, "random"))
     print(json.dumps({"kernel": "sample_negatives random (4M positives x 5)", "ms": ms,
                       "negatives_per_s": (1 << 22) * 5 / (ms * 1e-3)}))
+    from librecommender_b200.sampling import negatives_from_random
+    ph = pos[:1 << 20].cpu().numpy()
+    t0 = time.perf_counter()
+    negatives_from_random(np.random.default_rng(462), 1_000_000, ph, 5)
+    cpu_s = time.perf_counter() - t0
+    print(json.dumps({"kernel": "cpu_baseline: negatives_from_random (reference numpy stream, parity mode)",
+                      "negatives_per_s": (1 << 20) * 5 / cpu_s, "cores": 1, "kind": "reference-stream"}))
 
 
 if __name__ == "__main__":
