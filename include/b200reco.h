@@ -147,7 +147,28 @@ int b200_feat_forward(const b200_feat_layout* layout, const b200_feat_tables* ta
                       const int64_t* users, const int64_t* items, int64_t R, int64_t grid_items,
                       int64_t row_offset, float* concat, int64_t ld_concat, float* pw, int64_t ld_pw, float* lin,
                       float* fm_out, const float* lin_kernel, float lin_bias, const float* bn_scale,
-                      const float* bn_shift, const float* pw_kernel, float pw_bias, void* stream);
+                      const float* bn_shift, const float* pw_kernel, float pw_bias,
+                      float* ssum /* [R,K] sum_f e, or NULL */, float* sqsum /* [R,K] sum_f e^2 */,
+                      int64_t ld_s, void* stream);
+
+/* Hoisted all-items scoring: everything that depends on the user only or on the
+ * item only is computed once (b200_feat_forward over the user-side / item-side fields: S = sum e,
+ * Q = sum e^2, the linear partial, and for DeepFM the first MLP layer's partial products Pu, Pi);
+ * a (user, item) pair then costs K adds for the FM term and the SMALL layers of the MLP:
+ *   pw = 0.5((Su+Si)^2 - (Qu+Qi)),  lin = lu + li + lin_bias
+ *   FM     (fm.py:158-170):      out = lin + elu(<bn(pw), pw_kernel> + pw_bias)
+ *   DeepFM (deepfm.py:160-173):  h1 = relu(Pu[b] + Pi[n]); h2 = relu(h1 W2 + b2); deep = h2 W3 + b3
+ *                                (or deep = h1 W2 + b2 with two layers); out = <[lin, pw, deep], w_out> + b_out
+ * scores[b, n] for every b < B, n < N.  H1 <= 256, H2 <= 64, H3 <= 32; W2 [H1,H2], W3 [H2,H3] row-major. */
+int b200_fm_pair_scores(const float* Su, const float* Qu, const float* lu, int64_t B, const float* Si,
+                        const float* Qi, const float* li, int64_t N, int32_t K, float lin_bias,
+                        const float* bn_scale, const float* bn_shift, const float* pw_kernel,
+                        float pw_bias, float* scores, int64_t lds, void* stream);
+int b200_deepfm_pair_scores(const float* Su, const float* Qu, const float* lu, const float* Pu, int64_t B,
+                            const float* Si, const float* Qi, const float* li, const float* Pi,
+                            int64_t N, int32_t K, int32_t H1, int32_t H2, int32_t H3, float lin_bias,
+                            const float* W2, const float* b2, const float* W3, const float* b3,
+                            const float* w_out, float b_out, float* scores, int64_t lds, void* stream);
 
 /* Y = act(X Wt^T + b): tf_dense (libreco/layers/dense.py:52-80) with BN folded by the caller.
  * Wt is the TRANSPOSED kernel [dout, din]; fp32 SIMT (exact fma chain in k). */

@@ -44,6 +44,7 @@ struct Out {
   float* pw; int64_t ld_pw;           // [R, K]    FM pairwise term or null
   float* lin;                         // [R]       Dense1(linear features) incl. bias, or null
   float* fm_out;                      // [R]       full FM logit, or null
+  float* ssum; float* sqsum; int64_t ld_s;   // [R, K] sum_f e and sum_f e^2 (hoisted all-items scoring), or null
 };
 
 struct Head {           // weights of the heads that can be fused here
@@ -161,6 +162,7 @@ feat_forward_kernel(const b200_feat_layout L, const b200_feat_tables T, const in
     if (t < Tn && k < K) {
       const float pw = 0.5f * (s[t] * s[t] - s2[t]);
       if (o.pw) o.pw[r * o.ld_pw + k] = pw;
+      if (o.ssum) { o.ssum[r * o.ld_s + k] = s[t]; o.sqsum[r * o.ld_s + k] = s2[t]; }
       if (o.fm_out) {
         const float z = h.bn_scale ? fmaf(pw, h.bn_scale[k], h.bn_shift[k]) : pw;
         head_acc = fmaf(z, h.pw_kernel[k], head_acc);
@@ -251,7 +253,7 @@ feat_forward_lanefield_kernel(const b200_feat_layout L, const b200_feat_tables T
       }
     }
   }
-  if (!o.pw && !o.fm_out && !o.lin) return;
+  if (!o.pw && !o.fm_out && !o.lin && !o.ssum) return;
   // one reduction over the 32 lanes (= over the fields) per row
   float head_acc = 0.f;
 #pragma unroll
@@ -265,6 +267,7 @@ feat_forward_lanefield_kernel(const b200_feat_layout L, const b200_feat_tables T
       const float pw = 0.5f * (a * a - b);
       const int k = q * 4 + c;
       if (o.pw && lane == 0) o.pw[r * o.ld_pw + k] = pw;
+      if (o.ssum && lane == 0) { o.ssum[r * o.ld_s + k] = a; o.sqsum[r * o.ld_s + k] = b; }
       if (o.fm_out) {
         const float z = h.bn_scale ? fmaf(pw, h.bn_scale[k], h.bn_shift[k]) : pw;
         head_acc = fmaf(z, h.pw_kernel[k], head_acc);
@@ -380,7 +383,8 @@ extern "C" int b200_feat_forward(const b200_feat_layout* L, const b200_feat_tabl
                                  int64_t grid_items, int64_t row_offset, float* concat, int64_t ld_concat, float* pw,
                                  int64_t ld_pw, float* lin, float* fm_out, const float* lin_kernel,
                                  float lin_bias, const float* bn_scale, const float* bn_shift,
-                                 const float* pw_kernel, float pw_bias, void* stream) {
+                                 const float* pw_kernel, float pw_bias, float* ssum, float* sqsum,
+                                 int64_t ld_s, void* stream) {
   B200_REQUIRE(L && T && users, "b200_feat_forward: null pointer");
   B200_REQUIRE(grid_items > 0 || items, "b200_feat_forward: item ids missing");
   B200_REQUIRE(L->embed_size >= 1 && L->embed_size <= 32 * MAX_T, "embed size %d outside [1, %d]",
@@ -393,6 +397,8 @@ extern "C" int b200_feat_forward(const b200_feat_layout* L, const b200_feat_tabl
   while (lpr < L->embed_size && lpr < 32) lpr <<= 1;
   const int Tn = (L->embed_size + lpr - 1) / lpr;
   Out o; o.concat = concat; o.ld_concat = ld_concat; o.pw = pw; o.ld_pw = ld_pw; o.lin = lin; o.fm_out = fm_out;
+  o.ssum = ssum; o.sqsum = sqsum; o.ld_s = ld_s;
+  B200_REQUIRE((ssum == nullptr) == (sqsum == nullptr), "b200_feat_forward: ssum and sqsum go together");
   Head h; h.lin_kernel = lin_kernel; h.lin_bias = lin_bias; h.bn_scale = bn_scale; h.bn_shift = bn_shift;
   h.pw_kernel = pw_kernel; h.pw_bias = pw_bias;
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };

@@ -185,6 +185,43 @@ class _FeatModelBase:
     def _forward(self, layout, users_d, items_d, R, grid_items):
         raise NotImplementedError
 
+    # -- hoisted all-items scoring: one-sided partial sums -----------------------
+    def _side(self, which):
+        """(layout restricted to the fields of one side, their positions in the global field order)."""
+        cache = self.__dict__.setdefault("_side_cache", {})
+        if which not in cache:
+            sp = self.spec
+            L = FeatLayoutStruct.from_buffer_copy(sp.layout)
+            L.id_mask = 1 if which == "user" else 2
+            scols = sp.user_sparse_cols if which == "user" else sp.item_sparse_cols
+            dcols = sp.user_dense_cols if which == "user" else sp.item_dense_cols
+            L.n_sparse, L.n_dense = len(scols), len(dcols)
+            for f in range(len(scols)):
+                L.sparse_side[f], L.sparse_col[f] = (0 if which == "user" else 1), f
+            for f in range(len(dcols)):
+                L.dense_side[f], L.dense_col[f] = (0 if which == "user" else 1), f
+                L.dense_embed_row[f] = dcols[f]
+            pos = [0 if which == "user" else 1] + [2 + c for c in scols] + [2 + sp.n_sparse + c for c in dcols]
+            cache[which] = (L, pos)
+        return cache[which]
+
+    def _side_partials(self, which, ids_d, want_concat):
+        """S = sum_f e, Q = sum_f e^2, linear partial (no bias) and optionally the concatenated
+        embeddings of ONE side for the given ids."""
+        torch = self._torch
+        L, pos = self._side(which)
+        n = int(ids_d.numel())
+        S = torch.empty((n, self.K), dtype=torch.float32, device=self.device)
+        Q = torch.empty((n, self.K), dtype=torch.float32, device=self.device)
+        lin = torch.empty(n, dtype=torch.float32, device=self.device)
+        concat = torch.empty((n, len(pos) * self.K), dtype=torch.float32, device=self.device) if want_concat else None
+        lk = self.__dict__.setdefault("_side_lin", {})
+        if which not in lk:
+            lk[which] = self.lin_kernel[torch.as_tensor(pos, device=self.device)].contiguous()
+        self._feat_forward(L, ids_d, ids_d, n, 0, concat=concat, lin=lin, ssum=S, sqsum=Q,
+                           lin_kernel=lk[which], lin_bias=0.0)
+        return S, Q, lin, concat
+
     # -- public ------------------------------------------------------------------------------------
     def logits(self, users, items, sparse_rows=None, dense_rows=None):
         torch = self._torch
@@ -218,8 +255,8 @@ class _FeatModelBase:
             raise ValueError(f"`n_rec` {n_rec} exceeds num of items {self.n_items}")
         uid = torch.as_tensor(np.asarray(user_ids, dtype=np.int64)).to(self.device)
         B = uid.numel()
-        if rows_per_chunk is None:
-            rows_per_chunk = max(1, min(B, self.max_grid_rows() // max(self.n_items, 1)))
+        if rows_per_chunk is None:   # users per chunk: bound the [users, n_items] score matrix to ~1 GiB
+            rows_per_chunk = max(1, min(B, (1 << 28) // max(self.n_items, 1)))
         out_ids = torch.empty((B, n_rec), dtype=torch.int64, device=self.device)
         out_sc = torch.empty((B, n_rec), dtype=torch.float32, device=self.device)
         lib, stream = _lib.lib, _lib.current_stream()
@@ -248,16 +285,18 @@ class _FeatModelBase:
 
     # -- helpers -----------------------------------------------------------------------------------
     def _feat_forward(self, layout, users_d, items_d, R, grid_items, concat=None, pw=None, lin=None,
-                      fm_out=None, head=None, row_offset=0):
+                      fm_out=None, head=None, row_offset=0, ssum=None, sqsum=None, lin_kernel=None, lin_bias=None):
         head = head or {}
+        lk = lin_kernel if lin_kernel is not None else (self.lin_kernel if self.needs_linear else None)
+        lb = lin_bias if lin_bias is not None else (self.lin_bias if self.needs_linear else 0.0)
         _lib.check(_lib.lib.b200_feat_forward(
             ctypes.byref(layout), ctypes.byref(self.tables), _lib.ptr(users_d), _lib.ptr(items_d), R,
             grid_items, row_offset, _lib.ptr(concat), concat.stride(0) if concat is not None else 0,
             _lib.ptr(pw), pw.stride(0) if pw is not None else 0, _lib.ptr(lin), _lib.ptr(fm_out),
-            _lib.ptr(self.lin_kernel) if self.needs_linear else None,
-            self.lin_bias if self.needs_linear else 0.0,
+            _lib.ptr(lk), float(lb),
             _lib.ptr(head.get("bn_scale")), _lib.ptr(head.get("bn_shift")), _lib.ptr(head.get("pw_kernel")),
-            float(head.get("pw_bias", 0.0)), _lib.current_stream()))
+            float(head.get("pw_bias", 0.0)), _lib.ptr(ssum), _lib.ptr(sqsum),
+            ssum.stride(0) if ssum is not None else 0, _lib.current_stream()))
 
     def _mlp(self, x, layers):
         torch = self._torch
@@ -291,6 +330,25 @@ class FM(_FeatModelBase):
         out = self._torch.empty(R, dtype=self._torch.float32, device=self.device)
         self._feat_forward(layout, users_d, items_d, R, grid_items, fm_out=out, head=self.head)
         return out
+
+    def score_all_items(self, user_ids_d):
+        """Hoisted: item-side sums once per model, user-side sums once per call, K adds per pair."""
+        torch = self._torch
+        if self.K > 64:
+            return super().score_all_items(user_ids_d)
+        if "_item_side" not in self.__dict__:
+            ids = torch.arange(self.n_items, device=self.device)
+            self._item_side = self._side_partials("item", ids, False)[:3]
+        Si, Qi, li = self._item_side
+        Su, Qu, lu, _ = self._side_partials("user", user_ids_d, False)
+        b = int(user_ids_d.numel())
+        scores = torch.empty((b, self.n_items), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.b200_fm_pair_scores(
+            _lib.ptr(Su), _lib.ptr(Qu), _lib.ptr(lu), b, _lib.ptr(Si), _lib.ptr(Qi), _lib.ptr(li), self.n_items,
+            self.K, self.lin_bias, _lib.ptr(self.head["bn_scale"]), _lib.ptr(self.head["bn_shift"]),
+            _lib.ptr(self.head["pw_kernel"]), self.head["pw_bias"], _lib.ptr(scores), scores.stride(0),
+            _lib.current_stream()))
+        return scores
 
     def max_grid_rows(self):
         return 1 << 28
@@ -330,8 +388,54 @@ class DeepFM(_FeatModelBase):
                 _lib.current_stream()))
         return out
 
+    def _hoistable(self):
+        n = len(self.mlp)
+        dims = [w.shape[0] for w, _, _ in self.mlp]
+        return self.K <= 64 and n in (2, 3) and dims[0] <= 256 and dims[1] <= 64 and (n == 2 or dims[2] <= 32)
+
+    def _first_layer_partial(self, which, concat, with_bias):
+        torch = self._torch
+        cache = self.__dict__.setdefault("_w1_side", {})
+        if which not in cache:
+            _, pos = self._side(which)
+            cols = torch.cat([torch.arange(g * self.K, (g + 1) * self.K, device=self.device) for g in pos])
+            cache[which] = self.mlp[0][0][:, cols].contiguous()          # Wt [H1, F_side*K], BN already folded
+        Wt = cache[which]
+        out = torch.empty((concat.shape[0], Wt.shape[0]), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.b200_linear_f32(_lib.ptr(concat), concat.stride(0), concat.shape[0], _lib.ptr(Wt),
+                                            Wt.stride(0), _lib.ptr(self.mlp[0][1]) if with_bias else None,
+                                            Wt.shape[1], Wt.shape[0], 0, _lib.ptr(out), out.stride(0),
+                                            _lib.current_stream()))
+        return out
+
+    def score_all_items(self, user_ids_d):
+        """Hoisted: first-layer partial products per side, only the small layers per (user, item)."""
+        torch = self._torch
+        if not self._hoistable():
+            return super().score_all_items(user_ids_d)
+        if "_item_side" not in self.__dict__:
+            ids = torch.arange(self.n_items, device=self.device)
+            Si, Qi, li, ci = self._side_partials("item", ids, True)
+            self._item_side = (Si, Qi, li, self._first_layer_partial("item", ci, False))
+        Si, Qi, li, Pi = self._item_side
+        Su, Qu, lu, cu = self._side_partials("user", user_ids_d, True)
+        Pu = self._first_layer_partial("user", cu, True)
+        W2t, b2, _ = self.mlp[1]
+        three = len(self.mlp) == 3
+        if "_tail" not in self.__dict__:
+            self._tail = (W2t.t().contiguous(), self.mlp[2][0].t().contiguous() if three else None)
+        W2, W3 = self._tail
+        b = int(user_ids_d.numel())
+        scores = torch.empty((b, self.n_items), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.b200_deepfm_pair_scores(
+            _lib.ptr(Su), _lib.ptr(Qu), _lib.ptr(lu), _lib.ptr(Pu), b, _lib.ptr(Si), _lib.ptr(Qi), _lib.ptr(li),
+            _lib.ptr(Pi), self.n_items, self.K, Pu.shape[1], W2.shape[1], W3.shape[1] if three else 0,
+            self.lin_bias, _lib.ptr(W2), _lib.ptr(b2), _lib.ptr(W3), _lib.ptr(self.mlp[2][1]) if three else None,
+            _lib.ptr(self.out_kernel), self.out_bias, _lib.ptr(scores), scores.stride(0), _lib.current_stream()))
+        return scores
+
     def max_grid_rows(self):
-        # deep input bytes per row = F*K*4; keep a chunk under ~1 GiB and a whole number of users
+        # deep input bytes per row = F*K*4; keep a chunk under ~1 GiB
         return max(1, (1 << 30) // (self.F * self.K * 4))
 
 
@@ -520,7 +624,7 @@ class TwoTower:
         _lib.check(_lib.lib.b200_feat_forward(
             ctypes.byref(L), ctypes.byref(self.tables), _lib.ptr(ids_d), _lib.ptr(ids_d), n, 0, 0,
             _lib.ptr(x), x.stride(0), None, 0, None, None, None, 0.0, None, None, None, 0.0,
-            _lib.current_stream()))
+            None, None, 0, _lib.current_stream()))
         for Wt, b, relu in self.mlps[which]:
             y = torch.empty((n, Wt.shape[0]), dtype=torch.float32, device=self.device)
             _lib.check(_lib.lib.b200_linear_f32(_lib.ptr(x), x.stride(0), n, _lib.ptr(Wt), Wt.stride(0), _lib.ptr(b),

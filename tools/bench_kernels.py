@@ -139,6 +139,14 @@ def bench_feat():
     emit("feat_forward FM fused head (no intermediate)", ms, read + R * 4, {"rows": R})
     ms = timeit(lambda: model.logits(users[:1 << 18].cpu().numpy(), items[:1 << 18].cpu().numpy()), iters=3)
     print(json.dumps({"kernel": "DeepFM predict rows/s (gather + fp32 MLP 1792-128-64-32)", "rows_per_s": (1 << 18) / (ms * 1e-3)}))
+    # all-items scoring + top-100 (recommend_user of the TfBase models), hoisted kernels
+    uids = rng.integers(0, 1_000_000, 256)
+    for nm, mdl in (("FM", fm), ("DeepFM", model)):
+        mdl.recommend(uids[:8], 100, False)
+        ms_r = timeit(lambda: mdl.recommend(uids, 100, False), iters=3, warm=1)
+        print(json.dumps({"kernel": f"{nm} recommend_user all-items top-100 (N=100k items, 256 users/call, hoisted)",
+                          "ms": ms_r, "users_per_s": len(uids) / (ms_r * 1e-3),
+                          "pairs_per_s": len(uids) * 100_000 / (ms_r * 1e-3)}), flush=True)
     # CPU side: numpy restatement of the DeepFM graph (oracle port) on a bounded sample
     nu = 1 << 15
     uh, ih = users[:nu].cpu().numpy(), items[:nu].cpu().numpy()
