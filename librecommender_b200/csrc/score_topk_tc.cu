@@ -552,50 +552,66 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------
-// guess kernel: speculative threshold = pre_k-th largest sampled block maximum of the row
+// guess kernel: speculative threshold = pre_k-th largest sampled block maximum of the row.
+// One CTA per 32 consecutive rows: lane = row, the 8 warps stride the block index, so every load
+// of blockmax[i][row0..row0+31] is one coalesced 128-byte request; per-row 4 x 8-bit radix select
+// on shared-memory histograms.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int GUESS_THREADS = 256;
+__global__ void __launch_bounds__(GUESS_THREADS)
 guess_kernel(const float* __restrict__ blockmax, int n_vals /* lists * n_pre_tiles */, int B_pad,
              const RowMeta* __restrict__ meta, uint32_t* __restrict__ row_tau_key,
              uint32_t* __restrict__ guess_key) {
-  __shared__ uint32_t hist[256];
-  __shared__ uint32_t s_prefix, s_krem, s_found;
-  const int tid = threadIdx.x;
-  const int row = blockIdx.x;
+  __shared__ uint32_t hist[32][256 + 1];      // +1: rows land in different banks
+  __shared__ uint32_t s_prefix[32], s_krem[32], s_ok[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int row = blockIdx.x * 32 + lane;
   const RowMeta m = meta[row];
-  uint32_t prefix = 0, krem = (uint32_t)m.pre_k;
-  bool ok = m.active != 0;
-  for (int pass = 0; pass < 4 && ok; ++pass) {
+  if (wid == 0) { s_prefix[lane] = 0; s_krem[lane] = (uint32_t)m.pre_k; s_ok[lane] = m.active != 0; }
+  for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
-    for (int b = tid; b < 256; b += 128) hist[b] = 0;
+    for (int i = threadIdx.x; i < 32 * 257; i += GUESS_THREADS) (&hist[0][0])[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n_vals; i += 128) {
+    const uint32_t prefix = s_prefix[lane];
+    for (int i = wid; i < n_vals; i += GUESS_THREADS / 32) {
       const float v = blockmax[(int64_t)i * B_pad + row];
       const uint32_t key = float_to_key(v);
       if (v > -3.0e38f && (pass == 0 || (key >> (shift + 8)) == prefix))
-        atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        atomicAdd(&hist[lane][(key >> shift) & 255u], 1u);
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t c = 0;
-      int b = 255;
-      bool found = false;
-      for (; b >= 0; --b) {
-        if (c + hist[b] >= krem) { found = true; break; }
-        c += hist[b];
+    // digit resolution: warp w resolves rows w, w+8, w+16, w+24; lane l owns bins [8l, 8l+8)
+    for (int rr = wid; rr < 32; rr += GUESS_THREADS / 32) {
+      uint32_t mine[8], tot = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { mine[b] = hist[rr][lane * 8 + b]; tot += mine[b]; }
+      uint32_t incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += t;
       }
-      s_found = found;
-      s_prefix = (prefix << 8) | (uint32_t)(b < 0 ? 0 : b);
-      s_krem = krem - c;
+      const uint32_t excl = incl - tot;
+      const uint32_t krem = s_krem[rr];
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 0);
+      if (excl < krem && krem <= incl) {
+        uint32_t c = excl;
+#pragma unroll
+        for (int b = 7; b >= 0; --b) {
+          if (c + mine[b] >= krem) {
+            s_prefix[rr] = (s_prefix[rr] << 8) | (uint32_t)(lane * 8 + b);
+            s_krem[rr] = krem - c;
+            break;
+          }
+          c += mine[b];
+        }
+      }
+      if (lane == 0 && total < krem) s_ok[rr] = 0;   // fewer than pre_k sampled blocks: no speculation
     }
-    __syncthreads();
-    ok = s_found != 0;
-    prefix = s_prefix;
-    krem = s_krem;
     __syncthreads();
   }
-  if (tid == 0) {
-    const uint32_t key = ok ? prefix : 0u;   // 0 = no speculation for this row
+  if (wid == 0) {
+    const uint32_t key = s_ok[lane] ? s_prefix[lane] : 0u;   // 0 = no speculation for this row
     row_tau_key[row] = key;
     guess_key[row] = key;
   }
@@ -1067,7 +1083,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   if (ev_sweep_start) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_start, stream));
   if (pl.use_pre) {
     sweep_kernel<true><<<grid, SWEEP_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, sp);
-    guess_kernel<<<(unsigned)pl.B_pad, 128, 0, stream>>>(bm, LPS * pl.n_splits * pl.n_pre_tiles, pl.B_pad,
+    guess_kernel<<<(unsigned)(pl.B_pad / 32), GUESS_THREADS, 0, stream>>>(bm, LPS * pl.n_splits * pl.n_pre_tiles, pl.B_pad,
                                                           meta, tau, guess);
     count_launch(2);
   } else {

@@ -167,22 +167,24 @@ class EmbedScorer:
             self._ws = ws
         return ws
 
+    def recommend_device_async(self, user_ids_d, n_rec, filter_consumed=True, return_scores=False,
+                               path="auto"):
+        """Enqueue one recommend call on the current stream and return a handle WITHOUT synchronising;
+        ``handle.result()`` performs the (rare) exact-path repair of rows the fused path flagged and
+        returns the device tensors.  Lets a server keep the next batch in flight while the previous
+        one is checked."""
+        n_rec = int(n_rec)
+        if path == "exact" or (path == "auto" and not self.fused_ok(n_rec)):
+            return _Pending(self, user_ids_d, n_rec, filter_consumed, return_scores,
+                            self.recommend_exact(user_ids_d, n_rec, filter_consumed, return_scores), None)
+        ids, scores, status = self.recommend_fused(user_ids_d, n_rec, filter_consumed, return_scores)
+        return _Pending(self, user_ids_d, n_rec, filter_consumed, return_scores,
+                        (ids, scores) if return_scores else ids, status)
+
     def recommend_device(self, user_ids_d, n_rec, filter_consumed=True, return_scores=False,
                          path="auto"):
         """Device ids in, device results out; flagged rows are re-run on the exact path."""
-        torch = self._torch
-        n_rec = int(n_rec)
-        if path == "exact" or (path == "auto" and not self.fused_ok(n_rec)):
-            return self.recommend_exact(user_ids_d, n_rec, filter_consumed, return_scores)
-        ids, scores, status = self.recommend_fused(user_ids_d, n_rec, filter_consumed, return_scores)
-        bad = torch.nonzero(status).flatten()          # one sync; empty in the common case
-        if bad.numel():
-            res = self.recommend_exact(user_ids_d[bad], n_rec, filter_consumed, return_scores)
-            if return_scores:
-                ids[bad], scores[bad] = res[0], res[1]
-            else:
-                ids[bad] = res
-        return (ids, scores) if return_scores else ids
+        return self.recommend_device_async(user_ids_d, n_rec, filter_consumed, return_scores, path).result()
 
     def score_rows(self, user_ids_d):
         """Materialised exact fp32 scores [B, n_items] (used by the random_rec branch)."""
@@ -259,6 +261,29 @@ class EmbedScorer:
             _lib.ptr(self.U), self.U.stride(0), _lib.ptr(u), _lib.ptr(self.I), self.I.stride(0),
             _lib.ptr(i), u.numel(), self.d, mode, lo, hi, _lib.ptr(out), _lib.current_stream()))
         return out.cpu().numpy()
+
+
+class _Pending:
+    """Result handle of :meth:`EmbedScorer.recommend_device_async`."""
+
+    def __init__(self, scorer, uid_d, n_rec, filter_consumed, return_scores, res, status):
+        self.scorer, self.uid_d, self.n_rec = scorer, uid_d, n_rec
+        self.filter_consumed, self.return_scores = filter_consumed, return_scores
+        self.res, self.status = res, status
+
+    def result(self):
+        if self.status is not None:
+            torch = self.scorer._torch
+            bad = torch.nonzero(self.status).flatten()          # the only synchronisation
+            if bad.numel():
+                fix = self.scorer.recommend_exact(self.uid_d[bad], self.n_rec, self.filter_consumed,
+                                                  self.return_scores)
+                if self.return_scores:
+                    self.res[0][bad], self.res[1][bad] = fix[0], fix[1]
+                else:
+                    self.res[bad] = fix
+            self.status = None
+        return self.res
 
 
 # ---- cache of scorers keyed by the identity of the host arrays --------------------------------
