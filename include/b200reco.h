@@ -176,6 +176,14 @@ int b200_linear_f32(const float* X, int64_t ldx, int64_t R, const float* Wt, int
                     const float* bias, int32_t din, int32_t dout, int32_t relu, float* Y,
                     int64_t ldy, void* stream);
 
+/* Same contract as b200_linear_f32 on the tcgen05 tensor cores: operands split x = hi + lo into
+ * two tf32 values, three kind::tf32 products (hi*hi + lo*hi + hi*lo) in separate main / correction
+ * TMEM accumulators promoted to registers every 64 k: fp32-level accuracy, not tf32-level.
+ * Requires 16-byte aligned rows (ldx, ldw multiples of 4); callers use b200_linear_f32 otherwise. */
+int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
+                       const float* bias, int32_t din, int32_t dout, int32_t relu, float* Y,
+                       int64_t ldy, void* stream);
+
 /* out[r] = bias + <[a[r,:na], b[r,:nb], c[r,:nc]], w>: Dense(1) on a concatenation
  * (deepfm.py:172-173; the final Dense(1) of DIN / YouTubeRanking). */
 int b200_concat_dense(const float* a, int64_t lda, int32_t na, const float* b, int64_t ldb, int32_t nb,

@@ -47,6 +47,7 @@ SIGNATURES = {
     "b200_deepfm_pair_scores": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int32, c_int32, c_int32,
                                         c_int32, c_float, _P, _P, _P, _P, _P, c_float, _P, c_int64, _P]),
     "b200_linear_f32": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, c_int32, c_int32, c_int32, _P, c_int64, _P]),
+    "b200_linear_tf32x3": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, c_int32, c_int32, c_int32, _P, c_int64, _P]),
     "b200_concat_dense": (c_int, [_P, c_int64, c_int32, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, c_float,
                                   c_int64, _P, _P]),
     "b200_l2_normalize_rows": (c_int, [_P, c_int64, c_int64, c_int32, _P]),

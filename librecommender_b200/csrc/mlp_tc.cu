@@ -1,0 +1,355 @@
+// Dense layer on the 5th-generation tensor cores with fp32-level accuracy: Y = act(X Wt^T + b).
+//
+// Replaces tf_dense (reference libreco/layers/dense.py:52-80, BN folded by the caller) for the MLP
+// tails of DeepFM / DIN / YouTubeRanking / TwoTower when the layer is large enough to be
+// compute-bound on the SIMT path (b200_linear_f32).  The reference computes these layers in fp32
+// (TensorFlow MatMul); a plain tf32 or bf16 tensor-core GEMM would miss the 1e-5 parity bar, so
+// the operands are split  x = hi + lo  (hi = top 11 mantissa bits, lo = next 11) and three
+// tcgen05.mma kind::tf32 products are accumulated:  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term
+// is < 2^-22 |x||w|).  The tensor core truncates its fp32 accumulator once per MMA (measured: a
+// single accumulator over 48 MMAs drifts by ~2e-6 of sum|x w|), so (a) the dominant hi*hi products
+// and the 2^-11-times smaller cross products go to SEPARATE TMEM accumulators, and (b) both are
+// promoted to registers (round-to-nearest adds) every GC k-chunks = GC*4 MMAs per accumulator.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer: X tile [128 x 32 fp32] and Wt tile [n_pad x 32 fp32] per k-chunk
+//   warp 1      MMA issuer (one elected lane)
+//   warps 2-5   splitters: rewrite the landed tiles in place to `hi` and write the `lo` tiles
+//   warps 6-9   epilogue: TMEM -> registers (+=), then bias / ReLU / store at the end of a row tile
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+#include "../../include/b200reco.h"
+
+namespace b200 {
+namespace mlp {
+
+constexpr int TM = 128;          // rows per tile (UMMA M)
+constexpr int KC = 32;           // fp32 per k-chunk = one 128-byte swizzled row
+constexpr int GC = 2;            // k-chunks per accumulator group (promotion interval = 64 k)
+constexpr int NMAX = 128;        // output columns per CTA (grid.y covers wider layers)
+constexpr int MAXSTAGE = 4;
+constexpr int THREADS = 320;
+constexpr int A_BYTES = TM * KC * 4;   // 16 KB
+
+struct Params {
+  int64_t R;
+  int64_t ldy;
+  const float* bias;
+  float* Y;
+  int din, dout, n_pad, relu;
+  int n_tiles, n_chunks, nstage;
+};
+
+struct Smem {
+  uint64_t full[MAXSTAGE], split[MAXSTAGE], empty[MAXSTAGE];
+  uint64_t tmem_full[2], tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  // D = f32 (1 @ bit 4), A = B = tf32 (2 @ bits 7, 10), both K-major, dense
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// x -> (hi, lo): hi keeps the 10 explicit mantissa bits of tf32, lo = x - hi truncated the same
+// way, so whatever conversion the tensor core applies to its 32-bit containers is the identity
+__device__ __forceinline__ void split4(float4& v, float4& lo) {
+  const uint32_t M = 0xffffe000u;
+  float h;
+  h = __uint_as_float(__float_as_uint(v.x) & M); lo.x = __uint_as_float(__float_as_uint(v.x - h) & M); v.x = h;
+  h = __uint_as_float(__float_as_uint(v.y) & M); lo.y = __uint_as_float(__float_as_uint(v.y - h) & M); v.y = h;
+  h = __uint_as_float(__float_as_uint(v.z) & M); lo.z = __uint_as_float(__float_as_uint(v.z - h) & M); v.z = h;
+  h = __uint_as_float(__float_as_uint(v.w) & M); lo.w = __uint_as_float(__float_as_uint(v.w - h) & M); v.w = h;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                     const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = p.n_pad * KC * 4;
+  const int stage_bytes = 2 * A_BYTES + 2 * b_bytes;
+  Smem* ss = (Smem*)(smem + (size_t)p.nstage * stage_bytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int col0 = blockIdx.y * NMAX;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstage; ++s) {
+      ptx::mbar_init(&ss->full[s], 1);
+      ptx::mbar_init(&ss->split[s], 4);
+      ptx::mbar_init(&ss->empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&ss->tmem_full[a], 1);
+      ptx::mbar_init(&ss->tmem_empty[a], 4);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tensormap(&tmX);
+    ptx::prefetch_tensormap(&tmW);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(&ss->tmem_base, 4 * NMAX);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ss->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < p.n_chunks; ++kc) {
+          ptx::mbar_wait(&ss->empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&ss->full[stage], (uint32_t)(A_BYTES + b_bytes));
+          uint8_t* st = smem + (size_t)stage * stage_bytes;
+          ptx::tma_load_2d(st, &tmX, &ss->full[stage], kc * KC, tile * TM);
+          ptx::tma_load_2d(st + 2 * A_BYTES, &tmW, &ss->full[stage], kc * KC, col0);
+          if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_tf32(TM, p.n_pad);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t s_addr = ptx::smem_u32(smem);
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < p.n_chunks; ++kc) {
+          const int gpos = kc % GC;
+          if (gpos == 0) {   // new accumulator group
+            ptx::mbar_wait(&ss->tmem_empty[acc], acc_phase ^ 1);
+            ptx::tc_fence_after();
+          }
+          ptx::mbar_wait(&ss->split[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t st = s_addr + (uint32_t)(stage * stage_bytes);
+          const uint64_t a_hi = ptx::umma_desc_sw128_kmajor(st);
+          const uint64_t a_lo = ptx::umma_desc_sw128_kmajor(st + A_BYTES);
+          const uint64_t b_hi = ptx::umma_desc_sw128_kmajor(st + 2 * A_BYTES);
+          const uint64_t b_lo = ptx::umma_desc_sw128_kmajor(st + 2 * A_BYTES + b_bytes);
+          const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * NMAX);   // hi*hi
+          const uint32_t d_corr = d_main + NMAX;                            // lo*hi + hi*lo
+#pragma unroll
+          for (int k4 = 0; k4 < KC / 8; ++k4) {
+            // 8 tf32 = 32 bytes per MMA inside the 128-byte swizzled row: +2 in the >>4 field
+            const uint64_t o = (uint64_t)(k4 * 2);
+            const uint32_t cont = (uint32_t)((gpos | k4) != 0);
+            umma_tf32(d_main, a_hi + o, b_hi + o, idesc, cont);
+            umma_tf32(d_corr, a_lo + o, b_hi + o, idesc, cont);
+            umma_tf32(d_corr, a_hi + o, b_lo + o, idesc, 1u);
+          }
+          ptx::umma_commit(&ss->empty[stage]);
+          if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+          if (gpos == GC - 1 || kc == p.n_chunks - 1) {
+            ptx::umma_commit(&ss->tmem_full[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== splitters =====================
+    const int t = threadIdx.x - 64;          // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    const int b_vec = b_bytes / 16;          // float4 per B tile
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < p.n_chunks; ++kc) {
+        ptx::mbar_wait(&ss->full[stage], phase);
+        uint8_t* st = smem + (size_t)stage * stage_bytes;
+        float4* ah = (float4*)st;
+        float4* al = (float4*)(st + A_BYTES);
+#pragma unroll
+        for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
+          float4 v = ah[t + j * 128], lo;
+          split4(v, lo);
+          ah[t + j * 128] = v;
+          al[t + j * 128] = lo;
+        }
+        float4* bh = (float4*)(st + 2 * A_BYTES);
+        float4* bl = (float4*)(st + 2 * A_BYTES + b_bytes);
+        for (int j = t; j < b_vec; j += 128) {
+          float4 v = bh[j], lo;
+          split4(v, lo);
+          bh[j] = v;
+          bl[j] = lo;
+        }
+        ptx::fence_proxy_async_smem();       // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ss->split[stage]);
+        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int n_groups = (p.n_chunks + GC - 1) / GC;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      float y[NMAX];
+#pragma unroll
+      for (int i = 0; i < NMAX; ++i) y[i] = 0.f;
+      for (int g = 0; g < n_groups; ++g) {
+        ptx::mbar_wait(&ss->tmem_full[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * NMAX);
+#pragma unroll
+        for (int c = 0; c < NMAX / 32; ++c) {
+          if (c * 32 < p.n_pad) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(NMAX + c * 32), r);     // correction first
+            ptx::tmem_ld_wait_regs(r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[c * 32 + i] += __uint_as_float(r[i]);
+            ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(c * 32), r);
+            ptx::tmem_ld_wait_regs(r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[c * 32 + i] += __uint_as_float(r[i]);
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      const int64_t row = (int64_t)tile * TM + q * 32 + lane;
+      if (row < p.R) {
+        float* yr = p.Y + row * p.ldy + col0;
+        const int ncol = min(p.dout - col0, NMAX);
+        const bool vec = ((p.ldy & 3) == 0) && ((((uintptr_t)p.Y) & 15) == 0);
+#pragma unroll
+        for (int c4 = 0; c4 < NMAX / 4; ++c4) {
+          if (c4 * 4 < ncol) {
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = c4 * 4 + i;
+              float v = y[c] + ((c < ncol && p.bias) ? __ldg(p.bias + col0 + c) : 0.f);
+              o[i] = p.relu ? fmaxf(v, 0.f) : v;
+            }
+            if (vec && c4 * 4 + 3 < ncol) {
+              *(float4*)(yr + c4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                if (c4 * 4 + i < ncol) yr[c4 * 4 + i] = o[i];
+            }
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 4 * NMAX);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+// fp32 [rows, cols] row-major with leading dimension ld; box = [KC, box_rows], SWIZZLE_128B;
+// out-of-range elements (k >= cols, row >= rows) read as zero
+static int make_tmap_f32(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld,
+                         int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  B200_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)KC, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+}  // namespace mlp
+}  // namespace b200
+
+extern "C" int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
+                                  const float* bias, int32_t din, int32_t dout, int32_t relu, float* Y,
+                                  int64_t ldy, void* stream) {
+  using namespace b200;
+  using namespace b200::mlp;
+  B200_REQUIRE(R >= 0 && din > 0 && dout > 0, "bad shape");
+  B200_REQUIRE((ldx & 3) == 0 && (ldw & 3) == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)Wt & 15) == 0,
+               "b200_linear_tf32x3 needs 16-byte aligned rows (ldx, ldw multiples of 4)");
+  B200_REQUIRE(ldx >= din && ldw >= din && ldy >= dout, "leading dimension too small");
+  if (R == 0) return 0;
+  Params p;
+  p.R = R;
+  p.ldy = ldy;
+  p.bias = bias;
+  p.Y = Y;
+  p.din = din;
+  p.dout = dout;
+  p.relu = relu;
+  p.n_pad = dout >= NMAX ? NMAX : (dout + 31) / 32 * 32;
+  p.n_tiles = (int)((R + TM - 1) / TM);
+  p.n_chunks = (din + KC - 1) / KC;
+  const int stage_bytes = 2 * A_BYTES + 2 * p.n_pad * KC * 4;
+  p.nstage = min(MAXSTAGE, (200 * 1024) / stage_bytes);
+  const size_t smem = (size_t)p.nstage * stage_bytes + sizeof(Smem) + 1024;
+
+  CUtensorMap tmX, tmW;
+  if (make_tmap_f32(&tmX, X, R, din, ldx, TM)) return 1;
+  if (make_tmap_f32(&tmW, Wt, dout, din, ldw, p.n_pad)) return 1;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      220 * 1024));
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int gy = (dout + NMAX - 1) / NMAX;
+  const int gx = max(1, min(p.n_tiles, sms / gy));
+  linear_tf32x3_kernel<<<dim3(gx, gy), THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, p);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}

@@ -59,6 +59,29 @@ def _dev(x, device, dtype):
     return torch.as_tensor(np.ascontiguousarray(x)).to(device=device, dtype=dtype).contiguous()
 
 
+# Dense-layer kernel selection: "auto" sends layers that are compute-bound on the SIMT kernel
+# (din >= TC_MIN_DIN, enough rows to fill the SMs) to the tcgen05 3xTF32 kernel; both are this
+# library's own CUDA kernels and both meet the 1e-5 bar.  "f32" / "tf32x3" force one (tests).
+LINEAR_IMPL = "auto"
+TC_MIN_DIN = 64
+TC_MIN_ROWS = 4096
+
+
+def linear(x, Wt, b, relu):
+    """tf_dense (libreco/layers/dense.py:52-80) with BN folded: act(x Wt^T + b), fp32 device tensors."""
+    import torch
+
+    R, din, dout = x.shape[0], Wt.shape[1], Wt.shape[0]
+    y = torch.empty((R, dout), dtype=torch.float32, device=x.device)
+    aligned = (x.stride(0) % 4 == 0 and Wt.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0
+               and Wt.data_ptr() % 16 == 0)
+    use_tc = LINEAR_IMPL == "tf32x3" or (LINEAR_IMPL == "auto" and din >= TC_MIN_DIN and R >= TC_MIN_ROWS)
+    fn = _lib.lib.b200_linear_tf32x3 if (use_tc and aligned) else _lib.lib.b200_linear_f32
+    _lib.check(fn(_lib.ptr(x), x.stride(0), R, _lib.ptr(Wt), Wt.stride(0), _lib.ptr(b) if b is not None else None,
+                  din, dout, 1 if relu else 0, _lib.ptr(y), y.stride(0), _lib.current_stream()))
+    return y
+
+
 def _side_cols(user_cols, item_cols):
     n = len(user_cols) + len(item_cols)
     side, col = [0] * n, [0] * n
@@ -301,11 +324,7 @@ class _FeatModelBase:
     def _mlp(self, x, layers):
         torch = self._torch
         for Wt, b, relu in layers:
-            y = torch.empty((x.shape[0], Wt.shape[0]), dtype=torch.float32, device=self.device)
-            _lib.check(_lib.lib.b200_linear_f32(_lib.ptr(x), x.stride(0), x.shape[0], _lib.ptr(Wt), Wt.stride(0),
-                                                _lib.ptr(b), Wt.shape[1], Wt.shape[0], 1 if relu else 0,
-                                                _lib.ptr(y), y.stride(0), _lib.current_stream()))
-            x = y
+            x = linear(x, Wt, b, relu)
         return x
 
     def _upload_mlp(self, mlp):
@@ -401,12 +420,7 @@ class DeepFM(_FeatModelBase):
             cols = torch.cat([torch.arange(g * self.K, (g + 1) * self.K, device=self.device) for g in pos])
             cache[which] = self.mlp[0][0][:, cols].contiguous()          # Wt [H1, F_side*K], BN already folded
         Wt = cache[which]
-        out = torch.empty((concat.shape[0], Wt.shape[0]), dtype=torch.float32, device=self.device)
-        _lib.check(_lib.lib.b200_linear_f32(_lib.ptr(concat), concat.stride(0), concat.shape[0], _lib.ptr(Wt),
-                                            Wt.stride(0), _lib.ptr(self.mlp[0][1]) if with_bias else None,
-                                            Wt.shape[1], Wt.shape[0], 0, _lib.ptr(out), out.stride(0),
-                                            _lib.current_stream()))
-        return out
+        return linear(concat, Wt, self.mlp[0][1] if with_bias else None, False)
 
     def score_all_items(self, user_ids_d):
         """Hoisted: first-layer partial products per side, only the small layers per (user, item)."""
@@ -626,11 +640,7 @@ class TwoTower:
             _lib.ptr(x), x.stride(0), None, 0, None, None, None, 0.0, None, None, None, 0.0,
             None, None, 0, _lib.current_stream()))
         for Wt, b, relu in self.mlps[which]:
-            y = torch.empty((n, Wt.shape[0]), dtype=torch.float32, device=self.device)
-            _lib.check(_lib.lib.b200_linear_f32(_lib.ptr(x), x.stride(0), n, _lib.ptr(Wt), Wt.stride(0), _lib.ptr(b),
-                                                Wt.shape[1], Wt.shape[0], 1 if relu else 0, _lib.ptr(y),
-                                                y.stride(0), _lib.current_stream()))
-            x = y
+            x = linear(x, Wt, b, relu)
         if self.norm_embed:
             _lib.check(_lib.lib.b200_l2_normalize_rows(_lib.ptr(x), x.stride(0), n, x.shape[1],
                                                        _lib.current_stream()))

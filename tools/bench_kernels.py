@@ -186,8 +186,37 @@ def bench_topk_and_sampler():
                       "negatives_per_s": (1 << 20) * 5 / cpu_s, "cores": 1, "kind": "reference-stream"}))
 
 
+def bench_linear():
+    """Dense layer: exact-fma SIMT kernel vs the tcgen05 3xTF32 kernel (fp32-level accuracy)."""
+    from librecommender_b200 import _lib
+
+    tc_peak = 1368.6
+    try:
+        tc_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]
+    except Exception:
+        pass
+    for R, din, dout in ((1 << 20, 1792, 128), (1 << 20, 128, 64), (1 << 18, 512, 256)):
+        x = torch.randn(R, din, device="cuda")
+        Wt = torch.randn(dout, din, device="cuda") / din ** 0.5
+        b = torch.randn(dout, device="cuda")
+        y = torch.empty(R, dout, device="cuda")
+        for name in ("b200_linear_f32", "b200_linear_tf32x3"):
+            fn = getattr(_lib.lib, name)
+            ms = timeit(lambda: _lib.check(fn(_lib.ptr(x), din, R, _lib.ptr(Wt), din, _lib.ptr(b), din, dout, 1,
+                                              _lib.ptr(y), dout, _lib.current_stream())), iters=5, warm=3)
+            flop = 2.0 * R * din * dout
+            byt = 4.0 * (R * din + R * dout + dout * din)
+            print(json.dumps({"kernel": f"{name} [{R} x {din}] -> {dout}", "ms": ms,
+                              "tflops_effective": flop / (ms * 1e-3) / 1e12,
+                              "tensor_tflops_issued": (3 * flop / (ms * 1e-3) / 1e12) if "tf32" in name else None,
+                              "tf32_dense_peak_tflops": tc_peak / 2, "achieved_gbs": byt / (ms * 1e-3) / 1e9,
+                              "peak_gbs": PEAK, "hbm_frac": byt / (ms * 1e-3) / 1e9 / PEAK}), flush=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["spmm", "feat", "topk"]
+    which = sys.argv[1:] or ["spmm", "feat", "topk", "linear"]
+    if "linear" in which:
+        bench_linear()
     if "spmm" in which:
         bench_spmm()
     if "feat" in which:
