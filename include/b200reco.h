@@ -184,6 +184,35 @@ int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, 
                        const float* bias, int32_t din, int32_t dout, int32_t relu, float* Y,
                        int64_t ldy, void* stream);
 
+/* ---- training losses: value + gradient w.r.t. the scores in one pass ------
+ * All reductions are two-stage and deterministic.  `workspace` >= b200_loss_workspace_bytes().
+ * `loss_out` is a device scalar.  Gradient outputs may be NULL. */
+size_t b200_loss_workspace_bytes(void);
+
+/* mean over n of: kind 0 sigmoid cross entropy (torchops/loss.py:5-6, tfops/loss.py:14-18),
+ * 1 focal (torchops/loss.py:10-19, tfops/loss.py:52-58), 2 squared error (tfops/loss.py:5-8).
+ * dlogits[i] = d loss / d logits[i]. */
+int b200_pointwise_loss(const float* logits, const float* labels, int64_t n, int32_t kind, float alpha,
+                        float gamma, float* loss_out, float* dlogits, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* kind 0 bpr = -mean log sigmoid(pos - neg) (torchops/loss.py:22-24), 1 max-margin
+ * mean relu(margin - (pos - neg)) (:27-30, tfops/loss.py:61-64): n_neg must be a multiple of n_pos,
+ * negatives of positive j are neg[j*f .. (j+1)*f) (compute_pair_scores, :63-90), dpos has n_pos entries.
+ * kind 2 / 3 = sigmoid CE / focal over [pos (label 1), neg (label 0)] (:33-60), mean or sum. */
+int b200_pairwise_loss(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg, int32_t kind,
+                       float margin, float alpha, float gamma, int32_t mean, float* loss_out, float* dpos,
+                       float* dneg, void* workspace, size_t workspace_bytes, void* stream);
+
+/* In-batch sampled softmax of the two-tower models (tfops/loss.py:67-71, TwoTower.adjust_logits
+ * algorithms/two_tower.py:458-479).  S[B, B] holds U I^T on entry; logits = S / temperature
+ * - log(clip(correction[col], 1e-8, 1)) (correction may be NULL); when item_ids is given,
+ * off-diagonal columns carrying the row's own item id are masked with FLT_MIN-like padding.
+ * loss = mean_r (logsumexp(row r) - logit[r, r]).  write_grad: S is overwritten by d loss / d S. */
+int b200_softmax_inbatch_loss(float* S, int64_t lds, int32_t B, float temperature, const float* correction,
+                              const int64_t* item_ids, int32_t write_grad, float* loss_out, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* out[r] = bias + <[a[r,:na], b[r,:nb], c[r,:nc]], w>: Dense(1) on a concatenation
  * (deepfm.py:172-173; the final Dense(1) of DIN / YouTubeRanking). */
 int b200_concat_dense(const float* a, int64_t lda, int32_t na, const float* b, int64_t ldb, int32_t nb,
@@ -225,6 +254,16 @@ int b200_sample_negatives(const int64_t* users, const int64_t* items_pos, int64_
                           uint64_t seed, uint64_t step, const int64_t* indptr,
                           const int32_t* idx_sorted, int64_t n_users, const float* cdf, int64_t* out,
                           void* stream);
+
+/* a11: per-sample behaviour sequences at collate time (libreco/batch/sequence.py:33-71, mode
+ * "recent"; called from batch/collators.py:207-222).  consumed CSR in ARRIVAL order.  position =
+ * first occurrence of items[j] in the user's list; for items the user never consumed (sampled
+ * negatives) position = rand_pos[j] (the reference's random.randrange stream, parity mode) or a
+ * Philox draw when rand_pos is NULL.  seqs int32[n, max_seq_len] (padded with pad_index), lens int32[n]. */
+int b200_interacted_seqs(const int64_t* indptr, const int32_t* idx, int64_t n_users, const int64_t* users,
+                         const int64_t* items, int64_t n, int32_t max_seq_len, int32_t pad_index,
+                         const int64_t* rand_pos, uint64_t seed, uint64_t step, int32_t* seqs,
+                         int32_t* lens, void* stream);
 
 /* ---- a14: predict_from_embedding (libreco/prediction/predict.py:36-40) -----------------
  * out[r] = sum_k U[users[r],k] * I[items[r],k]; mode 0: raw, 1: expit (ranking),

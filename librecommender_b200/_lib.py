@@ -48,6 +48,11 @@ SIGNATURES = {
                                         c_int32, c_float, _P, _P, _P, _P, _P, c_float, _P, c_int64, _P]),
     "b200_linear_f32": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, c_int32, c_int32, c_int32, _P, c_int64, _P]),
     "b200_linear_tf32x3": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, c_int32, c_int32, c_int32, _P, c_int64, _P]),
+    "b200_loss_workspace_bytes": (c_size_t, []),
+    "b200_pointwise_loss": (c_int, [_P, _P, c_int64, c_int32, c_float, c_float, _P, _P, _P, c_size_t, _P]),
+    "b200_pairwise_loss": (c_int, [_P, c_int64, _P, c_int64, c_int32, c_float, c_float, c_float, c_int32, _P, _P, _P,
+                                   _P, c_size_t, _P]),
+    "b200_softmax_inbatch_loss": (c_int, [_P, c_int64, c_int32, c_float, _P, _P, c_int32, _P, _P, c_size_t, _P]),
     "b200_concat_dense": (c_int, [_P, c_int64, c_int32, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, c_float,
                                   c_int64, _P, _P]),
     "b200_l2_normalize_rows": (c_int, [_P, c_int64, c_int64, c_int32, _P]),
@@ -57,6 +62,8 @@ SIGNATURES = {
                                    _P, _P, _P, c_float, _P, c_int64, _P]),
     "b200_sample_negatives": (c_int, [_P, _P, c_int64, c_int32, c_int64, c_int32, c_int32, c_uint64, c_uint64,
                                       _P, _P, c_int64, _P, _P, _P]),
+    "b200_interacted_seqs": (c_int, [_P, _P, c_int64, _P, _P, c_int64, c_int32, c_int32, _P, c_uint64, c_uint64,
+                                     _P, _P, _P]),
     "b200_gather_dot": (c_int, [_P, c_int64, _P, _P, c_int64, _P, c_int64, c_int32, c_int32, c_float, c_float, _P, _P]),
 }
 

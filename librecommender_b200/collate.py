@@ -54,3 +54,54 @@ class DevicePairwiseCollator:
         if self.repeat_positives and self.num_neg > 1:
             return users_d.repeat_interleave(self.num_neg), items_d.repeat_interleave(self.num_neg), negatives_d
         return users_d, items_d, negatives_d
+
+
+def interacted_positions_host(user_consumed, user_indices, item_indices):
+    """PARITY mode helper: the positions ``get_interacted_seqs`` (libreco/batch/sequence.py:44-55)
+    would draw for samples whose item is not in the user's history, consuming Python's global
+    ``random`` stream exactly like the reference (one ``random.randrange(0, len)`` per such
+    sample, in batch order).  Returns int64[n] (-1 where the item is in the list: the kernel finds
+    the first occurrence itself)."""
+    import random
+
+    out = np.full(len(user_indices), -1, dtype=np.int64)
+    sets = {}
+    for j, (u, i) in enumerate(zip(user_indices, item_indices)):
+        u = int(u)
+        s = sets.get(u)
+        if s is None:
+            s = sets[u] = set(user_consumed[u])
+        if int(i) not in s:
+            out[j] = random.randrange(0, len(user_consumed[u]))
+    return out
+
+
+class DeviceSequenceBuilder:
+    """``get_interacted_seqs`` (libreco/batch/sequence.py:33-71, ``mode="recent"``) on the device:
+    the per-sample history window the sequence models (DIN, YouTubeRanking, …) train on
+    (``batch/collators.py:207-222``).  ``consumed`` is a :class:`~librecommender_b200.consumed.ConsumedCSR`
+    in arrival order; ``pad_index`` is ``n_items`` in the reference (``bases/tf_base.py`` seq models)."""
+
+    def __init__(self, consumed, max_seq_len: int, pad_index: int, seed: int = 42, device="cuda"):
+        self.consumed, self.max_seq_len, self.pad_index = consumed, int(max_seq_len), int(pad_index)
+        self.seed, self.step, self.device = int(seed), 0, device
+
+    def __call__(self, users_d, items_d, rand_pos_d=None):
+        import torch
+
+        from . import _lib
+
+        indptr, idx = self.consumed.device(users_d.device)
+        n = users_d.numel()
+        seqs = torch.empty((n, self.max_seq_len), dtype=torch.int32, device=users_d.device)
+        lens = torch.empty(n, dtype=torch.int32, device=users_d.device)
+        users_d = users_d.to(torch.int64).contiguous()
+        items_d = items_d.to(torch.int64).contiguous()
+        if rand_pos_d is not None:
+            rand_pos_d = rand_pos_d.to(torch.int64).contiguous()
+        _lib.check(_lib.lib.b200_interacted_seqs(
+            _lib.ptr(indptr), _lib.ptr(idx), self.consumed.n_users, _lib.ptr(users_d), _lib.ptr(items_d), n,
+            self.max_seq_len, self.pad_index, _lib.ptr(rand_pos_d), self.seed, self.step, _lib.ptr(seqs),
+            _lib.ptr(lens), _lib.current_stream()))
+        self.step += 1
+        return seqs, lens

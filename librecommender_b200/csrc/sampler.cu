@@ -120,10 +120,67 @@ __global__ void sample_negatives_kernel(const int64_t* __restrict__ users,
   }
 }
 
+// ---- per-sample behaviour sequences at collate time (libreco/batch/sequence.py:33-71, mode "recent")
+// One warp per sample.  position = FIRST occurrence of the item in the user's time-ordered consumed
+// list (list.index); an item the user never consumed (a sampled negative) takes a random position
+// (random.randrange(0, len) in the reference: `rand_pos` carries that stream in parity mode, else
+// Philox(seed, step, j)).  seq = consumed[max(0, position - L) : position], padded with pad_index;
+// len = min(position, L), 1 when position == 0 (reference :56-58).
+__global__ void interacted_seqs_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ idx,
+                                       int64_t n_users, const int64_t* __restrict__ users,
+                                       const int64_t* __restrict__ items, int64_t n, int L, int32_t pad_index,
+                                       const int64_t* __restrict__ rand_pos, uint64_t seed, uint64_t step,
+                                       int32_t* __restrict__ seqs, int32_t* __restrict__ lens) {
+  const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= n) return;
+  const int64_t u = users[j];
+  int64_t beg = 0, end = 0;
+  if (u >= 0 && u < n_users) { beg = indptr[u]; end = indptr[u + 1]; }
+  const int64_t clen = end - beg;
+  const int64_t item = items[j];
+  int64_t pos = -1;
+  for (int64_t base = 0; base < clen && pos < 0; base += 32) {
+    const bool in = base + lane < clen;
+    const bool hit = in && (int64_t)__ldg(idx + beg + base + lane) == item;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) pos = base + (__ffs(m) - 1);
+  }
+  if (pos < 0) {
+    if (clen == 0) pos = 0;
+    else if (rand_pos) pos = min(max(rand_pos[j], (int64_t)0), clen - 1);
+    else {
+      U4 c;
+      c.x = (uint32_t)j; c.y = (uint32_t)((uint64_t)j >> 32); c.z = 0x5e9u; c.w = (uint32_t)step;
+      const U4 r = philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+      pos = bounded(r.x, r.y, clen);
+    }
+  }
+  const int64_t count = pos < L ? pos : L;
+  const int64_t start = pos - count;
+  for (int t = lane; t < L; t += 32)
+    seqs[j * L + t] = t < count ? __ldg(idx + beg + start + t) : pad_index;
+  if (lane == 0) lens[j] = pos == 0 ? 1 : (int32_t)count;
+}
+
 }  // namespace sampler
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_interacted_seqs(const int64_t* indptr, const int32_t* idx, int64_t n_users,
+                                    const int64_t* users, const int64_t* items, int64_t n,
+                                    int32_t max_seq_len, int32_t pad_index, const int64_t* rand_pos,
+                                    uint64_t seed, uint64_t step, int32_t* seqs, int32_t* lens, void* stream) {
+  B200_REQUIRE(indptr && idx && users && items && seqs && lens, "b200_interacted_seqs: null pointer");
+  B200_REQUIRE(max_seq_len >= 1, "b200_interacted_seqs: max_seq_len must be positive");
+  if (n == 0) return 0;
+  sampler::interacted_seqs_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      indptr, idx, n_users, users, items, n, max_seq_len, pad_index, rand_pos, seed, step, seqs, lens);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int b200_sample_negatives(const int64_t* users, const int64_t* items_pos, int64_t n_pos,
                                      int32_t num_neg, int64_t n_items, int32_t mode,

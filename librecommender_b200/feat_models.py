@@ -488,6 +488,21 @@ def recent_sequences(user_consumed, n_users, n_items, max_seq_len):
     return seqs, lens
 
 
+def recent_sequences_csr(consumed, n_items, max_seq_len):
+    """Vectorised get_recent_seqs (libreco/batch/sequence.py:75-91) over a ConsumedCSR (arrival
+    order): no per-user Python loop — 10 M users in seconds instead of minutes."""
+    indptr, idx = consumed.indptr, consumed.idx
+    n_users = len(indptr) - 1
+    clen = np.diff(indptr)
+    lens = np.minimum(clen, max_seq_len).astype(np.int32)
+    seqs = np.full((n_users + 1, max_seq_len), n_items, dtype=np.int32)
+    t = np.arange(max_seq_len, dtype=np.int64)[None, :]
+    src = (indptr[1:] - lens)[:, None] + t
+    valid = t < lens[:, None]
+    seqs[:n_users][valid] = idx[src[valid]]
+    return seqs, np.append(lens, np.int32(1)).astype(np.int32)
+
+
 def permute_mlp_input(mlp, perm):
     """Re-order the input features of a dense_nn (first kernel rows + input BN) by `perm`."""
     out = dict(mlp)
