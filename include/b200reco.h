@@ -179,10 +179,16 @@ int b200_linear_f32(const float* X, int64_t ldx, int64_t R, const float* Wt, int
 /* Same contract as b200_linear_f32 on the tcgen05 tensor cores: operands split x = hi + lo into
  * two tf32 values, three kind::tf32 products (hi*hi + lo*hi + hi*lo) in separate main / correction
  * TMEM accumulators promoted to registers every 64 k: fp32-level accuracy, not tf32-level.
- * Requires 16-byte aligned rows (ldx, ldw multiples of 4); callers use b200_linear_f32 otherwise. */
+ * Requires 16-byte aligned X rows (ldx % 4 == 0).  Wsplit (optional, NULL allowed): the layer's
+ * weights pre-split once by b200_linear_tf32x3_split_weights — 2 * dout * split_ld(din) floats —
+ * which removes the per-tile weight splitting from the kernel; without it Wt rows must be 16-byte
+ * aligned too.  Callers use b200_linear_f32 for shapes that do not qualify. */
+int64_t b200_linear_tf32x3_split_ld(int32_t din);
+int b200_linear_tf32x3_split_weights(const float* Wt, int64_t ldw, int32_t din, int32_t dout, float* Wsplit,
+                                     void* stream);
 int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
-                       const float* bias, int32_t din, int32_t dout, int32_t relu, float* Y,
-                       int64_t ldy, void* stream);
+                       const float* Wsplit, const float* bias, int32_t din, int32_t dout, int32_t relu,
+                       float* Y, int64_t ldy, void* stream);
 
 /* ---- training losses: value + gradient w.r.t. the scores in one pass ------
  * All reductions are two-stage and deterministic.  `workspace` >= b200_loss_workspace_bytes().

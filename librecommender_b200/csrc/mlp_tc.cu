@@ -14,7 +14,8 @@
 // One persistent CTA per SM, warp-specialised:
 //   warp 0      TMA producer: X tile [128 x 32 fp32] and Wt tile [n_pad x 32 fp32] per k-chunk
 //   warp 1      MMA issuer (one elected lane)
-//   warps 2-5   splitters: rewrite the landed tiles in place to `hi` and write the `lo` tiles
+//   warps 2-5   splitters: write the `lo` tile next to every landed X tile (the X tile itself is the
+//               `hi` operand); the weight tiles arrive pre-split when the caller made a split copy
 //   warps 6-9   epilogue: TMEM -> registers (+=), then bias / ReLU / store at the end of a row tile
 #include "common.cuh"
 #include "ptx_sm100.cuh"
@@ -61,20 +62,35 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
       : "memory");
 }
 
-// x -> (hi, lo): hi keeps the 10 explicit mantissa bits of tf32, lo = x - hi truncated the same
-// way, so whatever conversion the tensor core applies to its 32-bit containers is the identity
-__device__ __forceinline__ void split4(float4& v, float4& lo) {
-  const uint32_t M = 0xffffe000u;
-  float h;
-  h = __uint_as_float(__float_as_uint(v.x) & M); lo.x = __uint_as_float(__float_as_uint(v.x - h) & M); v.x = h;
-  h = __uint_as_float(__float_as_uint(v.y) & M); lo.y = __uint_as_float(__float_as_uint(v.y - h) & M); v.y = h;
-  h = __uint_as_float(__float_as_uint(v.z) & M); lo.z = __uint_as_float(__float_as_uint(v.z - h) & M); v.z = h;
-  h = __uint_as_float(__float_as_uint(v.w) & M); lo.w = __uint_as_float(__float_as_uint(v.w - h) & M); v.w = h;
+// x -> (hi, lo): hi keeps the 10 explicit mantissa bits of tf32, lo = x - hi (exact in fp32).
+// The tensor core reads 32-bit containers and ignores the 13 low mantissa bits (truncation —
+// verified by tests/test_gpu_linear_tc.py: a rounding conversion would show up as a 2^-11 error),
+// so the X tile itself serves as the `hi` operand and only the `lo` tile is written.
+__device__ __forceinline__ float lo_part(float x) {
+  return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+}
+__device__ __forceinline__ float4 lo4(const float4 v) {
+  return make_float4(lo_part(v.x), lo_part(v.y), lo_part(v.z), lo_part(v.w));
 }
 
+// weights: explicit hi / lo copies, made once per layer (b200_linear_tf32x3_split_weights)
+__global__ void split_weights_kernel(const float* __restrict__ W, int64_t ldw, int din, int dout, int64_t ld,
+                                     float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)dout * ld) return;
+  const int r = (int)(i / ld), c = (int)(i % ld);
+  const float x = c < din ? W[(int64_t)r * ldw + c] : 0.f;
+  const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  out[i] = h;
+  out[(int64_t)dout * ld + i] = x - h;
+}
+
+// WSPLIT: tmW / tmWlo address the pre-split weight copies; otherwise the splitters also split the
+// weight tile of every stage (self-contained call, more shared-memory traffic).
+template <bool WSPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                     const Params p) {
+                     const __grid_constant__ CUtensorMap tmWlo, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_bytes = p.n_pad * KC * 4;
@@ -116,10 +132,11 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < p.n_chunks; ++kc) {
           ptx::mbar_wait(&ss->empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&ss->full[stage], (uint32_t)(A_BYTES + b_bytes));
+          ptx::mbar_arrive_expect_tx(&ss->full[stage], (uint32_t)(A_BYTES + (WSPLIT ? 2 : 1) * b_bytes));
           uint8_t* st = smem + (size_t)stage * stage_bytes;
           ptx::tma_load_2d(st, &tmX, &ss->full[stage], kc * KC, tile * TM);
           ptx::tma_load_2d(st + 2 * A_BYTES, &tmW, &ss->full[stage], kc * KC, col0);
+          if (WSPLIT) ptx::tma_load_2d(st + 2 * A_BYTES + b_bytes, &tmWlo, &ss->full[stage], kc * KC, col0);
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         }
       }
@@ -181,19 +198,11 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         float4* ah = (float4*)st;
         float4* al = (float4*)(st + A_BYTES);
 #pragma unroll
-        for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
-          float4 v = ah[t + j * 128], lo;
-          split4(v, lo);
-          ah[t + j * 128] = v;
-          al[t + j * 128] = lo;
-        }
-        float4* bh = (float4*)(st + 2 * A_BYTES);
-        float4* bl = (float4*)(st + 2 * A_BYTES + b_bytes);
-        for (int j = t; j < b_vec; j += 128) {
-          float4 v = bh[j], lo;
-          split4(v, lo);
-          bh[j] = v;
-          bl[j] = lo;
+        for (int j = 0; j < A_BYTES / 16 / 128; ++j) al[t + j * 128] = lo4(ah[t + j * 128]);
+        if (!WSPLIT) {
+          const float4* bh = (const float4*)(st + 2 * A_BYTES);
+          float4* bl = (float4*)(st + 2 * A_BYTES + b_bytes);
+          for (int j = t; j < b_vec; j += 128) bl[j] = lo4(bh[j]);
         }
         ptx::fence_proxy_async_smem();       // generic-proxy writes -> visible to the tensor core
         __syncwarp();
@@ -308,15 +317,31 @@ static int make_tmap_f32(CUtensorMap* m, const float* base, int64_t rows, int64_
 }  // namespace mlp
 }  // namespace b200
 
+extern "C" int64_t b200_linear_tf32x3_split_ld(int32_t din) { return ((int64_t)din + 3) / 4 * 4; }
+
+extern "C" int b200_linear_tf32x3_split_weights(const float* Wt, int64_t ldw, int32_t din, int32_t dout,
+                                                float* Wsplit, void* stream) {
+  using namespace b200;
+  using namespace b200::mlp;
+  B200_REQUIRE(Wt && Wsplit && din > 0 && dout > 0 && ldw >= din, "bad arguments");
+  const int64_t ld = b200_linear_tf32x3_split_ld(din);
+  const int64_t n = (int64_t)dout * ld;
+  split_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Wt, ldw, din, dout, ld, Wsplit);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 extern "C" int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
-                                  const float* bias, int32_t din, int32_t dout, int32_t relu, float* Y,
-                                  int64_t ldy, void* stream) {
+                                  const float* Wsplit, const float* bias, int32_t din, int32_t dout,
+                                  int32_t relu, float* Y, int64_t ldy, void* stream) {
   using namespace b200;
   using namespace b200::mlp;
   B200_REQUIRE(R >= 0 && din > 0 && dout > 0, "bad shape");
-  B200_REQUIRE((ldx & 3) == 0 && (ldw & 3) == 0 && ((uintptr_t)X & 15) == 0 && ((uintptr_t)Wt & 15) == 0,
-               "b200_linear_tf32x3 needs 16-byte aligned rows (ldx, ldw multiples of 4)");
-  B200_REQUIRE(ldx >= din && ldw >= din && ldy >= dout, "leading dimension too small");
+  B200_REQUIRE((ldx & 3) == 0 && ((uintptr_t)X & 15) == 0, "b200_linear_tf32x3 needs 16-byte aligned X rows (ldx % 4 == 0)");
+  B200_REQUIRE(Wsplit ? (((uintptr_t)Wsplit & 15) == 0) : ((ldw & 3) == 0 && ((uintptr_t)Wt & 15) == 0),
+               "b200_linear_tf32x3 needs 16-byte aligned weight rows (ldw % 4 == 0) or a split copy");
+  B200_REQUIRE(ldx >= din && (Wsplit || ldw >= din) && ldy >= dout, "leading dimension too small");
   if (R == 0) return 0;
   Params p;
   p.R = R;
@@ -333,13 +358,22 @@ extern "C" int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const 
   p.nstage = min(MAXSTAGE, (200 * 1024) / stage_bytes);
   const size_t smem = (size_t)p.nstage * stage_bytes + sizeof(Smem) + 1024;
 
-  CUtensorMap tmX, tmW;
+  CUtensorMap tmX, tmW, tmWlo;
   if (make_tmap_f32(&tmX, X, R, din, ldx, TM)) return 1;
-  if (make_tmap_f32(&tmW, Wt, dout, din, ldw, p.n_pad)) return 1;
+  if (Wsplit) {
+    const int64_t ld = b200_linear_tf32x3_split_ld(din);
+    if (make_tmap_f32(&tmW, Wsplit, dout, din, ld, p.n_pad)) return 1;
+    if (make_tmap_f32(&tmWlo, Wsplit + (int64_t)dout * ld, dout, din, ld, p.n_pad)) return 1;
+  } else {
+    if (make_tmap_f32(&tmW, Wt, dout, din, ldw, p.n_pad)) return 1;
+    tmWlo = tmW;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA_OK(cudaFuncSetAttribute(linear_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      220 * 1024));
+    B200_CUDA_OK(cudaFuncSetAttribute(linear_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       220 * 1024));
     attr_set = true;
   }
@@ -348,7 +382,10 @@ extern "C" int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int gy = (dout + NMAX - 1) / NMAX;
   const int gx = max(1, min(p.n_tiles, sms / gy));
-  linear_tf32x3_kernel<<<dim3(gx, gy), THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, p);
+  if (Wsplit)
+    linear_tf32x3_kernel<true><<<dim3(gx, gy), THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, tmWlo, p);
+  else
+    linear_tf32x3_kernel<false><<<dim3(gx, gy), THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, tmWlo, p);
   B200_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

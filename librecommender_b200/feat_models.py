@@ -67,18 +67,46 @@ TC_MIN_DIN = 64
 TC_MIN_ROWS = 4096
 
 
-def linear(x, Wt, b, relu):
+_SPLIT_CACHE = {}
+
+
+def split_weights(Wt):
+    """hi / lo tf32 copies of a layer's weights for b200_linear_tf32x3, made once per weight tensor
+    (keyed by storage pointer + shape + version counter, so in-place updates re-split)."""
+    import torch
+
+    key = (Wt.data_ptr(), tuple(Wt.shape), Wt.stride(0), Wt._version)
+    hit = _SPLIT_CACHE.get(key)
+    if hit is None:
+        dout, din = Wt.shape
+        ld = int(_lib.lib.b200_linear_tf32x3_split_ld(din))
+        buf = torch.empty(2 * dout * ld, dtype=torch.float32, device=Wt.device)
+        _lib.check(_lib.lib.b200_linear_tf32x3_split_weights(_lib.ptr(Wt), Wt.stride(0), din, dout, _lib.ptr(buf),
+                                                             _lib.current_stream()))
+        if len(_SPLIT_CACHE) > 256:
+            _SPLIT_CACHE.clear()
+        hit = _SPLIT_CACHE[key] = (buf, Wt)      # keep Wt alive so the pointer key stays unique
+    return hit[0]
+
+
+def linear(x, Wt, b, relu, cache_split=True):
     """tf_dense (libreco/layers/dense.py:52-80) with BN folded: act(x Wt^T + b), fp32 device tensors."""
     import torch
 
     R, din, dout = x.shape[0], Wt.shape[1], Wt.shape[0]
     y = torch.empty((R, dout), dtype=torch.float32, device=x.device)
-    aligned = (x.stride(0) % 4 == 0 and Wt.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0
-               and Wt.data_ptr() % 16 == 0)
+    bp = _lib.ptr(b) if b is not None else None
+    aligned = x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and x.stride(1) == 1 and Wt.stride(1) == 1
     use_tc = LINEAR_IMPL == "tf32x3" or (LINEAR_IMPL == "auto" and din >= TC_MIN_DIN and R >= TC_MIN_ROWS)
-    fn = _lib.lib.b200_linear_tf32x3 if (use_tc and aligned) else _lib.lib.b200_linear_f32
-    _lib.check(fn(_lib.ptr(x), x.stride(0), R, _lib.ptr(Wt), Wt.stride(0), _lib.ptr(b) if b is not None else None,
-                  din, dout, 1 if relu else 0, _lib.ptr(y), y.stride(0), _lib.current_stream()))
+    w_ok = cache_split or (Wt.stride(0) % 4 == 0 and Wt.data_ptr() % 16 == 0)
+    if use_tc and aligned and w_ok:
+        ws = split_weights(Wt) if cache_split else None
+        _lib.check(_lib.lib.b200_linear_tf32x3(_lib.ptr(x), x.stride(0), R, _lib.ptr(Wt), Wt.stride(0), _lib.ptr(ws), bp,
+                                               din, dout, 1 if relu else 0, _lib.ptr(y), y.stride(0),
+                                               _lib.current_stream()))
+    else:
+        _lib.check(_lib.lib.b200_linear_f32(_lib.ptr(x), x.stride(0), R, _lib.ptr(Wt), Wt.stride(0), bp, din, dout,
+                                            1 if relu else 0, _lib.ptr(y), y.stride(0), _lib.current_stream()))
     return y
 
 

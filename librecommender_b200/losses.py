@@ -87,7 +87,7 @@ def _make_functions():
             U, I = _f32(user_embeds), _f32(item_embeds)
             if U.shape != I.shape:
                 raise ValueError(f"user and item embeds shape doesn't match, got {tuple(U.shape)} and {tuple(I.shape)}")
-            S = linear(U, I, None, False)                    # [B, B] = U I^T on the library's GEMM
+            S = linear(U, I, None, False, cache_split=False)                    # [B, B] = U I^T on the library's GEMM
             B = S.shape[0]
             out = torch.empty((), dtype=torch.float32, device=U.device)
             ws = _workspace(U.device)
@@ -105,8 +105,8 @@ def _make_functions():
 
             G, U, I = ctx.saved_tensors
             # dU = G I, dI = G^T U: the same dense-layer kernel with the transposed operands
-            dU = linear(G, I.t().contiguous(), None, False)
-            dI = linear(G.t().contiguous(), U.t().contiguous(), None, False)
+            dU = linear(G, I.t().contiguous(), None, False, cache_split=False)
+            dI = linear(G.t().contiguous(), U.t().contiguous(), None, False, cache_split=False)
             return dU * g, dI * g, None, None, None
 
     return _Pointwise, _Pairwise, _InBatchSoftmax

@@ -9,16 +9,27 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _run(fn_name, x, Wt, b, relu):
+def _run(fn_name, x, Wt, b, relu, presplit=False):
     import torch
 
     from librecommender_b200 import _lib
 
     y = torch.empty((x.shape[0], Wt.shape[0]), dtype=torch.float32, device=x.device)
-    fn = getattr(_lib.lib, fn_name)
-    _lib.check(fn(_lib.ptr(x), x.stride(0), x.shape[0], _lib.ptr(Wt), Wt.stride(0),
-                  _lib.ptr(b) if b is not None else None, Wt.shape[1], Wt.shape[0], 1 if relu else 0,
-                  _lib.ptr(y), y.stride(0), _lib.current_stream()))
+    bp = _lib.ptr(b) if b is not None else None
+    if fn_name == "b200_linear_tf32x3":
+        ws = None
+        if presplit:
+            ld = int(_lib.lib.b200_linear_tf32x3_split_ld(Wt.shape[1]))
+            ws = torch.empty(2 * Wt.shape[0] * ld, dtype=torch.float32, device=x.device)
+            _lib.check(_lib.lib.b200_linear_tf32x3_split_weights(_lib.ptr(Wt), Wt.stride(0), Wt.shape[1], Wt.shape[0],
+                                                                 _lib.ptr(ws), _lib.current_stream()))
+        _lib.check(_lib.lib.b200_linear_tf32x3(_lib.ptr(x), x.stride(0), x.shape[0], _lib.ptr(Wt), Wt.stride(0),
+                                               _lib.ptr(ws), bp, Wt.shape[1], Wt.shape[0], 1 if relu else 0,
+                                               _lib.ptr(y), y.stride(0), _lib.current_stream()))
+    else:
+        _lib.check(_lib.lib.b200_linear_f32(_lib.ptr(x), x.stride(0), x.shape[0], _lib.ptr(Wt), Wt.stride(0), bp,
+                                            Wt.shape[1], Wt.shape[0], 1 if relu else 0, _lib.ptr(y), y.stride(0),
+                                            _lib.current_stream()))
     torch.cuda.synchronize()
     return y.cpu().numpy()
 
@@ -31,7 +42,8 @@ def _run(fn_name, x, Wt, b, relu):
     (20000, 160, 64, True, True),       # several tiles per CTA wave
     (777, 1024, 96, True, True),        # 8 accumulator groups
 ])
-def test_linear_tf32x3_matches_fp64(R, din, dout, relu, bias):
+@pytest.mark.parametrize("presplit", [False, True])
+def test_linear_tf32x3_matches_fp64(R, din, dout, relu, bias, presplit):
     import torch
 
     rng = np.random.default_rng(R + din)
@@ -49,7 +61,7 @@ def test_linear_tf32x3_matches_fp64(R, din, dout, relu, bias):
     if relu:
         ref = np.maximum(ref, 0.0)
 
-    got = _run("b200_linear_tf32x3", xd, Wd, bd, relu)
+    got = _run("b200_linear_tf32x3", xd, Wd, bd, relu, presplit)
     simt = _run("b200_linear_f32", xd, Wd, bd, relu)
     err = np.abs(got - ref) / (mag + 1e-30)
     err_simt = np.abs(simt - ref) / (mag + 1e-30)
@@ -75,6 +87,20 @@ def test_linear_tf32x3_strided_views():
     assert (np.abs(got - ref) <= 2e-6 * mag).all()
 
 
+def test_linear_tf32x3_presplit_allows_unaligned_weight_rows():
+    """Wt with ldw % 4 != 0 (a column slice) is fine once a split copy exists."""
+    import torch
+
+    rng = np.random.default_rng(9)
+    x = torch.from_numpy(rng.standard_normal((700, 64)).astype(np.float32)).cuda()
+    Wbig = torch.from_numpy((rng.standard_normal((48, 131)) * 0.1).astype(np.float32)).cuda()
+    Wt = Wbig[:, 3:3 + 64]
+    got = _run("b200_linear_tf32x3", x, Wt, None, True, presplit=True)
+    ref = np.maximum(x.double().cpu().numpy() @ Wt.double().cpu().numpy().T, 0)
+    mag = np.abs(x.cpu().numpy()).astype(np.float64) @ np.abs(Wt.cpu().numpy()).astype(np.float64).T
+    assert (np.abs(got - ref) <= 2e-6 * mag).all()
+
+
 def test_linear_tf32x3_rejects_misaligned():
     import torch
 
@@ -83,7 +109,7 @@ def test_linear_tf32x3_rejects_misaligned():
     x = torch.zeros((256, 35), device="cuda")
     Wt = torch.zeros((16, 35), device="cuda")
     y = torch.empty((256, 16), device="cuda")
-    rc = _lib.lib.b200_linear_tf32x3(_lib.ptr(x), x.stride(0), 256, _lib.ptr(Wt), Wt.stride(0), None, 35, 16, 0,
+    rc = _lib.lib.b200_linear_tf32x3(_lib.ptr(x), x.stride(0), 256, _lib.ptr(Wt), Wt.stride(0), None, None, 35, 16, 0,
                                      _lib.ptr(y), y.stride(0), _lib.current_stream())
     assert rc != 0
 

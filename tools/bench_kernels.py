@@ -200,10 +200,22 @@ def bench_linear():
         Wt = torch.randn(dout, din, device="cuda") / din ** 0.5
         b = torch.randn(dout, device="cuda")
         y = torch.empty(R, dout, device="cuda")
-        for name in ("b200_linear_f32", "b200_linear_tf32x3"):
-            fn = getattr(_lib.lib, name)
-            ms = timeit(lambda: _lib.check(fn(_lib.ptr(x), din, R, _lib.ptr(Wt), din, _lib.ptr(b), din, dout, 1,
-                                              _lib.ptr(y), dout, _lib.current_stream())), iters=5, warm=3)
+        ld = int(_lib.lib.b200_linear_tf32x3_split_ld(din))
+        ws = torch.empty(2 * dout * ld, device="cuda")
+        _lib.check(_lib.lib.b200_linear_tf32x3_split_weights(_lib.ptr(Wt), din, din, dout, _lib.ptr(ws),
+                                                             _lib.current_stream()))
+        calls = {
+            "b200_linear_f32": lambda: _lib.lib.b200_linear_f32(_lib.ptr(x), din, R, _lib.ptr(Wt), din, _lib.ptr(b), din,
+                                                                dout, 1, _lib.ptr(y), dout, _lib.current_stream()),
+            "b200_linear_tf32x3": lambda: _lib.lib.b200_linear_tf32x3(_lib.ptr(x), din, R, _lib.ptr(Wt), din, None,
+                                                                      _lib.ptr(b), din, dout, 1, _lib.ptr(y), dout,
+                                                                      _lib.current_stream()),
+            "b200_linear_tf32x3 (pre-split weights)": lambda: _lib.lib.b200_linear_tf32x3(
+                _lib.ptr(x), din, R, _lib.ptr(Wt), din, _lib.ptr(ws), _lib.ptr(b), din, dout, 1, _lib.ptr(y), dout,
+                _lib.current_stream()),
+        }
+        for name, call in calls.items():
+            ms = timeit(lambda: _lib.check(call()), iters=5, warm=3)
             flop = 2.0 * R * din * dout
             byt = 4.0 * (R * din + R * dout + dout * din)
             print(json.dumps({"kernel": f"{name} [{R} x {din}] -> {dout}", "ms": ms,
