@@ -170,6 +170,16 @@ int b200_deepfm_pair_scores(const float* Su, const float* Qu, const float* lu, c
                             const float* W2, const float* b2, const float* W3, const float* b3,
                             const float* w_out, float b_out, float* scores, int64_t lds, void* stream);
 
+/* multi_sparse_combine_embedding / multi_sparse_alone (libreco/tfops/features.py:47-118): the
+ * `len` sub-columns of one multi-sparse field (idx[r, 0..len)) pooled into one row:
+ * out[r] = sum_{t: idx != oov} table[idx[r,t]] / {1 | count | sqrt(count)} (combiner 0 sum, 1 mean,
+ * 2 sqrtn; division is div_no_nan).  K = 1 with ld = 1 pools the 1-D linear table.  Run once per
+ * (field, side) over the unique table: the pooled rows are appended to the shared sparse table and
+ * the field becomes an ordinary single-index field of b200_feat_forward. */
+int b200_multi_sparse_combine(const float* table, int64_t ld, int32_t K, const int32_t* idx, int64_t ld_idx,
+                              int32_t len, int64_t n, int32_t oov, int32_t combiner, float* out,
+                              int64_t ld_out, void* stream);
+
 /* Y = act(X Wt^T + b): tf_dense (libreco/layers/dense.py:52-80) with BN folded by the caller.
  * Wt is the TRANSPOSED kernel [dout, din]; fp32 SIMT (exact fma chain in k). */
 int b200_linear_f32(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,

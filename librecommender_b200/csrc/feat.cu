@@ -428,6 +428,42 @@ extern "C" int b200_feat_forward(const b200_feat_layout* L, const b200_feat_tabl
   return 0;
 }
 
+// multi_sparse_alone (reference libreco/tfops/features.py:87-118): one warp per row, lanes over K
+__global__ void multi_sparse_combine_kernel(const float* __restrict__ table, int64_t ld, int K,
+                                            const int32_t* __restrict__ idx, int64_t ld_idx, int len, int64_t n,
+                                            int32_t oov, int combiner, float* __restrict__ out, int64_t ld_out) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  int cnt = 0;
+  for (int t = 0; t < len; ++t) cnt += (idx[r * ld_idx + t] != oov);
+  float div = 1.f;
+  if (combiner == 1) div = (float)cnt;
+  else if (combiner == 2) div = sqrtf((float)cnt);
+  for (int k = lane; k < K; k += 32) {
+    float acc = 0.f;
+    for (int t = 0; t < len; ++t) {
+      const int32_t ix = idx[r * ld_idx + t];
+      if (ix != oov) acc += __ldg(table + (int64_t)ix * ld + k);   // oov row counts as the zero vector
+    }
+    out[r * ld_out + k] = (combiner == 0) ? acc : (div != 0.f ? acc / div : 0.f);   // div_no_nan
+  }
+}
+
+extern "C" int b200_multi_sparse_combine(const float* table, int64_t ld, int32_t K, const int32_t* idx,
+                                         int64_t ld_idx, int32_t len, int64_t n, int32_t oov,
+                                         int32_t combiner, float* out, int64_t ld_out, void* stream) {
+  B200_REQUIRE(table && idx && out, "b200_multi_sparse_combine: null pointer");
+  B200_REQUIRE(combiner >= 0 && combiner <= 2, "combiner must be 0 (sum), 1 (mean) or 2 (sqrtn)");
+  B200_REQUIRE(K >= 1 && len >= 1, "bad shape");
+  if (n == 0) return 0;
+  multi_sparse_combine_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      table, ld, K, idx, ld_idx, len, n, oov, combiner, out, ld_out);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int b200_linear_f32(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
                                const float* bias, int32_t din, int32_t dout, int32_t relu, float* Y,
                                int64_t ldy, void* stream) {

@@ -56,6 +56,8 @@ def _dev(x, device, dtype):
 
     if x is None:
         return None
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype).contiguous()
     return torch.as_tensor(np.ascontiguousarray(x)).to(device=device, dtype=dtype).contiguous()
 
 
@@ -149,6 +151,77 @@ def fold_mlp(mlp):
     return layers
 
 
+_COMBINERS = {"sum": 0, "mean": 1, "sqrtn": 2}
+
+
+def _spec_get(spec):
+    return spec.get if isinstance(spec, dict) else (lambda k, d=None: getattr(spec, k, d))
+
+
+def combine_multi_sparse(spec, weights, combiner="sqrtn", device=None):
+    """multi_sparse_combine_embedding (libreco/tfops/features.py:47-118) hoisted out of the row path.
+
+    A multi-sparse field (e.g. genre1..genre3 sharing one vocabulary and one OOV slot) is a function
+    of the user or of the item only, so its pooled embedding / pooled linear weight is computed ONCE
+    per unique-table row (``b200_multi_sparse_combine``) and appended to the shared sparse tables;
+    the field then is an ordinary single-index field for every downstream kernel.  Returns
+    ``(spec_dict, weights_dict)`` in the reduced field layout the reference's graph uses after
+    combining (``true_sparse_field_size``, feature/multi_sparse.py:146-157): plain sparse fields
+    first, then one field per multi-sparse group.  With ``combiner="normal"`` or no multi-sparse info
+    the inputs are returned unchanged."""
+    import torch
+
+    g = _spec_get(spec)
+    info = g("multi_sparse_combine_info")
+    if info is None or combiner not in _COMBINERS:
+        return spec, weights
+    ig = info.get if isinstance(info, dict) else (lambda k, d=None: getattr(info, k, d))
+    offs, lens, oovs = list(ig("field_offset")), list(ig("field_len")), [int(x) for x in ig("feat_oov")]
+    device = device if device is not None else _lib.require_cuda()
+    ucol, icol = list(g("user_sparse_col_index") or []), list(g("item_sparse_col_index") or [])
+    sparse_end = offs[0]
+    E = _dev(weights["sparse_embeds"], device, torch.float32)
+    K = E.shape[1]
+    lin = _dev(weights.get("sparse_linear"), device, torch.float32)
+    uniq = {"user": _dev(g("user_sparse_unique"), device, torch.int32) if ucol else None,
+            "item": _dev(g("item_sparse_unique"), device, torch.int32) if icol else None}
+    cols = {"user": ucol, "item": icol}
+    new_cols = {"user": [c for c in ucol if c < sparse_end], "item": [c for c in icol if c < sparse_end]}
+    new_uniq = {w: [uniq[w][:, [cols[w].index(c) for c in new_cols[w]]]] if new_cols[w] else [] for w in ("user", "item")}
+    add_e, add_l, base = [], [], E.shape[0]
+    for gi, (off, ln, oov) in enumerate(zip(offs, lens, oovs)):
+        which = "user" if off in ucol else "item"
+        members = list(range(off, off + ln))
+        if any(c not in cols[which] for c in members):
+            raise ValueError(f"multi-sparse field at offset {off} straddles the user / item sides")
+        idx = uniq[which][:, [cols[which].index(c) for c in members]].contiguous()
+        n = idx.shape[0]
+        ce = torch.empty((n, K), dtype=torch.float32, device=device)
+        _lib.check(_lib.lib.b200_multi_sparse_combine(_lib.ptr(E), E.stride(0), K, _lib.ptr(idx), idx.stride(0), ln, n,
+                                                      oov, _COMBINERS[combiner], _lib.ptr(ce), ce.stride(0),
+                                                      _lib.current_stream()))
+        add_e.append(ce)
+        if lin is not None:
+            cl = torch.empty(n, dtype=torch.float32, device=device)
+            _lib.check(_lib.lib.b200_multi_sparse_combine(_lib.ptr(lin), 1, 1, _lib.ptr(idx), idx.stride(0), ln, n, oov,
+                                                          _COMBINERS[combiner], _lib.ptr(cl), 1, _lib.current_stream()))
+            add_l.append(cl)
+        new_uniq[which].append((base + torch.arange(n, device=device, dtype=torch.int32)).view(-1, 1))
+        new_cols[which].append(sparse_end + gi)
+        base += n
+    out_spec = {k: g(k) for k in ("n_users", "n_items", "user_dense_col_index", "item_dense_col_index",
+                                  "user_dense_unique", "item_dense_unique")}
+    out_spec.update(user_sparse_col_index=new_cols["user"], item_sparse_col_index=new_cols["item"],
+                    user_sparse_unique=torch.cat(new_uniq["user"], dim=1).contiguous() if new_uniq["user"] else None,
+                    item_sparse_unique=torch.cat(new_uniq["item"], dim=1).contiguous() if new_uniq["item"] else None,
+                    n_sparse=sparse_end + len(offs), n_dense=g("n_dense"), multi_sparse_combine_info=None)
+    out_w = dict(weights)
+    out_w["sparse_embeds"] = torch.cat([E] + add_e, dim=0)
+    if lin is not None:
+        out_w["sparse_linear"] = torch.cat([lin] + add_l, dim=0)
+    return out_spec, out_w
+
+
 class FeatSpec:
     """Device-resident feature layout (from the reference's DataInfo or an equivalent dict)."""
 
@@ -209,7 +282,9 @@ class _FeatModelBase:
         import torch
 
         self._torch = torch
-        K = int(np.asarray(weights["user_embeds"]).shape[1])
+        K = int(weights["user_embeds"].shape[1])
+        if not isinstance(spec, FeatSpec):   # multi-sparse fields pooled once (default combiner as the reference's)
+            spec, weights = combine_multi_sparse(spec, weights, weights.get("multi_sparse_combiner", "sqrtn"), device)
         self.spec = spec if isinstance(spec, FeatSpec) else FeatSpec(spec, K, device)
         self.device = self.spec.device
         self.K = K
@@ -642,7 +717,8 @@ class TwoTower:
         import torch
 
         self._torch = torch
-        K = int(np.asarray(weights["user_embeds"]).shape[1])
+        K = int(weights["user_embeds"].shape[1])
+        spec, weights = combine_multi_sparse(spec, weights, weights.get("multi_sparse_combiner", "sqrtn"), device)
         self.base = FeatSpec(spec, K, device)
         self.device = self.base.device
         self.K = K

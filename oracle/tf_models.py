@@ -86,13 +86,43 @@ def row_features(spec, users, items):
     return sparse, dense
 
 
+def multi_sparse_combine(table, sparse, info, combiner):
+    """multi_sparse_combine_embedding + multi_sparse_alone (tfops/features.py:47-118).
+    `table` [V, K] or [V]; `sparse` [R, F_raw] raw global indices; returns [R, F', K] / [R, F'] with
+    F' = sparse_end + n_fields.  The field's OOV row counts as the zero vector (:94-100), mean / sqrtn
+    divide by the number of non-OOV sub-features with div_no_nan (:105-116)."""
+    one_d = table.ndim == 1
+    T = table.reshape(len(table), -1)
+    offs, lens, oovs = info["field_offset"], info["field_len"], info["feat_oov"]
+    out = []
+    if offs[0] > 0:
+        out.append(T[sparse[:, :offs[0]]])
+    for off, ln, oov in zip(offs, lens, oovs):
+        idx = sparse[:, off:off + ln]
+        e = T[idx] * (idx != oov)[:, :, None].astype(T.dtype)
+        r = e.sum(axis=1, keepdims=True)
+        if combiner in ("mean", "sqrtn"):
+            cnt = (idx != oov).sum(axis=1).astype(T.dtype).reshape(-1, 1, 1)
+            if combiner == "sqrtn":
+                cnt = np.sqrt(cnt)
+            r = np.divide(r, cnt, out=np.zeros_like(r), where=cnt != 0)
+        out.append(r)
+    res = np.concatenate(out, axis=1)
+    return res[:, :, 0] if one_d else res
+
+
 def _stacked_embeds(w, users, items, sparse, dense, dtype):
     """[R, F, K] field embeddings and [R, F] linear features (fm.py:174-255)."""
     P = [w["user_embeds"][users][:, None, :], w["item_embeds"][items][:, None, :]]
     lin = []
     if "user_linear" in w:
         lin = [w["user_linear"][users].reshape(-1, 1), w["item_linear"][items].reshape(-1, 1)]
-    if sparse is not None:
+    ms = w.get("multi_sparse")        # {"field_offset", "field_len", "feat_oov", "combiner"}
+    if sparse is not None and ms is not None and ms["combiner"] in ("sum", "mean", "sqrtn"):
+        P.append(multi_sparse_combine(w["sparse_embeds"], sparse, ms, ms["combiner"]))
+        if "sparse_linear" in w:
+            lin.append(multi_sparse_combine(w["sparse_linear"], sparse, ms, ms["combiner"]))
+    elif sparse is not None:
         P.append(w["sparse_embeds"][sparse])
         if "sparse_linear" in w:
             lin.append(w["sparse_linear"][sparse])
@@ -265,6 +295,40 @@ def make_spec(rng, n_users, n_items, user_sparse_sizes, item_sparse_sizes, n_use
         user_dense_unique=rng.standard_normal((n_users + 1, len(udc))).astype(np.float32) if udc else None,
         item_dense_unique=rng.standard_normal((n_items + 1, len(idc))).astype(np.float32) if idc else None,
     )
+    return spec
+
+
+def make_multi_sparse_spec(rng, n_users, n_items, user_sparse_sizes, item_sparse_sizes, groups,
+                           n_user_dense=1, n_item_dense=1, pad_frac=0.3):
+    """Layout with multi-sparse fields in the reference's convention (feature/multi_sparse.py:73-95,
+    feature/sparse.py:106-119): plain sparse columns first, then every multi-sparse field's
+    sub-columns consecutively; the sub-columns of one field share one vocabulary range and one OOV
+    slot (= the padding value of missing sub-features).  `groups` = [(side, vocab, length), ...]."""
+    spec = make_spec(rng, n_users, n_items, user_sparse_sizes, item_sparse_sizes, n_user_dense, n_item_dense,
+                     interleave=False)
+    fs0 = spec["n_sparse"]
+    off = spec["sparse_vocab"]
+    ucol, icol = list(spec["user_sparse_col_index"]), list(spec["item_sparse_col_index"])
+    uu = [spec["user_sparse_unique"]] if ucol else []
+    iu = [spec["item_sparse_unique"]] if icol else []
+    f_off, f_len, f_oov = [], [], []
+    col = fs0
+    for side, vocab, ln in groups:
+        n_rows = n_users if side == "user" else n_items
+        oov = off + vocab
+        t = off + rng.integers(0, vocab, size=(n_rows + 1, ln))
+        t[rng.random((n_rows + 1, ln)) < pad_frac] = oov          # padded (missing) sub-features
+        t[n_rows, :] = oov                                          # OOV row
+        t[: min(3, n_rows), :] = oov                                # rows with no feature at all -> div_no_nan
+        (uu if side == "user" else iu).append(t.astype(np.int32))
+        (ucol if side == "user" else icol).extend(range(col, col + ln))
+        f_off.append(col); f_len.append(ln); f_oov.append(oov)
+        col += ln
+        off += vocab + 1
+    spec.update(n_sparse=col, sparse_vocab=off, user_sparse_col_index=ucol, item_sparse_col_index=icol,
+                user_sparse_unique=np.concatenate(uu, axis=1) if uu else None,
+                item_sparse_unique=np.concatenate(iu, axis=1) if iu else None,
+                multi_sparse_combine_info=dict(field_offset=f_off, field_len=f_len, feat_oov=np.array(f_oov)))
     return spec
 
 
