@@ -43,3 +43,140 @@ def recommend_sharded(recommend_fn, user_ids, n_rec, group=None, gather=True):
     dist.all_gather(parts, buf, group=group)
     rows = [p[: hi - lo].cpu().numpy() for p, (lo, hi) in zip(parts, sizes)]
     return np.concatenate(rows, axis=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# LightGCN propagation over G ranks: 1-D row partition of L and E, ONE
+# exchange step per layer (all-gather of the [slab, d] blocks), SpMM on the local row block.
+# ------------------------------------------------------------------------------------------------
+class LightGCNShardPlan:
+    """Node -> (rank, slot) layout.  Users and items are dealt round-robin (`id % G`) so that every
+    rank owns an equal share of the USERS and of the ITEMS *and* popularity-sorted ids (Zipf heads)
+    spread over all ranks: the nnz per rank is balanced without a degree-aware partitioner.  A
+    rank's block is ``[su user slots | si item slots]``; the gathered matrix is the concatenation of
+    the G blocks (``G * slab`` rows, padding rows are zero and never referenced)."""
+
+    def __init__(self, n_users: int, n_items: int, world: int):
+        self.n_users, self.n_items, self.world = int(n_users), int(n_items), int(world)
+        self.su = -(-self.n_users // self.world)
+        self.si = -(-self.n_items // self.world)
+        self.slab = self.su + self.si
+
+    def position(self, nodes):
+        """Row of node ids (users 0..n_users-1, items n_users..) in the gathered layout."""
+        import torch
+
+        nodes = torch.as_tensor(nodes)
+        is_item = nodes >= self.n_users
+        u = torch.where(is_item, torch.zeros_like(nodes), nodes)
+        i = torch.where(is_item, nodes - self.n_users, torch.zeros_like(nodes))
+        pu = (u % self.world) * self.slab + (u // self.world)
+        pi = (i % self.world) * self.slab + self.su + (i // self.world)
+        return torch.where(is_item, pi, pu)
+
+    def local_nodes(self, rank: int):
+        """(node ids owned by `rank` in block order, their slots inside the block)."""
+        import torch
+
+        users = torch.arange(min(rank, self.n_users), self.n_users, self.world)   # empty when rank >= n_users
+        items = torch.arange(min(rank, self.n_items), self.n_items, self.world)
+        nodes = torch.cat([users, self.n_users + items])
+        slots = torch.cat([torch.arange(users.numel()), self.su + torch.arange(items.numel())])
+        return nodes, slots
+
+    def shard_csr(self, indptr, col, val, rank: int):
+        """Rows of `rank` (block order, `slab` rows incl. empty padding rows) of the global CSR, with
+        the column ids rewritten to gathered-layout rows.  Tensors stay on the CSR's device."""
+        import torch
+
+        dev = indptr.device
+        nodes, slots = self.local_nodes(rank)
+        nodes, slots = nodes.to(dev), slots.to(dev)
+        deg = torch.zeros(self.slab, dtype=torch.int64, device=dev)
+        deg[slots] = indptr[nodes + 1] - indptr[nodes]
+        lptr = torch.zeros(self.slab + 1, dtype=torch.int64, device=dev)
+        lptr[1:] = torch.cumsum(deg, 0)
+        # source positions of every local nnz: the owned rows are contiguous runs of the global CSR
+        starts = indptr[nodes]
+        d_own = indptr[nodes + 1] - starts
+        owner = torch.repeat_interleave(torch.arange(nodes.numel(), device=dev), d_own)
+        within = torch.arange(int(d_own.sum()), device=dev) - torch.repeat_interleave(
+            torch.cumsum(d_own, 0) - d_own, d_own)
+        src = starts[owner] + within
+        lcol = self.position(col[src].to(torch.int64)).to(torch.int32)
+        return lptr, lcol.contiguous(), val[src].contiguous()
+
+    def scatter_rows(self, E_full, rank: int):
+        """This rank's `[slab, d]` block of a global `[n_users + n_items, d]` matrix (zeros in padding)."""
+        import torch
+
+        nodes, slots = self.local_nodes(rank)
+        out = torch.zeros((self.slab, E_full.shape[1]), dtype=E_full.dtype, device=E_full.device)
+        out[slots.to(E_full.device)] = E_full[nodes.to(E_full.device)]
+        return out
+
+    def unpermute(self, gathered):
+        """Gathered layout `[G * slab, d]` -> global node order `[n_users + n_items, d]`."""
+        import torch
+
+        pos = self.position(torch.arange(self.n_users + self.n_items)).to(gathered.device)
+        return gathered[pos]
+
+
+def propagate_sharded(plan: LightGCNShardPlan, spmm_local, E0_local, n_layers: int, group=None):
+    """mean_{l=0..n_layers} L^l E0 on this rank's row block (lightgcn_module.py:74-88).
+
+    ``spmm_local(E_gathered [G*slab, d], acc [slab, d], final_div) -> out [slab, d]`` multiplies the
+    local row block of L (from :meth:`LightGCNShardPlan.shard_csr`) with the gathered layer input,
+    adds the product to ``acc`` and divides ``acc`` by ``final_div`` when it is > 0 — exactly the
+    fused epilogue of ``b200_spmm_csr`` (:func:`sharded_spmm_fn`).  One ``all_gather_into_tensor``
+    per layer is the only collective; the layer mean accumulates locally."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    assert world == plan.world, (world, plan.world)
+    cur = E0_local.contiguous()
+    acc = cur.clone()
+    if n_layers == 0:
+        return acc
+    full = torch.empty((plan.world * plan.slab, cur.shape[1]), dtype=cur.dtype, device=cur.device)
+    for layer in range(n_layers):
+        if world > 1:
+            dist.all_gather_into_tensor(full, cur, group=group)
+        else:
+            full.copy_(cur)
+        last = layer == n_layers - 1
+        cur = spmm_local(full, acc, float(n_layers + 1) if last else 0.0)
+    return acc
+
+
+def sharded_spmm_fn(local_graph, slab: int):
+    """``spmm_local`` for :func:`propagate_sharded` backed by the CUDA SpMM of a local
+    :class:`~librecommender_b200.lightgcn.SpmmGraph` (layer-mean epilogue fused)."""
+    import torch
+
+    bufs = {}
+
+    def fn(full, acc, final_div):
+        key = (full.shape[1], len(bufs) & 1)
+        out = bufs.setdefault(key, torch.empty((slab, full.shape[1]), dtype=torch.float32, device=full.device))
+        # the last layer's product is only needed inside acc
+        local_graph.spmm(full, out=None if final_div > 0 else out, acc=acc, acc_init=False, final_div=final_div)
+        return out
+
+    return fn
+
+
+def gather_embeddings(plan: LightGCNShardPlan, E_local, group=None):
+    """All ranks' blocks -> (user_embeds [n_users, d], item_embeds [n_items, d]) on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    full = torch.empty((plan.world * plan.slab, E_local.shape[1]), dtype=E_local.dtype, device=E_local.device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_gather_into_tensor(full, E_local.contiguous(), group=group)
+    else:
+        full.copy_(E_local)
+    out = plan.unpermute(full)
+    return out[: plan.n_users], out[plan.n_users:]

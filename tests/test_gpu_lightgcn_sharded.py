@@ -1,0 +1,29 @@
+"""2-GPU check of the sharded LightGCN propagation (NCCL all-gather per layer + local CUDA SpMM):
+bit-for-bit equal to the single-GPU propagation.  Skipped on boxes with one GPU (the CPU gloo test
+tests/test_lightgcn_sharded_cpu.py covers the sharding logic there)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_sharded_propagation_two_gpus_bit_exact():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LG_USERS="300000", LG_ITEMS="40000")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577",
+                        os.path.join(root, "tools", "lightgcn_sharded_check.py")],
+                       capture_output=True, text=True, env=env, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["world"] == 2 and d["max_abs_err_vs_single_gpu"] == 0.0
+    assert max(d["nnz_per_rank"]) <= 1.1 * min(d["nnz_per_rank"])

@@ -1,0 +1,94 @@
+"""CPU, world_size 2, gloo: the sharding logic of multi-GPU LightGCN propagation (row partition,
+column remap into the gathered layout, one all-gather per layer, un-permute).  The local multiply is
+a torch.sparse stand-in — the CUDA SpMM cannot run here — so this covers exactly the code that is
+new at N > 1; the result must equal the single-process scipy oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _graph(seed, n_users, n_items):
+    from oracle import lightgcn as ol
+
+    rng = np.random.default_rng(seed)
+    consumed = {u: rng.choice(n_items, size=int(rng.integers(1, min(12, n_items + 1))), replace=False).tolist() for u in range(n_users)}
+    L = ol.build_laplacian(n_users, n_items, consumed).tocsr()
+    L.sort_indices()
+    return consumed, L
+
+
+def _worker(rank, world, port, n_users, n_items, d, n_layers, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from librecommender_b200.parallel import LightGCNShardPlan, gather_embeddings, propagate_sharded
+
+    _, L = _graph(0, n_users, n_items)
+    E0 = torch.from_numpy(np.random.default_rng(1).standard_normal((n_users + n_items, d)).astype(np.float32))
+    plan = LightGCNShardPlan(n_users, n_items, world)
+    lptr, lcol, lval = plan.shard_csr(torch.from_numpy(L.indptr.astype(np.int64)),
+                                      torch.from_numpy(L.indices.astype(np.int32)),
+                                      torch.from_numpy(L.data.astype(np.float32)), rank)
+    Lloc = torch.sparse_csr_tensor(lptr, lcol.to(torch.int64), lval, size=(plan.slab, world * plan.slab))
+    def spmm_local(full, acc, final_div):      # stand-in for the CUDA SpMM with its fused epilogue
+        out = Lloc @ full
+        acc += out
+        if final_div > 0:
+            acc /= final_div
+        return out
+
+    out_local = propagate_sharded(plan, spmm_local, plan.scatter_rows(E0, rank), n_layers)
+    ue, ie = gather_embeddings(plan, out_local)
+    q.put((rank, ue.numpy(), ie.numpy(), int(lval.numel())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_users,n_items", [(37, 23), (40, 10), (5, 64)])
+def test_sharded_propagation_matches_oracle_gloo_world2(n_users, n_items):
+    from oracle import lightgcn as ol
+
+    world, port, d, n_layers = 2, _free_port(), 8, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_users, n_items, d, n_layers, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _, L = _graph(0, n_users, n_items)
+    E0 = np.random.default_rng(1).standard_normal((n_users + n_items, d)).astype(np.float32)
+    ref = np.concatenate(ol.propagate(L, E0[:n_users], E0[n_users:], n_layers))
+    assert sum(r[3] for r in res) == L.nnz                          # the row blocks tile the matrix
+    for rank, ue, ie, _ in res:
+        np.testing.assert_allclose(np.concatenate([ue, ie]), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_plan_layout_roundtrip():
+    from librecommender_b200.parallel import LightGCNShardPlan
+
+    for nu, ni, w in ((10, 3, 4), (7, 7, 2), (1, 9, 8)):
+        plan = LightGCNShardPlan(nu, ni, w)
+        pos = plan.position(torch.arange(nu + ni))
+        assert len(set(pos.tolist())) == nu + ni and int(pos.max()) < w * plan.slab
+        seen = []
+        for r in range(w):
+            nodes, slots = plan.local_nodes(r)
+            np.testing.assert_array_equal(plan.position(nodes).numpy(), r * plan.slab + slots.numpy())
+            seen += nodes.tolist()
+        assert sorted(seen) == list(range(nu + ni))
