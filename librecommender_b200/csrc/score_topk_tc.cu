@@ -677,7 +677,8 @@ finalize_kernel(const FinalizeParams p) {
       const int n = s_cnt[s];
       const float* ls = p.cand_s + slot * (int64_t)(CAPG * GW);
       const int32_t* lb = p.cand_b + slot * (int64_t)CAPG;
-      for (int i0 = lane; i0 < n * GW; i0 += 32 * 8) {   // 8 independent loads in flight per lane
+      for (int b0 = 0; b0 < n * GW; b0 += 32 * 8) {   // warp-uniform trip count; 8 loads in flight per lane
+        const int i0 = b0 + lane;
         float v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -687,9 +688,14 @@ finalize_kernel(const FinalizeParams p) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int i = i0 + q * 32;
-          if (i < n * GW && v[q] >= low) {
-            const int pos = atomicAdd(&s_nu, 1);
-            if (pos < MAXU) { u_s[pos] = v[q]; u_id[pos] = lb[i / GW] + (i % GW); }
+          const bool hit = i < n * GW && v[q] >= low;
+          const unsigned m = __ballot_sync(0xffffffffu, hit);
+          if (m) {   // one shared-memory atomic per warp and step instead of one per element
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_nu, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            if (hit && pos < MAXU) { u_s[pos] = v[q]; u_id[pos] = lb[i / GW] + (i % GW); }
           }
         }
       }
@@ -842,23 +848,71 @@ finalize_kernel(const FinalizeParams p) {
     mine[t] = comp;
   }
   __syncthreads();
+  if (P <= 2 * FIN_THREADS) {
+    // common case (<= 512 candidates): bitonic network over keys held in REGISTERS (element
+    // e = tid + t * 256).  Partners inside the thread (j >= 256) are exchanged directly, partners
+    // inside the warp (j < 32) with shuffles; only the stages with 32 <= j < 256 go through shared
+    // memory (double-buffered: one barrier per such stage instead of one per stage).
+    constexpr int EPT = 2;
+    const int ept = P <= FIN_THREADS ? 1 : 2;
+    unsigned long long x[EPT];
 #pragma unroll
-  for (int t = 0; t < MAXC / FIN_THREADS; ++t) {
-    const int i = tid + t * FIN_THREADS;
-    if (i < P) c_sort[i] = mine[t];
-  }
-  __syncthreads();
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < P; i += FIN_THREADS) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = c_sort[i], b = c_sort[ixj];
-          const bool desc = ((i & k) == 0);
-          if (desc ? (a < b) : (a > b)) { c_sort[i] = b; c_sort[ixj] = a; }
+    for (int t = 0; t < EPT; ++t) x[t] = (t < ept) ? mine[t] : 0ull;
+    int buf = 0;
+#pragma unroll 1
+    for (int k = 2; k <= P; k <<= 1) {
+#pragma unroll 1
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        if (j >= FIN_THREADS) {          // only k = 512, j = 256: elements tid and tid + 256, descending
+          const unsigned long long a = x[0], b = x[1];
+          x[0] = a > b ? a : b;
+          x[1] = a > b ? b : a;
+          continue;
+        }
+        unsigned long long y[EPT];
+        if (j >= 32) {
+          unsigned long long* sb = c_sort + buf * (EPT * FIN_THREADS);
+#pragma unroll
+          for (int t = 0; t < EPT; ++t) if (t < ept) sb[t * FIN_THREADS + tid] = x[t];
+          __syncthreads();
+#pragma unroll
+          for (int t = 0; t < EPT; ++t) if (t < ept) y[t] = sb[t * FIN_THREADS + (tid ^ j)];
+          buf ^= 1;
+        } else {
+#pragma unroll
+          for (int t = 0; t < EPT; ++t) y[t] = __shfl_xor_sync(0xffffffffu, x[t], j);
+        }
+#pragma unroll
+        for (int t = 0; t < EPT; ++t) {
+          const int e = tid + t * FIN_THREADS;
+          const bool take_max = (((e & k) == 0) == ((e & j) == 0));   // descending blocks keep the max first
+          x[t] = take_max ? (x[t] > y[t] ? x[t] : y[t]) : (x[t] < y[t] ? x[t] : y[t]);
         }
       }
-      __syncthreads();
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < EPT; ++t) if (t < ept) c_sort[t * FIN_THREADS + tid] = x[t];
+    __syncthreads();
+  } else {
+#pragma unroll
+    for (int t = 0; t < MAXC / FIN_THREADS; ++t) {
+      const int i = tid + t * FIN_THREADS;
+      if (i < P) c_sort[i] = mine[t];
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < P; i += FIN_THREADS) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = c_sort[i], b = c_sort[ixj];
+            const bool desc = ((i & k) == 0);
+            if (desc ? (a < b) : (a > b)) { c_sort[i] = b; c_sort[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
     }
   }
   {
