@@ -666,36 +666,70 @@ finalize_kernel(const FinalizeParams p) {
   const uint32_t tk = p.row_tau_key[row];
   const float low = tk ? key_to_float(tk) : __int_as_float(0xff800000);
   if (tid == 0) { s_nu = 0; s_nc = 0; }
-  // list lengths first (one parallel round of loads), then one warp per list
+  // list lengths first (one parallel round of loads), their exclusive prefix, then ONE parallel round
+  // over all group records of the row: thread <-> record, so the number of dependent global round
+  // trips does not grow with the number of lists
   int* s_cnt = reinterpret_cast<int*>(c_sort);          // c_sort is free until the hash set is built
+  int* s_off = s_cnt + p.n_lists;                       // [n_lists + 1]
   for (int s = tid; s < p.n_lists; s += FIN_THREADS) s_cnt[s] = p.cand_cnt[(int64_t)s * p.B_pad + row];
   __syncthreads();
+  if (tid < 32) {   // warp 0: chunked scan of the list lengths
+    const int per = (p.n_lists + 31) / 32;
+    const int b = min(tid * per, p.n_lists), e = min(b + per, p.n_lists);
+    int sum = 0;
+    for (int s = b; s < e; ++s) sum += s_cnt[s];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += t;
+    }
+    int run = incl - sum;
+    for (int s = b; s < e; ++s) { s_off[s] = run; run += s_cnt[s]; }
+    if (tid == 31) s_off[p.n_lists] = incl;
+  }
+  __syncthreads();
   {
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int s = wid; s < p.n_lists; s += FIN_THREADS / 32) {
-      const int64_t slot = (int64_t)s * p.B_pad + row;
-      const int n = s_cnt[s];
-      const float* ls = p.cand_s + slot * (int64_t)(CAPG * GW);
-      const int32_t* lb = p.cand_b + slot * (int64_t)CAPG;
-      for (int b0 = 0; b0 < n * GW; b0 += 32 * 8) {   // warp-uniform trip count; 8 loads in flight per lane
-        const int i0 = b0 + lane;
-        float v[8];
+    const int lane = tid & 31;
+    const int total = s_off[p.n_lists];
+    constexpr int UN = 3;                                // records in flight per thread
+    for (int g0 = 0; g0 < total; g0 += FIN_THREADS * UN) {   // block-uniform trip count
+      float4 a[UN], b[UN];
+      int base[UN];
+      bool ok[UN];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int i = i0 + q * 32;
-          v[q] = (i < n * GW) ? __ldcs(ls + i) : __int_as_float(0xff800000);
+      for (int q = 0; q < UN; ++q) {
+        const int g = g0 + q * FIN_THREADS + tid;
+        ok[q] = g < total;
+        a[q] = b[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        base[q] = 0;
+        if (ok[q]) {
+          int lo = 0, hi = p.n_lists - 1;                // last list whose first record is <= g
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (s_off[mid] <= g) lo = mid; else hi = mid - 1;
+          }
+          const int j = g - s_off[lo];
+          const int64_t slot = (int64_t)lo * p.B_pad + row;
+          const float4* ls = reinterpret_cast<const float4*>(p.cand_s + slot * (int64_t)(CAPG * GW)) + 2 * j;
+          a[q] = __ldcs(ls);
+          b[q] = __ldcs(ls + 1);
+          base[q] = __ldcs(p.cand_b + slot * (int64_t)CAPG + j);
         }
+      }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int i = i0 + q * 32;
-          const bool hit = i < n * GW && v[q] >= low;
+      for (int q = 0; q < UN; ++q) {
+        const float v[8] = {a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, b[q].y, b[q].z, b[q].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const bool hit = ok[q] && v[e] >= low;
           const unsigned m = __ballot_sync(0xffffffffu, hit);
-          if (m) {   // one shared-memory atomic per warp and step instead of one per element
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&s_nu, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const int pos = base + __popc(m & ((1u << lane) - 1u));
-            if (hit && pos < MAXU) { u_s[pos] = v[q]; u_id[pos] = lb[i / GW] + (i % GW); }
+          if (m) {   // one shared-memory atomic per warp and element slot
+            int pos0 = 0;
+            if (lane == 0) pos0 = atomicAdd(&s_nu, __popc(m));
+            pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+            const int pos = pos0 + __popc(m & ((1u << lane) - 1u));
+            if (hit && pos < MAXU) { u_s[pos] = v[e]; u_id[pos] = base[q] + e; }
           }
         }
       }
