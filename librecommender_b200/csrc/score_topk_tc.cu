@@ -49,7 +49,9 @@ constexpr int CAPG = 256;      // candidate GROUP records per (row, list); list 
 constexpr int GW = 8;          // a record = the 8 coarse scores of one 8-column group + its first item id
 constexpr int NB = 1024;       // bins of the per-row global coarse-score histogram
 constexpr int TRIG = 96;       // uncounted records that trigger a compaction
-constexpr int EPI_WARPS = 8;   // LPS epilogue warps per TMEM lane quadrant (column groups of a tile); 16 measured slower
+constexpr int EPI_WARPS = 8;   // LPS epilogue warps per TMEM lane quadrant (column groups of a tile).  16 warps with
+                               // 32-column steps (96 registers, no spills to speak of) measured 1.9x SLOWER: 2.74 ms vs 1.43 ms
+constexpr int STEP = EPI_WARPS == 8 ? 64 : 32;   // accumulator columns per epilogue step (registers: 576 threads -> 113/thread)
 constexpr int LPS = EPI_WARPS / 4;   // candidate lists per (row, item split) = column groups per tile
 constexpr int CW = 256 / LPS;        // accumulator columns one epilogue warp scans per tile
 constexpr int KROW_MAX = 288;  // fast-path limit for k_row = K + c_u
@@ -120,7 +122,7 @@ __global__ void prep_items_kernel(const float* __restrict__ I, int64_t ldi, int6
 
 __global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
                                   const int64_t* __restrict__ user_ids, int64_t B, int B_pad, int d,
-                                  int d_pad, int K, int64_t N, int filter,
+                                  int d_pad, int K, int64_t N, int filter, float pre_scale,
                                   const int64_t* __restrict__ indptr, int64_t n_users,
                                   const CatalogHeader* __restrict__ hdr,
                                   __nv_bfloat16* __restrict__ A, RowMeta* __restrict__ meta,
@@ -155,7 +157,10 @@ __global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
     m.apply = apply;
     m.capped = k_row < k_full;
     m.k_row = (int32_t)k_row;
-    m.pre_k = 16 + m.k_row / 6;
+    // speculative threshold = pre_k-th largest SAMPLED block maximum: about pre_k / f items of the
+    // whole catalogue lie above it (f = sampled fraction), pre_scale = 2.67 f keeps that at
+    // >= 2.67 k_row + 16 / f (16 + k_row / 6 at the nominal f = 1/16)
+    m.pre_k = 16 + (int32_t)ceilf(pre_scale * (float)m.k_row);
     m.active = real;
     meta[row] = m;
     row_tau_key[row] = 0u;  // below every finite float
@@ -286,6 +291,15 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], float (&g)[4
     g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
   }
   return fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+}
+
+__device__ __forceinline__ void tmem_load_step(uint32_t taddr, uint32_t (&r)[64]) {
+  ptx::tmem_ld_32x32b_x64(taddr, r);
+  ptx::tmem_ld_wait_regs64(r);
+}
+__device__ __forceinline__ void tmem_load_step(uint32_t taddr, uint32_t (&r)[32]) {
+  ptx::tmem_ld_32x32b_x32(taddr, r);
+  ptx::tmem_ld_wait_regs(r);
 }
 
 template <bool PRE>
@@ -496,19 +510,18 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int n_base = t * TN + cg * CW;
         const bool tail = t >= last_full;
 #pragma unroll 1
-        for (int ch = 0; ch < CW / 64; ++ch) {
-          // 64 accumulator columns per step: two independent max trees in flight
-          uint32_t r[64];
-          ptx::tmem_ld_32x32b_x64(taddr + (uint32_t)(ch * 64), r);
-          ptx::tmem_ld_wait_regs64(r);
+        for (int ch = 0; ch < CW / STEP; ++ch) {
+          // STEP accumulator columns per step: independent max trees in flight
+          uint32_t r[STEP];
+          tmem_load_step(taddr + (uint32_t)(ch * STEP), r);
           if (tail) {   // zero-padded item rows (>= N) must never be collected: only the last tile
-            const int lim = (int)max((int64_t)0, min((int64_t)64, p.N - (int64_t)(n_base + ch * 64)));
+            const int lim = (int)max((int64_t)0, min((int64_t)STEP, p.N - (int64_t)(n_base + ch * STEP)));
 #pragma unroll
-            for (int j = 0; j < 64; ++j) if (j >= lim) r[j] = 0xff800000u;
+            for (int j = 0; j < STEP; ++j) if (j >= lim) r[j] = 0xff800000u;
           }
-          float g[8];
+          float g[STEP / 8];
 #pragma unroll
-          for (int gq = 0; gq < 8; ++gq) {
+          for (int gq = 0; gq < STEP / 8; ++gq) {
             const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
             const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
             g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
@@ -518,7 +531,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           // which of its 8 scores are candidates.  Cold groups cost 4 instructions.
           bool pushed = false;
 #pragma unroll
-          for (int gq = 0; gq < 8; ++gq) {
+          for (int gq = 0; gq < STEP / 8; ++gq) {
             if (__any_sync(0xffffffffu, g[gq] >= tau)) {
               if (g[gq] >= tau) {
                 float4* dst = reinterpret_cast<float4*>(my_s + (size_t)cnt * GW);
@@ -526,7 +539,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                      __uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
                 dst[1] = make_float4(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]),
                                      __uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
-                my_b[cnt] = n_base + ch * 64 + gq * 8;
+                my_b[cnt] = n_base + ch * STEP + gq * 8;
                 ++cnt;
               }
               pushed = true;
@@ -1006,6 +1019,7 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct Plan {
   int B_pad, d_pad, KB, m_tiles, total_tiles, n_splits, tiles_per_split, nstage, n_pre_tiles;
   bool use_pre;
+  float pre_scale;   // 2.67 x sampled fraction of the item tiles (see prep_users_kernel)
   int64_t N_pad;
   size_t smem_bytes;
   // workspace offsets
@@ -1038,6 +1052,15 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->n_pre_tiles = (pl->tiles_per_split + PRE_STRIDE - 1) / PRE_STRIDE;
   // speculation needs enough sampled blocks per row to take a stable order statistic
   pl->use_pre = (long)LPS * pl->n_splits * pl->n_pre_tiles >= 256;
+  {   // sampled fraction of the item tiles (every PRE_STRIDE-th tile of every split)
+    long sampled = 0;
+    for (int sp = 0; sp < pl->n_splits; ++sp) {
+      const int t0 = sp * pl->tiles_per_split;
+      const int t1 = t0 + pl->tiles_per_split < pl->total_tiles ? t0 + pl->tiles_per_split : pl->total_tiles;
+      sampled += (t1 - t0 + PRE_STRIDE - 1) / PRE_STRIDE;
+    }
+    pl->pre_scale = 2.67f * (float)sampled / (float)pl->total_tiles;
+  }
   const size_t budget = 227 * 1024 - 1024 /*align*/ - sizeof(SweepSmem) - (size_t)pl->KB * A_KB_BYTES;
   int ns = (int)(budget / ((size_t)pl->KB * B_KB_BYTES));
   if (ns > 6) ns = 6;
@@ -1136,8 +1159,8 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   const __nv_bfloat16* Ibf = (const __nv_bfloat16*)((const char*)catalog + 256);
 
   prep_users_kernel<<<(unsigned)ceil_div64((int64_t)pl.B_pad * 32, 256), 256, 0, stream>>>(
-      U, ldu, user_ids, B, pl.B_pad, d, pl.d_pad, K, N, filter, indptr, n_users, hdr, A, meta, tau,
-      status);
+      U, ldu, user_ids, B, pl.B_pad, d, pl.d_pad, K, N, filter, pl.pre_scale, indptr, n_users, hdr, A, meta,
+      tau, status);
   // cnt and ghist are adjacent in the workspace: one memset
   B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (pl.off_cs - pl.off_cnt), stream));
 
