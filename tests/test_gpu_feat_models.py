@@ -210,3 +210,30 @@ def test_two_tower_embeddings_and_retrieval(norm):
     Uh, Ih = U.cpu().numpy(), I.cpu().numpy()
     ref = orc.recommend_from_embedding("ranking", list(range(50)), 10, Uh, Ih, 300, consumed, True)
     assert orc.near_tie_mask(ref, got, orc.embed_scores(Uh, Ih, list(range(50)), 300), 1e-6).all()
+
+
+def test_recommend_tf_feat_shim():
+    """libreco/recommendation/recommend.py:81-105 seam: same arguments, engine underneath."""
+    import types
+
+    from librecommender_b200 import feat_models as fmods
+    from librecommender_b200.recommendation import recommend_tf_feat
+    from oracle import tf_models as tm
+
+    rng, spec = _case(21, n_users=90, n_items=400, K=16)
+    N = spec["n_items"]
+    w = tm.make_fm_weights(rng, spec, 16, True)
+    consumed = {u: rng.choice(N, size=int(rng.integers(1, 30)), replace=False).tolist() for u in range(90)}
+    engine = fmods.FM(spec, w, consumed)
+    model = types.SimpleNamespace(n_items=N, task="ranking", user_consumed=consumed, model_name="FM",
+                                  b200_engine=engine)
+    users = rng.choice(90, size=20, replace=False).tolist()
+    ids = recommend_tf_feat(model, users, 10, None, None, True, False)
+    np.testing.assert_array_equal(ids, engine.recommend(users, 10, True))
+    assert ids.shape == (20, 10) and ids.dtype == np.int64
+    rnd = recommend_tf_feat(model, users, 10, None, None, True, True)          # random_rec branch
+    assert rnd.shape == (20, 10) and (rnd >= 0).all() and (rnd < N).all()
+    for r, u in enumerate(users):
+        assert not set(ids[r].tolist()) & set(consumed[u])
+        assert not set(rnd[r].tolist()) & set(consumed[u])
+        assert len(set(rnd[r].tolist())) == 10
