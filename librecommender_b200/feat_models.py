@@ -155,7 +155,20 @@ _COMBINERS = {"sum": 0, "mean": 1, "sqrtn": 2}
 
 
 def _spec_get(spec):
-    return spec.get if isinstance(spec, dict) else (lambda k, d=None: getattr(spec, k, d))
+    """Uniform read access to a layout description: a plain dict (tests, fixtures) or the reference's
+    ``DataInfo`` object (libreco/data/data_info.py:107-290), whose column indices live in
+    ``data_info.user_sparse_col.index`` etc. (`Feature(name, index)` tuples, :209-247)."""
+    if isinstance(spec, dict):
+        return spec.get
+
+    def g(k, d=None):
+        if k.endswith("_col_index") and not hasattr(spec, k):
+            feat = getattr(spec, k[: -len("_index")], None)
+            return list(feat.index) if feat is not None and getattr(feat, "index", None) is not None else d
+        v = getattr(spec, k, d)
+        return d if v is None else v
+
+    return g
 
 
 def combine_multi_sparse(spec, weights, combiner="sqrtn", device=None):
@@ -229,7 +242,7 @@ class FeatSpec:
         import torch
 
         self.device = device if device is not None else _lib.require_cuda()
-        g = spec.get if isinstance(spec, dict) else (lambda k, d=None: getattr(spec, k, d))
+        g = _spec_get(spec)
         self.n_users, self.n_items = int(g("n_users")), int(g("n_items"))
         ucol, icol = list(g("user_sparse_col_index") or []), list(g("item_sparse_col_index") or [])
         udc, idc = list(g("user_dense_col_index") or []), list(g("item_dense_col_index") or [])

@@ -99,3 +99,34 @@ def test_default_combiner_is_sqrtn_like_the_reference():
     got = FM(spec, w).logits(users, items).cpu().numpy()          # no combiner key given
     w["multi_sparse"] = dict(info, combiner="sqrtn")
     _close(got, tm.fm_forward(w, users, items, sparse, dense, dtype=np.float64))
+
+
+@pytest.mark.parametrize("name", ["FM", "DeepFM"])
+def test_real_movielens_multi_sparse_layout(name):
+    """The reference's own DataInfo layout (examples/multi_sparse_example.py columns): engine on the
+    unique tables vs the oracle fed with the reference's own per-row index matrix."""
+    from librecommender_b200 import feat_models as fm
+    from oracle import tf_models as tm
+    from _fixtures import load_multi_sparse_spec as load_spec
+
+    g, spec = load_spec()
+    info = spec["multi_sparse_combine_info"]
+    reduced = spec["n_sparse"] - (sum(info["field_len"]) - len(info["field_len"]))
+    rng = np.random.default_rng(7)
+    spec_w = dict(spec, n_sparse=reduced)
+    if name == "FM":
+        w, fwd = tm.make_fm_weights(rng, spec_w, 16, use_bn=False), tm.fm_forward
+    else:
+        w, fwd = tm.make_deepfm_weights(rng, spec_w, 16, (128, 64, 32), False), tm.deepfm_forward
+    w["multi_sparse"] = dict(info, combiner="sqrtn")           # the reference's default combiner
+    u, it = g["train_users"], g["train_items"]
+    ref = fwd(w, u, it, g["train_sparse"].astype(np.int64), g["train_dense"], dtype=np.float64)
+    model = getattr(fm, name)(spec, w)
+    assert model.spec.n_sparse == reduced == 3
+    got = model.logits(u, it).cpu().numpy()
+    # raw "age" up to 56 makes the FM pairwise term cancel in fp32 (see test_gpu_movielens_c1.py)
+    Pm, _ = tm._stacked_embeds(tm._cast(w, np.float64), u, it, g["train_sparse"].astype(np.int64),
+                               g["train_dense"], np.float64)
+    cond = 0.5 * (np.square(Pm.sum(1)) + np.square(Pm).sum(1)).sum(1)
+    scale = np.maximum(np.abs(ref), np.abs(ref).mean())
+    assert (np.abs(got - ref) <= 1e-5 * scale + 1e-6 * cond + 1e-6).all(), float(np.abs(got - ref).max())
