@@ -200,6 +200,51 @@ int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, 
                        const float* Wsplit, const float* bias, int32_t din, int32_t dout, int32_t relu,
                        float* Y, int64_t ldy, void* stream);
 
+/* ---- training step of the FM-family models (reference graph in training mode:
+ * libreco/algorithms/fm.py:152-171, tf.layers.batch_normalization(training=True),
+ * libreco/training/tf_trainer.py:112-123 tf.train.AdamOptimizer + BN update ops) --------------- */
+
+/* y = gamma * (x - mean_batch) / sqrt(var_batch + eps) + beta over the R rows of x [R, K]; the batch
+ * variance is the biased one (tf.nn.moments); moving_* (nullable) are updated with `momentum`. */
+int b200_bn_train_forward(const float* x, int64_t ldx, int64_t R, int32_t K, const float* gamma,
+                          const float* beta, float eps, float momentum, float* y, int64_t ldy,
+                          float* batch_mean, float* batch_var, float* moving_mean, float* moving_var,
+                          void* stream);
+
+/* z = <y, pw_kernel> + pw_bias; logit = lin + lin_bias + elu(z)   (fm.py:156,169-170).  The two
+ * biases are DEVICE scalars (trainable variables; NULL = 0): no host round trip per step. */
+int b200_fm_head_forward(const float* y, int64_t ldy, int64_t R, int32_t K, const float* pw_kernel,
+                         const float* pw_bias, const float* lin, const float* lin_bias, float* z,
+                         float* logit, void* stream);
+
+/* d loss / d logit -> d loss / d pw [R, K] through elu, Dense(1) and (batch_mean != NULL) the batch-norm
+ * with batch statistics; ADDS the gradients of pw_kernel [K], pw_bias [1], gamma / beta [K] and
+ * (nullable) the bias of the linear term to the given buffers.  Deterministic. */
+size_t b200_fm_head_backward_workspace_bytes(int64_t R, int32_t K);
+int b200_fm_head_backward(const float* dlogit, const float* z, const float* pw, int64_t ld, int64_t R,
+                          int32_t K, const float* batch_mean, const float* batch_var, const float* gamma,
+                          const float* beta, float eps, const float* pw_kernel, float* dpw, int64_t ld_dpw,
+                          float* g_pw_kernel, float* g_pw_bias, float* g_gamma, float* g_beta,
+                          float* g_lin_bias, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Backward of b200_feat_forward: for every row and field f, d e_f = dpw[r] * (S[r] - e_f) (FM pairwise
+ * term; S = sum_f e from the forward) + dconcat[r, f*K..] (deep input; nullable), scatter-ADDED into
+ * dense gradient buffers shaped like the tables; with dlogit: the linear-feature gradients
+ * (g_*_linear, g_lin_kernel [2+F_s+F_d]).  Float atomics (summation order is not fixed). */
+int b200_feat_backward(const b200_feat_layout* layout, const b200_feat_tables* tables, const int64_t* users,
+                       const int64_t* items, int64_t R, const float* dpw, int64_t ld_dpw, const float* S,
+                       int64_t ld_s, const float* dconcat, int64_t ld_dconcat, const float* dlogit,
+                       const float* lin_kernel, float* g_user_embeds, float* g_item_embeds,
+                       float* g_sparse_embeds, float* g_dense_embeds, float* g_user_linear,
+                       float* g_item_linear, float* g_sparse_linear, float* g_dense_linear,
+                       float* g_lin_kernel, void* stream);
+
+/* tf.train.AdamOptimizer over a WHOLE variable (what _apply_sparse_shared does for embedding
+ * variables: m, v decayed everywhere, every row updated): lr_t = lr sqrt(1-b2^t)/(1-b1^t),
+ * m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2, param -= lr_t m / (sqrt(v) + eps); grad is zeroed. */
+int b200_adam_dense(float* param, float* m, float* v, float* grad, int64_t n, float lr, float beta1,
+                    float beta2, float eps, int64_t step, void* stream);
+
 /* ---- training losses: value + gradient w.r.t. the scores in one pass ------
  * All reductions are two-stage and deterministic.  `workspace` >= b200_loss_workspace_bytes().
  * `loss_out` is a device scalar.  Gradient outputs may be NULL. */

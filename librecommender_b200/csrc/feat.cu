@@ -15,29 +15,13 @@
 // lpr = min(32, pow2 >= K) lanes per row, lanes stride the embedding width; field indices are
 // loaded cooperatively and broadcast by shuffle, 4 gathers in flight.
 #include "common.cuh"
+#include "feat_common.cuh"
 #include "../../include/b200reco.h"
 
 namespace b200 {
 namespace feat {
 
 constexpr int MAX_T = 8;   // K <= 256
-
-__device__ __forceinline__ float subwarp_sum(float v, int lpr, uint32_t gmask) {
-  for (int o = lpr >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
-  return v;
-}
-
-// field f of row r -> (table row index) for sparse fields, value for dense fields
-__device__ __forceinline__ int32_t sparse_index(const b200_feat_layout& L, int64_t r, int64_t u, int64_t it, int f) {
-  if (L.sparse_rows) return L.sparse_rows[r * L.ld_sparse_rows + f];
-  return L.sparse_side[f] == 0 ? __ldg(L.user_sparse_unique + u * L.ld_us + L.sparse_col[f])
-                               : __ldg(L.item_sparse_unique + it * L.ld_is + L.sparse_col[f]);
-}
-__device__ __forceinline__ float dense_value(const b200_feat_layout& L, int64_t r, int64_t u, int64_t it, int f) {
-  if (L.dense_rows) return L.dense_rows[r * L.ld_dense_rows + f];
-  return L.dense_side[f] == 0 ? __ldg(L.user_dense_unique + u * L.ld_ud + L.dense_col[f])
-                              : __ldg(L.item_dense_unique + it * L.ld_id + L.dense_col[f]);
-}
 
 struct Out {
   float* concat; int64_t ld_concat;   // [R, F*K]  (deep / tower input) or null

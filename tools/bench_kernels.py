@@ -225,8 +225,51 @@ def bench_linear():
                               "peak_gbs": PEAK, "hbm_frac": byt / (ms * 1e-3) / 1e9 / PEAK}), flush=True)
 
 
+def bench_train():
+    """FM training step (gather fwd, BN, head, loss, backward scatter, TF-Adam over every variable)."""
+    from librecommender_b200.training import FMTrainer
+    from oracle import fm_train as ft
+    from oracle import tf_models as tm
+
+    for tag, n_users, n_items, n_f, R in (("C1-like (6k users x 3.2k items, 5 sparse + 1 dense)", 5958, 3231, 5, 2048),
+                                          ("C3-like (1M users x 100k items, 100 sparse + 10 dense)", 1_000_000, 100_000,
+                                           100, 8192)):
+        rng = np.random.default_rng(0)
+        if n_f == 5:
+            spec = tm.make_spec(rng, n_users, n_items, [2, 21], [18, 18, 18], 1, 0, interleave=False)
+        else:
+            us = [int(x) for x in np.exp(rng.uniform(np.log(10), np.log(2e5), 50))]
+            its = [int(x) for x in np.exp(rng.uniform(np.log(10), np.log(2e5), 50))]
+            spec = tm.make_spec(rng, n_users, n_items, us, its, 5, 5, interleave=False)
+        w = tm.make_fm_weights(rng, spec, 16, True)
+        tr = FMTrainer(spec, w, use_bn=True, lr=1e-3)
+        users = torch.as_tensor(rng.integers(0, n_users, R)).cuda()
+        items = torch.as_tensor(rng.integers(0, n_items, R)).cuda()
+        labels = torch.as_tensor((rng.random(R) < 0.3).astype(np.float32)).cuda()
+        ms = timeit(lambda: tr.step(users, items, labels), iters=10, warm=3)
+        n_par = sum(int(v.numel()) for v in tr.params.values())
+        print(json.dumps({"kernel": f"FM training step, {tag}, batch {R}", "ms": ms,
+                          "interactions_per_s": R / (ms * 1e-3), "trainable_floats": n_par,
+                          "adam_dense_bytes_per_step": n_par * 4 * 7,
+                          "adam_gbs_if_alone": n_par * 4 * 7 / (ms * 1e-3) / 1e9}), flush=True)
+        if n_users <= 10000:       # CPU baseline: the numpy restatement of the same step (oracle port)
+            st = ft.init_state(w, True, dtype=np.float32)
+            uh, ih, lh = users.cpu().numpy(), items.cpu().numpy(), labels.cpu().numpy()
+            sp, de = tm.row_features(spec, uh, ih)
+            ft.train_step(st, uh, ih, sp, de, lh, 1e-3)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                ft.train_step(st, uh, ih, sp, de, lh, 1e-3)
+            cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+            print(json.dumps({"kernel": f"cpu_baseline: FM training step (oracle port, numpy), {tag}", "ms": cpu_ms,
+                              "interactions_per_s": R / (cpu_ms * 1e-3), "cores": os.cpu_count(), "kind": "port"}),
+                  flush=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["spmm", "feat", "topk", "linear"]
+    which = sys.argv[1:] or ["spmm", "feat", "topk", "linear", "train"]
+    if "train" in which:
+        bench_train()
     if "linear" in which:
         bench_linear()
     if "spmm" in which:
