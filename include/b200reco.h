@@ -239,6 +239,33 @@ int b200_feat_backward(const b200_feat_layout* layout, const b200_feat_tables* t
                        float* g_item_linear, float* g_sparse_linear, float* g_dense_linear,
                        float* g_lin_kernel, void* stream);
 
+/* Pieces of dense_nn in training mode (libreco/layers/dense.py:12-49) and of the DeepFM head
+ * (algorithms/deepfm.py:172-173).  The Dense layers themselves run on b200_linear_*:
+ * dX = dY Wk^T and dWt = dY^T X are calls of the same kernel on transposed views. */
+
+/* out[k] += sum_r (wrow ? wrow[r] : 1) * X[r,k] * (Y ? Y[r,k] : 1)   (bias gradients, weighted column
+ * sums of the head); double accumulation, deterministic. */
+int b200_col_reduce(const float* X, int64_t ldx, int64_t R, int32_t K, const float* wrow, const float* Y,
+                    int64_t ldy, float* out, void* stream);
+
+/* Backward of b200_bn_train_forward (batch statistics): dx, and g_gamma / g_beta ADDED.  relu_mask != 0:
+ * x is a ReLU output and the result is additionally masked with x > 0 (Dense -> ReLU -> BN blocks).
+ * workspace: 16 bytes per column. */
+int b200_bn_train_backward(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t R, int32_t K,
+                           const float* batch_mean, const float* batch_var, const float* gamma, float eps,
+                           int32_t relu_mask, float* dx, int64_t lddx, float* g_gamma, float* g_beta,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int b200_relu_backward(const float* dy, const float* a, int64_t n, float* dx, void* stream);
+
+/* logit = <[lin + lin_bias, pw[0..K), deep[0..H)], out_kernel> + out_bias (biases: device scalars or NULL);
+ * backward: dlin = dlogit * w[0], dpw = dlogit * w[1..K], ddeep = dlogit * w[1+K..]. */
+int b200_deepfm_head_forward(const float* lin, const float* lin_bias, const float* pw, int64_t ldpw, int32_t K,
+                             const float* deep, int64_t lddeep, int32_t H, const float* out_kernel,
+                             const float* out_bias, int64_t R, float* logit, void* stream);
+int b200_deepfm_head_backward(const float* dlogit, const float* out_kernel, int32_t K, int32_t H, int64_t R,
+                              float* dlin, float* dpw, int64_t lddpw, float* ddeep, int64_t lddeep,
+                              void* stream);
+
 /* tf.train.AdamOptimizer over a WHOLE variable (what _apply_sparse_shared does for embedding
  * variables: m, v decayed everywhere, every row updated): lr_t = lr sqrt(1-b2^t)/(1-b1^t),
  * m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2, param -= lr_t m / (sqrt(v) + eps); grad is zeroed. */

@@ -250,11 +250,166 @@ __global__ void adam_dense_kernel(float* __restrict__ p, float* __restrict__ m, 
   g[i] = 0.f;
 }
 
+// ---- generic pieces for the MLP tails (dense_nn in training mode, libreco/layers/dense.py:12-49) ----
+
+// out[k] = sum_r (w ? w[r] : 1) * X[r,k] * (Y ? Y[r,k] : 1): 32 columns x 8 row lanes per block,
+// coalesced along the columns, double accumulation, fixed reduction order (deterministic).
+__global__ void __launch_bounds__(256)
+col_reduce_kernel(const float* __restrict__ X, int64_t ldx, int64_t R, int K, const float* __restrict__ w,
+                  const float* __restrict__ Y, int64_t ldy, double* __restrict__ out_d, float* __restrict__ out_f) {
+  __shared__ double sh[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + tx;
+  double s = 0.0;
+  if (k < K) {
+    for (int64_t r = ty; r < R; r += 8) {
+      double v = (double)X[r * ldx + k];
+      if (Y) v *= (double)Y[r * ldy + k];
+      if (w) v *= (double)w[r];
+      s += v;
+    }
+  }
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && k < K) {
+    double t = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sh[j][tx];
+    if (out_d) out_d[k] = t;
+    if (out_f) out_f[k] += (float)t;
+  }
+}
+
+// BN backward with batch statistics.  s1 = sum dy, s2 = sum dy * x (workspace, doubles).
+__global__ void bn_backward_apply_kernel(const float* __restrict__ dy, int64_t lddy, const float* __restrict__ x,
+                                         int64_t ldx, int64_t R, int K, const float* __restrict__ mean,
+                                         const float* __restrict__ var, const float* __restrict__ gamma, float eps,
+                                         int relu_mask, const double* __restrict__ s1, const double* __restrict__ s2,
+                                         float* __restrict__ dx, int64_t lddx, float* __restrict__ g_gamma,
+                                         float* __restrict__ g_beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K) {
+    const int k = (int)i;
+    const double inv = 1.0 / sqrt((double)var[k] + (double)eps);
+    g_gamma[k] += (float)(inv * (s2[k] - (double)mean[k] * s1[k]));   // sum dy * xhat
+    g_beta[k] += (float)s1[k];
+  }
+  if (i >= R * K) return;
+  const int64_t r = i / K;
+  const int k = (int)(i % K);
+  const float inv = rsqrtf(var[k] + eps);
+  const float xv = x[r * ldx + k];
+  const float xh = (xv - mean[k]) * inv;
+  const float T = inv * (float)(s2[k] - (double)mean[k] * s1[k]);
+  const float invR = 1.f / (float)R;
+  float d = gamma[k] * inv * (dy[r * lddy + k] - (float)s1[k] * invR - xh * T * invR);
+  if (relu_mask && !(xv > 0.f)) d = 0.f;      // x = relu(h): pass the gradient only where h > 0
+  dx[r * lddx + k] = d;
+}
+
+__global__ void relu_backward_kernel(const float* __restrict__ dy, const float* __restrict__ a, int64_t n,
+                                     float* __restrict__ dx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dx[i] = a[i] > 0.f ? dy[i] : 0.f;
+}
+
+// DeepFM head (deepfm.py:172-173): logit = <[lin + lin_bias, pw, deep], w_out> + b_out
+__global__ void deepfm_head_forward_kernel(const float* __restrict__ lin, const float* __restrict__ lin_bias,
+                                           const float* __restrict__ pw, int64_t ldpw, int K,
+                                           const float* __restrict__ deep, int64_t lddeep, int H,
+                                           const float* __restrict__ w, const float* __restrict__ b, int64_t R,
+                                           float* __restrict__ logit) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float acc = (b ? __ldg(b) : 0.f) + (lin[r] + (lin_bias ? __ldg(lin_bias) : 0.f)) * __ldg(w);
+  for (int k = 0; k < K; ++k) acc = fmaf(pw[r * ldpw + k], __ldg(w + 1 + k), acc);
+  for (int j = 0; j < H; ++j) acc = fmaf(deep[r * lddeep + j], __ldg(w + 1 + K + j), acc);
+  logit[r] = acc;
+}
+
+__global__ void deepfm_head_backward_kernel(const float* __restrict__ dlogit, const float* __restrict__ w, int K,
+                                            int H, int64_t R, float* __restrict__ dlin, float* __restrict__ dpw,
+                                            int64_t lddpw, float* __restrict__ ddeep, int64_t ldd) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = 1 + K + H;
+  if (i >= R * W) return;
+  const int64_t r = i / W;
+  const int c = (int)(i % W);
+  const float v = dlogit[r] * __ldg(w + c);
+  if (c == 0) dlin[r] = v;
+  else if (c <= K) dpw[r * lddpw + (c - 1)] = v;
+  else ddeep[r * ldd + (c - 1 - K)] = v;
+}
+
 }  // namespace train
 }  // namespace b200
 
 using namespace b200;
 using namespace b200::train;
+
+extern "C" int b200_col_reduce(const float* X, int64_t ldx, int64_t R, int32_t K, const float* wrow,
+                               const float* Y, int64_t ldy, float* out, void* stream) {
+  B200_REQUIRE(X && out && K > 0, "b200_col_reduce: bad arguments");
+  if (R == 0) return 0;
+  col_reduce_kernel<<<(unsigned)((K + 31) / 32), 256, 0, (cudaStream_t)stream>>>(X, ldx, R, K, wrow, Y, ldy, nullptr, out);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200_bn_train_backward(const float* dy, int64_t lddy, const float* x, int64_t ldx, int64_t R,
+                                      int32_t K, const float* batch_mean, const float* batch_var,
+                                      const float* gamma, float eps, int32_t relu_mask, float* dx, int64_t lddx,
+                                      float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  B200_REQUIRE(dy && x && batch_mean && batch_var && gamma && dx && g_gamma && g_beta, "b200_bn_train_backward: null pointer");
+  B200_REQUIRE(workspace && workspace_bytes >= (size_t)K * 16, "workspace too small (need 16 bytes per column)");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* s1 = (double*)workspace;
+  double* s2 = s1 + K;
+  const unsigned gb = (unsigned)((K + 31) / 32);
+  col_reduce_kernel<<<gb, 256, 0, st>>>(dy, lddy, R, K, nullptr, nullptr, 0, s1, nullptr);
+  col_reduce_kernel<<<gb, 256, 0, st>>>(dy, lddy, R, K, nullptr, x, ldx, s2, nullptr);
+  bn_backward_apply_kernel<<<(unsigned)ceil_div64(R * K, 256), 256, 0, st>>>(
+      dy, lddy, x, ldx, R, K, batch_mean, batch_var, gamma, eps, relu_mask, s1, s2, dx, lddx, g_gamma, g_beta);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch(3);
+  return 0;
+}
+
+extern "C" int b200_relu_backward(const float* dy, const float* a, int64_t n, float* dx, void* stream) {
+  B200_REQUIRE(dy && a && dx, "b200_relu_backward: null pointer");
+  if (n == 0) return 0;
+  relu_backward_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, a, n, dx);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200_deepfm_head_forward(const float* lin, const float* lin_bias, const float* pw, int64_t ldpw,
+                                        int32_t K, const float* deep, int64_t lddeep, int32_t H,
+                                        const float* out_kernel, const float* out_bias, int64_t R, float* logit,
+                                        void* stream) {
+  B200_REQUIRE(lin && pw && deep && out_kernel && logit, "b200_deepfm_head_forward: null pointer");
+  if (R == 0) return 0;
+  deepfm_head_forward_kernel<<<(unsigned)ceil_div64(R, 256), 256, 0, (cudaStream_t)stream>>>(
+      lin, lin_bias, pw, ldpw, K, deep, lddeep, H, out_kernel, out_bias, R, logit);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200_deepfm_head_backward(const float* dlogit, const float* out_kernel, int32_t K, int32_t H,
+                                         int64_t R, float* dlin, float* dpw, int64_t lddpw, float* ddeep,
+                                         int64_t lddeep, void* stream) {
+  B200_REQUIRE(dlogit && out_kernel && dlin && dpw && ddeep, "b200_deepfm_head_backward: null pointer");
+  if (R == 0) return 0;
+  deepfm_head_backward_kernel<<<(unsigned)ceil_div64(R * (1 + K + H), 256), 256, 0, (cudaStream_t)stream>>>(
+      dlogit, out_kernel, K, H, R, dlin, dpw, lddpw, ddeep, lddeep);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
 
 extern "C" int b200_bn_train_forward(const float* x, int64_t ldx, int64_t R, int32_t K, const float* gamma,
                                      const float* beta, float eps, float momentum, float* y, int64_t ldy,

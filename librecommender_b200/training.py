@@ -146,3 +146,203 @@ class FMTrainer:
             w["fm_bn"] = dict(gamma=p["bn_gamma"].cpu().numpy(), beta=p["bn_beta"].cpu().numpy(),
                               mean=self.moving_mean.cpu().numpy(), var=self.moving_var.cpu().numpy())
         return w
+
+
+class DeepFMTrainer:
+    """DeepFM training step on the device: ``libreco/algorithms/deepfm.py:143-175`` with
+    ``dense_nn`` in training mode (``libreco/layers/dense.py:12-49``: BN(input) -> [Dense -> ReLU ->
+    BN] x (L-1) -> Dense, no dropout = the reference's default), mean sigmoid CE, TF-Adam.
+
+    The Dense layers run on the library's own GEMM kernels (``feat_models.linear``: tcgen05 3xTF32 or
+    exact-fma SIMT) — forward ``Y = X Wt^T + b``, backward ``dX = dY Wt`` and ``dWt = dY^T X`` are the
+    same kernel on transposed operands.  ``weights`` uses the inference layout of
+    ``feat_models.DeepFM`` / ``oracle.tf_models.make_deepfm_weights``."""
+
+    def __init__(self, spec, weights, use_bn=True, lr=1e-3, epsilon=1e-5, device=None):
+        import torch
+
+        self._torch = torch
+        K = int(weights["user_embeds"].shape[1])
+        self.spec = spec if isinstance(spec, FeatSpec) else FeatSpec(spec, K, device)
+        self.device, self.K = self.spec.device, K
+        self.F = 2 + self.spec.n_sparse + self.spec.n_dense
+        self.use_bn, self.lr, self.epsilon, self.t = bool(use_bn), float(lr), float(epsilon), 0
+        f32 = torch.float32
+        p = {k: _dev(weights[k], self.device, f32).clone() for k in _TABLES if weights.get(k) is not None}
+        for k in ("lin_kernel", "out_kernel"):
+            p[k] = _dev(np.asarray(weights[k]).reshape(-1), self.device, f32).clone()
+        for k in ("lin_bias", "out_bias"):
+            p[k] = _dev(np.asarray(weights[k]).reshape(1), self.device, f32).clone()
+        mlp = weights["mlp"]
+        self.n_layers = len(mlp["kernels"])
+        for i in range(self.n_layers):       # trainable layout = transposed kernel [dout, din] (what the GEMM reads)
+            p[f"Wt{i}"] = _dev(np.ascontiguousarray(np.asarray(mlp["kernels"][i]).T), self.device, f32).clone()
+            p[f"b{i}"] = _dev(mlp["biases"][i], self.device, f32).clone()
+        self.moving = {}
+        if self.use_bn:
+            bns = [mlp.get("bn_in")] + list(mlp.get("bns") or [])
+            for j, bn in enumerate(bns):
+                p[f"bn{j}_gamma"] = _dev(bn["gamma"], self.device, f32).clone()
+                p[f"bn{j}_beta"] = _dev(bn["beta"], self.device, f32).clone()
+                self.moving[j] = (_dev(bn["mean"], self.device, f32).clone(), _dev(bn["var"], self.device, f32).clone())
+        self.H = int(p[f"Wt{self.n_layers - 1}"].shape[0])
+        self.params = p
+        self.grads = {k: torch.zeros_like(v) for k, v in p.items()}
+        self.m = {k: torch.zeros_like(v) for k, v in p.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in p.items()}
+        T = FeatTablesStruct()
+        for k in _TABLES:
+            setattr(T, k, p[k].data_ptr() if k in p else None)
+        self.tables = T
+        self._lws = torch.empty(int(_lib.lib.b200_loss_workspace_bytes()), dtype=torch.uint8, device=self.device)
+
+    # ---- small wrappers ---------------------------------------------------------------------------
+    def _bn_forward(self, x, j):
+        torch = self._torch
+        p = self.params
+        R, C = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=self.device)
+        var = torch.empty(C, dtype=torch.float32, device=self.device)
+        mm, mv = self.moving[j]
+        _lib.check(_lib.lib.b200_bn_train_forward(
+            _lib.ptr(x), x.stride(0), R, C, _lib.ptr(p[f"bn{j}_gamma"]), _lib.ptr(p[f"bn{j}_beta"]), BN_EPS,
+            BN_MOMENTUM, _lib.ptr(y), y.stride(0), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(mm), _lib.ptr(mv),
+            _lib.current_stream()))
+        return y, (mean, var)
+
+    def _bn_backward(self, dy, x, stats, j, relu_mask):
+        torch = self._torch
+        p, g = self.params, self.grads
+        R, C = x.shape
+        dx = torch.empty_like(x)
+        ws = torch.empty(C * 2, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib.b200_bn_train_backward(
+            _lib.ptr(dy), dy.stride(0), _lib.ptr(x), x.stride(0), R, C, _lib.ptr(stats[0]), _lib.ptr(stats[1]),
+            _lib.ptr(p[f"bn{j}_gamma"]), BN_EPS, 1 if relu_mask else 0, _lib.ptr(dx), dx.stride(0),
+            _lib.ptr(g[f"bn{j}_gamma"]), _lib.ptr(g[f"bn{j}_beta"]), _lib.ptr(ws), ws.numel() * 8,
+            _lib.current_stream()))
+        return dx
+
+    def _col_reduce(self, X, out, wrow=None):
+        _lib.check(_lib.lib.b200_col_reduce(_lib.ptr(X), X.stride(0) if X.dim() == 2 else 1, X.shape[0],
+                                            X.shape[1] if X.dim() == 2 else 1, _lib.ptr(wrow), None, 0,
+                                            _lib.ptr(out), _lib.current_stream()))
+
+    # ---- forward / step ---------------------------------------------------------------------------
+    def forward(self, users_d, items_d):
+        from .feat_models import linear
+
+        torch = self._torch
+        lib, st, p, K = _lib.lib, _lib.current_stream(), self.params, self.K
+        R = int(users_d.numel())
+        f32, dev = torch.float32, self.device
+        c = dict(R=R, concat=torch.empty((R, self.F * K), dtype=f32, device=dev),
+                 pw=torch.empty((R, K), dtype=f32, device=dev), lin=torch.empty(R, dtype=f32, device=dev),
+                 S=torch.empty((R, K), dtype=f32, device=dev), Q=torch.empty((R, K), dtype=f32, device=dev))
+        _lib.check(lib.b200_feat_forward(
+            ctypes.byref(self.spec.layout), ctypes.byref(self.tables), _lib.ptr(users_d), _lib.ptr(items_d), R, 0, 0,
+            _lib.ptr(c["concat"]), c["concat"].stride(0), _lib.ptr(c["pw"]), K, _lib.ptr(c["lin"]), None,
+            _lib.ptr(p["lin_kernel"]), 0.0, None, None, None, 0.0, _lib.ptr(c["S"]), _lib.ptr(c["Q"]), K, st))
+        a = c["concat"]
+        c["bn_stats"], c["dense_in"], c["relu_out"] = {}, [], []
+        if self.use_bn:
+            a, c["bn_stats"][0] = self._bn_forward(a, 0)
+        for i in range(self.n_layers):
+            last = i == self.n_layers - 1
+            c["dense_in"].append(a)
+            a = linear(a, p[f"Wt{i}"], p[f"b{i}"], not last, cache_split=False)     # weights change every step
+            if not last:
+                c["relu_out"].append(a)
+                if self.use_bn:
+                    a, c["bn_stats"][i + 1] = self._bn_forward(a, i + 1)
+        c["deep"] = a
+        c["logit"] = torch.empty(R, dtype=f32, device=dev)
+        _lib.check(lib.b200_deepfm_head_forward(
+            _lib.ptr(c["lin"]), _lib.ptr(p["lin_bias"]), _lib.ptr(c["pw"]), K, K, _lib.ptr(a), a.stride(0), self.H,
+            _lib.ptr(p["out_kernel"]), _lib.ptr(p["out_bias"]), R, _lib.ptr(c["logit"]), st))
+        self._cache = c
+        return c["logit"]
+
+    def backward(self, labels_d):
+        """Loss + every gradient buffer filled (before the optimiser); returns the device loss."""
+        from .feat_models import linear
+
+        torch = self._torch
+        lib, st, p, g, K, H = _lib.lib, _lib.current_stream(), self.params, self.grads, self.K, self.H
+        c = self._cache
+        R, f32, dev = c["R"], torch.float32, self.device
+        loss = torch.empty((), dtype=f32, device=dev)
+        dlogit = torch.empty(R, dtype=f32, device=dev)
+        _lib.check(lib.b200_pointwise_loss(_lib.ptr(c["logit"]), _lib.ptr(labels_d), R, 0, 0.25, 2.0, _lib.ptr(loss),
+                                           _lib.ptr(dlogit), _lib.ptr(self._lws), self._lws.numel(), st))
+        dlin = torch.empty(R, dtype=f32, device=dev)
+        dpw = torch.empty((R, K), dtype=f32, device=dev)
+        da = torch.empty((R, H), dtype=f32, device=dev)
+        _lib.check(lib.b200_deepfm_head_backward(_lib.ptr(dlogit), _lib.ptr(p["out_kernel"]), K, H, R, _lib.ptr(dlin),
+                                                 _lib.ptr(dpw), K, _lib.ptr(da), H, st))
+        # out_kernel = [w_lin | w_pw (K) | w_deep (H)]: weighted column sums with the row weights dlogit
+        gk = g["out_kernel"]
+        lin_full = c["lin"] + p["lin_bias"]                      # elementwise add of a device scalar (plumbing)
+        self._col_reduce(lin_full.view(R, 1), gk[0:1], dlogit)
+        self._col_reduce(c["pw"], gk[1:1 + K], dlogit)
+        self._col_reduce(c["deep"], gk[1 + K:], dlogit)
+        self._col_reduce(dlogit.view(R, 1), g["out_bias"])
+        self._col_reduce(dlin.view(R, 1), g["lin_bias"])
+        # ---- dense_nn backward
+        for i in range(self.n_layers - 1, -1, -1):
+            if i != self.n_layers - 1:
+                r_out = c["relu_out"][i]
+                if self.use_bn:
+                    da = self._bn_backward(da, r_out, c["bn_stats"][i + 1], i + 1, True)
+                else:
+                    dh = torch.empty_like(da)
+                    _lib.check(lib.b200_relu_backward(_lib.ptr(da), _lib.ptr(r_out), da.numel(), _lib.ptr(dh), st))
+                    da = dh
+            x = c["dense_in"][i]
+            da = da.contiguous()
+            # dWt [dout, din] = dY^T X ; db = column sums of dY ; dX = dY Wt
+            g[f"Wt{i}"] += linear(da.t().contiguous(), x.t().contiguous(), None, False, cache_split=False)
+            self._col_reduce(da, g[f"b{i}"])
+            da = linear(da, p[f"Wt{i}"].t().contiguous(), None, False, cache_split=False)
+        dconcat = self._bn_backward(da, c["concat"], c["bn_stats"][0], 0, False) if self.use_bn else da
+        gp = lambda k: _lib.ptr(g[k]) if k in g else None      # noqa: E731
+        _lib.check(lib.b200_feat_backward(
+            ctypes.byref(self.spec.layout), ctypes.byref(self.tables), _lib.ptr(c["users"]), _lib.ptr(c["items"]), R,
+            _lib.ptr(dpw), K, _lib.ptr(c["S"]), K, _lib.ptr(dconcat), dconcat.stride(0), _lib.ptr(dlin),
+            _lib.ptr(p["lin_kernel"]), gp("user_embeds"), gp("item_embeds"), gp("sparse_embeds"), gp("dense_embeds"),
+            gp("user_linear"), gp("item_linear"), gp("sparse_linear"), gp("dense_linear"), gp("lin_kernel"), st))
+        return loss
+
+    def step(self, users_d, items_d, labels_d):
+        torch = self._torch
+        users_d = users_d.to(torch.int64).contiguous()
+        items_d = items_d.to(torch.int64).contiguous()
+        labels_d = labels_d.to(torch.float32).contiguous()
+        self.forward(users_d, items_d)
+        self._cache["users"], self._cache["items"] = users_d, items_d
+        loss = self.backward(labels_d)
+        self.t += 1
+        lib, st = _lib.lib, _lib.current_stream()
+        for k, v in self.params.items():
+            _lib.check(lib.b200_adam_dense(_lib.ptr(v), _lib.ptr(self.m[k]), _lib.ptr(self.v[k]), _lib.ptr(self.grads[k]),
+                                           v.numel(), self.lr, BETA1, BETA2, self.epsilon, self.t, st))
+        self._cache = None
+        return loss
+
+    def export_weights(self):
+        p = self.params
+        w = {k: p[k].cpu().numpy() for k in _TABLES if k in p}
+        w.update(lin_kernel=p["lin_kernel"].cpu().numpy(), lin_bias=np.float32(p["lin_bias"].cpu().numpy()[0]),
+                 out_kernel=p["out_kernel"].cpu().numpy(), out_bias=np.float32(p["out_bias"].cpu().numpy()[0]))
+        n = self.n_layers
+        mlp = dict(kernels=[p[f"Wt{i}"].t().contiguous().cpu().numpy() for i in range(n)],
+                   biases=[p[f"b{i}"].cpu().numpy() for i in range(n)])
+        if self.use_bn:
+            def bn(j):
+                return dict(gamma=p[f"bn{j}_gamma"].cpu().numpy(), beta=p[f"bn{j}_beta"].cpu().numpy(),
+                            mean=self.moving[j][0].cpu().numpy(), var=self.moving[j][1].cpu().numpy())
+            mlp["bn_in"] = bn(0)
+            mlp["bns"] = [bn(i + 1) for i in range(n - 1)]
+        w["mlp"] = mlp
+        return w

@@ -1,0 +1,93 @@
+"""GPU parity of the device DeepFM training step (librecommender_b200/training.py::DeepFMTrainer)
+against oracle/deepfm_train.py (numpy float64; gradient math pinned to torch autograd by
+tests/test_deepfm_train_cpu.py; TensorFlow conventions unpinned): raw gradients of one batch,
+parameters after 1 and 3 steps, BN moving statistics, exported weights in the inference engine."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed, use_bn, hidden, R=1536, K=16):
+    from oracle import tf_models as tm
+
+    rng = np.random.default_rng(seed)
+    spec = tm.make_spec(rng, 300, 500, [7, 30, 12], [11, 5, 40, 8], 1, 2)
+    w = tm.make_deepfm_weights(rng, spec, K, hidden, use_bn)
+    batches = []
+    for _ in range(3):
+        users, items = rng.integers(0, 300, R), rng.integers(0, 500, R)
+        batches.append((users, items, (rng.random(R) < 0.35).astype(np.float32)))
+    return spec, w, batches
+
+
+def _map_params(st_params):
+    """oracle names (W{i} = [din, dout]) -> trainer names (Wt{i} = [dout, din])."""
+    out = {}
+    for k, v in st_params.items():
+        if k.startswith("W") and k[1:].isdigit():
+            out["Wt" + k[1:]] = v.T
+        else:
+            out[k] = v
+    return out
+
+
+@pytest.mark.parametrize("use_bn,hidden", [(True, (128, 64, 32)), (False, (64, 32)), (True, (48,))])
+def test_gradients_of_one_batch_match_oracle(use_bn, hidden):
+    import torch
+
+    from librecommender_b200.training import DeepFMTrainer
+    from oracle import deepfm_train as dt_
+    from oracle import tf_models as tm
+
+    spec, w, batches = _case(5, use_bn, hidden)
+    users, items, labels = batches[0]
+    tr = DeepFMTrainer(spec, w, use_bn=use_bn)
+    st = dt_.init_state(w, use_bn)
+    sparse, dense = tm.row_features(spec, users, items)
+    ref_loss, ref_out, ref_g, _ = dt_.forward_backward(st, users, items, sparse, dense, labels)
+    u, i, y = torch.as_tensor(users).cuda(), torch.as_tensor(items).cuda(), torch.as_tensor(labels).cuda()
+    logits = tr.forward(u, i)
+    np.testing.assert_allclose(logits.cpu().numpy(), ref_out, rtol=3e-5, atol=3e-5)
+    tr._cache["users"], tr._cache["items"] = u, i
+    loss = tr.backward(y)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - ref_loss) < 2e-5
+    for k, ref in _map_params(ref_g).items():
+        got = tr.grads[k].cpu().numpy().astype(np.float64).reshape(ref.shape)
+        scale = max(np.abs(ref).max(), 1e-8)
+        assert np.abs(got - ref).max() <= 5e-4 * scale + 1e-9, (k, float(np.abs(got - ref).max()), scale)
+
+
+@pytest.mark.parametrize("use_bn", [True, False])
+def test_training_steps_match_oracle(use_bn):
+    import torch
+
+    from librecommender_b200.feat_models import DeepFM
+    from librecommender_b200.training import DeepFMTrainer
+    from oracle import deepfm_train as dt_
+    from oracle import tf_models as tm
+
+    spec, w, batches = _case(11, use_bn, (128, 64, 32))
+    lr, eps = 1e-2, 1e-5
+    tr = DeepFMTrainer(spec, w, use_bn=use_bn, lr=lr, epsilon=eps)
+    st = dt_.init_state(w, use_bn)
+    for step, (users, items, labels) in enumerate(batches):
+        sparse, dense = tm.row_features(spec, users, items)
+        ref_loss = dt_.train_step(st, users, items, sparse, dense, labels, lr, eps)
+        loss = tr.step(torch.as_tensor(users).cuda(), torch.as_tensor(items).cuda(), torch.as_tensor(labels).cuda())
+        assert abs(float(loss) - ref_loss) <= 1e-3 * max(1.0, abs(ref_loss)) * (step + 1), (step, float(loss), ref_loss)
+        if step == 0:
+            for k, ref in _map_params(st["params"]).items():
+                got = tr.params[k].cpu().numpy().astype(np.float64).reshape(ref.shape)
+                err = np.abs(got - ref).max()
+                assert err <= 2e-2 * lr + 1e-6, (k, err)       # first Adam step moves every touched weight by ~lr
+    if use_bn:
+        for j, (mm, mv) in tr.moving.items():
+            np.testing.assert_allclose(mm.cpu().numpy(), st["moving"][f"bn{j}"][0], rtol=2e-3, atol=2e-4)
+            np.testing.assert_allclose(mv.cpu().numpy(), st["moving"][f"bn{j}"][1], rtol=2e-3, atol=2e-4)
+    users, items, _ = batches[0]
+    got = DeepFM(spec, tr.export_weights()).logits(users, items).cpu().numpy()
+    sparse, dense = tm.row_features(spec, users, items)
+    ref = tm.deepfm_forward(dt_.export_weights(st), users, items, sparse, dense, dtype=np.float64)
+    assert np.abs(got - ref).max() <= 3e-2 * max(1.0, np.abs(ref).max())

@@ -252,6 +252,27 @@ def bench_train():
                           "interactions_per_s": R / (ms * 1e-3), "trainable_floats": n_par,
                           "adam_dense_bytes_per_step": n_par * 4 * 7,
                           "adam_gbs_if_alone": n_par * 4 * 7 / (ms * 1e-3) / 1e9}), flush=True)
+        from librecommender_b200.training import DeepFMTrainer
+        from oracle import deepfm_train as dft
+
+        wd = tm.make_deepfm_weights(rng, spec, 16, (128, 64, 32), True)
+        trd = DeepFMTrainer(spec, wd, use_bn=True, lr=1e-3)
+        ms_d = timeit(lambda: trd.step(users, items, labels), iters=10, warm=3)
+        print(json.dumps({"kernel": f"DeepFM training step (128-64-32, BN), {tag}, batch {R}", "ms": ms_d,
+                          "interactions_per_s": R / (ms_d * 1e-3),
+                          "trainable_floats": sum(int(v.numel()) for v in trd.params.values())}), flush=True)
+        if n_users <= 10000:
+            std = dft.init_state(wd, True, dtype=np.float32)
+            uh, ih, lh = users.cpu().numpy(), items.cpu().numpy(), labels.cpu().numpy()
+            sp, de = tm.row_features(spec, uh, ih)
+            dft.train_step(std, uh, ih, sp, de, lh, 1e-3)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                dft.train_step(std, uh, ih, sp, de, lh, 1e-3)
+            cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+            print(json.dumps({"kernel": f"cpu_baseline: DeepFM training step (oracle port, numpy), {tag}", "ms": cpu_ms,
+                              "interactions_per_s": R / (cpu_ms * 1e-3), "cores": os.cpu_count(), "kind": "port"}),
+                  flush=True)
         if n_users <= 10000:       # CPU baseline: the numpy restatement of the same step (oracle port)
             st = ft.init_state(w, True, dtype=np.float32)
             uh, ih, lh = users.cpu().numpy(), items.cpu().numpy(), labels.cpu().numpy()
