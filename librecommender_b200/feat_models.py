@@ -682,6 +682,62 @@ class YouTubeRanking(_SeqModelBase):
         perm = np.concatenate([np.arange(0, 2 * K), np.arange(3 * K, (F + 1) * K), np.arange(2 * K, 3 * K)])
         self.mlp = self._upload_mlp(permute_mlp_input(weights["mlp"], perm))
 
+    # ---- hoisted all-items scoring: everything user-only or item-only once ----
+    def _hoistable(self):
+        dims = [w.shape[0] for w, _, _ in self.mlp]
+        n = len(dims)
+        return self.K <= 64 and n in (2, 3) and dims[0] <= 256 and dims[1] <= 64 and (n == 2 or dims[2] <= 32)
+
+    def _side_input(self, which, ids_d):
+        """Concatenated field embeddings of ONE side for the given ids (+ the pooled history for users)
+        and the matching columns of the first MLP layer."""
+        torch = self._torch
+        L, pos = self._side(which)
+        n = int(ids_d.numel())
+        width = len(pos) * self.K + (self.K if which == "user" else 0)
+        x = torch.empty((n, width), dtype=torch.float32, device=self.device)
+        self._feat_forward(L, ids_d, ids_d, n, 0, concat=x)
+        if which == "user":
+            self._seq_block(ids_d, ids_d, n, 0, 0, x[:, len(pos) * self.K:])
+        cache = self.__dict__.setdefault("_w1_side", {})
+        if which not in cache:
+            groups = list(pos) + ([self.F] if which == "user" else [])     # pooled block sits after the F fields
+            cols = torch.cat([torch.arange(g * self.K, (g + 1) * self.K, device=self.device) for g in groups])
+            cache[which] = self.mlp[0][0][:, cols].contiguous()
+        return x, cache[which]
+
+    def score_all_items(self, user_ids_d):
+        """youtube_ranking.py:199-218 over the implicit (user, item) grid: the first Dense layer splits
+        into a user part (id, user features, pooled history) and an item part, computed once per user /
+        once per item; a pair then costs H1 adds + the small layers (the DeepFM pair kernel with an
+        empty FM part)."""
+        torch = self._torch
+        if not self._hoistable():
+            return super().score_all_items(user_ids_d)
+        if "_item_part" not in self.__dict__:
+            xi, Wi = self._side_input("item", torch.arange(self.n_items, device=self.device))
+            self._item_part = linear(xi, Wi, None, False)
+            three = len(self.mlp) == 3
+            self._tail = (self.mlp[1][0].t().contiguous(), self.mlp[2][0].t().contiguous() if three else None)
+            self._w_out = torch.cat([torch.zeros(1 + self.K, dtype=torch.float32, device=self.device),
+                                     self.out_kernel]).contiguous()
+            self._zeros_i = torch.zeros((self.n_items, self.K + 1), dtype=torch.float32, device=self.device)
+        xu, Wu = self._side_input("user", user_ids_d)
+        Pu = linear(xu, Wu, self.mlp[0][1], False)
+        Pi = self._item_part
+        W2, W3 = self._tail
+        three = W3 is not None
+        b = int(user_ids_d.numel())
+        zu = torch.zeros((b, self.K + 1), dtype=torch.float32, device=self.device)
+        zi = self._zeros_i
+        scores = torch.empty((b, self.n_items), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.b200_deepfm_pair_scores(
+            _lib.ptr(zu), _lib.ptr(zu), _lib.ptr(zu), _lib.ptr(Pu), b, _lib.ptr(zi), _lib.ptr(zi), _lib.ptr(zi),
+            _lib.ptr(Pi), self.n_items, self.K, Pu.shape[1], W2.shape[1], W3.shape[1] if three else 0, 0.0,
+            _lib.ptr(W2), _lib.ptr(self.mlp[1][1]), _lib.ptr(W3), _lib.ptr(self.mlp[2][1]) if three else None,
+            _lib.ptr(self._w_out), self.out_bias, _lib.ptr(scores), scores.stride(0), _lib.current_stream()))
+        return scores
+
     def _seq_block(self, users_d, items_d, n, grid_items, row_offset, out_view):
         E = self.t["item_embeds"]
         _lib.check(_lib.lib.b200_seq_pool(

@@ -140,14 +140,18 @@ def test_din_logits(use_bn):
     _close(model.logits(users, items).cpu().numpy()[ok], ref64[ok], 1e-5)
 
 
-def test_youtube_ranking_logits_and_recommend():
+@pytest.mark.parametrize("hidden,hoisted", [((64, 32), True), ((128, 64, 32), True), ((300, 64, 32), False)])
+def test_youtube_ranking_logits_and_recommend(hidden, hoisted):
+    """recommend goes through the hoisted all-items scorer when the MLP fits the pair kernel, else
+    through the flat (user, item) grid — both against the oracle's B*N-row evaluation."""
     from librecommender_b200.feat_models import YouTubeRanking
     from oracle import ranking as orc
     from oracle import tf_models as tm
 
     rng, spec, consumed, seqs, lens = _seq_case(22)
-    w = tm.make_seq_weights(rng, spec, 16, (64, 32), True, din=False)
+    w = tm.make_seq_weights(rng, spec, 16, hidden, True, din=False)
     model = YouTubeRanking(spec, w, seqs, lens, consumed)
+    assert model._hoistable() == hoisted
     users = rng.integers(0, 151, size=500)
     items = rng.integers(0, 400, size=500)
     sparse, dense = tm.row_features(spec, users, items)

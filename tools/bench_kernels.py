@@ -225,6 +225,39 @@ def bench_linear():
                               "peak_gbs": PEAK, "hbm_frac": byt / (ms * 1e-3) / 1e9 / PEAK}), flush=True)
 
 
+def bench_seq():
+    """Sequence models at a C4-like shape (item sparse fields 3, K = 16 -> K' = 64, T = 50)."""
+    from librecommender_b200.consumed import ConsumedCSR
+    from librecommender_b200.feat_models import DIN, YouTubeRanking, recent_sequences_csr
+    from oracle import tf_models as tm
+
+    rng = np.random.default_rng(0)
+    n_users, n_items, T = 200_000, 100_000, 50
+    spec = tm.make_spec(rng, n_users, n_items, [50, 1000], [1000, 10000, 100000], 1, 0, interleave=False)
+    deg = np.minimum(rng.poisson(80, n_users), 1000).astype(np.int64) + 1
+    indptr = np.concatenate([[0], np.cumsum(deg)])
+    idx = rng.integers(0, n_items, indptr[-1]).astype(np.int32)
+    csr = ConsumedCSR(indptr, idx)
+    seqs, lens = recent_sequences_csr(csr, n_items, T)
+    R = 1 << 18
+    users = rng.integers(0, n_users, R)
+    items = rng.integers(0, n_items, R)
+    for name, cls, din in (("YouTubeRanking", YouTubeRanking, False), ("DIN", DIN, True)):
+        w = tm.make_seq_weights(rng, spec, 16, (128, 64, 32), True, din=din)
+        model = cls(spec, w, seqs, lens, csr)
+        ms = timeit(lambda: model.logits(users, items), iters=3, warm=1)
+        print(json.dumps({"kernel": f"{name} predict rows/s (T={T}, hidden 128-64-32)", "rows_per_s": R / (ms * 1e-3)}),
+              flush=True)
+        nu = 64 if not din else 4
+        uid = rng.integers(0, n_users, nu)
+        model.recommend(uid[:2], 100, True)
+        ms = timeit(lambda: model.recommend(uid, 100, True), iters=2, warm=1)
+        print(json.dumps({"kernel": f"{name} recommend_user all-items top-100 (N={n_items}, {nu} users/call, "
+                                    f"{'hoisted' if getattr(model, '_hoistable', lambda: False)() and not din else 'flat grid'})",
+                          "ms": ms, "users_per_s": nu / (ms * 1e-3), "pairs_per_s": nu * n_items / (ms * 1e-3)}),
+              flush=True)
+
+
 def bench_train():
     """FM training step (gather fwd, BN, head, loss, backward scatter, TF-Adam over every variable)."""
     from librecommender_b200.training import FMTrainer
@@ -288,9 +321,11 @@ def bench_train():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["spmm", "feat", "topk", "linear", "train"]
+    which = sys.argv[1:] or ["spmm", "feat", "topk", "linear", "train", "seq"]
     if "train" in which:
         bench_train()
+    if "seq" in which:
+        bench_seq()
     if "linear" in which:
         bench_linear()
     if "spmm" in which:
