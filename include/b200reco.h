@@ -331,6 +331,19 @@ int b200_din_attention(const float* G, int64_t ldg, int32_t Kp, const int64_t* i
                        const float* k1, const float* b1, const float* k2, float b2, float* out,
                        int64_t ld_out, void* stream);
 
+/* DIN all-items scoring, hoisted per user (SURVEY.md 8d row "a7 DIN all-items"): the keys of ONE
+ * user (item ids seq[0..len) of the behaviour sequence, rows of the item feature table G [*, Kp]) turn
+ * the attention MLP's Dense(16) into a plain GEMM over the candidate items:
+ *   b200_din_user_weights      -> Wt [16 len, Kp], bias [16 len]  (row t*16+j)
+ *   Z = b200_linear_*(G[:N], Wt, bias)                             [N, 16 len]
+ *   b200_din_attention_hoisted -> out[n] = sum_t softmax_t((<k2, sigmoid(Z[n, t, :])> + b2) / sqrt(Kp)) k_t
+ * (attention.py:28-64; len == 0 -> zeros). */
+int b200_din_user_weights(const float* G, int64_t ldg, int32_t Kp, const int32_t* seq, int32_t len,
+                          const float* k1, const float* b1, float* Wt, int64_t ldw, float* bias, void* stream);
+int b200_din_attention_hoisted(const float* Z, int64_t ldz, int64_t N, const float* G, int64_t ldg, int32_t Kp,
+                               const int32_t* seq, int32_t len, const float* k2, float b2, float* out,
+                               int64_t ld_out, void* stream);
+
 /* ---- a12: negative sampling (libreco/sampling/negatives.py:17-82; collators.py:138-166) ---
  * Counter-based (Philox4x32-10) device sampler; result = f(seed, step, index) only.
  * mode 0 random, 1 unconsumed (needs users + per-user SORTED consumed CSR), 2 popular (needs the

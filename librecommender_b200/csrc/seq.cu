@@ -179,11 +179,121 @@ din_attention_kernel(const float* __restrict__ G, int64_t ldg, int Kp, const int
   }
 }
 
+// ---- DIN all-items scoring, hoisted (SURVEY.md 8d "a7 DIN all-items": per user one GEMM
+// [N, K'] x [K', 16 len] on the tensor cores instead of N x len re-associated mat-vecs) -------------
+// For ONE user the keys k_t are fixed and only the query q_n = G[n] varies:
+//   z[t][j](n) = <q_n, A_t[:, j]> + c_t[j],  A_t[c][j] = (W1q + W1d)[c][j] + k_t[c] W1p[c][j],
+//   c_t[j] = b1[j] + sum_c k_t[c] (W1k - W1d)[c][j]
+// din_user_weights builds Wt [16 len, K'] (row (t, j) = A_t[:, j]) and the bias [16 len]; the GEMM runs
+// on b200_linear_*; din_attention_hoisted turns Z [N, 16 len] into the attention output [N, K'].
+__global__ void __launch_bounds__(128)
+din_user_weights_kernel(const float* __restrict__ G, int64_t ldg, int Kp, const int32_t* __restrict__ seq, int len,
+                        const float* __restrict__ k1, const float* __restrict__ b1, float* __restrict__ Wt,
+                        int64_t ldw, float* __restrict__ bias) {
+  __shared__ float red[4];
+  const int row = blockIdx.x;                 // (t, j)
+  const int t = row / HID, j = row % HID;
+  if (t >= len) return;
+  const float* key = G + (int64_t)seq[t] * ldg;
+  float part = 0.f;
+  for (int c = threadIdx.x; c < Kp; c += blockDim.x) {
+    const float kv = __ldg(key + c);
+    const float wq = __ldg(k1 + (int64_t)c * HID + j);
+    const float wk = __ldg(k1 + (int64_t)(Kp + c) * HID + j);
+    const float wd = __ldg(k1 + (int64_t)(2 * Kp + c) * HID + j);
+    const float wp = __ldg(k1 + (int64_t)(3 * Kp + c) * HID + j);
+    Wt[(int64_t)row * ldw + c] = (wq + wd) + kv * wp;
+    part = fmaf(kv, wk - wd, part);
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) bias[row] = red[0] + red[1] + red[2] + red[3] + __ldg(b1 + j);
+}
+
+// one warp per item: scores a_t from Z (two sequence positions per 32-lane load), softmax over the
+// len positions, out = sum_t p_t k_t  (attention.py:49-64; len == 0 -> zeros)
+__global__ void __launch_bounds__(128)
+din_attention_hoisted_kernel(const float* __restrict__ Z, int64_t ldz, int64_t N, const float* __restrict__ G,
+                             int64_t ldg, int Kp, const int32_t* __restrict__ seq, int len,
+                             const float* __restrict__ k2, float b2, float* __restrict__ out, int64_t ld_out) {
+  __shared__ float s_att[4][MAX_T];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * 4 + wid;
+  if (n >= N) return;
+  const float scale = rsqrtf((float)Kp);
+  const float w2 = __ldg(k2 + (lane & 15));
+  const float* z = Z + n * ldz;
+  float amax = -3.0e38f;
+  for (int t0 = 0; t0 < len; t0 += 2) {
+    const int t = t0 + (lane >> 4);
+    float v = 0.f;
+    if (t < len) v = w2 / (1.0f + expf(-__ldg(z + t * HID + (lane & 15))));
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    const float a = (v + b2) * scale;
+    if ((lane & 15) == 0 && t < len) s_att[wid][t] = a;
+  }
+  __syncwarp();
+  for (int t = lane; t < len; t += 32) amax = fmaxf(amax, s_att[wid][t]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  float den = 0.f;
+  for (int t = lane; t < len; t += 32) den += expf(s_att[wid][t] - amax);
+  den = warp_sum(den);
+  const int TK = (Kp + 31) / 32;
+  float acc[MAX_TK];
+#pragma unroll
+  for (int tt = 0; tt < MAX_TK; ++tt) acc[tt] = 0.f;
+  for (int t = 0; t < len; ++t) {
+    const float p = expf(s_att[wid][t] - amax) / den;
+    const float* key = G + (int64_t)__ldg(seq + t) * ldg;
+#pragma unroll
+    for (int tt = 0; tt < MAX_TK; ++tt) {
+      const int c = lane + tt * 32;
+      if (tt < TK && c < Kp) acc[tt] = fmaf(p, __ldg(key + c), acc[tt]);
+    }
+  }
+#pragma unroll
+  for (int tt = 0; tt < MAX_TK; ++tt) {
+    const int c = lane + tt * 32;
+    if (tt < TK && c < Kp) out[n * ld_out + c] = acc[tt];
+  }
+}
+
 }  // namespace seq
 }  // namespace b200
 
 using namespace b200;
 using namespace b200::seq;
+
+extern "C" int b200_din_user_weights(const float* G, int64_t ldg, int32_t Kp, const int32_t* seq, int32_t len,
+                                     const float* k1, const float* b1, float* Wt, int64_t ldw, float* bias,
+                                     void* stream) {
+  B200_REQUIRE(G && seq && k1 && b1 && Wt && bias, "b200_din_user_weights: null pointer");
+  B200_REQUIRE(Kp >= 1 && ldw >= Kp && len >= 0 && len <= MAX_T, "b200_din_user_weights: bad shape");
+  if (len == 0) return 0;
+  din_user_weights_kernel<<<(unsigned)(len * HID), 128, 0, (cudaStream_t)stream>>>(G, ldg, Kp, seq, len, k1, b1, Wt,
+                                                                                  ldw, bias);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200_din_attention_hoisted(const float* Z, int64_t ldz, int64_t N, const float* G, int64_t ldg,
+                                          int32_t Kp, const int32_t* seq, int32_t len, const float* k2, float b2,
+                                          float* out, int64_t ld_out, void* stream) {
+  B200_REQUIRE(G && seq && k2 && out && (Z || len == 0), "b200_din_attention_hoisted: null pointer");
+  B200_REQUIRE(Kp >= 1 && Kp <= 32 * MAX_TK && len >= 0 && len <= MAX_T, "b200_din_attention_hoisted: bad shape");
+  if (N == 0) return 0;
+  din_attention_hoisted_kernel<<<(unsigned)ceil_div64(N, 4), 128, 0, (cudaStream_t)stream>>>(
+      Z, ldz, N, G, ldg, Kp, seq, len, k2, b2, out, ld_out);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
 
 extern "C" int b200_seq_pool(const float* E, int64_t lde, int32_t d, int64_t pad_index,
                              const int32_t* seqs, int64_t ld_seq, const int32_t* lens, int32_t T,

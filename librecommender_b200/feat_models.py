@@ -769,6 +769,78 @@ class DIN(_SeqModelBase):
                         b2=float(np.asarray(att["b2"]).reshape(-1)[0]))
         self.mlp = self._upload_mlp(weights["mlp"])
 
+    # ---- hoisted all-items scoring (SURVEY.md 8d "a7 DIN all-items") ---------------------------------
+    def _hoistable(self):
+        dims = [w.shape[0] for w, _, _ in self.mlp]
+        n = len(dims)
+        return (self.K <= 64 and n in (2, 3) and dims[0] <= 256 and dims[1] <= 64 and (n == 2 or dims[2] <= 32)
+                and self.Kp % 4 == 0)
+
+    def _side_concat(self, which, ids_d):
+        torch = self._torch
+        L, pos = self._side(which)
+        n = int(ids_d.numel())
+        x = torch.empty((n, len(pos) * self.K), dtype=torch.float32, device=self.device)
+        self._feat_forward(L, ids_d, ids_d, n, 0, concat=x)
+        cache = self.__dict__.setdefault("_w1_side", {})
+        if which not in cache:
+            cols = torch.cat([torch.arange(g * self.K, (g + 1) * self.K, device=self.device) for g in pos])
+            cache[which] = self.mlp[0][0][:, cols].contiguous()
+        return x, cache[which]
+
+    def score_all_items(self, user_ids_d):
+        """din.py:165-250 over (this user) x (every item).  Per user: the attention's Dense(16) becomes
+        one GEMM [N, K'] x [K', 16 len] on the library GEMM kernel (tcgen05 3xTF32 for large N), a warp
+        per item finishes sigmoid / Dense(1) / softmax / weighted key sum, the first MLP layer splits
+        into user / item / attention parts and the pair kernel runs the small layers."""
+        torch = self._torch
+        if not self._hoistable():
+            return super().score_all_items(user_ids_d)
+        N, Kp, FK = self.n_items, self.Kp, self.F * self.K
+        if "_item_part" not in self.__dict__:
+            xi, Wi = self._side_concat("item", torch.arange(N, device=self.device))
+            self._item_part = linear(xi, Wi, None, False)
+            self._w_att = self.mlp[0][0][:, FK:FK + Kp].contiguous()           # [H1, K']
+            three = len(self.mlp) == 3
+            self._tail = (self.mlp[1][0].t().contiguous(), self.mlp[2][0].t().contiguous() if three else None)
+            self._w_out = torch.cat([torch.zeros(1 + self.K, dtype=torch.float32, device=self.device),
+                                     self.out_kernel]).contiguous()
+            self._zeros_i = torch.zeros((N, self.K + 1), dtype=torch.float32, device=self.device)
+        W2, W3 = self._tail
+        three = W3 is not None
+        b = int(user_ids_d.numel())
+        xu, Wu = self._side_concat("user", user_ids_d)
+        Pu_all = linear(xu, Wu, self.mlp[0][1], False)                           # [b, H1] incl. bias
+        scores = torch.empty((b, N), dtype=torch.float32, device=self.device)
+        zu = torch.zeros((1, self.K + 1), dtype=torch.float32, device=self.device)
+        lens_h = self.lens[user_ids_d].clamp(0, self.T).cpu().numpy()            # one small D2H per call
+        Gn = self.G[:N]
+        att = torch.empty((N, Kp), dtype=torch.float32, device=self.device)
+        lib, st = _lib.lib, _lib.current_stream()
+        for r in range(b):
+            ln = int(lens_h[r])
+            seq = self.seqs[user_ids_d[r]]                                       # int32 [T] view (device)
+            Z = None
+            if ln > 0:
+                Wt = torch.empty((16 * ln, Kp), dtype=torch.float32, device=self.device)
+                bias = torch.empty(16 * ln, dtype=torch.float32, device=self.device)
+                _lib.check(lib.b200_din_user_weights(_lib.ptr(self.G), self.G.stride(0), Kp, _lib.ptr(seq), ln,
+                                                     _lib.ptr(self.att["k1"]), _lib.ptr(self.att["b1"]), _lib.ptr(Wt),
+                                                     Wt.stride(0), _lib.ptr(bias), st))
+                Z = linear(Gn, Wt, bias, False, cache_split=False)               # [N, 16 ln]
+            _lib.check(lib.b200_din_attention_hoisted(
+                _lib.ptr(Z), Z.stride(0) if Z is not None else 0, N, _lib.ptr(self.G), self.G.stride(0), Kp,
+                _lib.ptr(seq), ln, _lib.ptr(self.att["k2"]), self.att["b2"], _lib.ptr(att), att.stride(0), st))
+            Pi = self._item_part + linear(att, self._w_att, None, False)         # [N, H1]
+            Pu = Pu_all[r:r + 1]
+            _lib.check(lib.b200_deepfm_pair_scores(
+                _lib.ptr(zu), _lib.ptr(zu), _lib.ptr(zu), _lib.ptr(Pu), 1, _lib.ptr(self._zeros_i),
+                _lib.ptr(self._zeros_i), _lib.ptr(self._zeros_i), _lib.ptr(Pi), N, self.K, Pu.shape[1], W2.shape[1],
+                W3.shape[1] if three else 0, 0.0, _lib.ptr(W2), _lib.ptr(self.mlp[1][1]), _lib.ptr(W3),
+                _lib.ptr(self.mlp[2][1]) if three else None, _lib.ptr(self._w_out), self.out_bias,
+                _lib.ptr(scores[r]), scores.stride(0), st))
+        return scores
+
     def _seq_block(self, users_d, items_d, n, grid_items, row_offset, out_view):
         _lib.check(_lib.lib.b200_din_attention(
             _lib.ptr(self.G), self.G.stride(0), self.Kp, _lib.ptr(items_d), _lib.ptr(self.seqs),

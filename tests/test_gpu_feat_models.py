@@ -185,6 +185,28 @@ def test_din_recommend_all_items():
     assert (got == ref).mean() > 0.97
 
 
+@pytest.mark.parametrize("hidden", [(32, 16), (128, 64, 32)])
+def test_din_hoisted_scores_equal_flat_grid(hidden):
+    """Per-user GEMM formulation of the attention vs the per-row kernel, incl. a user without history
+    (len 0 -> zero attention output) and the OOV user row (len 1, pad key)."""
+    import torch
+
+    from librecommender_b200 import feat_models as fmods
+    from librecommender_b200.feat_models import DIN
+
+    rng, spec, consumed, seqs, lens = _seq_case(31, T=20)
+    from oracle import tf_models as tm
+
+    w = tm.make_seq_weights(rng, spec, 16, hidden, True, din=True)
+    model = DIN(spec, w, seqs, lens, consumed)
+    assert model._hoistable()
+    uid = torch.tensor([0, 7, 149, 150, 33], device="cuda")          # 149: no history, 150: OOV row
+    hoisted = model.score_all_items(uid).cpu().numpy()
+    flat = fmods._FeatModelBase.score_all_items(model, uid).cpu().numpy()
+    scale = np.maximum(np.abs(flat), np.abs(flat).mean())
+    assert (np.abs(hoisted - flat) <= 1e-5 * scale + 1e-6).all(), float(np.abs(hoisted - flat).max())
+
+
 @pytest.mark.parametrize("norm", [True, False])
 def test_two_tower_embeddings_and_retrieval(norm):
     from librecommender_b200.engine import EmbedScorer

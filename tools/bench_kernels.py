@@ -253,7 +253,7 @@ def bench_seq():
         model.recommend(uid[:2], 100, True)
         ms = timeit(lambda: model.recommend(uid, 100, True), iters=2, warm=1)
         print(json.dumps({"kernel": f"{name} recommend_user all-items top-100 (N={n_items}, {nu} users/call, "
-                                    f"{'hoisted' if getattr(model, '_hoistable', lambda: False)() and not din else 'flat grid'})",
+                                    f"{'hoisted' if getattr(model, '_hoistable', lambda: False)() else 'flat grid'})",
                           "ms": ms, "users_per_s": nu / (ms * 1e-3), "pairs_per_s": nu * n_items / (ms * 1e-3)}),
               flush=True)
 
