@@ -331,6 +331,13 @@ int b200_din_attention(const float* G, int64_t ldg, int32_t Kp, const int64_t* i
                        const float* k1, const float* b1, const float* k2, float b2, float* out,
                        int64_t ld_out, void* stream);
 
+/* NGCF layer pieces (libreco/algorithms/torch_modules/ngcf_module.py:100-121): the
+ * propagation L E is b200_spmm_csr, the two Dense products are b200_linear_*; these are the
+ * element-wise parts: out = a * b, and out[r] = normalize_2(leaky_relu(self[r] + pair[r], slope)). */
+int b200_mul_elementwise(const float* a, const float* b, int64_t n, float* out, void* stream);
+int b200_ngcf_combine(const float* self_part, int64_t lda, const float* pair_part, int64_t ldb, int64_t R,
+                      int32_t d, float negative_slope, float* out, int64_t ld_out, void* stream);
+
 /* DIN all-items scoring, hoisted per user (SURVEY.md 8d row "a7 DIN all-items"): the keys of ONE
  * user (item ids seq[0..len) of the behaviour sequence, rows of the item feature table G [*, Kp]) turn
  * the attention MLP's Dense(16) into a plain GEMM over the candidate items:

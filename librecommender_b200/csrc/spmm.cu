@@ -316,3 +316,60 @@ extern "C" int b200_spmm_csr(const int64_t* indptr, const int32_t* col, const fl
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }
+
+// ---- NGCF layer epilogue (reference libreco/algorithms/torch_modules/ngcf_module.py:104-121) ---------
+// mul:      out[r, :] = a[r, :] * b[r, :]                      (side ⊙ E, the input of the pair GEMM)
+// combine:  m = leaky_relu(a + b, 0.2); out[r, :] = m / max(||m||_2, 1e-12)   (F.normalize, eps 1e-12)
+namespace b200 {
+namespace ngcf {
+
+__global__ void mul_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] * b[i];
+}
+
+__global__ void combine_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
+                               int64_t R, int d, float slope, float* __restrict__ out, int64_t ldo) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float ss = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    float m = a[r * lda + k] + b[r * ldb + k];
+    m = m > 0.f ? m : slope * m;
+    ss = fmaf(m, m, ss);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int k = lane; k < d; k += 32) {
+    float m = a[r * lda + k] + b[r * ldb + k];
+    m = m > 0.f ? m : slope * m;
+    out[r * ldo + k] = m * inv;
+  }
+}
+
+}  // namespace ngcf
+}  // namespace b200
+
+extern "C" int b200_mul_elementwise(const float* a, const float* b, int64_t n, float* out, void* stream) {
+  B200_REQUIRE(a && b && out, "b200_mul_elementwise: null pointer");
+  if (n == 0) return 0;
+  b200::ngcf::mul_rows_kernel<<<(unsigned)b200::ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, out);
+  B200_CUDA_OK(cudaGetLastError());
+  b200::count_launch();
+  return 0;
+}
+
+extern "C" int b200_ngcf_combine(const float* self_part, int64_t lda, const float* pair_part, int64_t ldb,
+                                 int64_t R, int32_t d, float negative_slope, float* out, int64_t ld_out,
+                                 void* stream) {
+  B200_REQUIRE(self_part && pair_part && out && d > 0, "b200_ngcf_combine: bad arguments");
+  if (R == 0) return 0;
+  b200::ngcf::combine_kernel<<<(unsigned)b200::ceil_div64(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      self_part, lda, pair_part, ldb, R, d, negative_slope, out, ld_out);
+  B200_CUDA_OK(cudaGetLastError());
+  b200::count_launch();
+  return 0;
+}
