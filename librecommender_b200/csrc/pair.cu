@@ -59,8 +59,15 @@ struct DeepArgs {
   int64_t lds;
 };
 
-// thread per (user b, item n): h1 never leaves registers/L1, W2/W3 are broadcast from shared memory
-__global__ void __launch_bounds__(128)
+// Two items per thread (the W2 / W3 rows read from shared memory are reused for both), the item-side
+// first-layer rows Pi staged through shared memory in 32-column chunks with coalesced loads (a
+// thread walking its own 512-byte row straight from global memory was the limiter of the first
+// version: 0.8 G pairs/s).  fp32 fma chains in the same k order as before: results unchanged.
+constexpr int PAIR_THREADS = 128;
+constexpr int PAIR_ITEMS = 2 * PAIR_THREADS;   // items per block iteration
+constexpr int KCH = 32;                        // Pi columns per staged chunk
+
+__global__ void __launch_bounds__(PAIR_THREADS)
 deepfm_pair_kernel(const DeepArgs a) {
   extern __shared__ float sm[];
   float* w2 = sm;                         // [H1][MAXH2]  (padded with zeros)
@@ -68,70 +75,87 @@ deepfm_pair_kernel(const DeepArgs a) {
   float* pu = w3 + MAXH2 * MAXH3;         // [H1]
   float* su = pu + a.H1;                  // [K]
   float* qu = su + a.K;                   // [K]
+  float* tile = qu + a.K;                 // [PAIR_ITEMS][KCH + 1]
   const int64_t b = blockIdx.y;
-  for (int i = threadIdx.x; i < a.H1 * MAXH2; i += blockDim.x) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < a.H1 * MAXH2; i += PAIR_THREADS) {
     const int k = i / MAXH2, j = i % MAXH2;
     w2[i] = j < a.H2 ? a.W2[(size_t)k * a.H2 + j] : 0.f;
   }
-  for (int i = threadIdx.x; i < MAXH2 * MAXH3; i += blockDim.x) {
+  for (int i = tid; i < MAXH2 * MAXH3; i += PAIR_THREADS) {
     const int k = i / MAXH3, j = i % MAXH3;
     w3[i] = (a.H3 > 0 && k < a.H2 && j < a.H3) ? a.W3[(size_t)k * a.H3 + j] : 0.f;
   }
-  for (int i = threadIdx.x; i < a.H1; i += blockDim.x) pu[i] = a.Pu[b * a.H1 + i];
-  for (int i = threadIdx.x; i < a.K; i += blockDim.x) { su[i] = a.Su[b * a.K + i]; qu[i] = a.Qu[b * a.K + i]; }
+  for (int i = tid; i < a.H1; i += PAIR_THREADS) pu[i] = a.Pu[b * a.H1 + i];
+  for (int i = tid; i < a.K; i += PAIR_THREADS) { su[i] = a.Su[b * a.K + i]; qu[i] = a.Qu[b * a.K + i]; }
   __syncthreads();
   const float lub = a.lu[b] + a.lin_bias;
   const int n_deep = a.H3 > 0 ? a.H3 : a.H2;
-  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < a.N; n += (int64_t)gridDim.x * blockDim.x) {
-    // output head starts with the linear and pairwise blocks of w_out
-    float out = a.b_out + (lub + __ldg(a.li + n)) * __ldg(a.w_out);
-    for (int k = 0; k < a.K; ++k) {
-      const float s = su[k] + __ldg(a.Si + n * a.K + k);
-      const float q = qu[k] + __ldg(a.Qi + n * a.K + k);
-      out = fmaf(0.5f * (s * s - q), __ldg(a.w_out + 1 + k), out);
-    }
-    float h2[MAXH2];
+  for (int64_t base = (int64_t)blockIdx.x * PAIR_ITEMS; base < a.N; base += (int64_t)gridDim.x * PAIR_ITEMS) {
+    float h2[2][MAXH2];
 #pragma unroll
-    for (int j = 0; j < MAXH2; ++j) h2[j] = 0.f;
-    const float* pi = a.Pi + n * a.H1;
-    for (int k = 0; k < a.H1; ++k) {
-      const float h1 = fmaxf(pu[k] + __ldg(pi + k), 0.f);
-      const float4* wrow = reinterpret_cast<const float4*>(w2 + (size_t)k * MAXH2);
-#pragma unroll
-      for (int j4 = 0; j4 < MAXH2 / 4; ++j4) {
-        const float4 w = wrow[j4];
-        h2[4 * j4 + 0] = fmaf(h1, w.x, h2[4 * j4 + 0]);
-        h2[4 * j4 + 1] = fmaf(h1, w.y, h2[4 * j4 + 1]);
-        h2[4 * j4 + 2] = fmaf(h1, w.z, h2[4 * j4 + 2]);
-        h2[4 * j4 + 3] = fmaf(h1, w.w, h2[4 * j4 + 3]);
+    for (int j = 0; j < MAXH2; ++j) { h2[0][j] = 0.f; h2[1][j] = 0.f; }
+    for (int kc = 0; kc < a.H1; kc += KCH) {
+      __syncthreads();                                   // previous chunk fully consumed
+      const int kw = min(KCH, a.H1 - kc);
+      for (int r = wid; r < PAIR_ITEMS; r += PAIR_THREADS / 32) {      // one 128-byte row segment per warp step
+        const int64_t n = base + r;
+        tile[r * (KCH + 1) + lane] = (n < a.N && lane < kw) ? __ldg(a.Pi + n * a.H1 + kc + lane) : 0.f;
       }
-    }
-    if (a.H3 > 0) {
-      float h3[MAXH3];
+      __syncthreads();
+      const float* t0 = tile + tid * (KCH + 1);
+      const float* t1 = tile + (tid + PAIR_THREADS) * (KCH + 1);
+#pragma unroll 2      // keep the loop body inside the instruction cache (a fully unrolled chunk is 150 KB of code)
+      for (int kk = 0; kk < kw; ++kk) {
+        const float p = pu[kc + kk];
+        const float ha = fmaxf(p + t0[kk], 0.f);
+        const float hb = fmaxf(p + t1[kk], 0.f);
+        const float4* wrow = reinterpret_cast<const float4*>(w2 + (size_t)(kc + kk) * MAXH2);
 #pragma unroll
-      for (int j = 0; j < MAXH3; ++j) h3[j] = j < a.H3 ? __ldg(a.b3 + j) : 0.f;
-#pragma unroll
-      for (int k = 0; k < MAXH2; ++k) {
-        const float v = k < a.H2 ? fmaxf(h2[k] + __ldg(a.b2 + k), 0.f) : 0.f;
-        const float4* wrow = reinterpret_cast<const float4*>(w3 + (size_t)k * MAXH3);
-#pragma unroll
-        for (int j4 = 0; j4 < MAXH3 / 4; ++j4) {
+        for (int j4 = 0; j4 < MAXH2 / 4; ++j4) {
           const float4 w = wrow[j4];
-          h3[4 * j4 + 0] = fmaf(v, w.x, h3[4 * j4 + 0]);
-          h3[4 * j4 + 1] = fmaf(v, w.y, h3[4 * j4 + 1]);
-          h3[4 * j4 + 2] = fmaf(v, w.z, h3[4 * j4 + 2]);
-          h3[4 * j4 + 3] = fmaf(v, w.w, h3[4 * j4 + 3]);
+          h2[0][4 * j4 + 0] = fmaf(ha, w.x, h2[0][4 * j4 + 0]);
+          h2[0][4 * j4 + 1] = fmaf(ha, w.y, h2[0][4 * j4 + 1]);
+          h2[0][4 * j4 + 2] = fmaf(ha, w.z, h2[0][4 * j4 + 2]);
+          h2[0][4 * j4 + 3] = fmaf(ha, w.w, h2[0][4 * j4 + 3]);
+          h2[1][4 * j4 + 0] = fmaf(hb, w.x, h2[1][4 * j4 + 0]);
+          h2[1][4 * j4 + 1] = fmaf(hb, w.y, h2[1][4 * j4 + 1]);
+          h2[1][4 * j4 + 2] = fmaf(hb, w.z, h2[1][4 * j4 + 2]);
+          h2[1][4 * j4 + 3] = fmaf(hb, w.w, h2[1][4 * j4 + 3]);
         }
       }
-#pragma unroll
-      for (int j = 0; j < MAXH3; ++j)
-        if (j < n_deep) out = fmaf(h3[j], __ldg(a.w_out + 1 + a.K + j), out);
-    } else {
-#pragma unroll
-      for (int j = 0; j < MAXH2; ++j)
-        if (j < n_deep) out = fmaf(h2[j] + __ldg(a.b2 + j), __ldg(a.w_out + 1 + a.K + j), out);
     }
-    a.scores[b * a.lds + n] = out;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int64_t n = base + tid + e * PAIR_THREADS;
+      if (n >= a.N) continue;
+      // output head starts with the linear and pairwise blocks of w_out
+      float out = a.b_out + (lub + __ldg(a.li + n)) * __ldg(a.w_out);
+      for (int k = 0; k < a.K; ++k) {
+        const float s = su[k] + __ldg(a.Si + n * a.K + k);
+        const float q = qu[k] + __ldg(a.Qi + n * a.K + k);
+        out = fmaf(0.5f * (s * s - q), __ldg(a.w_out + 1 + k), out);
+      }
+      if (a.H3 > 0) {
+        // third layer with the OUTPUT index as the (rolled) outer loop: 64 fma per iteration on
+        // register-resident activations, a few hundred bytes of code instead of 2 x 2048 unrolled fma
+        float v[MAXH2];
+#pragma unroll
+        for (int k = 0; k < MAXH2; ++k) v[k] = k < a.H2 ? fmaxf(h2[e][k] + __ldg(a.b2 + k), 0.f) : 0.f;
+#pragma unroll 1
+        for (int j = 0; j < a.H3; ++j) {
+          float h3 = __ldg(a.b3 + j);
+#pragma unroll
+          for (int k = 0; k < MAXH2; ++k) h3 = fmaf(v[k], w3[k * MAXH3 + j], h3);
+          out = fmaf(h3, __ldg(a.w_out + 1 + a.K + j), out);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < MAXH2; ++j)
+          if (j < n_deep) out = fmaf(h2[e][j] + __ldg(a.b2 + j), __ldg(a.w_out + 1 + a.K + j), out);
+      }
+      a.scores[b * a.lds + n] = out;
+    }
   }
 }
 
@@ -175,14 +199,14 @@ extern "C" int b200_deepfm_pair_scores(const float* Su, const float* Qu, const f
   a.Su = Su; a.Qu = Qu; a.lu = lu; a.Pu = Pu; a.Si = Si; a.Qi = Qi; a.li = li; a.Pi = Pi; a.N = N;
   a.K = K; a.H1 = H1; a.H2 = H2; a.H3 = H3; a.lin_bias = lin_bias; a.W2 = W2; a.b2 = b2; a.W3 = W3;
   a.b3 = b3; a.w_out = w_out; a.b_out = b_out; a.scores = scores; a.lds = lds;
-  const size_t smem = ((size_t)H1 * MAXH2 + MAXH2 * MAXH3 + H1 + 2 * K) * sizeof(float);
+  const size_t smem = ((size_t)H1 * MAXH2 + MAXH2 * MAXH3 + H1 + 2 * K + PAIR_ITEMS * (KCH + 1)) * sizeof(float);
   static bool attr = false;
   if (!attr) {
-    B200_CUDA_OK(cudaFuncSetAttribute(deepfm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    B200_CUDA_OK(cudaFuncSetAttribute(deepfm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
     attr = true;
   }
-  const unsigned gx = (unsigned)min((int64_t)512, ceil_div64(N, 128));
-  deepfm_pair_kernel<<<dim3(gx, (unsigned)B), 128, smem, (cudaStream_t)stream>>>(a);
+  const unsigned gx = (unsigned)min((int64_t)512, ceil_div64(N, PAIR_ITEMS));
+  deepfm_pair_kernel<<<dim3(gx, (unsigned)B), PAIR_THREADS, smem, (cudaStream_t)stream>>>(a);
   count_launch();
   B200_CUDA_OK(cudaGetLastError());
   return 0;
