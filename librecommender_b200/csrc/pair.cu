@@ -75,7 +75,7 @@ deepfm_pair_kernel(const DeepArgs a) {
   float* pu = w3 + MAXH2 * MAXH3;         // [H1]
   float* su = pu + a.H1;                  // [K]
   float* qu = su + a.K;                   // [K]
-  float* tile = qu + a.K;                 // [PAIR_ITEMS][KCH + 1]
+  float* tile = qu + a.K;                 // 2 x [PAIR_ITEMS][KCH + 1]  (double buffer)
   const int64_t b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int i = tid; i < a.H1 * MAXH2; i += PAIR_THREADS) {
@@ -91,21 +91,52 @@ deepfm_pair_kernel(const DeepArgs a) {
   __syncthreads();
   const float lub = a.lu[b] + a.lin_bias;
   const int n_deep = a.H3 > 0 ? a.H3 : a.H2;
-  for (int64_t base = (int64_t)blockIdx.x * PAIR_ITEMS; base < a.N; base += (int64_t)gridDim.x * PAIR_ITEMS) {
+  // The (item tile, k-chunk) sequence of this block is one stream of staged chunks: chunk c+1 is
+  // fetched with cp.async into the other half of `tile` while chunk c is consumed.
+  const int nch = (a.H1 + KCH - 1) / KCH;
+  const int64_t n_iters = a.N > (int64_t)blockIdx.x * PAIR_ITEMS
+                              ? (a.N - (int64_t)blockIdx.x * PAIR_ITEMS + (int64_t)gridDim.x * PAIR_ITEMS - 1) /
+                                    ((int64_t)gridDim.x * PAIR_ITEMS)
+                              : 0;
+  const int64_t n_chunks = n_iters * nch;
+  auto fetch = [&](int64_t c) {
+    const int64_t base = ((int64_t)blockIdx.x + (c / nch) * gridDim.x) * PAIR_ITEMS;
+    const int kc = (int)(c % nch) * KCH;
+    const int kw = min(KCH, a.H1 - kc);
+    float* dst = tile + (c & 1) * (PAIR_ITEMS * (KCH + 1));
+    for (int r = wid; r < PAIR_ITEMS; r += PAIR_THREADS / 32) {      // one 128-byte row segment per warp step
+      const int64_t n = base + r;
+      float* d = dst + r * (KCH + 1) + lane;
+      if (n < a.N && lane < kw) {
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(d);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(a.Pi + n * a.H1 + kc + lane) : "memory");
+      } else {
+        *d = 0.f;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (n_chunks > 0) fetch(0);
+  for (int64_t it = 0; it < n_iters; ++it) {
+    const int64_t base = ((int64_t)blockIdx.x + it * gridDim.x) * PAIR_ITEMS;
     float h2[2][MAXH2];
 #pragma unroll
     for (int j = 0; j < MAXH2; ++j) { h2[0][j] = 0.f; h2[1][j] = 0.f; }
-    for (int kc = 0; kc < a.H1; kc += KCH) {
-      __syncthreads();                                   // previous chunk fully consumed
+    for (int ci = 0; ci < nch; ++ci) {
+      const int64_t c = it * nch + ci;
+      const int kc = ci * KCH;
       const int kw = min(KCH, a.H1 - kc);
-      for (int r = wid; r < PAIR_ITEMS; r += PAIR_THREADS / 32) {      // one 128-byte row segment per warp step
-        const int64_t n = base + r;
-        tile[r * (KCH + 1) + lane] = (n < a.N && lane < kw) ? __ldg(a.Pi + n * a.H1 + kc + lane) : 0.f;
+      if (c + 1 < n_chunks) {
+        fetch(c + 1);                                    // the other buffer: freed by the barrier below (previous round)
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
-      __syncthreads();
-      const float* t0 = tile + tid * (KCH + 1);
-      const float* t1 = tile + (tid + PAIR_THREADS) * (KCH + 1);
-#pragma unroll 2      // keep the loop body inside the instruction cache (a fully unrolled chunk is 150 KB of code)
+      __syncthreads();                                   // chunk c landed for every thread
+      const float* tb = tile + (c & 1) * (PAIR_ITEMS * (KCH + 1));
+      const float* t0 = tb + tid * (KCH + 1);
+      const float* t1 = tb + (tid + PAIR_THREADS) * (KCH + 1);
+#pragma unroll 2      // keep the loop body inside the instruction cache
       for (int kk = 0; kk < kw; ++kk) {
         const float p = pu[kc + kk];
         const float ha = fmaxf(p + t0[kk], 0.f);
@@ -124,6 +155,7 @@ deepfm_pair_kernel(const DeepArgs a) {
           h2[1][4 * j4 + 3] = fmaf(hb, w.w, h2[1][4 * j4 + 3]);
         }
       }
+      __syncthreads();                                   // chunk c consumed: its buffer may be refilled
     }
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
@@ -199,7 +231,7 @@ extern "C" int b200_deepfm_pair_scores(const float* Su, const float* Qu, const f
   a.Su = Su; a.Qu = Qu; a.lu = lu; a.Pu = Pu; a.Si = Si; a.Qi = Qi; a.li = li; a.Pi = Pi; a.N = N;
   a.K = K; a.H1 = H1; a.H2 = H2; a.H3 = H3; a.lin_bias = lin_bias; a.W2 = W2; a.b2 = b2; a.W3 = W3;
   a.b3 = b3; a.w_out = w_out; a.b_out = b_out; a.scores = scores; a.lds = lds;
-  const size_t smem = ((size_t)H1 * MAXH2 + MAXH2 * MAXH3 + H1 + 2 * K + PAIR_ITEMS * (KCH + 1)) * sizeof(float);
+  const size_t smem = ((size_t)H1 * MAXH2 + MAXH2 * MAXH3 + H1 + 2 * K + 2 * PAIR_ITEMS * (KCH + 1)) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     B200_CUDA_OK(cudaFuncSetAttribute(deepfm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
