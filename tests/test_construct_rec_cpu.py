@@ -102,3 +102,41 @@ def test_recommend_tf_feat_requires_engine_and_validates():
         recommend_tf_feat(model, 0, 5, {"sex": "F"}, None, True, False)
     with pytest.raises(ValueError, match="exceeds num of items"):
         recommend_tf_feat(model, [0], 11, None, None, True, False)
+
+
+def _cold_data_info(seed=7):
+    rng_items = np.random.default_rng(3).permutation(500)[:40] + 1000
+    di = types.SimpleNamespace(
+        id2item={i: int(rng_items[i]) for i in range(40)}, item2id={int(rng_items[i]): i for i in range(40)},
+        popular_items=[int(x) for x in rng_items[:15]], np_rng=np.random.default_rng(seed))
+    return di
+
+
+@pytest.mark.parametrize("strategy", ["average", "popular"])
+@pytest.mark.parametrize("inner_id", [True, False])
+def test_cold_start_rec_draws_like_the_reference(strategy, inner_id):
+    """cold_start.py: one np_rng.choice(pool, n_rec) per user, in user order, with replacement."""
+    from librecommender_b200.recommendation import cold_start_rec
+
+    default_recs = np.arange(5, 25)
+    users = ["u9", "u3", "u5"]
+    got = cold_start_rec(_cold_data_info(), default_recs, strategy, users, 6, inner_id)
+    di = _cold_data_info()
+    assert list(got) == users
+    for u in users:
+        if strategy == "average":
+            picked = di.np_rng.choice(default_recs, 6)
+            want = picked if inner_id else np.array([di.id2item[i] for i in picked])
+        else:
+            picked = di.np_rng.choice(di.popular_items, 6)
+            want = np.array([di.item2id[i] for i in picked]) if inner_id else picked
+        np.testing.assert_array_equal(got[u], want)
+    if reference_available():
+        load_reference()
+        from libreco.recommendation.cold_start import cold_start_rec as ref_cold
+
+        ref = ref_cold(_cold_data_info(), default_recs, strategy, users, 6, inner_id)
+        for u in users:
+            np.testing.assert_array_equal(got[u], ref[u])
+    with pytest.raises(ValueError, match="Unknown cold start strategy"):
+        cold_start_rec(_cold_data_info(), default_recs, "nearest", users, 6, inner_id)
