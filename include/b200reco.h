@@ -180,6 +180,14 @@ int b200_multi_sparse_combine(const float* table, int64_t ld, int32_t K, const i
                               int32_t len, int64_t n, int32_t oov, int32_t combiner, float* out,
                               int64_t ld_out, void* stream);
 
+/* Row gather / scatter-add on ONE rank's slice of a row-sharded embedding table (SURVEY.md 8e row 2:
+ * tables larger than one GPU; the exchange of indices and rows is torch.distributed all-to-all,
+ * librecommender_b200/parallel.py::RowShardedTable).  out[r] = table[idx[r]]; table[idx[r]] += rows[r]. */
+int b200_gather_rows(const float* table, int64_t ld, int32_t d, const int64_t* idx, int64_t n, float* out,
+                     int64_t ld_out, void* stream);
+int b200_scatter_add_rows(float* table, int64_t ld, int32_t d, const int64_t* idx, int64_t n,
+                          const float* rows, int64_t ld_rows, void* stream);
+
 /* Y = act(X Wt^T + b): tf_dense (libreco/layers/dense.py:52-80) with BN folded by the caller.
  * Wt is the TRANSPOSED kernel [dout, din]; fp32 SIMT (exact fma chain in k). */
 int b200_linear_f32(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,

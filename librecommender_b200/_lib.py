@@ -48,6 +48,8 @@ SIGNATURES = {
                                         c_int32, c_float, _P, _P, _P, _P, _P, c_float, _P, c_int64, _P]),
     "b200_multi_sparse_combine": (c_int, [_P, c_int64, c_int32, _P, c_int64, c_int32, c_int64, c_int32, c_int32, _P,
                                           c_int64, _P]),
+    "b200_gather_rows": (c_int, [_P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
+    "b200_scatter_add_rows": (c_int, [_P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "b200_linear_f32": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, c_int32, c_int32, c_int32, _P, c_int64, _P]),
     "b200_linear_tf32x3_split_ld": (c_int64, [c_int32]),
     "b200_linear_tf32x3_split_weights": (c_int, [_P, c_int64, c_int32, c_int32, _P, _P]),

@@ -448,6 +448,46 @@ extern "C" int b200_multi_sparse_combine(const float* table, int64_t ld, int32_t
   return 0;
 }
 
+// plain row gather / scatter-add for row-sharded tables: one sub-warp per row
+__global__ void gather_rows_kernel(const float* __restrict__ table, int64_t ld, int d, const int64_t* __restrict__ idx,
+                                   int64_t n, float* __restrict__ out, int64_t ld_out) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const float* src = table + idx[r] * ld;
+  for (int k = lane; k < d; k += 32) out[r * ld_out + k] = __ldg(src + k);
+}
+
+__global__ void scatter_add_rows_kernel(float* __restrict__ table, int64_t ld, int d, const int64_t* __restrict__ idx,
+                                        int64_t n, const float* __restrict__ rows, int64_t ld_rows) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n) return;
+  float* dst = table + idx[r] * ld;
+  for (int k = lane; k < d; k += 32) atomicAdd(dst + k, rows[r * ld_rows + k]);
+}
+
+extern "C" int b200_gather_rows(const float* table, int64_t ld, int32_t d, const int64_t* idx, int64_t n,
+                                float* out, int64_t ld_out, void* stream) {
+  B200_REQUIRE(table && idx && out && d > 0, "b200_gather_rows: bad arguments");
+  if (n == 0) return 0;
+  gather_rows_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(table, ld, d, idx, n, out, ld_out);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200_scatter_add_rows(float* table, int64_t ld, int32_t d, const int64_t* idx, int64_t n,
+                                     const float* rows, int64_t ld_rows, void* stream) {
+  B200_REQUIRE(table && idx && rows && d > 0, "b200_scatter_add_rows: bad arguments");
+  if (n == 0) return 0;
+  scatter_add_rows_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(table, ld, d, idx, n, rows,
+                                                                                           ld_rows);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int b200_linear_f32(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
                                const float* bias, int32_t din, int32_t dout, int32_t relu, float* Y,
                                int64_t ldy, void* stream) {

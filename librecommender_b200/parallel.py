@@ -180,3 +180,104 @@ def gather_embeddings(plan: LightGCNShardPlan, E_local, group=None):
         full.copy_(E_local)
     out = plan.unpermute(full)
     return out[: plan.n_users], out[plan.n_users:]
+
+
+# ------------------------------------------------------------------------------------------------
+# Row-sharded embedding table: engaged only when a table exceeds one GPU.
+# Row r lives on rank r % G at slot r // G.  A lookup is index all-to-all -> local gather -> row
+# all-to-all; the gradient path mirrors it (rows to the owners, local scatter-add).
+# ------------------------------------------------------------------------------------------------
+def _cuda_gather(local_rows, slots):
+    import torch
+
+    from . import _lib
+
+    out = torch.empty((slots.numel(), local_rows.shape[1]), dtype=torch.float32, device=local_rows.device)
+    _lib.check(_lib.lib.b200_gather_rows(_lib.ptr(local_rows), local_rows.stride(0), local_rows.shape[1],
+                                         _lib.ptr(slots), slots.numel(), _lib.ptr(out), out.stride(0),
+                                         _lib.current_stream()))
+    return out
+
+
+def _cuda_scatter_add(local_rows, slots, rows):
+    from . import _lib
+
+    _lib.check(_lib.lib.b200_scatter_add_rows(_lib.ptr(local_rows), local_rows.stride(0), local_rows.shape[1],
+                                              _lib.ptr(slots), slots.numel(), _lib.ptr(rows), rows.stride(0),
+                                              _lib.current_stream()))
+
+
+class RowShardedTable:
+    """One rank's slice ``local_rows [ceil(n_rows / G), d]`` of a table sharded by ``row % G``.
+
+    ``lookup(ids)``: every rank passes ITS OWN ids (its slice of the batch) and gets its rows.
+    ``scatter_add(ids, grads)``: the transposed exchange, ``table[ids] += grads`` on the owners.
+    ``gather_fn`` / ``scatter_fn`` default to the CUDA kernels; the CPU gloo test injects torch
+    stand-ins for exactly these two local operations."""
+
+    def __init__(self, local_rows, n_rows: int, group=None, gather_fn=None, scatter_fn=None):
+        import torch.distributed as dist
+
+        self.local, self.n_rows, self.group = local_rows, int(n_rows), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.gather_fn = gather_fn or _cuda_gather
+        self.scatter_fn = scatter_fn or _cuda_scatter_add
+
+    @staticmethod
+    def shard(full_table, world: int, rank: int):
+        """Rows rank, rank + G, ... of a full table (how a checkpoint is split)."""
+        return full_table[rank::world].contiguous()
+
+    def _route(self, ids):
+        """Sort the request by owner: (order, per-owner counts sent / received, remote slots received)."""
+        import torch
+        import torch.distributed as dist
+
+        ids = ids.to(torch.int64)
+        owner = ids % self.world
+        order = torch.argsort(owner, stable=True)
+        send_counts = torch.bincount(owner, minlength=self.world)
+        recv_counts = torch.empty_like(send_counts)
+        if self.world > 1:
+            dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        else:
+            recv_counts.copy_(send_counts)
+        send_l, recv_l = send_counts.tolist(), recv_counts.tolist()
+        slots_out = (ids[order] // self.world).contiguous()
+        slots_in = torch.empty(int(sum(recv_l)), dtype=torch.int64, device=ids.device)
+        if self.world > 1:
+            dist.all_to_all_single(slots_in, slots_out, recv_l, send_l, group=self.group)
+        else:
+            slots_in.copy_(slots_out)
+        return order, send_l, recv_l, slots_in
+
+    def lookup(self, ids):
+        import torch
+        import torch.distributed as dist
+
+        order, send_l, recv_l, slots_in = self._route(ids)
+        rows_out = self.gather_fn(self.local, slots_in)                 # rows other ranks asked this rank for
+        d = self.local.shape[1]
+        rows_in = torch.empty((int(sum(send_l)), d), dtype=rows_out.dtype, device=rows_out.device)
+        if self.world > 1:
+            dist.all_to_all_single(rows_in, rows_out.contiguous(), [c for c in send_l], [c for c in recv_l],
+                                   group=self.group)
+        else:
+            rows_in.copy_(rows_out)
+        out = torch.empty_like(rows_in)
+        out[order] = rows_in                                            # back to the caller's order
+        return out
+
+    def scatter_add(self, ids, grads):
+        import torch
+        import torch.distributed as dist
+
+        order, send_l, recv_l, slots_in = self._route(ids)
+        g_out = grads[order].contiguous()
+        g_in = torch.empty((int(sum(recv_l)), grads.shape[1]), dtype=grads.dtype, device=grads.device)
+        if self.world > 1:
+            dist.all_to_all_single(g_in, g_out, recv_l, send_l, group=self.group)
+        else:
+            g_in.copy_(g_out)
+        self.scatter_fn(self.local, slots_in, g_in)

@@ -27,3 +27,38 @@ def test_sharded_propagation_two_gpus_bit_exact():
     d = json.loads(line)
     assert d["world"] == 2 and d["max_abs_err_vs_single_gpu"] == 0.0
     assert max(d["nnz_per_rank"]) <= 1.1 * min(d["nnz_per_rank"])
+
+
+def test_row_sharded_table_two_gpus():
+    """Index / row all-to-all over NCCL around the CUDA gather and scatter-add kernels."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ST_ROWS="300000", ST_IDS="65536")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29579",
+                        os.path.join(root, "tools", "sharded_table_check.py")],
+                       capture_output=True, text=True, env=env, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["lookup_exact"] and d["scatter_add_max_err"] < 1e-3
+
+
+def test_gather_and_scatter_rows_single_gpu():
+    """The two local kernels of the sharded table against torch indexing (world size 1 path)."""
+    import torch
+
+    from librecommender_b200.parallel import RowShardedTable
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    full = torch.randn(5000, 48, device="cuda", generator=g)
+    t = RowShardedTable(full.clone(), 5000)
+    ids = torch.randint(0, 5000, (20000,), device="cuda", generator=g)
+    assert torch.equal(t.lookup(ids), full[ids])
+    grads = torch.randn(20000, 48, device="cuda", generator=g)
+    t.scatter_add(ids, grads)
+    expect = full.clone().index_add_(0, ids, grads)
+    assert float((t.local - expect).abs().max()) < 1e-4
+    assert t.lookup(ids[:0]).shape == (0, 48)
