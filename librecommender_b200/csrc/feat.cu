@@ -469,8 +469,8 @@ __global__ void scatter_add_rows_kernel(float* __restrict__ table, int64_t ld, i
 
 extern "C" int b200_gather_rows(const float* table, int64_t ld, int32_t d, const int64_t* idx, int64_t n,
                                 float* out, int64_t ld_out, void* stream) {
+  if (n == 0) return 0;      // empty requests carry null pointers (a rank that asked for nothing)
   B200_REQUIRE(table && idx && out && d > 0, "b200_gather_rows: bad arguments");
-  if (n == 0) return 0;
   gather_rows_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(table, ld, d, idx, n, out, ld_out);
   count_launch();
   B200_CUDA_OK(cudaGetLastError());
@@ -479,8 +479,8 @@ extern "C" int b200_gather_rows(const float* table, int64_t ld, int32_t d, const
 
 extern "C" int b200_scatter_add_rows(float* table, int64_t ld, int32_t d, const int64_t* idx, int64_t n,
                                      const float* rows, int64_t ld_rows, void* stream) {
-  B200_REQUIRE(table && idx && rows && d > 0, "b200_scatter_add_rows: bad arguments");
   if (n == 0) return 0;
+  B200_REQUIRE(table && idx && rows && d > 0, "b200_scatter_add_rows: bad arguments");
   scatter_add_rows_kernel<<<(unsigned)ceil_div64(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(table, ld, d, idx, n, rows,
                                                                                            ld_rows);
   count_launch();
