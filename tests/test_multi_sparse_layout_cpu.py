@@ -55,3 +55,49 @@ def test_spec_getter_reads_a_live_datainfo():
     assert g("n_users") == di.n_users and g("n_items") == di.n_items
     assert g("multi_sparse_combine_info").field_offset == [2]
     assert g("item_dense_unique") is None
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference not mounted")
+@pytest.mark.parametrize("which", ["plain", "multi_sparse"])
+def test_row_features_equal_reference_get_original_feats(which):
+    """oracle.tf_models.row_features (the per-row feed the kernels reproduce from the unique tables)
+    against the reference's own prediction-time function (prediction/preprocess.py:15-57) on live
+    DataInfo objects of both sample layouts, incl. the OOV user / item rows."""
+    import importlib.util
+    import sys
+
+    from libreco.prediction.preprocess import get_original_feats
+
+    from librecommender_b200.feat_models import _spec_get
+
+    gen = "gen_movielens_multi_sparse.py" if which == "multi_sparse" else "gen_movielens_feat.py"
+    path = os.path.join(os.path.dirname(__file__), "golden", gen)
+    spec_ = importlib.util.spec_from_file_location(f"gen_{which}", path)
+    mod = importlib.util.module_from_spec(spec_)
+    sys.modules[f"gen_{which}"] = mod
+    spec_.loader.exec_module(mod)
+    if which == "multi_sparse":
+        _, di = mod.build()
+    else:
+        import pandas as pd
+        from libreco.data import DatasetFeat, split_by_ratio_chrono
+        from oracle.ref_loader import REFERENCE_ROOT
+
+        data = pd.read_csv(os.path.join(REFERENCE_ROOT, "examples/sample_data/sample_movielens_merged.csv"))
+        train, _ = split_by_ratio_chrono(data, test_size=0.2)
+        _, di = DatasetFeat.build_trainset(train, ["sex", "age", "occupation"], ["genre1", "genre2", "genre3"],
+                                           ["sex", "occupation", "genre1", "genre2", "genre3"], ["age"])
+    g = _spec_get(di)
+    spec = {k: g(k) for k in ("n_users", "n_items", "user_sparse_unique", "item_sparse_unique", "user_dense_unique",
+                              "item_dense_unique")}
+    for k in ("user_sparse_col_index", "item_sparse_col_index", "user_dense_col_index", "item_dense_col_index"):
+        spec[k] = g(k) or []
+    spec["n_sparse"] = len(spec["user_sparse_col_index"]) + len(spec["item_sparse_col_index"])
+    spec["n_dense"] = len(spec["user_dense_col_index"]) + len(spec["item_dense_col_index"])
+    rng = np.random.default_rng(0)
+    users = np.concatenate([rng.integers(0, di.n_users, 500), [di.n_users]])      # + the OOV user row
+    items = np.concatenate([rng.integers(0, di.n_items, 500), [di.n_items]])
+    _, _, ref_sparse, ref_dense = get_original_feats(di, users, items, True, True)
+    sparse, dense = tm.row_features(spec, users, items)
+    np.testing.assert_array_equal(sparse, ref_sparse)
+    np.testing.assert_array_equal(dense, ref_dense)
