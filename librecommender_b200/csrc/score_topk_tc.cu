@@ -52,6 +52,10 @@ constexpr int TRIG = 96;       // uncounted records that trigger a compaction
 constexpr int EPI_WARPS = 8;   // LPS epilogue warps per TMEM lane quadrant (column groups of a tile).  16 warps with
                                // 32-column steps (96 registers, no spills to speak of) measured 1.9x SLOWER: 2.74 ms vs 1.43 ms
 constexpr int STEP = EPI_WARPS == 8 ? 64 : 32;   // accumulator columns per epilogue step (registers: 576 threads -> 113/thread)
+// Also measured and rejected: 32-column steps with the NEXT tcgen05.ld in flight while the current
+// step is processed (software pipelining around tcgen05.wait::ld).  ptxas keeps the kernel at 168
+// registers, the second pending 32-register buffer plus the duplicated step body spill ~300 bytes
+// into the hot loop, and the sweep runs at 4.84 ms instead of 1.43 ms.
 constexpr int LPS = EPI_WARPS / 4;   // candidate lists per (row, item split) = column groups per tile
 constexpr int CW = 256 / LPS;        // accumulator columns one epilogue warp scans per tile
 constexpr int KROW_MAX = 288;  // fast-path limit for k_row = K + c_u
