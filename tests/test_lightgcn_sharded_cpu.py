@@ -92,3 +92,34 @@ def test_plan_layout_roundtrip():
             np.testing.assert_array_equal(plan.position(nodes).numpy(), r * plan.slab + slots.numpy())
             seen += nodes.tolist()
         assert sorted(seen) == list(range(nu + ni))
+
+
+@pytest.mark.parametrize("world", [1, 3, 4, 8])
+def test_plan_single_process_simulation_any_world(world):
+    """The same partition / remap logic for world sizes the gloo test does not spawn: all ranks are
+    simulated in one process (the all-gather is a concatenation of the per-rank blocks)."""
+    from librecommender_b200.parallel import LightGCNShardPlan
+    from oracle import lightgcn as ol
+
+    n_users, n_items, d, n_layers = 29, 17, 5, 3
+    _, L = _graph(4, n_users, n_items)
+    E0 = torch.from_numpy(np.random.default_rng(2).standard_normal((n_users + n_items, d)).astype(np.float32))
+    plan = LightGCNShardPlan(n_users, n_items, world)
+    ip = torch.from_numpy(L.indptr.astype(np.int64))
+    ci = torch.from_numpy(L.indices.astype(np.int32))
+    va = torch.from_numpy(L.data.astype(np.float32))
+    locals_, nnz = [], 0
+    for r in range(world):
+        lptr, lcol, lval = plan.shard_csr(ip, ci, va, r)
+        nnz += int(lval.numel())
+        locals_.append(torch.sparse_csr_tensor(lptr, lcol.to(torch.int64), lval, size=(plan.slab, world * plan.slab)))
+    assert nnz == L.nnz
+    cur = [plan.scatter_rows(E0, r) for r in range(world)]
+    acc = [c.clone() for c in cur]
+    for _ in range(n_layers):
+        full = torch.cat(cur, dim=0)                         # what all_gather_into_tensor produces
+        cur = [locals_[r] @ full for r in range(world)]
+        acc = [a + c for a, c in zip(acc, cur)]
+    out = plan.unpermute(torch.cat(acc, dim=0) / (n_layers + 1)).numpy()
+    ref = np.concatenate(ol.propagate(L, E0[:n_users].numpy(), E0[n_users:].numpy(), n_layers))
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-6)
