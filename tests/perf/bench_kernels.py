@@ -1,6 +1,6 @@
 """Secondary kernel measurements (HBM-bound rows of SURVEY.md §8d): achieved GB/s against the
 measured copy bandwidth.  CUDA-event timing, 3 warm-ups, inputs larger than L2.
-    python tools/bench_kernels.py > gpurun_out/kernels.jsonl
+    python tests/perf/bench_kernels.py > gpurun_out/kernels.jsonl
 """
 import json
 import os
@@ -10,7 +10,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 PEAK = 6572.2

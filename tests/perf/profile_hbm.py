@@ -2,7 +2,7 @@
 achieved HBM GB/s (gather, SpMM)").  One SpMM layer on a Zipf bipartite graph, the DeepFM-shaped
 feature gather (forward) and its gradient scatter (backward).
     ncu --set full --clock-control none -k regex:"spmm|feat_forward|feat_backward" -s 6 -c 6 \
-        -o gpurun_out/prof_hbm python tools/profile_hbm.py
+        -o gpurun_out/prof_hbm python tests/perf/profile_hbm.py
 """
 import os
 import sys
@@ -10,7 +10,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from librecommender_b200.lightgcn import SpmmGraph  # noqa: E402
 from librecommender_b200.training import FMTrainer  # noqa: E402
 from oracle import tf_models as tm  # noqa: E402

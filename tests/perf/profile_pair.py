@@ -1,6 +1,6 @@
 """Driver for ncu captures of the hoisted DeepFM pair kernel (csrc/pair.cu).
     ncu --set full --clock-control none --import-source on -k regex:deepfm_pair -s 1 -c 1 \
-        -o gpurun_out/prof_pair python tools/profile_pair.py
+        -o gpurun_out/prof_pair python tests/perf/profile_pair.py
 """
 import os
 import sys
@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from librecommender_b200.feat_models import DeepFM  # noqa: E402
 from oracle import tf_models as tm  # noqa: E402
 
