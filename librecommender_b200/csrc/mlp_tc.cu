@@ -5,8 +5,9 @@
 // compute-bound on the SIMT path (b200_linear_f32).  The reference computes these layers in fp32
 // (TensorFlow MatMul); a plain tf32 or bf16 tensor-core GEMM would miss the 1e-5 parity bar, so
 // the operands are split  x = hi + lo  (hi = top 11 mantissa bits, lo = next 11) and three
-// tcgen05.mma kind::tf32 products are accumulated:  hi*hi + lo*hi + hi*lo  (the dropped lo*lo term
-// is < 2^-22 |x||w|).  The tensor core truncates its fp32 accumulator once per MMA (measured: a
+// tcgen05.mma kind::tf32 products are accumulated:  hi*hi + lo*hi + hi*lo  (truncation keeps 10
+// explicit mantissa bits, |lo| < 2^-10 |x|: the dropped lo*lo term is < 2^-20 |x||w| and the two
+// truncated cross terms add < 2^-20 each; tests/test_tf32x3_model_cpu.py).  The tensor core truncates its fp32 accumulator once per MMA (measured: a
 // single accumulator over 48 MMAs drifts by ~2e-6 of sum|x w|), so (a) the dominant hi*hi products
 // and the 2^-11-times smaller cross products go to SEPARATE TMEM accumulators, and (b) both are
 // promoted to registers (round-to-nearest adds) every GC k-chunks = GC*4 MMAs per accumulator.

@@ -1,7 +1,8 @@
 """Numeric model of the 3xTF32 operand split used by b200_linear_tf32x3 (csrc/mlp_tc.cu): x = hi + lo
 with hi = the tf32 truncation of x and lo = x - hi (itself truncated to tf32 by the tensor core),
 product ~ hi*hi' + lo*hi' + hi*lo'.  Checks in exact float64 arithmetic that the representation +
-dropped-term error is below 2^-20 * sum|x w| for every input (the measured kernel error, which also
+dropped-term error is below 3 * 2^-20 * sum|x w| for every input (truncation keeps 10 explicit
+mantissa bits: |lo| < 2^-10 |x|, so lo*lo' < 2^-20 |x w| and the two truncated cross terms add 2^-20 each) (the measured kernel error, which also
 contains the fp32 accumulation, is <= 1e-6 * sum|x w|: tests/test_gpu_linear_tc.py)."""
 import numpy as np
 import pytest
@@ -25,7 +26,7 @@ def test_three_product_split_error_bound(din):
     exact = x.astype(f) @ w.astype(f)
     mag = np.abs(x).astype(f) @ np.abs(w).astype(f)
     err = np.abs(approx - exact) / mag
-    assert err.max() <= 2.0 ** -20, float(err.max())
+    assert err.max() <= 3 * 2.0 ** -20, float(err.max())
     # a single tf32 product (no split) is three orders of magnitude worse: why the split exists
     single = np.abs(xh.astype(f) @ wh.astype(f) - exact) / mag
     assert single.max() > 50 * err.max()
