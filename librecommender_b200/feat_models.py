@@ -14,7 +14,7 @@
 from __future__ import annotations
 
 import ctypes
-from ctypes import POINTER, Structure, c_float, c_int32, c_int64, c_void_p
+from ctypes import Structure, c_int32, c_int64, c_void_p
 
 import numpy as np
 

@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib
-from .consumed import ConsumedCSR, as_csr
+from .consumed import as_csr
 
 
 def build_laplacian_csr(user_consumed, n_users, n_items, device=None):
