@@ -7,8 +7,11 @@ TwoTower-style retrieval, 10 M users x 1 M items, embed 64, top-100, consumed fi
     torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU (users sharded)
 
 One JSON line on rank 0 (see the driver contract).  A "step" = one recommend call for a batch of
-`--batch` distinct users per rank.  `value` is device-resident (user ids already in HBM, result
-left in HBM); `e2e` goes through the reference-facing call with HOST ids in and HOST ids out.
+`--batch` distinct users per rank (run as launches of <= 16384 users).  `value` is device-resident
+(user ids already in HBM, result left in HBM); `e2e` goes through the reference-facing seam
+`recommend_from_embedding(model, <python list of user ids>, n_rec, ...)` with HOST ids in and a
+fresh HOST int64[B, n_rec] array out.  For N > 1 the same run also times the two paths that DO have
+a collective (sharded LightGCN propagation, row-sharded embedding lookup) under `secondary`.
 """
 from __future__ import annotations
 
@@ -36,13 +39,16 @@ def parse():
     ap.add_argument("--users", type=int, default=10_000_000)
     ap.add_argument("--items", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=64)
-    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--batch", type=int, default=32768)
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--mean-consumed", type=float, default=50.0)
     ap.add_argument("--cpu-users", type=int, default=64, help="users per CPU-baseline call")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", default="auto", choices=["auto", "exact"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip the collective legs at N > 1")
+    ap.add_argument("--epi-warps", type=int, default=0, help="tuning: epilogue warps per TMEM quadrant (2|3)")
+    ap.add_argument("--pre-coef", type=float, default=0.0, help="tuning: speculative rank coefficient")
     return ap.parse_args()
 
 
@@ -161,9 +167,31 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU baseline: the reference's algorithm (oracle port, same numpy primitives) on host cores
 # --------------------------------------------------------------------------------------------
-def cpu_baseline_run(args, U_rows_fn, I_host, consumed_fn, seconds, users_per_call, max_calls=None):
+def _reference_fn():
+    """The reference's OWN recommend_from_embedding (mounted /root/reference or the byte-identical
+    staged copy oracle/_ref) when present -> kind "reference"; else the oracle port -> kind "port"."""
+    try:
+        from oracle.ref_loader import load_reference, reference_available, reference_kind
+
+        if reference_available():
+            load_reference()
+            from libreco.recommendation import recommend_from_embedding as ref_fn
+
+            return ref_fn, "reference", reference_kind()
+    except Exception as e:   # pragma: no cover
+        print(f"[bench] reference import failed ({e!r}); timing the oracle port", file=sys.stderr)
+    return None, "port", "absent"
+
+
+def cpu_baseline_run(args, U_rows_fn, I_host, consumed_fn, seconds, users_per_call, max_calls=None,
+                     keep_first=None):
+    """Time the reference algorithm on host cores.  Users are renumbered 0..n-1 for the call (the
+    reference indexes ``user_embeddings[user_ids]`` and ``model.user_consumed[user]``)."""
+    import types
+
     from oracle.ranking import recommend_from_embedding_numpy_path
 
+    ref_fn, kind, _ = _reference_fn()
     rng = np.random.default_rng(SEED_Q + 77)
     done_users, t_total, calls = 0, 0.0, 0
     per_call = []
@@ -171,11 +199,20 @@ def cpu_baseline_run(args, U_rows_fn, I_host, consumed_fn, seconds, users_per_ca
         users = rng.choice(args.users, size=users_per_call, replace=False).astype(np.int64)
         rows = U_rows_fn(users)
         consumed = consumed_fn(users)
+        local = list(range(users_per_call))
+        consumed_local = {j: consumed[int(u)] for j, u in enumerate(users.tolist()) if int(u) in consumed}
+        model = types.SimpleNamespace(task="ranking", n_items=args.items, n_users=users_per_call,
+                                      user_consumed=consumed_local)
         t0 = time.perf_counter()
-        ids = recommend_from_embedding_numpy_path(users.tolist(), args.topk, rows, I_host, args.items,
-                                                  consumed, True)
+        if ref_fn is not None:
+            ids = ref_fn(model, local, args.topk, rows, I_host, True, False)
+        else:
+            ids = recommend_from_embedding_numpy_path(local, args.topk, rows, I_host, args.items,
+                                                      consumed_local, True)
         dt = time.perf_counter() - t0
         assert ids.shape == (users_per_call, args.topk)
+        if keep_first is not None and not keep_first:
+            keep_first.update(users=users, ids=np.asarray(ids), rows=rows, consumed=consumed)
         calls += 1
         if calls > 1 or max_calls == 1:   # first call is the warm-up unless only one is allowed
             t_total += dt
@@ -183,7 +220,7 @@ def cpu_baseline_run(args, U_rows_fn, I_host, consumed_fn, seconds, users_per_ca
             per_call.append(dt)
         if (max_calls and calls >= max_calls + (0 if max_calls == 1 else 1)) or t_total >= seconds:
             break
-    return done_users / max(t_total, 1e-9), per_call
+    return done_users / max(t_total, 1e-9), per_call, kind
 
 
 def host_views(U, I, indptr, idx):
@@ -228,10 +265,15 @@ def main():
                 f"top-{args.topk}, filter_consumed, batch {args.batch} users/step/GPU")
     config = {"workload": workload, "users": args.users, "items": args.items, "embed": args.dim,
               "n_rec": args.topk, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
+              "users_per_launch": min(args.batch, 16384),
               "parallelism": f"users sharded x{world}, item table replicated, no data-path collective",
-              "l2": "inputs larger than L2 (item table 256 MB fp32 + 128 MB bf16, user table 2.56 GB)",
-              "device_leg": "2 calls in flight on one stream (async handle, check of batch i after enqueue of i+1)",
-              "e2e_leg": "synchronous reference-facing call: pinned H2D ids, kernels, D2H ids + status, one sync"}
+              "l2": "inputs larger than L2 (item table 256 MB fp32 + 128 MB fp16, user table 2.56 GB)",
+              "device_leg": "2 steps in flight on one stream (async handle, check of step i after enqueue of i+1)",
+              "e2e_leg": "synchronous reference-facing seam recommend_from_embedding(model, python list of ids, ...): "
+                         "list -> H2D ids, kernels, D2H ids + status (side stream, chunk-pipelined), one sync, "
+                         "fresh host int64 array",
+              "cpu_arm": f"{args.cpu_users} users per call (np.tile in the reference needs 8*B*N bytes: "
+                         f"B = {args.batch} would need {8 * args.batch * args.items / 1e9:.0f} GB), same catalogue"}
 
     U, I = make_tables(args, device)
     indptr, idx = make_consumed_csr(args, device)
@@ -246,22 +288,23 @@ def main():
             pass
         I_host, rows_fn, cons_fn = host_views(U, I, indptr, idx)
         ncalls = max(1, args.steps)
-        for _ in range(max(0, args.warmup)):
+        for _ in range(max(0, min(args.warmup, 2))):
             cpu_baseline_run(args, rows_fn, I_host, cons_fn, 0.0, args.cpu_users, max_calls=1)
-        t0 = time.perf_counter()
-        ups, per_call = cpu_baseline_run(args, rows_fn, I_host, cons_fn, 1e9, args.cpu_users,
-                                         max_calls=ncalls if ncalls > 1 else 1)
+        ups, per_call, kind = cpu_baseline_run(args, rows_fn, I_host, cons_fn, 1e9, args.cpu_users,
+                                               max_calls=ncalls if ncalls > 1 else 1)
         ms = 1e3 * float(np.mean(per_call))
         cores = os.cpu_count()
+        what = ("the reference's own libreco.recommendation.recommend_from_embedding (unmodified, "
+                "oracle/_ref or /root/reference)" if kind == "reference" else
+                "oracle port of recommend.py:57-78 + ranking.py:10-78")
         line = {
             "impl": "reference", "metric": "recommend_user users/sec (all-items top-K)", "value": ups,
             "unit": "users/s", "n_gpus": args.gpus, "steps": len(per_call), "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": ups, "unit": "users/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": ups, "unit": "users/s", "cores": cores, "kind": kind,
                              "sample": f"{args.cpu_users} users per call x {len(per_call)} calls, full "
-                                       f"{args.items}-item catalogue (oracle port of recommend.py:57-78 + "
-                                       "ranking.py:10-78, numpy/OpenBLAS on all host threads)"},
+                                       f"{args.items}-item catalogue ({what}, numpy/OpenBLAS on all host threads)"},
             "e2e": {"value": ups, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -269,15 +312,25 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ this repo's CUDA path
-    from librecommender_b200 import _lib
-    from librecommender_b200.consumed import ConsumedCSR
-    from librecommender_b200.engine import EmbedScorer
+    import types
 
+    from librecommender_b200 import _lib
+    from librecommender_b200 import recommend_from_embedding
+    from librecommender_b200.consumed import ConsumedCSR
+    from librecommender_b200.engine import scorer_for
+
+    if args.epi_warps or args.pre_coef:
+        _lib.check(_lib.lib.b200_recommend_embed_tune(args.epi_warps, args.pre_coef))
     csr = ConsumedCSR.from_device_tensors(indptr, idx)
-    scorer = EmbedScorer(U, I, args.items, csr, n_users=args.users, device=device)
+    # the object the reference's seam receives: `model` with n_items / n_users / task / user_consumed,
+    # and the two embedding tables (device-resident here, as TwoTower.set_embeddings leaves them)
+    model = types.SimpleNamespace(task="ranking", n_items=args.items, n_users=args.users, user_consumed=csr)
+    scorer = scorer_for(model, U, I)
+    plan = scorer.fused_plan(args.batch, args.topk)
     n_batches = args.warmup + args.steps
-    batches_h = [torch.from_numpy(b).pin_memory() for b in make_batches(args, rank, n_batches)]
-    batches_d = [b.to(device) for b in batches_h]
+    batches_np = make_batches(args, rank, n_batches)
+    batches_list = [b.tolist() for b in batches_np]            # what the reference passes: a python list
+    batches_d = [torch.from_numpy(b).to(device) for b in batches_np]
     torch.cuda.synchronize()
 
     def barrier():
@@ -306,37 +359,58 @@ def main():
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    # two calls in flight: batch i+1 is enqueued before batch i is checked (rows the fused path
+    # two steps in flight: step i+1 is enqueued before step i is checked (rows the fused path
     # could not prove are repaired in .result(); every check happens inside the timed region)
-    out, pending = None, None
+    out, pending, fallback_dev = None, None, 0
     for i in range(args.warmup, n_batches):
         nxt = scorer.recommend_device_async(batches_d[i], args.topk, True, False, args.path)
         if pending is not None:
             out = pending.result()
+            fallback_dev += scorer.last_fallback_rows
         pending = nxt
     out = pending.result()
+    fallback_dev += scorer.last_fallback_rows
     e1.record()
     barrier()
-    clocks = sampler.stop()
     launches = _lib.launch_count() - launches0
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     sweep_ms = [a.elapsed_time(b) for a, b in scorer.events]
     scorer.events = None
     value = world * args.batch * args.steps / (dev_ms * 1e-3)
 
-    # ---- end-to-end leg: host ids in, host ids out ---------------------------------------
+    # ---- end-to-end leg: python list of host ids in, fresh host ids out ---------------------
     for i in range(min(args.warmup, 2)):
-        scorer.recommend(batches_h[i], args.topk, True, False, args.path)
+        recommend_from_embedding(model, batches_list[i], args.topk, U, I, True, False)
     barrier()
     e0.record()
-    res = None
+    res, fallback_e2e = None, 0
     for i in range(args.warmup, n_batches):
-        res = scorer.recommend(batches_h[i], args.topk, True, False, args.path)
+        res = recommend_from_embedding(model, batches_list[i], args.topk, U, I, True, False)
+        fallback_e2e += scorer.last_fallback_rows
     e1.record()
     barrier()
+    clocks = sampler.stop()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * args.batch * args.steps / (e2e_ms * 1e-3)
     assert res.shape == (args.batch, args.topk) and res.dtype == np.int64 and (res >= 0).all()
+
+    # ---- parity of one TIMED batch, outside the timed region: fused result vs the exact path ----
+    last = batches_d[n_batches - 1]
+    n_chk = min(args.batch, 8192)
+    exact_ids = scorer.recommend_exact(last[:n_chk], args.topk, True, False).cpu().numpy()
+    parity = {"checked_rows": int(n_chk),
+              "e2e_ids_equal_exact_path": float((res[:n_chk] == exact_ids).all(axis=1).mean()),
+              "device_ids_equal_exact_path": float((out[:n_chk].cpu().numpy() == exact_ids).all(axis=1).mean())}
+
+    # ---- secondary: the paths that have a collective (only at N > 1) -------------------------
+    secondary = None
+    if distributed and not args.no_secondary:
+        try:
+            from librecommender_b200 import bench_collectives
+
+            secondary = bench_collectives.run(rank, world, device, max_over_ranks, barrier)
+        except Exception as e:   # the primary line must survive
+            secondary = {"error": repr(e)}
 
     if distributed:
         import torch.distributed as dist
@@ -354,41 +428,63 @@ def main():
         pass
     roofline = None
     if sweep_ms:
-        flops = 2.0 * args.dim * args.items * args.batch               # per launch (2*d*N per user)
+        rows_per_launch = min(args.batch, 16384)
+        flops = 2.0 * args.dim * args.items * rows_per_launch          # per launch (2*d*N per user)
         avg_ms = float(np.mean(sweep_ms))
         achieved = flops / (avg_ms * 1e-3) / 1e12
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "sweep_traffic.json")))["dram_bytes_per_launch"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "sweep_traffic.json")))
+            traffic = tr["dram_bytes_per_launch"]
         except Exception:
             pass
-        roofline = {"bound": "tensor", "kernel": "b200::tc::sweep_kernel", "achieved": achieved,
+        roofline = {"bound": "tensor", "kernel": "b200::tc::sweep_kernel (PRE + guess + MAIN)", "achieved": achieved,
                     "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks
-                    else "fallback 1400 (of fallback)",
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured; fp16 runs at the bf16 rate)"
+                    if peaks else "fallback 1400 (of fallback)",
                     "traffic": traffic, "avg_launch_ms": avg_ms, "launches_timed": len(sweep_ms),
+                    "rows_per_launch": rows_per_launch,
                     "share_of_step": avg_ms * len(sweep_ms) / max(dev_ms, 1e-9) if not distributed else None}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         I_host, rows_fn, cons_fn = host_views(U, I, indptr, idx)
-        ups, per_call = cpu_baseline_run(args, rows_fn, I_host, cons_fn, args.cpu_seconds, args.cpu_users)
-        cpu = {"value": ups, "unit": "users/s", "cores": os.cpu_count(), "kind": "port",
+        first = {}
+        ups, per_call, kind = cpu_baseline_run(args, rows_fn, I_host, cons_fn, args.cpu_seconds, args.cpu_users,
+                                               keep_first=first)
+        what = ("the reference's own recommend_from_embedding, unmodified" if kind == "reference"
+                else "oracle port of the reference's numpy path")
+        cpu = {"value": ups, "unit": "users/s", "cores": os.cpu_count(), "kind": kind,
                "sample": f"{args.cpu_users} users per call x {len(per_call)} calls against the full "
-                         f"{args.items}-item catalogue (oracle port of the reference's numpy path)"}
+                         f"{args.items}-item catalogue ({what})"}
+        # the CPU arm's answer for its first call doubles as the checker of the CUDA path on those users
+        from oracle.ranking import near_tie_mask
+
+        got = recommend_from_embedding(model, first["users"].tolist(), args.topk, U, I, True, False)
+        full = first["rows"] @ I_host[:args.items].T
+        parity["cpu_reference_rows"] = int(len(first["users"]))
+        parity["ids_equal_cpu_reference"] = float((got == first["ids"]).mean())
+        parity["ids_equal_cpu_reference_outside_near_ties"] = bool(
+            near_tie_mask(first["ids"], got, full, 1e-6).all())
 
     line = {
         "metric": "recommend_user users/sec (all-items top-K)", "value": value, "unit": "users/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 scores (bf16 tensor-core candidate pass + exact fp32 re-score)",
+        "vs_baseline": None, "dtype": "f32 scores (fp16 tensor-core candidate pass + exact fp32 re-score)",
         "data": "synthetic", "config": config, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "users/s", "h2d_bytes_per_step": args.batch * 8,
-                "d2h_bytes_per_step": args.batch * args.topk * 8, "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": args.batch * args.topk * 8 + args.batch * 4,
+                "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "path": args.path,
+        "path": args.path, "plan": plan,
+        "fallback_rows": {"device_leg": int(fallback_dev), "e2e_leg": int(fallback_e2e),
+                          "rows_per_leg": int(args.batch * args.steps)},
+        "parity": parity,
     }
+    if secondary is not None:
+        line["secondary"] = secondary
     print(json.dumps(line))
     return 0
 

@@ -65,13 +65,25 @@ int b200_score_rows_f32(const float* U, int64_t ldu, const int64_t* user_ids, in
 
 /* ---- a1+a2 fused: recommend_from_embedding + rank_recommendations on the tensor cores -----
  * (recommend.py:57-78 + ranking.py:10-78, never materialising [B,N]).
- * catalog: device buffer prepared ONCE per item table (bf16 K-major copy + max row norm).
+ * catalog: device buffer prepared ONCE per item table (fp16 K-major copy scaled by a power of two
+ * so that the largest row norm lies in [64, 128), + that norm).
  * Result per row: the K best non-consumed items by EXACT fp32 score (same definition as
  * b200_score_rows_f32), sorted (score desc, id asc).  row_status[r] (device int32[B]) = 1 marks a
  * row the fused path could not prove exact (failed threshold speculation, too many near-ties, or a
  * heavy user whose capped candidate budget did not suffice): its out_ids are -1 and the caller
  * re-runs it through b200_score_rows_f32 + b200_mask_consumed + b200_topk_rows.
- * Limits: d <= 256, K <= 288. */
+ * row_status codes: 1 sweep list overflow, 2 too few collected, 3 failed speculation, 4 candidate
+ * set outside [K, 2048], 5 capped row not provable.
+ * Limits: d <= 256, K <= 288.
+ * b200_recommend_embed_plan reports how a call of that shape will run: out[0] = 1 when the
+ * speculative pre-pass (sweep<PRE> + guess_kernel) is used, out[1] item splits, out[2] item tiles
+ * per split, out[3] user tiles, out[4] sampled tiles per split, out[5] TMA stages, out[6] epilogue
+ * warps per TMEM lane quadrant, out[7] records per candidate list (n_out >= 8).
+ * b200_recommend_embed_tune (process-wide, not thread-safe; 0 keeps a value): epilogue warps per
+ * TMEM lane quadrant of the main pass (2 or 3) and the rank coefficient c of the speculative
+ * threshold (about c * k_row items are expected above it). */
+int b200_recommend_embed_tune(int32_t epilogue_warps_per_quadrant, float pre_rank_coef);
+int b200_recommend_embed_plan(int64_t B, int64_t N, int32_t d, int32_t K, int32_t* out, int32_t n_out);
 int b200_embed_catalog_bytes(int64_t N, int32_t d, size_t* bytes);
 int b200_embed_catalog_prepare(const float* I, int64_t ldi, int64_t N, int32_t d, void* catalog,
                                size_t bytes, void* stream);

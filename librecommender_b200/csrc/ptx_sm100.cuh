@@ -174,9 +174,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
   return d;
 }
 
-// instruction descriptor: D=f32, A=B=bf16, both K-major, dense
+// instruction descriptor: D=f32 (bits 4-5 = 1), A / B format (bits 7-9 / 10-12: 0 = f16, 1 = bf16),
+// both K-major, dense, N>>3 at bit 17, M>>4 at bit 24
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_f16_f32(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -5,16 +5,17 @@
 // the [B, N] score matrix.
 //
 // Pipeline (all on one stream, no host sync):
-//   prep_items   (once per item table)  fp32 [N,d] -> bf16 [N_pad, d_pad] (K-major, zero padded)
-//                                        + max item L2 norm
-//   prep_users   gather U[user_ids] -> bf16 [B_pad, d_pad]; per-row error bound eps, k_row
+//   prep_items   (once per item table)  fp32 [N,d] -> fp16 [N_pad, d_pad] (K-major, zero padded),
+//                                        scaled by a power of two so that max ||I_i|| is in [64,128)
+//   prep_users   gather U[user_ids] -> fp16 [B_pad, d_pad], every row scaled by its own power of
+//                two (row norm in [64,128)); per-row error bound eps, k_row
 //   sweep<PRE>   tensor-core pass over every 16th item tile that only records, per user row, the
 //                maximum coarse score of each sampled 128-item block (one coalesced store per
 //                tile, no divergence); guess_kernel turns the block maxima into a SPECULATIVE
 //                per-row threshold (the pre_k-th largest block maximum).
 //   sweep<MAIN>  persistent tcgen05 kernel over all item tiles: TMA -> smem (SWIZZLE_128B) ->
-//                tcgen05.mma (bf16 in, fp32 accumulate in TMEM, 128x256 tile, double-buffered
-//                accumulator) -> 8 epilogue warps read TMEM (tcgen05.ld) and keep, per user row,
+//                tcgen05.mma (fp16 in, fp32 accumulate in TMEM, 128x256 tile, double-buffered
+//                accumulator) -> epilogue warps read TMEM (tcgen05.ld) and keep, per user row,
 //                every item whose COARSE score is >= tau.  tau starts at the speculative value and
 //                is only ever raised by a rigorous bound: (k_row-th best coarse score counted so
 //                far in the row's global histogram) - 2*eps.
@@ -24,8 +25,13 @@
 //                (sequential fma = the library's exact-score definition), sorts by
 //                (score desc, id asc), emits K ids.
 //
-// Exactness argument: |coarse - exact| <= eps for every (user, item) (bf16 rounding of both
-// operands, |delta| <= 2^-8 each, plus a generous accumulation term).  Let c_k be the k-th
+// Coarse scores live in a SCALED domain: coarse(u, i) ~ s_u * s_i * <u, i> with s_u, s_i powers of
+// two (exact scalings), so the fp16 operands keep 11 significant bits whatever the magnitude of the
+// embeddings; every threshold of a row (tau, eps, R, histogram range) is in that row's scaled units.
+//
+// Exactness argument: |coarse - s_u s_i exact| <= eps for every (user, item) (fp16 rounding of both
+// operands, |delta| <= 2^-11 each, plus an absolute term that covers fp16 subnormals even if the
+// tensor core flushed them, plus a generous accumulation term).  Let c_k be the k-th
 // largest coarse score.  Every item of the exact top-k has coarse >= c_k - 2 eps.  The lists hold
 // every item with coarse >= T, T = the largest threshold ever used for the row; finalize proves
 // T <= c_k - 2 eps (rigorous raises satisfy it by construction, the speculative start value is
@@ -37,47 +43,50 @@
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "../../include/b200reco.h"
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace b200 {
 namespace tc {
 
 constexpr int TM = 128;        // users per tile (UMMA M)
 constexpr int TN = 256;        // items per tile (UMMA N)
-constexpr int KBLK = 64;       // bf16 per 128-byte swizzled row
-constexpr int CAPG = 256;      // candidate GROUP records per (row, list); list = (item split, column half)
+constexpr int KBLK = 64;       // fp16 per 128-byte swizzled row
+constexpr int CAPG_MAX = 256;  // candidate GROUP records per (row, list), upper limit (runtime capg <= this)
 constexpr int GW = 8;          // a record = the 8 coarse scores of one 8-column group + its first item id
 constexpr int NB = 1024;       // bins of the per-row global coarse-score histogram
-constexpr int TRIG = 96;       // uncounted records that trigger a compaction
-constexpr int EPI_WARPS = 8;   // LPS epilogue warps per TMEM lane quadrant (column groups of a tile).  16 warps with
-                               // 32-column steps (96 registers, no spills to speak of) measured 1.9x SLOWER: 2.74 ms vs 1.43 ms
-constexpr int STEP = EPI_WARPS == 8 ? 64 : 32;   // accumulator columns per epilogue step (registers: 576 threads -> 113/thread)
-// Also measured and rejected: 32-column steps with the NEXT tcgen05.ld in flight while the current
-// step is processed (software pipelining around tcgen05.wait::ld).  ptxas keeps the kernel at 168
-// registers, the second pending 32-register buffer plus the duplicated step body spill ~300 bytes
-// into the hot loop, and the sweep runs at 4.84 ms instead of 1.43 ms.
-constexpr int LPS = EPI_WARPS / 4;   // candidate lists per (row, item split) = column groups per tile
-constexpr int CW = 256 / LPS;        // accumulator columns one epilogue warp scans per tile
+constexpr int STEP = 64;       // accumulator columns per epilogue step (one tcgen05.ld.32x32b.x64)
+constexpr int STEPS_PER_TILE = TN / STEP;   // 4
+// Epilogue organisation: W warps per TMEM lane quadrant (4 quadrants => 4W epilogue warps).  The
+// 64-column steps of every tile are dealt to the W warps of a quadrant (W = 2: two adjacent steps
+// each, W = 4: one step each, W = 3: round-robin over the running step count).  Each warp owns one
+// candidate list per (row, item split): n_lists = W * n_splits.
+constexpr int W_PRE = 2;       // the pre-pass always runs with 2 warps per quadrant (block = 128 columns)
 constexpr int KROW_MAX = 288;  // fast-path limit for k_row = K + c_u
 constexpr int MAX_KB = 4;      // d_pad <= 256
 constexpr int PRE_STRIDE = 16; // the pre-pass visits every 16th item tile of a split
 constexpr int A_KB_BYTES = TM * KBLK * 2;   // 16 KB
 constexpr int B_KB_BYTES = TN * KBLK * 2;   // 32 KB
-constexpr int SWEEP_THREADS = 64 + 32 * EPI_WARPS;  // warp0 TMA, warp1 MMA, warps 2.. epilogue
 constexpr int MAXU = 3072;                  // finalize: collected elements per row (union of the lists)
 constexpr int MAXC = 2048;                  // finalize: candidates per row after the c_k - 2 eps cut
 constexpr int FIN_THREADS = 256;
-constexpr float ERR_COEF = 0.0082f;  // 2^-7*(1+2^-9) for bf16 x bf16 products + accumulation slack
+// |coarse - exact| <= ERR_COEF * ||u|| * ||i|| (+ absolute subnormal term, + accumulation slack):
+// fp16 x fp16 products, both operands rounded to nearest: (1 + 2^-11)^2 - 1 = 2^-10 (1 + 2^-12)
+constexpr float ERR_COEF = 0.00097705f;
+
+__host__ __device__ constexpr int sweep_threads(int W) { return 64 + 128 * W; }
 
 struct CatalogHeader {   // first 256 bytes of the catalog buffer (device)
-  uint32_t max_norm_bits;  // max_i ||I_i||_2 (fp32 bits; non-negative so uint order == float order)
+  uint32_t max_norm_bits;  // max_i ||I_i||_2 of the UNSCALED rows (fp32 bits; non-negative so uint order == float order)
   int32_t d, d_pad;
   int64_t N, N_pad;
+  float scale;             // power of two applied to every item row before the fp16 rounding
+  float max_norm_scaled;   // scale * max norm (rounded up), in [64, 128) unless the table is all zero
 };
 
 struct RowMeta {
-  float eps2;       // 2 * eps
+  float eps2;       // 2 * eps                                   (scaled units of the row)
   float R;          // |coarse score| <= R for every item (Cauchy-Schwarz on the row norms)
+  float scale;      // s_u * s_i: coarse ~ scale * exact
   int32_t k_row;    // K (+ consumed count when the filter applies)
   int32_t pre_k;    // rank of the block maximum used as speculative threshold
   int32_t active;   // 0: pad row (never collects)
@@ -90,37 +99,63 @@ struct SweepParams {
   int64_t N;
   int32_t B_pad, m_tiles, n_splits, tiles_per_split, total_tiles, KB, nstage;
   int32_t n_pre_tiles;        // sampled tiles per split in the pre-pass
+  int32_t capg, trig;         // records per list / uncounted records that trigger a compaction
   const RowMeta* meta;        // [B_pad]
   uint32_t* row_tau_key;      // [B_pad]  running max of tau (order-preserving key)
   int32_t* row_status;        // [B_pad]  1 = needs the exact path
   uint32_t* ghist;            // [B_pad][NB]  coarse-score histogram of every counted candidate
-  float* cand_s;              // [LPS*n_splits][B_pad][CAPG][GW]  group records: 8 coarse scores ...
-  int32_t* cand_b;            // [LPS*n_splits][B_pad][CAPG]      ... and the item id of the first column
-  int32_t* cand_cnt;          // [LPS*n_splits][B_pad]            records per list
-  float* blockmax;            // [LPS*n_splits][n_pre_tiles][B_pad]   (pre-pass output)
+  float* cand_s;              // [W*n_splits][B_pad][capg][GW]  group records: 8 coarse scores ...
+  int32_t* cand_b;            // [W*n_splits][B_pad][capg]      ... and the item id of the first column
+  int32_t* cand_cnt;          // [W*n_splits][B_pad]            records per list
+  float* blockmax;            // [W_PRE*n_splits][n_pre_tiles][B_pad]   (pre-pass output)
 };
 
 // ------------------------------------------------------------------------------------------
 // prep kernels
 // ------------------------------------------------------------------------------------------
+// power of two s with s * nrm in [64, 128) (1 for a zero / non-finite norm)
+__device__ __forceinline__ float pow2_scale_for(float nrm) {
+  if (!(nrm > 0.f) || !(nrm < 3.0e38f)) return 1.f;
+  int x;
+  frexpf(nrm, &x);                 // nrm = m * 2^x, m in [0.5, 1)
+  int e = 7 - x;                   // m * 2^7 in [64, 128)
+  e = max(-120, min(120, e));
+  return ldexpf(1.f, e);
+}
+
+__global__ void item_norm_kernel(const float* __restrict__ I, int64_t ldi, int64_t N, int d,
+                                 CatalogHeader* hdr) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  float ss = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const float v = __ldg(I + row * ldi + k);
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) atomicMax(&hdr->max_norm_bits, __float_as_uint(sqrtf(ss) * 1.0001f));  // round up a little
+}
+
+__global__ void item_scale_kernel(CatalogHeader* hdr) {
+  const float mx = __uint_as_float(hdr->max_norm_bits);
+  const float s = pow2_scale_for(mx);
+  hdr->scale = s;
+  hdr->max_norm_scaled = mx * s;
+}
+
 __global__ void prep_items_kernel(const float* __restrict__ I, int64_t ldi, int64_t N, int d,
-                                  int d_pad, int64_t N_pad, __nv_bfloat16* __restrict__ out,
-                                  CatalogHeader* hdr) {
+                                  int d_pad, int64_t N_pad, __half* __restrict__ out,
+                                  const CatalogHeader* __restrict__ hdr) {
   // one warp per item row
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= N_pad) return;
-  float ss = 0.f;
+  const float s = hdr->scale;
   for (int k = lane; k < d_pad; k += 32) {
     float v = 0.f;
-    if (row < N && k < d) v = __ldg(I + row * ldi + k);
-    ss = fmaf(v, v, ss);
-    out[row * d_pad + k] = __float2bfloat16_rn(v);
-  }
-  ss = warp_sum(ss);
-  if (lane == 0 && row < N) {
-    const float nrm = sqrtf(ss) * 1.0001f;  // round up a little
-    atomicMax(&hdr->max_norm_bits, __float_as_uint(nrm));
+    if (row < N && k < d) v = __ldg(I + row * ldi + k) * s;
+    out[row * d_pad + k] = __float2half_rn(v);
   }
 }
 
@@ -129,7 +164,7 @@ __global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
                                   int d_pad, int K, int64_t N, int filter, float pre_scale,
                                   const int64_t* __restrict__ indptr, int64_t n_users,
                                   const CatalogHeader* __restrict__ hdr,
-                                  __nv_bfloat16* __restrict__ A, RowMeta* __restrict__ meta,
+                                  __half* __restrict__ A, RowMeta* __restrict__ meta,
                                   uint32_t* __restrict__ row_tau_key, int32_t* __restrict__ row_status) {
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -137,19 +172,29 @@ __global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
   const bool real = row < B;
   const int64_t u = real ? user_ids[row] : 0;
   float ss = 0.f;
-  for (int k = lane; k < d_pad; k += 32) {
-    float v = 0.f;
-    if (real && k < d) v = __ldg(U + u * ldu + k);
+  for (int k = lane; k < d; k += 32) {
+    const float v = real ? __ldg(U + u * ldu + k) : 0.f;
     ss = fmaf(v, v, ss);
-    A[row * d_pad + k] = __float2bfloat16_rn(v);
   }
   ss = warp_sum(ss);
+  const float nrm = sqrtf(ss) * 1.0001f;
+  const float su = pow2_scale_for(nrm);
+  for (int k = lane; k < d_pad; k += 32) {
+    float v = 0.f;
+    if (real && k < d) v = __ldg(U + u * ldu + k) * su;      // exact scaling, then one fp16 rounding
+    A[row * d_pad + k] = __float2half_rn(v);
+  }
   if (lane == 0) {
     RowMeta m;
-    const float max_norm = __uint_as_float(hdr->max_norm_bits);
+    const float nu = nrm * su, ni = hdr->max_norm_scaled;    // scaled norms (< 128 each)
+    // relative part (operand rounding + fp32 accumulation slack) + absolute part: an operand below
+    // the fp16 normal range is off by at most 2^-25 (rounded) resp. 2^-14 (if the tensor core
+    // flushed subnormals); sum_k |x_k| * 2^-14 <= sqrt(d) * ||x|| * 2^-14 for both operands
     const float coef = ERR_COEF + (float)d_pad * 2.4e-7f;
-    m.eps2 = 2.f * coef * (sqrtf(ss) * 1.0001f) * max_norm + 1e-30f;
-    m.R = 1.02f * (sqrtf(ss) * 1.0001f) * max_norm + 1e-30f;
+    const float abs_term = sqrtf((float)d_pad) * 6.2e-5f * (nu + ni);
+    m.eps2 = 2.f * (coef * nu * ni + abs_term) + 1e-30f;
+    m.R = 1.02f * nu * ni + 1e-30f;
+    m.scale = su * hdr->scale;
     int64_t c = 0;
     if (real && filter && indptr && u >= 0 && u < n_users) c = indptr[u + 1] - indptr[u];
     const bool apply = c > 0 && (int64_t)K + c <= N;
@@ -162,8 +207,8 @@ __global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
     m.capped = k_row < k_full;
     m.k_row = (int32_t)k_row;
     // speculative threshold = pre_k-th largest SAMPLED block maximum: about pre_k / f items of the
-    // whole catalogue lie above it (f = sampled fraction), pre_scale = 2.67 f keeps that at
-    // >= 2.67 k_row + 16 / f (16 + k_row / 6 at the nominal f = 1/16)
+    // whole catalogue lie above it (f = sampled fraction); pre_scale = c * f keeps that at
+    // >= c * k_row + 16 / f
     m.pre_k = 16 + (int32_t)ceilf(pre_scale * (float)m.k_row);
     m.active = real;
     meta[row] = m;
@@ -200,12 +245,12 @@ __device__ __forceinline__ int score_bin(float s, float R, float inv_w) {
 //     lower bound of the k-th largest coarse score over everything counted so far
 //     (counts are a subset of the items at or above each edge), tau = edge - eps2;
 //  3. the list is rewritten keeping the records whose maximum is >= tau.
-// Records live in registers (CAPG/32 per lane).  Returns the new count; *tau_out = new tau.
+// Records live in registers (CAPG_MAX/32 per lane).  Returns the new count; *tau_out = new tau.
 __device__ __noinline__ int compact_row(float* __restrict__ ls, int32_t* __restrict__ lb, int n,
                                            int n_counted, int k, float eps2, float R, float tau_old,
                                            uint32_t* __restrict__ gh, int lane, float* tau_out) {
   const float inv_w = (float)NB / (2.f * R);
-  constexpr int PER = CAPG / 32;
+  constexpr int PER = CAPG_MAX / 32;
   float4 e0[PER], e1[PER];
   int32_t bs[PER];
 #pragma unroll
@@ -286,28 +331,23 @@ __device__ __noinline__ int compact_row(float* __restrict__ ls, int32_t* __restr
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-// group maxima (8 columns each) and the chunk maximum of 32 accumulator columns
-__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], float (&g)[4]) {
+// 4-bit mask of the 64-column steps of running tile `tc` that warp `j` of its quadrant handles
+template <int W>
+__device__ __forceinline__ uint32_t step_mask(uint32_t tc, int j) {
+  if (W == 1) return 0xFu;
+  if (W == 2) return 0x3u << (2 * j);
+  if (W == 4) return 1u << j;
+  // W == 3: step s of running tile tc has running index 4 tc + s; 4 tc mod 3 == tc mod 3
+  uint32_t m = 0;
+  const int r = (int)(tc % 3u);
 #pragma unroll
-  for (int gq = 0; gq < 4; ++gq) {
-    const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
-    const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
-    g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
-  }
-  return fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+  for (int s = 0; s < STEPS_PER_TILE; ++s)
+    if ((r + s) % 3 == j) m |= 1u << s;
+  return m;
 }
 
-__device__ __forceinline__ void tmem_load_step(uint32_t taddr, uint32_t (&r)[64]) {
-  ptx::tmem_ld_32x32b_x64(taddr, r);
-  ptx::tmem_ld_wait_regs64(r);
-}
-__device__ __forceinline__ void tmem_load_step(uint32_t taddr, uint32_t (&r)[32]) {
-  ptx::tmem_ld_32x32b_x32(taddr, r);
-  ptx::tmem_ld_wait_regs(r);
-}
-
-template <bool PRE>
-__global__ void __launch_bounds__(SWEEP_THREADS, 1)
+template <bool PRE, int W>
+__global__ void __launch_bounds__(sweep_threads(W), 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const SweepParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -327,7 +367,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int a = 0; a < 2; ++a)
       for (int hh = 0; hh < 2; ++hh) {
         ptx::mbar_init(&ss->tmem_full[a][hh], 1);
-        ptx::mbar_init(&ss->tmem_empty[a][hh], EPI_WARPS / 2);
+        // one arrival per processed step: 4 lane quadrants x 2 steps per column half
+        ptx::mbar_init(&ss->tmem_empty[a][hh], 4 * (STEPS_PER_TILE / 2));
       }
     ptx::mbar_init(&ss->a_full, 1);
     ptx::mbar_init(&ss->a_empty, 1);
@@ -371,7 +412,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(TM, TN / 2);
+      constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(TM, TN / 2);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -386,8 +427,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         ptx::mbar_wait(&ss->a_full, uiter & 1);
         for (int t = t0; t < t1; t += STRIDE) {
           ptx::mbar_wait(&ss->full[stage], phase);
-          // one N=128 MMA group per column half: the two halves of the accumulator are released by
-          // (and handed to) their own four epilogue warps, so a slow warp only stalls its half
+          // one N=128 MMA group per column half: each half of the accumulator has its own
+          // full / empty barrier pair, so its epilogue steps start as soon as that half is done
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             ptx::mbar_wait(&ss->tmem_empty[acc][hh], acc_phase ^ 1);
@@ -399,12 +440,12 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   b_addr + (uint32_t)((stage * p.KB + kb) * B_KB_BYTES + hh * (TN / 2) * KBLK * 2));
 #pragma unroll
               for (int k4 = 0; k4 < KBLK / 16; ++k4) {
-                // advance 16 bf16 = 32 bytes inside the 128-byte swizzled row: +2 in the >>4 field
+                // advance 16 fp16 = 32 bytes inside the 128-byte swizzled row: +2 in the >>4 field
                 ptx::umma_f16(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc,
                               (uint32_t)((kb | k4) != 0));
               }
             }
-            ptx::umma_commit(&ss->tmem_full[acc][hh]);   // this half is ready for its epilogue warps
+            ptx::umma_commit(&ss->tmem_full[acc][hh]);   // this half is ready for its epilogue steps
           }
           ptx::umma_commit(&ss->empty[stage]);           // smem stage reusable when these MMAs finish
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
@@ -415,13 +456,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else {
-    // ===================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves ==========
+    // ===================== epilogue: 4 TMEM lane quadrants x W warps ==========
     const int q = warp & 3;                 // TMEM lanes [32q, 32q+32) (hardware: warp id % 4)
-    const int cg = (warp - 2) >> 2;         // column group: columns [CW*cg, CW*cg + CW) of every tile
-    const int half = (cg * 2) / LPS;        // accumulator half (= MMA group / barrier pair) it belongs to
+    const int j = (warp - 2) >> 2;          // warp index inside its quadrant
     const int trow = q * 32 + lane;         // row inside the tile
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t tc = 0;                        // running tile count of this CTA (accumulator stage / phase)
     const float pinf = __int_as_float(0x7f800000);
     const float ninf = __int_as_float(0xff800000);
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -429,30 +468,36 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int t0 = split * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
       const int grow = m * TM + trow;
-      const int list_id = split * LPS + cg;
+      const int list_id = split * W + j;
 
       if (PRE) {
         // ---- pre-pass: per sampled tile the maximum coarse score of this warp's 128 columns ----
         float* bm = p.blockmax + (int64_t)list_id * p.n_pre_tiles * p.B_pad + grow;
         int ti = 0;
-        for (int t = t0; t < t1; t += STRIDE, ++ti) {
-          ptx::mbar_wait(&ss->tmem_full[acc][half], acc_phase);
+        for (int t = t0; t < t1; t += STRIDE, ++ti, ++tc) {
+          const int acc = (int)(tc & 1u);
+          const uint32_t acc_phase = (tc >> 1) & 1u;
+          ptx::mbar_wait(&ss->tmem_full[acc][j], acc_phase);     // W_PRE == 2: warp j <-> column half j
           ptx::tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cg * CW);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + j * (TN / 2));
           float tm = ninf;
 #pragma unroll 1
-          for (int ch = 0; ch < CW / 32; ++ch) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32b_x32(taddr + (uint32_t)(ch * 32), r);
-            ptx::tmem_ld_wait_regs(r);
-            float g[4];
-            tm = fmaxf(tm, chunk_max(r, g));
+          for (int ch = 0; ch < (TN / 2) / STEP; ++ch) {
+            uint32_t r[STEP];
+            ptx::tmem_ld_32x32b_x64(taddr + (uint32_t)(ch * STEP), r);
+            ptx::tmem_ld_wait_regs64(r);
+            float g[STEP / 8];
+#pragma unroll
+            for (int gq = 0; gq < STEP / 8; ++gq) {
+              const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
+              const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+              g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
+            }
+            tm = fmaxf(tm, fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7])));
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][j]);
           }
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
           // tiles that contain zero-padded item rows would bias the estimate: drop them
           if ((int64_t)(t + 1) * TN > p.N) tm = ninf;
           bm[(int64_t)ti * p.B_pad] = tm;
@@ -464,8 +509,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // ---- main pass ----
       const RowMeta meta = p.meta[grow];
       const int64_t list0 = (int64_t)list_id * p.B_pad + (m * TM + q * 32);  // lane 0's slot
-      float* my_s = p.cand_s + (list0 + lane) * (int64_t)(CAPG * GW);
-      int32_t* my_b = p.cand_b + (list0 + lane) * (int64_t)CAPG;
+      float* my_s = p.cand_s + (list0 + lane) * (int64_t)(p.capg * GW);
+      int32_t* my_b = p.cand_b + (list0 + lane) * (int64_t)p.capg;
       bool active = meta.active != 0;
       float tau = active ? ninf : pinf;
       int cnt = 0, n_counted = 0;
@@ -486,8 +531,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const float s_R = __shfl_sync(0xffffffffu, meta.R, src);
           const float s_tau = __shfl_sync(0xffffffffu, tau, src);
           float new_tau;
-          const int w = compact_row(p.cand_s + (list0 + src) * (int64_t)(CAPG * GW),
-                                    p.cand_b + (list0 + src) * (int64_t)CAPG, s_cnt, s_cntd, s_k, s_e, s_R,
+          const int w = compact_row(p.cand_s + (list0 + src) * (int64_t)(p.capg * GW),
+                                    p.cand_b + (list0 + src) * (int64_t)p.capg, s_cnt, s_cntd, s_k, s_e, s_R,
                                     s_tau, p.ghist + (int64_t)(m * TM + q * 32 + src) * NB, lane, &new_tau);
           if (lane == src) {
             cnt = w;
@@ -495,7 +540,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             // also pick up what other lists of this row published meanwhile
             tau = fmaxf(new_tau, key_to_float(max(__ldcg(p.row_tau_key + grow), 1u)));
             atomicMax(p.row_tau_key + grow, float_to_key(new_tau));
-            if (w > CAPG - 16) {  // too many near-ties to bound: hand the row to the exact path
+            if (w > p.capg - 16) {  // too many near-ties to bound: hand the row to the exact path
               active = false;
               tau = pinf;
               cnt = 0;
@@ -507,21 +552,30 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       };
 
       const int last_full = (int)(p.N / TN);   // tiles >= last_full contain padded item rows
-      for (int t = t0; t < t1; ++t) {
-        ptx::mbar_wait(&ss->tmem_full[acc][half], acc_phase);
-        ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + cg * CW);
-        const int n_base = t * TN + cg * CW;
+      for (int t = t0; t < t1; ++t, ++tc) {
+        const int acc = (int)(tc & 1u);
+        const uint32_t acc_phase = (tc >> 1) & 1u;
+        const uint32_t smask = step_mask<W>(tc, j);
         const bool tail = t >= last_full;
-#pragma unroll 1
-        for (int ch = 0; ch < CW / STEP; ++ch) {
-          // STEP accumulator columns per step: independent max trees in flight
-          uint32_t r[STEP];
-          tmem_load_step(taddr + (uint32_t)(ch * STEP), r);
-          if (tail) {   // zero-padded item rows (>= N) must never be collected: only the last tile
-            const int lim = (int)max((int64_t)0, min((int64_t)STEP, p.N - (int64_t)(n_base + ch * STEP)));
 #pragma unroll
-            for (int j = 0; j < STEP; ++j) if (j >= lim) r[j] = 0xff800000u;
+        for (int s = 0; s < STEPS_PER_TILE; ++s) {
+          if (!((smask >> s) & 1u)) continue;             // warp-uniform
+          const int half = s >> 1;
+          ptx::mbar_wait(&ss->tmem_full[acc][half], acc_phase);
+          ptx::tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + s * STEP);
+          const int n_base = t * TN + s * STEP;
+          uint32_t r[STEP];
+          ptx::tmem_ld_32x32b_x64(taddr, r);
+          ptx::tmem_ld_wait_regs64(r);
+          // the accumulator columns of this step are in registers: hand them back to the MMA issuer
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
+          if (tail) {   // zero-padded item rows (>= N) must never be collected: only the last tile
+            const int lim = (int)max((int64_t)0, min((int64_t)STEP, p.N - (int64_t)n_base));
+#pragma unroll
+            for (int c = 0; c < STEP; ++c) if (c >= lim) r[c] = 0xff800000u;
           }
           float g[STEP / 8];
 #pragma unroll
@@ -530,33 +584,34 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
             g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
           }
-          // Warp-uniform tests, one per 8-column group: a group that is hot in some lane is pushed
-          // WHOLE by that lane (two 16-byte stores + its first item id); finalize_kernel sorts out
-          // which of its 8 scores are candidates.  Cold groups cost 4 instructions.
-          bool pushed = false;
+          // ONE warp-uniform test per 64-column step (cold steps: max tree + 3 instructions).
+          const float mm = fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]));
+          if (__any_sync(0xffffffffu, mm >= tau)) {
+            // hot step: per-lane mask of the 8-column groups at or above tau, OR-reduced over the
+            // warp (one REDUX) so that the 8 group branches below are independent uniform tests.
+            // A group that is hot in some lane is pushed WHOLE by that lane (two 16-byte stores +
+            // its first item id); finalize_kernel sorts out which of its 8 scores are candidates.
+            uint32_t hm = 0;
 #pragma unroll
-          for (int gq = 0; gq < STEP / 8; ++gq) {
-            if (__any_sync(0xffffffffu, g[gq] >= tau)) {
-              if (g[gq] >= tau) {
-                float4* dst = reinterpret_cast<float4*>(my_s + (size_t)cnt * GW);
-                dst[0] = make_float4(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]),
-                                     __uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
-                dst[1] = make_float4(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]),
-                                     __uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
-                my_b[cnt] = n_base + ch * STEP + gq * 8;
-                ++cnt;
+            for (int gq = 0; gq < STEP / 8; ++gq) hm |= (g[gq] >= tau) ? (1u << gq) : 0u;
+            const uint32_t any = __reduce_or_sync(0xffffffffu, hm);
+#pragma unroll
+            for (int gq = 0; gq < STEP / 8; ++gq) {
+              if (any & (1u << gq)) {
+                if (hm & (1u << gq)) {
+                  float4* dst = reinterpret_cast<float4*>(my_s + (size_t)cnt * GW);
+                  dst[0] = make_float4(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]),
+                                       __uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
+                  dst[1] = make_float4(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]),
+                                       __uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
+                  my_b[cnt] = n_base + gq * 8;
+                  ++cnt;
+                }
               }
-              pushed = true;
             }
+            compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > p.trig) || (cnt > p.capg - 8)));
           }
-          if (pushed)   // warp-uniform
-            compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > TRIG) || (cnt > CAPG - 8)));
         }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
       p.cand_cnt[list0 + lane] = cnt;
     }
@@ -639,7 +694,7 @@ guess_kernel(const float* __restrict__ blockmax, int n_vals /* lists * n_pre_til
 // ------------------------------------------------------------------------------------------
 struct FinalizeParams {
   int64_t B, N;
-  int32_t B_pad, n_lists, K, d;
+  int32_t B_pad, n_lists, K, d, capg;
   const RowMeta* meta;
   int32_t* row_status;
   const uint32_t* row_tau_key;     // [B_pad] final threshold of the row (speculative start or rigorous raises)
@@ -728,10 +783,10 @@ finalize_kernel(const FinalizeParams p) {
           }
           const int j = g - s_off[lo];
           const int64_t slot = (int64_t)lo * p.B_pad + row;
-          const float4* ls = reinterpret_cast<const float4*>(p.cand_s + slot * (int64_t)(CAPG * GW)) + 2 * j;
+          const float4* ls = reinterpret_cast<const float4*>(p.cand_s + slot * (int64_t)(p.capg * GW)) + 2 * j;
           a[q] = __ldcs(ls);
           b[q] = __ldcs(ls + 1);
-          base[q] = __ldcs(p.cand_b + slot * (int64_t)CAPG + j);
+          base[q] = __ldcs(p.cand_b + slot * (int64_t)p.capg + j);
         }
       }
 #pragma unroll
@@ -764,8 +819,8 @@ finalize_kernel(const FinalizeParams p) {
       for (int s = 0; s < p.n_lists; ++s) {
         const int64_t slot = (int64_t)s * p.B_pad + row;
         const int n = p.cand_cnt[slot];
-        const float* ls = p.cand_s + slot * (int64_t)(CAPG * GW);
-        const int32_t* lb = p.cand_b + slot * (int64_t)CAPG;
+        const float* ls = p.cand_s + slot * (int64_t)(p.capg * GW);
+        const int32_t* lb = p.cand_b + slot * (int64_t)p.capg;
         for (int i = tid; i < n * GW; i += FIN_THREADS) {
           const float v = ls[i];
           if (v >= low) f(v, lb[i / GW] + (i % GW));
@@ -972,7 +1027,8 @@ finalize_kernel(const FinalizeParams p) {
     // exact < thr + eps = c_k - eps; the row is only accepted if the K-th survivor is above that.
     const unsigned long long kth = c_sort[p.K - 1];
     const bool short_row = kth == 0ull;
-    const bool unsafe = meta.capped && key_to_float((uint32_t)(kth >> 32)) < thr + 0.5f * meta.eps2;
+    // exact scores are unscaled: bring the K-th one into the row's coarse (scaled) units first
+    const bool unsafe = meta.capped && key_to_float((uint32_t)(kth >> 32)) * meta.scale < thr + 0.5f * meta.eps2;
     if (short_row || unsafe) { __syncthreads(); give_up(5); return; }
   }
   for (int i = tid; i < p.K; i += FIN_THREADS) {
@@ -1002,7 +1058,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 [rows, d_pad] row-major, box = [KBLK, box_rows], SWIZZLE_128B
+// fp16 [rows, d_pad] row-major, box = [KBLK, box_rows], SWIZZLE_128B
 static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int d_pad, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   B200_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available");
@@ -1010,7 +1066,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int d_pad, 
   cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
   cuuint32_t box[2] = {(cuuint32_t)KBLK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -1020,10 +1076,16 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int d_pad, 
 static inline int pad_to(int64_t x, int m) { return (int)((x + m - 1) / m * m); }
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+
+// ---- tuning knobs (defaults compiled in; b200_recommend_embed_tune overrides them per process) ----
+static int g_epi_w = 2;            // epilogue warps per TMEM lane quadrant in the main pass: 2 or 3
+static float g_pre_coef = 2.67f;   // speculative rank target = g_pre_coef * k_row (+ 16 / sampled fraction)
+
 struct Plan {
   int B_pad, d_pad, KB, m_tiles, total_tiles, n_splits, tiles_per_split, nstage, n_pre_tiles;
+  int W, n_lists, capg, trig;
   bool use_pre;
-  float pre_scale;   // 2.67 x sampled fraction of the item tiles (see prep_users_kernel)
+  float pre_scale;   // g_pre_coef x sampled fraction of the item tiles (see prep_users_kernel)
   int64_t N_pad;
   size_t smem_bytes;
   // workspace offsets
@@ -1039,6 +1101,7 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->N_pad = (N + TN - 1) / TN * TN;
   pl->m_tiles = pl->B_pad / TM;
   pl->total_tiles = (int)(pl->N_pad / TN);
+  pl->W = g_epi_w;
   // item splits: minimise makespan = waves * (tiles per split + per-unit overhead)
   const int ovh = 12;
   long best = -1;
@@ -1054,8 +1117,9 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->tiles_per_split = (pl->total_tiles + bestS - 1) / bestS;
   pl->n_splits = (pl->total_tiles + pl->tiles_per_split - 1) / pl->tiles_per_split;
   pl->n_pre_tiles = (pl->tiles_per_split + PRE_STRIDE - 1) / PRE_STRIDE;
+  pl->n_lists = pl->W * pl->n_splits;
   // speculation needs enough sampled blocks per row to take a stable order statistic
-  pl->use_pre = (long)LPS * pl->n_splits * pl->n_pre_tiles >= 256;
+  pl->use_pre = (long)W_PRE * pl->n_splits * pl->n_pre_tiles >= 256;
   {   // sampled fraction of the item tiles (every PRE_STRIDE-th tile of every split)
     long sampled = 0;
     for (int sp = 0; sp < pl->n_splits; ++sp) {
@@ -1063,8 +1127,13 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
       const int t1 = t0 + pl->tiles_per_split < pl->total_tiles ? t0 + pl->tiles_per_split : pl->total_tiles;
       sampled += (t1 - t0 + PRE_STRIDE - 1) / PRE_STRIDE;
     }
-    pl->pre_scale = 2.67f * (float)sampled / (float)pl->total_tiles;
+    pl->pre_scale = g_pre_coef * (float)sampled / (float)pl->total_tiles;
   }
+  // With the speculative threshold about g_pre_coef * k_row + 16 / f candidates per row (<= ~1500
+  // at k_row = 288) are spread over the lists; the lists are sized for that and the compaction runs
+  // only when a list is about to overflow (the speculation was far off).
+  pl->capg = (pl->use_pre && pl->n_lists >= 16) ? 128 : CAPG_MAX;
+  pl->trig = pl->use_pre ? pl->capg : 96;
   const size_t budget = 227 * 1024 - 1024 /*align*/ - sizeof(SweepSmem) - (size_t)pl->KB * A_KB_BYTES;
   int ns = (int)(budget / ((size_t)pl->KB * B_KB_BYTES));
   if (ns > 6) ns = 6;
@@ -1077,12 +1146,26 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->off_tau = off; off += al256((size_t)pl->B_pad * 4);
   pl->off_guess = off; off += al256((size_t)pl->B_pad * 4);
   pl->off_status = off; off += al256((size_t)pl->B_pad * 4);
-  pl->off_cnt = off; off += al256((size_t)LPS * pl->n_splits * pl->B_pad * 4);
+  pl->off_cnt = off; off += al256((size_t)pl->n_lists * pl->B_pad * 4);
   pl->off_hist = off; off += al256((size_t)pl->B_pad * NB * 4);
-  pl->off_cs = off; off += al256((size_t)LPS * pl->n_splits * pl->B_pad * CAPG * GW * 4);
-  pl->off_cb = off; off += al256((size_t)LPS * pl->n_splits * pl->B_pad * CAPG * 4);
-  pl->off_bm = off; off += al256((size_t)LPS * pl->n_splits * pl->n_pre_tiles * pl->B_pad * 4);
+  pl->off_cs = off; off += al256((size_t)pl->n_lists * pl->B_pad * pl->capg * GW * 4);
+  pl->off_cb = off; off += al256((size_t)pl->n_lists * pl->B_pad * pl->capg * 4);
+  pl->off_bm = off; off += al256((size_t)W_PRE * pl->n_splits * pl->n_pre_tiles * pl->B_pad * 4);
   pl->total = off + 256;
+  return 0;
+}
+
+template <bool PRE, int W>
+static int launch_sweep(int grid, const Plan& pl, cudaStream_t stream, const CUtensorMap& tmA,
+                        const CUtensorMap& tmB, const SweepParams& sp) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel<PRE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024));
+    attr_set = true;
+  }
+  sweep_kernel<PRE, W><<<grid, sweep_threads(W), pl.smem_bytes, stream>>>(tmA, tmB, sp);
+  count_launch();
   return 0;
 }
 
@@ -1111,14 +1194,42 @@ extern "C" int b200_embed_catalog_prepare(const float* I, int64_t ldi, int64_t N
   const int d_pad = pad_to(d, KBLK);
   const int64_t N_pad = (N + TN - 1) / TN * TN;
   CatalogHeader h;
-  h.max_norm_bits = 0; h.d = d; h.d_pad = d_pad; h.N = N; h.N_pad = N_pad;
+  memset(&h, 0, sizeof(h));
+  h.d = d; h.d_pad = d_pad; h.N = N; h.N_pad = N_pad; h.scale = 1.f;
   B200_CUDA_OK(cudaMemcpyAsync(catalog, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
-  __nv_bfloat16* tab = (__nv_bfloat16*)((char*)catalog + 256);
-  const int64_t threads = N_pad * 32;
-  prep_items_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
-      I, ldi, N, d, d_pad, N_pad, tab, (CatalogHeader*)catalog);
-  count_launch();
+  __half* tab = (__half*)((char*)catalog + 256);
+  // pass 1: max row norm -> power-of-two scale; pass 2: scaled fp16 copy
+  item_norm_kernel<<<(unsigned)ceil_div64(N * 32, 256), 256, 0, stream>>>(I, ldi, N, d, (CatalogHeader*)catalog);
+  item_scale_kernel<<<1, 1, 0, stream>>>((CatalogHeader*)catalog);
+  prep_items_kernel<<<(unsigned)ceil_div64(N_pad * 32, 256), 256, 0, stream>>>(
+      I, ldi, N, d, d_pad, N_pad, tab, (const CatalogHeader*)catalog);
+  count_launch(3);
   B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200_recommend_embed_tune(int32_t epilogue_warps_per_quadrant, float pre_rank_coef) {
+  if (epilogue_warps_per_quadrant != 0) {
+    B200_REQUIRE(epilogue_warps_per_quadrant >= 2 && epilogue_warps_per_quadrant <= 3,
+                 "b200_recommend_embed_tune: epilogue warps per quadrant must be 2 or 3");
+    g_epi_w = epilogue_warps_per_quadrant;
+  }
+  if (pre_rank_coef != 0.f) {
+    B200_REQUIRE(pre_rank_coef >= 1.0f && pre_rank_coef <= 16.f,
+                 "b200_recommend_embed_tune: rank coefficient out of [1, 16]");
+    g_pre_coef = pre_rank_coef;
+  }
+  return 0;
+}
+
+extern "C" int b200_recommend_embed_plan(int64_t B, int64_t N, int32_t d, int32_t K, int32_t* out,
+                                         int32_t n_out) {
+  B200_REQUIRE(out && n_out >= 8 && B >= 1 && N >= 1 && d >= 1 && K >= 1,
+               "b200_recommend_embed_plan: bad arguments");
+  Plan pl;
+  if (int rc = make_plan(B, N, d, &pl)) return rc;
+  out[0] = pl.use_pre ? 1 : 0; out[1] = pl.n_splits; out[2] = pl.tiles_per_split; out[3] = pl.m_tiles;
+  out[4] = pl.n_pre_tiles; out[5] = pl.nstage; out[6] = pl.W; out[7] = pl.capg;
   return 0;
 }
 
@@ -1149,7 +1260,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   if (int rc = make_plan(B, N, d, &pl)) return rc;
   B200_REQUIRE(workspace_bytes >= pl.total, "workspace too small (%zu < %zu)", workspace_bytes, pl.total);
   char* ws = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
-  __nv_bfloat16* A = (__nv_bfloat16*)(ws + pl.off_A);
+  __half* A = (__half*)(ws + pl.off_A);
   RowMeta* meta = (RowMeta*)(ws + pl.off_meta);
   uint32_t* tau = (uint32_t*)(ws + pl.off_tau);
   uint32_t* guess = (uint32_t*)(ws + pl.off_guess);
@@ -1160,32 +1271,26 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   int32_t* cand_b = (int32_t*)(ws + pl.off_cb);
   float* bm = (float*)(ws + pl.off_bm);
   const CatalogHeader* hdr = (const CatalogHeader*)catalog;
-  const __nv_bfloat16* Ibf = (const __nv_bfloat16*)((const char*)catalog + 256);
+  const __half* Ih = (const __half*)((const char*)catalog + 256);
 
   prep_users_kernel<<<(unsigned)ceil_div64((int64_t)pl.B_pad * 32, 256), 256, 0, stream>>>(
       U, ldu, user_ids, B, pl.B_pad, d, pl.d_pad, K, N, filter, pl.pre_scale, indptr, n_users, hdr, A, meta,
       tau, status);
+  count_launch();
   // cnt and ghist are adjacent in the workspace: one memset
   B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (pl.off_cs - pl.off_cnt), stream));
 
   CUtensorMap tmA, tmB;
   if (int rc = make_tmap(&tmA, A, pl.B_pad, pl.d_pad, TM)) return rc;
-  if (int rc = make_tmap(&tmB, Ibf, pl.N_pad, pl.d_pad, TN)) return rc;
+  if (int rc = make_tmap(&tmB, Ih, pl.N_pad, pl.d_pad, TN)) return rc;
 
   SweepParams sp;
   sp.N = N; sp.B_pad = pl.B_pad; sp.m_tiles = pl.m_tiles; sp.n_splits = pl.n_splits;
   sp.tiles_per_split = pl.tiles_per_split; sp.total_tiles = pl.total_tiles; sp.KB = pl.KB;
-  sp.nstage = pl.nstage; sp.n_pre_tiles = pl.n_pre_tiles; sp.meta = meta; sp.row_tau_key = tau;
+  sp.nstage = pl.nstage; sp.n_pre_tiles = pl.n_pre_tiles; sp.capg = pl.capg; sp.trig = pl.trig;
+  sp.meta = meta; sp.row_tau_key = tau;
   sp.row_status = status; sp.ghist = ghist; sp.cand_s = cand_s; sp.cand_b = cand_b; sp.cand_cnt = cnt;
   sp.blockmax = bm;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      227 * 1024));
-    B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      227 * 1024));
-    attr_set = true;
-  }
   const int n_units = pl.m_tiles * pl.n_splits;
   static int sm_count = 0;
   if (!sm_count) {
@@ -1197,25 +1302,30 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
 
   if (ev_sweep_start) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_start, stream));
   if (pl.use_pre) {
-    sweep_kernel<true><<<grid, SWEEP_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, sp);
-    guess_kernel<<<(unsigned)(pl.B_pad / 32), GUESS_THREADS, 0, stream>>>(bm, LPS * pl.n_splits * pl.n_pre_tiles, pl.B_pad,
-                                                          meta, tau, guess);
-    count_launch(2);
+    if (int rc = launch_sweep<true, W_PRE>(grid, pl, stream, tmA, tmB, sp)) return rc;
+    guess_kernel<<<(unsigned)(pl.B_pad / 32), GUESS_THREADS, 0, stream>>>(
+        bm, W_PRE * pl.n_splits * pl.n_pre_tiles, pl.B_pad, meta, tau, guess);
+    count_launch();
   } else {
     B200_CUDA_OK(cudaMemsetAsync(guess, 0, (size_t)pl.B_pad * 4, stream));
   }
-  sweep_kernel<false><<<grid, SWEEP_THREADS, pl.smem_bytes, stream>>>(tmA, tmB, sp);
+  {
+    int rc;
+    if (pl.W == 2) rc = launch_sweep<false, 2>(grid, pl, stream, tmA, tmB, sp);
+    else rc = launch_sweep<false, 3>(grid, pl, stream, tmA, tmB, sp);
+    if (rc) return rc;
+  }
   if (ev_sweep_stop) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_stop, stream));
 
   FinalizeParams fp;
-  fp.B = B; fp.N = N; fp.B_pad = pl.B_pad; fp.n_lists = LPS * pl.n_splits; fp.K = K; fp.d = d;
+  fp.B = B; fp.N = N; fp.B_pad = pl.B_pad; fp.n_lists = pl.n_lists; fp.K = K; fp.d = d; fp.capg = pl.capg;
   fp.meta = meta; fp.row_status = status; fp.row_tau_key = tau; fp.tau_guess_key = guess;
   fp.cand_s = cand_s; fp.cand_b = cand_b; fp.cand_cnt = cnt;
   fp.U = U; fp.ldu = ldu; fp.I = I; fp.ldi = ldi; fp.user_ids = user_ids; fp.indptr = indptr;
   fp.idx = idx; fp.out_ids = out_ids; fp.out_scores = out_scores;
   finalize_kernel<<<(unsigned)B, FIN_THREADS, 0, stream>>>(fp);
+  count_launch();
   B200_CUDA_OK(cudaMemcpyAsync(row_status, status, (size_t)B * 4, cudaMemcpyDeviceToDevice, stream));
-  count_launch(3);
   B200_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -333,16 +333,10 @@ extern "C" int b200_topk_rows_workspace_bytes(int64_t B, int64_t N, int32_t K, s
   return 0;
 }
 
-extern "C" int b200_topk_rows(const float* scores, int64_t ld, int64_t B, int64_t N, int32_t K,
-                              int64_t* out_ids, float* out_scores, void* workspace,
-                              size_t workspace_bytes, void* stream_) {
-  B200_REQUIRE(scores && out_ids && workspace, "b200_topk_rows: null pointer");
-  B200_REQUIRE(K >= 1 && K <= kMaxK, "b200_topk_rows: n_rec %d outside [1, %d]", K, kMaxK);
-  B200_REQUIRE((int64_t)K <= N, "`n_rec` %d exceeds num of items %lld", K, (long long)N);
-  B200_REQUIRE(N < (1ll << 31), "b200_topk_rows: N must be < 2^31");
-  B200_REQUIRE(B <= 65535, "b200_topk_rows: at most 65535 rows per call (got %lld)", (long long)B);
-  if (B == 0) return 0;
-  cudaStream_t stream = (cudaStream_t)stream_;
+// one launch group over at most 65535 rows (gridDim.y limit)
+static int topk_rows_chunk(const float* scores, int64_t ld, int64_t B, int64_t N, int32_t K,
+                           int64_t* out_ids, float* out_scores, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream) {
   const int64_t C = ceil_div64(N, kTopkChunk);
   TopkWorkspace w;
   char* base = (char*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -364,5 +358,24 @@ extern "C" int b200_topk_rows(const float* scores, int64_t ld, int64_t B, int64_
   sort_rows_kernel<<<(unsigned)B, threads, (size_t)P * 8, stream>>>(w, K, P, out_ids, out_scores);
   count_launch(6);
   B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200_topk_rows(const float* scores, int64_t ld, int64_t B, int64_t N, int32_t K,
+                              int64_t* out_ids, float* out_scores, void* workspace,
+                              size_t workspace_bytes, void* stream_) {
+  B200_REQUIRE(scores && out_ids && workspace, "b200_topk_rows: null pointer");
+  B200_REQUIRE(K >= 1 && K <= kMaxK, "b200_topk_rows: n_rec %d outside [1, %d]", K, kMaxK);
+  B200_REQUIRE((int64_t)K <= N, "`n_rec` %d exceeds num of items %lld", K, (long long)N);
+  B200_REQUIRE(N < (1ll << 31), "b200_topk_rows: N must be < 2^31");
+  // any number of rows: groups of <= 65535 rows run back to back on the stream and share the workspace
+  const int64_t kRows = 65535;
+  for (int64_t r0 = 0; r0 < B; r0 += kRows) {
+    const int64_t b = B - r0 < kRows ? B - r0 : kRows;
+    if (int rc = topk_rows_chunk(scores + r0 * ld, ld, b, N, K, out_ids + r0 * K,
+                                 out_scores ? out_scores + r0 * K : nullptr, workspace, workspace_bytes,
+                                 (cudaStream_t)stream_))
+      return rc;
+  }
   return 0;
 }

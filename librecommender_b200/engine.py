@@ -56,6 +56,7 @@ class EmbedScorer:
         self.set_consumed(user_consumed)
         self._torch = torch
         self.events = None  # optional list collecting (start, stop) CUDA events of the sweep kernel
+        self.last_fallback_rows = 0   # rows of the latest call that were repaired on the exact path
         self.catalog = None
         if self.d <= FUSED_MAX_D:
             self._prepare_catalog()
@@ -123,9 +124,43 @@ class EmbedScorer:
     def fused_ok(self, n_rec) -> bool:
         return self.catalog is not None and n_rec <= FUSED_MAX_K
 
-    def recommend_fused(self, user_ids_d, n_rec, filter_consumed=True, return_scores=False):
+    def fused_plan(self, B, n_rec) -> dict:
+        """How ``b200_recommend_embed`` will run a call of ``B`` users (``b200_recommend_embed_plan``):
+        whether the speculative pre-pass is used, the item splits, the epilogue organisation."""
+        out = (ctypes.c_int32 * 8)()
+        _lib.check(_lib.lib.b200_recommend_embed_plan(min(int(B), FUSED_ROWS_PER_CALL), self.n_items, self.d,
+                                                      int(n_rec), out, 8))
+        keys = ("use_pre", "n_splits", "tiles_per_split", "m_tiles", "n_pre_tiles", "tma_stages",
+                "epilogue_warps_per_quadrant", "records_per_list")
+        return dict(zip(keys, [int(v) for v in out]))
+
+    def _fused_chunk(self, uid_chunk, n_rec, use_filter, out_ids, out_scores, status):
+        """One ``b200_recommend_embed`` call (<= FUSED_ROWS_PER_CALL rows) on the current stream."""
+        torch = self._torch
+        b = int(uid_chunk.numel())
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(_lib.lib.b200_recommend_embed_workspace_bytes(b, self.n_items, self.d, n_rec, ctypes.byref(nbytes)))
+        ws = self._workspace(nbytes.value)
+        ev0 = ev1 = None
+        if self.events is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()   # creates the cudaEvent_t; re-recorded inside the C-ABI call
+            e1.record()
+            ev0, ev1 = ctypes.c_void_p(e0.cuda_event), ctypes.c_void_p(e1.cuda_event)
+        _lib.check(_lib.lib.b200_recommend_embed(
+            _lib.ptr(self.U), self.U.stride(0), _lib.ptr(uid_chunk), b,
+            _lib.ptr(self.I), self.I.stride(0), self.n_items, self.d, _lib.ptr(self.catalog),
+            _lib.ptr(self.indptr_d), _lib.ptr(self.idx_d), self.csr.n_users, use_filter, n_rec,
+            _lib.ptr(out_ids), _lib.ptr(out_scores) if out_scores is not None else None,
+            _lib.ptr(status), _lib.ptr(ws), nbytes.value, _lib.current_stream(), ev0, ev1))
+        if self.events is not None:
+            self.events.append((e0, e1))
+
+    def recommend_fused(self, user_ids_d, n_rec, filter_consumed=True, return_scores=False, on_chunk=None):
         """Tensor-core path (b200_recommend_embed).  Returns (ids, scores|None, status):
-        rows with status != 0 hold -1 ids and must be re-run on the exact path."""
+        rows with status != 0 hold -1 ids and must be re-run on the exact path.  ``on_chunk(r0, r1)``
+        is called after the kernels of rows [r0, r1) have been enqueued."""
         torch = self._torch
         B = int(user_ids_d.numel())
         N = self.n_items
@@ -134,29 +169,13 @@ class EmbedScorer:
         out_ids = torch.empty((B, n_rec), dtype=torch.int64, device=self.device)
         out_scores = torch.empty((B, n_rec), dtype=torch.float32, device=self.device) if return_scores else None
         status = torch.empty(B, dtype=torch.int32, device=self.device)
-        stream = _lib.current_stream()
         use_filter = 1 if (filter_consumed and self.csr.nnz > 0) else 0
         for r0 in range(0, B, FUSED_ROWS_PER_CALL):
-            b = min(FUSED_ROWS_PER_CALL, B - r0)
-            nbytes = ctypes.c_size_t(0)
-            _lib.check(_lib.lib.b200_recommend_embed_workspace_bytes(b, N, self.d, n_rec, ctypes.byref(nbytes)))
-            ws = self._workspace(nbytes.value)
-            ev0 = ev1 = None
-            if self.events is not None:
-                e0 = torch.cuda.Event(enable_timing=True)
-                e1 = torch.cuda.Event(enable_timing=True)
-                e0.record()   # creates the cudaEvent_t; re-recorded inside the C-ABI call
-                e1.record()
-                ev0, ev1 = ctypes.c_void_p(e0.cuda_event), ctypes.c_void_p(e1.cuda_event)
-            _lib.check(_lib.lib.b200_recommend_embed(
-                _lib.ptr(self.U), self.U.stride(0), _lib.ptr(user_ids_d[r0:r0 + b]), b,
-                _lib.ptr(self.I), self.I.stride(0), N, self.d, _lib.ptr(self.catalog),
-                _lib.ptr(self.indptr_d), _lib.ptr(self.idx_d), self.csr.n_users, use_filter, n_rec,
-                _lib.ptr(out_ids[r0:r0 + b]),
-                _lib.ptr(out_scores[r0:r0 + b]) if return_scores else None,
-                _lib.ptr(status[r0:r0 + b]), _lib.ptr(ws), nbytes.value, stream, ev0, ev1))
-            if self.events is not None:
-                self.events.append((e0, e1))
+            r1 = min(B, r0 + FUSED_ROWS_PER_CALL)
+            self._fused_chunk(user_ids_d[r0:r1], n_rec, use_filter, out_ids[r0:r1],
+                              out_scores[r0:r1] if return_scores else None, status[r0:r1])
+            if on_chunk is not None:
+                on_chunk(r0, r1)
         return out_ids, out_scores, status
 
     def _workspace(self, nbytes):
@@ -200,18 +219,32 @@ class EmbedScorer:
         return scores[:, :N]
 
     def _pinned(self, name, shape, dtype):
-        """Small ring of pinned host staging buffers (a returned array stays valid for the next
-        three calls; it is a fresh view each time, like the reference's fresh ndarray)."""
+        """Pinned host staging buffer for one result.  The reference contract is "a fresh ndarray
+        per call": the numpy array handed to the caller VIEWS the pinned buffer, and a buffer is
+        recycled only after that array (and every view derived from it) has been garbage collected
+        (tracked with a weak reference) — never while the caller can still read it."""
         torch = self._torch
-        ring = self.__dict__.setdefault("_pin_ring", {})
+        pool = self.__dict__.setdefault("_pin_pool", {})
         key = (name, tuple(shape), dtype)
-        if key not in ring:            # page-locking is slow: allocate the whole ring once
-            if len(ring) > 24:
-                ring.clear()
-            ring[key] = ([torch.empty(shape, dtype=dtype, pin_memory=True) for _ in range(4)], 0)
-        bufs, pos = ring[key]
-        ring[key] = (bufs, pos + 1)
-        return bufs[pos % 4]
+        slots = pool.setdefault(key, [])
+        for slot in slots:
+            if slot[1] is None or slot[1]() is None:
+                return slot
+        if sum(len(v) for v in pool.values()) >= 64:      # the caller keeps everything: drop dead shapes
+            for k in [k for k, v in pool.items() if k != key and all(s[1] is None or s[1]() is None for s in v)]:
+                del pool[k]
+        slot = [torch.empty(shape, dtype=dtype, pin_memory=True), None]
+        slots.append(slot)
+        return slot
+
+    @staticmethod
+    def _export(slot):
+        """numpy view of a pinned slot, registered so that the slot is not reused while it lives."""
+        import weakref
+
+        arr = slot[0].numpy()
+        slot[1] = weakref.ref(arr)
+        return arr
 
     def recommend(self, user_ids, n_rec, filter_consumed=True, return_scores=False, path="auto"):
         """Host ids in, host ``int64[B, n_rec]`` out (the reference-facing call): one H2D of the
@@ -229,19 +262,37 @@ class EmbedScorer:
             if return_scores:
                 return res[0].cpu().numpy(), res[1].cpu().numpy()
             return res.cpu().numpy()
-        ids_d, sc_d, status_d = self.recommend_fused(uid_d, n_rec, filter_consumed, return_scores)
-        ids_h = self._pinned("ids", (B, n_rec), torch.int64)
-        st_h = self._pinned("status", (B,), torch.int32)
-        ids_h.copy_(ids_d, non_blocking=True)
-        st_h.copy_(status_d, non_blocking=True)
-        sc_h = None
-        if return_scores:
-            sc_h = self._pinned("scores", (B, n_rec), torch.float32)
-            sc_h.copy_(sc_d, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        ids = ids_h.numpy()
-        scores = sc_h.numpy() if return_scores else None
-        bad = np.flatnonzero(st_h.numpy())
+        ids_slot = self._pinned("ids", (B, n_rec), torch.int64)
+        st_slot = self._pinned("status", (B,), torch.int32)
+        sc_slot = self._pinned("scores", (B, n_rec), torch.float32) if return_scores else None
+        # the D2H of chunk i runs on a side stream while the kernels of chunk i+1 execute
+        main = torch.cuda.current_stream()
+        side = self.__dict__.get("_copy_stream")
+        if side is None:
+            side = self._copy_stream = torch.cuda.Stream(device=self.device)
+        res = {}
+
+        def on_chunk(r0, r1):
+            ev = torch.cuda.Event()
+            ev.record(main)
+            res.setdefault("chunks", []).append((r0, r1, ev))
+
+        ids_d, sc_d, status_d = self.recommend_fused(uid_d, n_rec, filter_consumed, return_scores, on_chunk)
+        with torch.cuda.stream(side):
+            for r0, r1, ev in res.get("chunks", []):
+                side.wait_event(ev)
+                ids_slot[0][r0:r1].copy_(ids_d[r0:r1], non_blocking=True)
+                st_slot[0][r0:r1].copy_(status_d[r0:r1], non_blocking=True)
+                if return_scores:
+                    sc_slot[0][r0:r1].copy_(sc_d[r0:r1], non_blocking=True)
+        side.synchronize()
+        for t in (ids_d, sc_d, status_d):            # the side stream used them: keep the allocator informed
+            if t is not None:
+                t.record_stream(side)
+        ids = self._export(ids_slot)
+        scores = self._export(sc_slot) if return_scores else None
+        bad = np.flatnonzero(st_slot[0].numpy())
+        self.last_fallback_rows = int(len(bad))
         if len(bad):                       # rows the fused path could not prove: exact path
             bad_d = torch.as_tensor(bad, device=self.device)
             fix = self.recommend_exact(uid_d[bad_d], n_rec, filter_consumed, return_scores)
@@ -275,6 +326,7 @@ class _Pending:
         if self.status is not None:
             torch = self.scorer._torch
             bad = torch.nonzero(self.status).flatten()          # the only synchronisation
+            self.scorer.last_fallback_rows = int(bad.numel())
             if bad.numel():
                 fix = self.scorer.recommend_exact(self.uid_d[bad], self.n_rec, self.filter_consumed,
                                                   self.return_scores)
@@ -286,19 +338,45 @@ class _Pending:
         return self.res
 
 
-# ---- cache of scorers keyed by the identity of the host arrays --------------------------------
+# ---- cache of scorers: identity of the host arrays + a content fingerprint ----------------------
 _scorers: dict = {}
 
 
+def _fingerprint(a):
+    """Cheap content token of a host array: shape, data pointer and the float64 sum of a strided
+    sample (<= 64 Ki elements, ends included).  The reference's ALS / BPR update
+    ``user_embeds_np`` / ``item_embeds_np`` IN PLACE every epoch (``als.py:153-168``) and call
+    ``recommend_user`` in between: such an update changes (practically) every sampled element, so
+    the cached device tables are refreshed.  A point edit of a row the sample does not touch is
+    not seen — call :func:`invalidate_scorers` after one."""
+    if hasattr(a, "data_ptr"):                      # torch tensor (host or device)
+        flat = a.detach().reshape(-1)
+        n = int(flat.numel())
+        step = max(1, n // 65536)
+        return (tuple(a.shape), int(a.data_ptr()), float(flat[::step].double().sum()), float(flat[-1]) if n else 0.0)
+    arr = np.asarray(a)
+    flat = arr.reshape(-1)
+    n = flat.size
+    step = max(1, n // 65536)
+    return (arr.shape, int(arr.ctypes.data), float(flat[::step].sum(dtype=np.float64)), float(flat[-1]) if n else 0.0)
+
+
+def invalidate_scorers():
+    """Drop every cached device copy (after editing embeddings / consumed lists in place)."""
+    _scorers.clear()
+
+
 def scorer_for(model, user_embeddings, item_embeddings) -> EmbedScorer:
-    key = (id(user_embeddings), id(item_embeddings), id(model.user_consumed), int(model.n_items))
+    key = (id(user_embeddings), id(item_embeddings), int(model.n_items))
+    fp = (_fingerprint(user_embeddings), _fingerprint(item_embeddings))
     hit = _scorers.get(key)
-    if hit is not None and hit[0] is user_embeddings and hit[1] is item_embeddings:
-        return hit[2]
+    if (hit is not None and hit[0] is user_embeddings and hit[1] is item_embeddings
+            and hit[2] is model.user_consumed and hit[3] == fp):
+        return hit[4]
     n_users = getattr(model, "n_users", None)
     sc = EmbedScorer(user_embeddings, item_embeddings, model.n_items, model.user_consumed,
                      n_users=n_users)
     if len(_scorers) > 4:
         _scorers.clear()
-    _scorers[key] = (user_embeddings, item_embeddings, sc)
+    _scorers[key] = (user_embeddings, item_embeddings, model.user_consumed, fp, sc)
     return sc

@@ -114,7 +114,7 @@ class DeviceNegativeSampler:
         self.indptr = self.idx_sorted = None
         self.n_users = 0
         if user_consumed is not None:
-            csr = as_csr(user_consumed, n_users if n_users is not None else 0)
+            csr = as_csr(user_consumed, n_users)   # n_users None: derived from the dict's largest key
             indptr, idx = csr.device(self.device)
             self.n_users = csr.n_users
             # per-user sorted copy for the binary-search rejection test

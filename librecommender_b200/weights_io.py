@@ -38,13 +38,19 @@ def load_embed_model(path, model_name):
 
 def to_tf_variables(weights, extra_names=None):
     """Engine weight dict -> ``{tf variable name: array}``.  Tables use the fixed embedding-scope
-    names; every other entry needs a name in `extra_names` ({engine key: tf name}); 1-D linear tables
-    get the trailing unit axis TensorFlow stores (``[V, 1]``)."""
+    names; every other entry needs a name in `extra_names` ({engine key: tf name}).  Shapes follow the
+    reference's ``var_shape``s: ``user_linear_var`` / ``item_linear_var`` are ``[V, 1]``
+    (``fm.py:181-196``), ``sparse_linear_var`` / ``dense_linear_var`` stay 1-D
+    (``[sparse_feature_size]`` / ``[dense_field_size]``, ``fm.py:219-249``, ``deepfm.py:224-256``)."""
     out = {}
     for k, name in EMBEDDING_SCOPE.items():
         if weights.get(k) is not None:
             a = np.asarray(weights[k], dtype=np.float32)
-            out[name] = a.reshape(-1, 1) if k.endswith("_linear") else a
+            if k in ("user_linear", "item_linear"):
+                a = a.reshape(-1, 1)
+            elif k in ("sparse_linear", "dense_linear"):
+                a = a.reshape(-1)
+            out[name] = a
     for k, name in (extra_names or {}).items():
         out[name] = np.asarray(weights[k], dtype=np.float32)
     return out

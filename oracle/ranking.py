@@ -44,7 +44,15 @@ def build_consumed_unique(user_indices, item_indices):
 def _row_topk(scores: np.ndarray, ids: np.ndarray, n_rec: int):
     """Top ``n_rec`` of one row under (score desc, id asc)."""
     # lexsort: last key is primary.  -scores ascending == scores descending.
-    order = np.lexsort((ids, -scores.astype(np.float64)))[:n_rec]
+    n = len(scores)
+    if n > 4 * n_rec + 1024:
+        # same answer, less sorting: every item of the top n_rec has a score >= the n_rec-th largest
+        # value v, so only the items with score >= v (ties at v included) need the full ordering
+        v = np.partition(scores, n - n_rec)[n - n_rec]
+        sel = np.nonzero(scores >= v)[0]
+        order = sel[np.lexsort((ids[sel], -scores[sel].astype(np.float64)))][:n_rec]
+    else:
+        order = np.lexsort((ids, -scores.astype(np.float64)))[:n_rec]
     return ids[order], scores[order]
 
 

@@ -1,5 +1,5 @@
 """A numpy MODEL of the fused scorer's selection algorithm (csrc/score_topk_tc.cu header: coarse
-bf16 scores, error bound eps, speculative threshold from sampled block maxima, collection of every
+fp16 scores of power-of-two scaled rows, error bound eps, speculative threshold from sampled block maxima, collection of every
 item with coarse >= tau, finalize with the a-posteriori speculation check, cut at c_k - 2 eps,
 consumed filter, exact fp32 re-score).  It checks the EXACTNESS ARGUMENT itself, independent of any
 kernel: whenever the model accepts a row, its top-K equals the exact top-K of the oracle; rows it
@@ -10,14 +10,21 @@ import pytest
 
 from oracle import ranking as orc
 
-ERR_COEF = 0.0082
+ERR_COEF = 0.00097705
 KROW_MAX = 288
 
 
-def _bf16(x):
-    b = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
-    b = (b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000
-    return b.astype(np.uint32).view(np.float32)
+def _pow2_scale(nrm):
+    """power of two s with s * nrm in [64, 128) — pow2_scale_for in the kernel source"""
+    if not (nrm > 0):
+        return 1.0
+    m, x = np.frexp(np.float32(nrm))
+    return float(np.ldexp(1.0, 7 - int(x)))
+
+
+def _f16(x):
+    """round-to-nearest-even to fp16 (subnormals kept), returned as float64"""
+    return np.asarray(x, dtype=np.float32).astype(np.float16).astype(np.float64)
 
 
 def _exact_scores(u, I):
@@ -33,8 +40,13 @@ def model_row(u, I, consumed, K, stride=2, block=16, guess_scale=1.0, stats=None
     """Returns (ids or None, status).  status 0 = accepted, 2 = too few collected, 3 = failed
     speculation, 5 = capped row not provable."""
     N, d = I.shape
-    coarse = (_bf16(u).astype(np.float64)[None, :] * _bf16(I).astype(np.float64)).sum(1).astype(np.float32)
-    eps = (ERR_COEF + d * 2.4e-7) * float(np.linalg.norm(u)) * float(np.linalg.norm(I, axis=1).max())
+    nu = float(np.linalg.norm(u.astype(np.float64))) * 1.0001
+    ni = float(np.linalg.norm(I.astype(np.float64), axis=1).max()) * 1.0001
+    su, si = _pow2_scale(nu), _pow2_scale(ni)
+    # everything below lives in the row's SCALED units (coarse ~ su * si * exact)
+    coarse = (_f16(u * np.float32(su))[None, :] * _f16(I * np.float32(si))).sum(1).astype(np.float32)
+    d_pad = -(-d // 64) * 64
+    eps = (ERR_COEF + d_pad * 2.4e-7) * (nu * su) * (ni * si) + np.sqrt(d_pad) * 6.2e-5 * (nu * su + ni * si)
     apply = len(consumed) > 0 and K + len(consumed) <= N
     k_full = K + (len(consumed) if apply else 0)
     k_row = min(k_full, KROW_MAX)
@@ -66,7 +78,7 @@ def model_row(u, I, consumed, K, stride=2, block=16, guess_scale=1.0, stats=None
     cand, ex = cand[order], ex[order]
     if len(cand) < K:
         return None, 5
-    if capped and ex[K - 1] < thr + eps:                      # an uncollected item could still beat it
+    if capped and ex[K - 1] * (su * si) < thr + eps:          # an uncollected item could still beat it
         return None, 5
     return cand[:K], 0
 

@@ -25,7 +25,10 @@ def test_embed_and_tf_variable_roundtrip(tmp_path):
              sparse_linear=rng.standard_normal(30).astype(np.float32), lin_kernel=rng.standard_normal(5).astype(np.float32))
     io.save_tf_variables(str(tmp_path), "fm", w, extra_names={"lin_kernel": "dense/kernel:0"})
     raw = np.load(os.path.join(tmp_path, "fm_tf_variables.npz"))
-    assert raw["embedding/user_linear_var:0"].shape == (11, 1)       # TF stores the 1-D tables as [V, 1]
+    # shapes = the reference's var_shape values (fm.py:181-249): id tables [V, 1], feature tables 1-D
+    assert raw["embedding/user_linear_var:0"].shape == (11, 1)
+    assert raw["embedding/item_linear_var:0"].shape == (7, 1)
+    assert raw["embedding/sparse_linear_var:0"].shape == (30,)
     back = io.load_tf_variables(str(tmp_path), "fm", extra_names={"lin_kernel": "dense/kernel:0"})
     for k in w:
         np.testing.assert_array_equal(np.asarray(back[k]).reshape(w[k].shape), w[k])

@@ -19,8 +19,12 @@ def main():
     torch.cuda.set_device(0)
     U, I = bench.make_tables(args, dev)
     indptr, idx = bench.make_consumed_csr(args, dev)
+    from librecommender_b200 import _lib
     from librecommender_b200.consumed import ConsumedCSR
     from librecommender_b200.engine import EmbedScorer
+
+    if args.epi_warps or args.pre_coef:
+        _lib.check(_lib.lib.b200_recommend_embed_tune(args.epi_warps, args.pre_coef))
 
     sc = EmbedScorer(U, I, args.items, ConsumedCSR.from_device_tensors(indptr, idx), n_users=args.users, device=dev)
     batches = [torch.from_numpy(b).to(dev) for b in bench.make_batches(args, 0, args.steps)]
