@@ -402,22 +402,17 @@ def main():
               "e2e_ids_equal_exact_path": float((res[:n_chk] == exact_ids).all(axis=1).mean()),
               "device_ids_equal_exact_path": float((out[:n_chk].cpu().numpy() == exact_ids).all(axis=1).mean())}
 
-    # ---- secondary: the paths that have a collective (only at N > 1) -------------------------
-    secondary = None
-    if distributed and not args.no_secondary:
-        try:
-            from librecommender_b200 import bench_collectives
-
-            secondary = bench_collectives.run(rank, world, device, max_over_ranks, barrier)
-        except Exception as e:   # the primary line must survive
-            secondary = {"error": repr(e)}
-
-    if distributed:
+    run_secondary = distributed and not args.no_secondary
+    if distributed and not run_secondary:
         import torch.distributed as dist
 
         dist.barrier()
         dist.destroy_process_group()
-    if rank != 0:
+    if rank != 0 and not run_secondary:
+        return 0
+
+    if rank != 0:            # other ranks only take part in the collective legs
+        finish_with_secondary({}, run_secondary, rank, world, device, max_over_ranks, barrier)
         return 0
 
     # ---- roofline of the dominant kernel (tcgen05 sweep) ----------------------------------
@@ -483,10 +478,45 @@ def main():
                           "rows_per_leg": int(args.batch * args.steps)},
         "parity": parity,
     }
-    if secondary is not None:
-        line["secondary"] = secondary
-    print(json.dumps(line))
+    finish_with_secondary(line, run_secondary, rank, world, device, max_over_ranks, barrier)
     return 0
+
+
+def finish_with_secondary(line, run_secondary, rank, world, device, max_over_ranks, barrier):
+    """Print the ONE JSON line (rank 0).  At N > 1 the collective legs run first, under a watchdog: if
+    they do not finish in time (a hung exchange must not cost the primary measurement) the line is
+    printed with the time-out recorded and every rank exits."""
+    if not run_secondary:
+        print(json.dumps(line))
+        return
+    import torch.distributed as dist
+
+    done = threading.Event()
+    deadline_s = float(os.environ.get("B200_SECONDARY_DEADLINE_S", "420"))
+
+    def watchdog():
+        if not done.wait(deadline_s):
+            if rank == 0:
+                line["secondary"] = {"error": f"collective legs exceeded {deadline_s:.0f} s"}
+                print(json.dumps(line), flush=True)
+            os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
+    try:
+        from librecommender_b200 import bench_collectives
+
+        secondary = bench_collectives.run(rank, world, device, max_over_ranks, barrier)
+    except Exception as e:   # the primary line must survive
+        secondary = {"error": repr(e)[:400]}
+    done.set()
+    if rank == 0:
+        line["secondary"] = secondary
+        print(json.dumps(line), flush=True)
+    try:
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        pass
 
 
 if __name__ == "__main__":

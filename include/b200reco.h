@@ -96,6 +96,21 @@ int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* user_ids, i
                          void* ev_sweep_start /* cudaEvent_t or NULL: recorded on `stream` */,
                          void* ev_sweep_stop  /* just before / after the tcgen05 sweep kernel */);
 
+/* ---- 8e row 2: row-sharded embedding table over NVLink peer memory ------------------------
+ * (the reference has ONE table, libreco/layers/embedding.py:16-23; here row r lives on GPU r % G at
+ * slot r / G).  shards: HOST array of n_ranks DEVICE pointers, shards[g] = GPU g's shard
+ * [ceil(n_rows / G), ld] as mapped into this process (symmetric / peer-mapped allocation; for
+ * n_ranks == 1 an ordinary device pointer).  One kernel does the gather AND the exchange:
+ *   gather:      out[i, :d] = shards[ids[i] % G][(ids[i] / G) * ld + :d]        (peer loads)
+ *   scatter_add: shards[ids[i] % G][(ids[i] / G) * ld + :d] += rows[i, :d]      (peer float atomics)
+ * The caller orders the kernels against the owners' updates (stream-ordered barrier on the symmetric
+ * memory signal pads).  n_ranks <= 16. */
+int b200_peer_gather_rows(const void* const* shards, int32_t n_ranks, int64_t ld, int32_t d,
+                          const int64_t* ids, int64_t n, float* out, int64_t ld_out, void* stream);
+int b200_peer_scatter_add_rows(void* const* shards, int32_t n_ranks, int64_t ld, int32_t d,
+                               const int64_t* ids, int64_t n, const float* rows, int64_t ld_rows,
+                               void* stream);
+
 /* ---- a10: LightGCN propagation (libreco/algorithms/torch_modules/lightgcn_module.py:66-88) -
  * out[r,:] = sum_j val[j] * E[col[j],:] over the CSR row r (fma in CSR order), optionally fused with
  * the layer-mean: acc = (acc_init ? E[r,:] : acc[r,:]) + out[r,:], then acc /= final_div if > 0.
@@ -155,6 +170,9 @@ typedef struct {       /* TF scope "embedding" (SURVEY.md Appendix C), fp32, row
  *   lin    [R]                 Dense1(concat of linear features) + bias (fm.py:156)
  *   fm_out [R]                 lin + elu(Dense1(BN(pw)))               (fm.py:165-170); BN folded
  *                              to scale/shift (inference), bn_scale NULL = use_bn False */
+/* process-wide switch (A/B measurements, tests): 1 = the bulk-copy (TMA) staged persistent gather for
+ * eligible shapes (K % 4 == 0, K <= 32, >= 2048 rows), 0 = the register-gather kernels only. */
+int b200_feat_forward_tune(int32_t use_tma_staging);
 int b200_feat_forward(const b200_feat_layout* layout, const b200_feat_tables* tables,
                       const int64_t* users, const int64_t* items, int64_t R, int64_t grid_items,
                       int64_t row_offset, float* concat, int64_t ld_concat, float* pw, int64_t ld_pw, float* lin,

@@ -42,6 +42,7 @@ SIGNATURES = {
     "b200_spmm_chunk": (c_int, []),
     "b200_spmm_csr": (c_int, [_P, _P, _P, c_int64, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, c_int32,
                               c_float, _P, _P, c_int64, _P, _P, c_int64, _P, _P]),
+    "b200_feat_forward_tune": (c_int, [c_int32]),
     "b200_feat_forward": (c_int, [_P, _P, _P, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, c_float,
                                   _P, _P, _P, c_float, _P, _P, c_int64, _P]),
     "b200_fm_pair_scores": (c_int, [_P, _P, _P, c_int64, _P, _P, _P, c_int64, c_int32, c_float, _P, _P, _P, c_float,
@@ -51,6 +52,8 @@ SIGNATURES = {
     "b200_multi_sparse_combine": (c_int, [_P, c_int64, c_int32, _P, c_int64, c_int32, c_int64, c_int32, c_int32, _P,
                                           c_int64, _P]),
     "b200_gather_rows": (c_int, [_P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
+    "b200_peer_gather_rows": (c_int, [_P, c_int32, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
+    "b200_peer_scatter_add_rows": (c_int, [_P, c_int32, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "b200_scatter_add_rows": (c_int, [_P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "b200_linear_f32": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, c_int32, c_int32, c_int32, _P, c_int64, _P]),
     "b200_linear_tf32x3_split_ld": (c_int64, [c_int32]),

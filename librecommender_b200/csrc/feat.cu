@@ -21,6 +21,14 @@
 namespace b200 {
 namespace feat {
 
+// feat_tma.cu: persistent bulk-copy staged gather (1 = launched, 0 = shape not eligible, < 0 = error)
+int launch_feat_forward_tma(const b200_feat_layout* L, const b200_feat_tables* T, const int64_t* users,
+                            const int64_t* items, int64_t R, int64_t grid_items, int64_t row_offset,
+                            float* concat, int64_t ld_concat, float* pw, int64_t ld_pw, float* lin,
+                            float* fm_out, const float* lin_kernel, float lin_bias, const float* bn_scale,
+                            const float* bn_shift, const float* pw_kernel, float pw_bias, float* ssum,
+                            float* sqsum, int64_t ld_s, cudaStream_t stream);
+
 constexpr int MAX_T = 8;   // K <= 256
 
 struct Out {
@@ -362,6 +370,13 @@ __global__ void l2_normalize_kernel(float* __restrict__ x, int64_t ld, int64_t R
 using namespace b200;
 using namespace b200::feat;
 
+static int g_feat_tma = 1;   // b200_feat_forward_tune: 1 = TMA-staged kernel where eligible, 0 = register kernels only
+
+extern "C" int b200_feat_forward_tune(int32_t use_tma_staging) {
+  g_feat_tma = use_tma_staging ? 1 : 0;
+  return 0;
+}
+
 extern "C" int b200_feat_forward(const b200_feat_layout* L, const b200_feat_tables* T,
                                  const int64_t* users, const int64_t* items, int64_t R,
                                  int64_t grid_items, int64_t row_offset, float* concat, int64_t ld_concat, float* pw,
@@ -389,6 +404,14 @@ extern "C" int b200_feat_forward(const b200_feat_layout* L, const b200_feat_tabl
   const int K = L->embed_size;
   const bool fast = K % 4 == 0 && K <= 32 && al16(T->user_embeds) && al16(T->item_embeds) &&
                     al16(T->sparse_embeds) && al16(T->dense_embeds) && al16(concat) && (ld_concat % 4 == 0);
+  if (fast && g_feat_tma) {
+    // large row counts: TMA-staged persistent kernel (many more row reads in flight per SM)
+    const int rc = launch_feat_forward_tma(L, T, users, items, R, grid_items, row_offset, concat, ld_concat, pw, ld_pw,
+                                           lin, fm_out, lin_kernel, lin_bias, bn_scale, bn_shift, pw_kernel, pw_bias,
+                                           ssum, sqsum, ld_s, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    if (rc == 1) return 0;
+  }
   if (fast) {
     const unsigned blocks = (unsigned)ceil_div64(R * 32, 256);
     cudaStream_t st = (cudaStream_t)stream;

@@ -248,7 +248,8 @@ __device__ __forceinline__ int score_bin(float s, float R, float inv_w) {
 // Records live in registers (CAPG_MAX/32 per lane).  Returns the new count; *tau_out = new tau.
 __device__ __noinline__ int compact_row(float* __restrict__ ls, int32_t* __restrict__ lb, int n,
                                            int n_counted, int k, float eps2, float R, float tau_old,
-                                           uint32_t* __restrict__ gh, int lane, float* tau_out) {
+                                           uint32_t* __restrict__ gh, int lane, int32_t n_items,
+                                           float* tau_out) {
   const float inv_w = (float)NB / (2.f * R);
   constexpr int PER = CAPG_MAX / 32;
   float4 e0[PER], e1[PER];
@@ -270,8 +271,8 @@ __device__ __noinline__ int compact_row(float* __restrict__ ls, int32_t* __restr
     if (i >= n_counted && i < n) {
       const float v[GW] = {e0[j].x, e0[j].y, e0[j].z, e0[j].w, e1[j].x, e1[j].y, e1[j].z, e1[j].w};
 #pragma unroll
-      for (int q = 0; q < GW; ++q)
-        if (v[q] >= tau_old) atomicAdd(gh + score_bin(v[q], R, inv_w), 1u);
+      for (int q = 0; q < GW; ++q)   // zero-padded item rows (id >= N) are not items: never counted
+        if (v[q] >= tau_old && bs[j] + q < n_items) atomicAdd(gh + score_bin(v[q], R, inv_w), 1u);
     }
   }
   __threadfence();
@@ -331,22 +332,17 @@ __device__ __noinline__ int compact_row(float* __restrict__ ls, int32_t* __restr
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-// 4-bit mask of the 64-column steps of running tile `tc` that warp `j` of its quadrant handles
+// Steps of running tile `tc` that warp `j` of its quadrant handles: s = first, first + stride, ... < end
 template <int W>
-__device__ __forceinline__ uint32_t step_mask(uint32_t tc, int j) {
-  if (W == 1) return 0xFu;
-  if (W == 2) return 0x3u << (2 * j);
-  if (W == 4) return 1u << j;
-  // W == 3: step s of running tile tc has running index 4 tc + s; 4 tc mod 3 == tc mod 3
-  uint32_t m = 0;
-  const int r = (int)(tc % 3u);
-#pragma unroll
-  for (int s = 0; s < STEPS_PER_TILE; ++s)
-    if ((r + s) % 3 == j) m |= 1u << s;
-  return m;
+__device__ __forceinline__ void step_range(uint32_t tc, int j, int& first, int& end, int& stride) {
+  if (W == 2) { first = 2 * j; end = 2 * j + 2; stride = 1; }
+  else if (W == 4) { first = j; end = j + 1; stride = 1; }
+  else {   // W == 3: step s of running tile tc has running index 4 tc + s, and 4 tc mod 3 == tc mod 3
+    first = (j + 3 - (int)(tc % 3u)) % 3; end = STEPS_PER_TILE; stride = 3;
+  }
 }
 
-template <bool PRE, int W>
+template <bool PRE, int W, int EPI>
 __global__ void __launch_bounds__(sweep_threads(W), 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const SweepParams p) {
@@ -533,7 +529,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           float new_tau;
           const int w = compact_row(p.cand_s + (list0 + src) * (int64_t)(p.capg * GW),
                                     p.cand_b + (list0 + src) * (int64_t)p.capg, s_cnt, s_cntd, s_k, s_e, s_R,
-                                    s_tau, p.ghist + (int64_t)(m * TM + q * 32 + src) * NB, lane, &new_tau);
+                                    s_tau, p.ghist + (int64_t)(m * TM + q * 32 + src) * NB, lane, (int32_t)p.N,
+                                    &new_tau);
           if (lane == src) {
             cnt = w;
             n_counted = w;
@@ -551,66 +548,129 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       };
 
-      const int last_full = (int)(p.N / TN);   // tiles >= last_full contain padded item rows
+      // Zero-padded item rows of the last tile (ids >= N, coarse score exactly 0) may be collected when
+      // tau <= 0; compact_row and finalize_kernel ignore ids >= N, so the sweep needs no tail code.
       for (int t = t0; t < t1; ++t, ++tc) {
         const int acc = (int)(tc & 1u);
         const uint32_t acc_phase = (tc >> 1) & 1u;
-        const uint32_t smask = step_mask<W>(tc, j);
-        const bool tail = t >= last_full;
-#pragma unroll
-        for (int s = 0; s < STEPS_PER_TILE; ++s) {
-          if (!((smask >> s) & 1u)) continue;             // warp-uniform
+        int s_first, s_end, s_stride;
+        step_range<W>(tc, j, s_first, s_end, s_stride);
+#pragma unroll 1
+        for (int s = s_first; s < s_end; s += s_stride) {   // ONE copy of the step body for every step
           const int half = s >> 1;
           ptx::mbar_wait(&ss->tmem_full[acc][half], acc_phase);
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + s * STEP);
           const int n_base = t * TN + s * STEP;
-          uint32_t r[STEP];
-          ptx::tmem_ld_32x32b_x64(taddr, r);
-          ptx::tmem_ld_wait_regs64(r);
-          // the accumulator columns of this step are in registers: hand them back to the MMA issuer
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
-          if (tail) {   // zero-padded item rows (>= N) must never be collected: only the last tile
-            const int lim = (int)max((int64_t)0, min((int64_t)STEP, p.N - (int64_t)n_base));
+          if (EPI != 1) {
+            // ---- variants 0 / 2 / 3: every test and push on register-resident scores ------------------
+            uint32_t r[STEP];
+            ptx::tmem_ld_32x32b_x64(taddr, r);
+            ptx::tmem_ld_wait_regs64(r);
+            // the accumulator columns of this step are in registers: hand them back to the MMA issuer now
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
+            float g[STEP / 8];
 #pragma unroll
-            for (int c = 0; c < STEP; ++c) if (c >= lim) r[c] = 0xff800000u;
+            for (int gq = 0; gq < STEP / 8; ++gq) {
+              const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
+              const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+              g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
+            }
+            auto push_group = [&](int gq) {   // this lane's group gq goes to its candidate list WHOLE
+              float4* dst = reinterpret_cast<float4*>(my_s + (size_t)cnt * GW);
+              dst[0] = make_float4(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]),
+                                   __uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
+              dst[1] = make_float4(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]),
+                                   __uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
+              my_b[cnt] = n_base + gq * 8;
+              ++cnt;
+            };
+            if (EPI == 0) {
+              // variant 0: warp-uniform tests, one vote per 8-column group (cold group: 3 instructions)
+              bool pushed = false;
+#pragma unroll
+              for (int gq = 0; gq < STEP / 8; ++gq) {
+                if (__any_sync(0xffffffffu, g[gq] >= tau)) {
+                  if (g[gq] >= tau) push_group(gq);
+                  pushed = true;
+                }
+              }
+              if (pushed)   // warp-uniform
+                compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > p.trig) || (cnt > p.capg - 8)));
+            } else if (EPI == 2) {
+              // variant 2: ONE vote per 64-column step; hot steps build the per-lane group mask, OR-reduce
+              // it (REDUX) and run the pushes under independent uniform tests
+              const float mm = fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]));
+              if (__any_sync(0xffffffffu, mm >= tau)) {
+                uint32_t hm = 0;
+#pragma unroll
+                for (int gq = 0; gq < STEP / 8; ++gq) hm |= (g[gq] >= tau) ? (1u << gq) : 0u;
+                const uint32_t any = __reduce_or_sync(0xffffffffu, hm);
+#pragma unroll
+                for (int gq = 0; gq < STEP / 8; ++gq)
+                  if (any & (1u << gq))
+                    if (hm & (1u << gq)) push_group(gq);
+                compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > p.trig) || (cnt > p.capg - 8)));
+              }
+            } else {
+              // variant 3: no votes at all in the group tests: divergent per-lane branches straight from the
+              // compare (the hardware skips a push block no lane takes); one vote per step for the overflow check
+              const int cnt0 = cnt;
+#pragma unroll
+              for (int gq = 0; gq < STEP / 8; ++gq)
+                if (g[gq] >= tau) push_group(gq);
+              if (__any_sync(0xffffffffu, cnt != cnt0))
+                compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > p.trig) || (cnt > p.capg - 8)));
+            }
+            continue;
           }
+          // ---- variant 1: one test per step, hot groups re-read from tensor memory ------------------
           float g[STEP / 8];
+          {
+            uint32_t r[STEP];
+            ptx::tmem_ld_32x32b_x64(taddr, r);
+            ptx::tmem_ld_wait_regs64(r);
 #pragma unroll
-          for (int gq = 0; gq < STEP / 8; ++gq) {
-            const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
-            const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
-            g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
-          }
+            for (int gq = 0; gq < STEP / 8; ++gq) {
+              const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
+              const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+              g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
+            }
+          }   // the 64 accumulator values are dead from here on: only the 8 group maxima stay in registers
           // ONE warp-uniform test per 64-column step (cold steps: max tree + 3 instructions).
           const float mm = fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]));
           if (__any_sync(0xffffffffu, mm >= tau)) {
-            // hot step: per-lane mask of the 8-column groups at or above tau, OR-reduced over the
-            // warp (one REDUX) so that the 8 group branches below are independent uniform tests.
-            // A group that is hot in some lane is pushed WHOLE by that lane (two 16-byte stores +
-            // its first item id); finalize_kernel sorts out which of its 8 scores are candidates.
+            // hot step: per-lane mask of the 8-column groups at or above tau, OR-reduced over the warp
+            // (one REDUX).  Every group that is hot in some lane is RE-READ from tensor memory (8 columns,
+            // warp-uniform dynamic address) and pushed WHOLE by the lanes it is hot in (two 16-byte stores
+            // + its first item id); finalize_kernel sorts out which of its 8 scores are candidates.
             uint32_t hm = 0;
 #pragma unroll
             for (int gq = 0; gq < STEP / 8; ++gq) hm |= (g[gq] >= tau) ? (1u << gq) : 0u;
-            const uint32_t any = __reduce_or_sync(0xffffffffu, hm);
-#pragma unroll
-            for (int gq = 0; gq < STEP / 8; ++gq) {
-              if (any & (1u << gq)) {
-                if (hm & (1u << gq)) {
-                  float4* dst = reinterpret_cast<float4*>(my_s + (size_t)cnt * GW);
-                  dst[0] = make_float4(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]),
-                                       __uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
-                  dst[1] = make_float4(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]),
-                                       __uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
-                  my_b[cnt] = n_base + gq * 8;
-                  ++cnt;
-                }
+            uint32_t any = __reduce_or_sync(0xffffffffu, hm);
+#pragma unroll 1
+            while (any) {
+              const int gq = __ffs(any) - 1;
+              any &= any - 1;
+              uint32_t v[8];
+              ptx::tmem_ld_32x32b_x8(taddr + (uint32_t)(gq * 8), v);
+              ptx::tmem_ld_wait_regs8(v);
+              if ((hm >> gq) & 1u) {
+                float4* dst = reinterpret_cast<float4*>(my_s + (size_t)cnt * GW);
+                dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+                dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+                my_b[cnt] = n_base + gq * 8;
+                ++cnt;
               }
             }
             compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > p.trig) || (cnt > p.capg - 8)));
           }
+          // this step's accumulator columns are no longer needed: hand them back to the MMA issuer
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
         }
       }
       p.cand_cnt[list0 + lane] = cnt;
@@ -794,7 +854,7 @@ finalize_kernel(const FinalizeParams p) {
         const float v[8] = {a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, b[q].y, b[q].z, b[q].w};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const bool hit = ok[q] && v[e] >= low;
+          const bool hit = ok[q] && v[e] >= low && (int64_t)(base[q] + e) < p.N;   // never a zero-padded item row
           const unsigned m = __ballot_sync(0xffffffffu, hit);
           if (m) {   // one shared-memory atomic per warp and element slot
             int pos0 = 0;
@@ -823,7 +883,7 @@ finalize_kernel(const FinalizeParams p) {
         const int32_t* lb = p.cand_b + slot * (int64_t)p.capg;
         for (int i = tid; i < n * GW; i += FIN_THREADS) {
           const float v = ls[i];
-          if (v >= low) f(v, lb[i / GW] + (i % GW));
+          if (v >= low && (int64_t)(lb[i / GW] + (i % GW)) < p.N) f(v, lb[i / GW] + (i % GW));
         }
       }
     }
@@ -1079,6 +1139,7 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // ---- tuning knobs (defaults compiled in; b200_recommend_embed_tune overrides them per process) ----
 static int g_epi_w = 2;            // epilogue warps per TMEM lane quadrant in the main pass: 2 or 3
+static int g_epi = 0;              // epilogue variant of the main pass (see sweep_kernel): 0 group tests, 1 step test
 static float g_pre_coef = 2.67f;   // speculative rank target = g_pre_coef * k_row (+ 16 / sampled fraction)
 
 struct Plan {
@@ -1155,16 +1216,16 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   return 0;
 }
 
-template <bool PRE, int W>
+template <bool PRE, int W, int EPI>
 static int launch_sweep(int grid, const Plan& pl, cudaStream_t stream, const CUtensorMap& tmA,
                         const CUtensorMap& tmB, const SweepParams& sp) {
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel<PRE, W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel<PRE, W, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));
     attr_set = true;
   }
-  sweep_kernel<PRE, W><<<grid, sweep_threads(W), pl.smem_bytes, stream>>>(tmA, tmB, sp);
+  sweep_kernel<PRE, W, EPI><<<grid, sweep_threads(W), pl.smem_bytes, stream>>>(tmA, tmB, sp);
   count_launch();
   return 0;
 }
@@ -1209,10 +1270,12 @@ extern "C" int b200_embed_catalog_prepare(const float* I, int64_t ldi, int64_t N
 }
 
 extern "C" int b200_recommend_embed_tune(int32_t epilogue_warps_per_quadrant, float pre_rank_coef) {
-  if (epilogue_warps_per_quadrant != 0) {
-    B200_REQUIRE(epilogue_warps_per_quadrant >= 2 && epilogue_warps_per_quadrant <= 3,
-                 "b200_recommend_embed_tune: epilogue warps per quadrant must be 2 or 3");
-    g_epi_w = epilogue_warps_per_quadrant;
+  if (epilogue_warps_per_quadrant != 0) {   // W + 10 * (epilogue variant)
+    const int w = epilogue_warps_per_quadrant % 10, epi = epilogue_warps_per_quadrant / 10;
+    B200_REQUIRE(w >= 2 && w <= 4 && epi >= 0 && epi <= 3,
+                 "b200_recommend_embed_tune: epilogue warps per quadrant must be 2, 3 or 4 (+ 10 x variant 0..3)");
+    g_epi_w = w;
+    g_epi = epi;
   }
   if (pre_rank_coef != 0.f) {
     B200_REQUIRE(pre_rank_coef >= 1.0f && pre_rank_coef <= 16.f,
@@ -1302,7 +1365,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
 
   if (ev_sweep_start) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_start, stream));
   if (pl.use_pre) {
-    if (int rc = launch_sweep<true, W_PRE>(grid, pl, stream, tmA, tmB, sp)) return rc;
+    if (int rc = launch_sweep<true, W_PRE, 0>(grid, pl, stream, tmA, tmB, sp)) return rc;
     guess_kernel<<<(unsigned)(pl.B_pad / 32), GUESS_THREADS, 0, stream>>>(
         bm, W_PRE * pl.n_splits * pl.n_pre_tiles, pl.B_pad, meta, tau, guess);
     count_launch();
@@ -1311,8 +1374,13 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   }
   {
     int rc;
-    if (pl.W == 2) rc = launch_sweep<false, 2>(grid, pl, stream, tmA, tmB, sp);
-    else rc = launch_sweep<false, 3>(grid, pl, stream, tmA, tmB, sp);
+    // main-pass variants (b200_recommend_embed_tune): W = 2 with every epilogue variant, W = 3 / 4 with variant 0
+    if (pl.W == 3) rc = launch_sweep<false, 3, 0>(grid, pl, stream, tmA, tmB, sp);
+    else if (pl.W == 4) rc = launch_sweep<false, 4, 0>(grid, pl, stream, tmA, tmB, sp);
+    else if (g_epi == 1) rc = launch_sweep<false, 2, 1>(grid, pl, stream, tmA, tmB, sp);
+    else if (g_epi == 2) rc = launch_sweep<false, 2, 2>(grid, pl, stream, tmA, tmB, sp);
+    else if (g_epi == 3) rc = launch_sweep<false, 2, 3>(grid, pl, stream, tmA, tmB, sp);
+    else rc = launch_sweep<false, 2, 0>(grid, pl, stream, tmA, tmB, sp);
     if (rc) return rc;
   }
   if (ev_sweep_stop) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_stop, stream));

@@ -281,3 +281,229 @@ class RowShardedTable:
         else:
             g_in.copy_(g_out)
         self.scatter_fn(self.local, slots_in, g_in)
+
+
+# ------------------------------------------------------------------------------------------------
+# Row-sharded table over NVLink PEER MEMORY (the B200 path of SURVEY.md §8e row 2).  Every rank's
+# shard lives in symmetric memory (torch.distributed._symmetric_memory: CUDA VMM allocations
+# mapped into every process of the node), so one CUDA kernel per direction does the gather AND
+# the exchange (`b200_peer_gather_rows` / `b200_peer_scatter_add_rows`): no bucketing by owner, no
+# index all-to-all, no row all-to-all, no host synchronisation.
+# ------------------------------------------------------------------------------------------------
+class PeerShardedTable:
+    """``local_rows``: this rank's ``[ceil(n_rows / G), d]`` shard (rows rank, rank + G, ...).
+    ``lookup(ids)`` -> ``[len(ids), d]`` rows for ANY global ids; ``scatter_add(ids, grads)`` adds
+    into the owners' shards; ``sync()`` is a stream-ordered barrier over all ranks (signal pads in
+    the symmetric allocation) — call it between a phase that writes the table and one that reads."""
+
+    def __init__(self, local_rows, n_rows: int, group=None):
+        import ctypes
+
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.n_rows, self.d = int(n_rows), int(local_rows.shape[1])
+        rows_loc = -(-self.n_rows // self.world)
+        dev = local_rows.device
+        self.local = symm.empty((rows_loc, self.d), dtype=torch.float32, device=dev)
+        self.local.zero_()
+        self.local[: local_rows.shape[0]].copy_(local_rows)
+        self.handle = symm.rendezvous(self.local, self.group)
+        ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self._shards = (ctypes.c_void_p * self.world)(*ptrs)
+        self.sync()
+
+    def sync(self):
+        self.handle.barrier(channel=0)
+
+    def lookup(self, ids, out=None):
+        import torch
+
+        from . import _lib
+
+        ids = ids.to(torch.int64).contiguous()
+        n = int(ids.numel())
+        if out is None:
+            out = torch.empty((n, self.d), dtype=torch.float32, device=ids.device)
+        _lib.check(_lib.lib.b200_peer_gather_rows(self._shards, self.world, self.local.stride(0), self.d,
+                                                  _lib.ptr(ids), n, _lib.ptr(out), out.stride(0),
+                                                  _lib.current_stream()))
+        return out
+
+    def scatter_add(self, ids, grads):
+        import torch
+
+        from . import _lib
+
+        ids = ids.to(torch.int64).contiguous()
+        grads = grads.contiguous()
+        _lib.check(_lib.lib.b200_peer_scatter_add_rows(self._shards, self.world, self.local.stride(0), self.d,
+                                                       _lib.ptr(ids), int(ids.numel()), _lib.ptr(grads),
+                                                       grads.stride(0), _lib.current_stream()))
+
+
+# ------------------------------------------------------------------------------------------------
+# LightGCN propagation with the exchange OVERLAPPED with the SpMM (SURVEY.md §8e row 3: "chunked so
+# SpMM on column block g starts as soon as slab g lands").  The local row block of L is split by
+# SOURCE RANK of the column into G sub-matrices; per layer the own block multiplies at once, and
+# block g multiplies as soon as slab g has arrived.  Two exchange engines:
+#   * ring   — G-1 steps of paired isend / irecv (NCCL on GPUs, gloo in the CPU tests);
+#   * peer   — the slabs live in symmetric memory and every rank PULLS its peers' slabs with the
+#              copy engines over NVLink (no SM, no NCCL), ordered by one device-side barrier per layer.
+# The layer product is accumulated block by block (deterministic order: own block, then source
+# ranks r-1, r-2, ...), so it agrees with the single-GPU result to float rounding (not bit-for-bit;
+# `propagate_sharded` above is the bit-exact, non-overlapped variant).
+# ------------------------------------------------------------------------------------------------
+def split_column_blocks(lptr, lcol, lval, slab: int, world: int):
+    """Local CSR (columns in the gathered layout, `world * slab` of them) -> one CSR per source rank
+    with block-local column ids.  The order of the entries inside a row is preserved."""
+    import torch
+
+    dev = lptr.device
+    n_rows = lptr.numel() - 1
+    deg = lptr[1:] - lptr[:-1]
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=dev), deg)
+    blk = (lcol.to(torch.int64) // slab)
+    out = []
+    for g in range(world):
+        sel = torch.nonzero(blk == g).flatten()               # ascending: row order and in-row order kept
+        ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+        ptr[1:] = torch.cumsum(torch.bincount(rows[sel], minlength=n_rows), 0)
+        out.append((ptr, (lcol[sel].to(torch.int64) - g * slab).to(torch.int32).contiguous(), lval[sel].contiguous()))
+    return out
+
+
+class RingExchange:
+    """Slab exchange by G-1 paired isend / irecv steps; works with nccl (CUDA tensors, on a side
+    stream) and gloo (CPU tensors, synchronous)."""
+
+    def __init__(self, world, rank, group=None):
+        self.world, self.rank, self.group = world, rank, group
+        self._stream = None
+
+    def start(self, cur, slots):
+        """Begin the exchange of `cur` [slab, d]; slots[g] receives rank g's slab.  Returns a list of
+        (source rank, wait_fn) in arrival order; wait_fn() makes the CURRENT stream wait for that slab."""
+        import torch
+        import torch.distributed as dist
+
+        arrivals = []
+        if self.world == 1:
+            return arrivals
+        cuda = cur.is_cuda
+        if cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=cur.device)
+            ready = torch.cuda.Event()
+            ready.record()                               # `cur` is complete on the compute stream here
+            self._stream.wait_event(ready)
+        for s in range(1, self.world):
+            dst, src = (self.rank + s) % self.world, (self.rank - s) % self.world
+            ops = [dist.P2POp(dist.isend, cur, dst, self.group), dist.P2POp(dist.irecv, slots[src], src, self.group)]
+            if cuda:
+                with torch.cuda.stream(self._stream):
+                    works = dist.batch_isend_irecv(ops)
+                    for w in works:
+                        w.wait()                         # side stream waits for the NCCL op
+                    ev = torch.cuda.Event()
+                    ev.record(self._stream)
+                arrivals.append((src, (lambda e=ev: torch.cuda.current_stream().wait_event(e))))
+            else:
+                works = dist.batch_isend_irecv(ops)
+                arrivals.append((src, (lambda ws=works: [w.wait() for w in ws])))
+        return arrivals
+
+    def make_slabs(self, slab, d, device, dtype):
+        """(list of G receive buffers, 2 ping-pong `cur` buffers)."""
+        import torch
+
+        return ([torch.empty((slab, d), dtype=dtype, device=device) for _ in range(self.world)],
+                [torch.empty((slab, d), dtype=dtype, device=device) for _ in range(2)])
+
+
+class PeerPullExchange:
+    """Slabs in symmetric memory: after one device-side barrier every rank pulls its peers' slabs with
+    cudaMemcpyAsync (copy engines over NVLink) on side streams; the SMs only run the SpMM."""
+
+    def __init__(self, world, rank, group=None):
+        self.world, self.rank, self.group = world, rank, group
+        self._streams = None
+        self._cur_syms = None
+
+    def make_slabs(self, slab, d, device, dtype):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        grp = self.group if self.group is not None else dist.group.WORLD
+        self._cur = [symm.empty((slab, d), dtype=dtype, device=device) for _ in range(2)]
+        self._hdl = [symm.rendezvous(t, grp) for t in self._cur]
+        self._shape, self._dtype = (slab, d), dtype
+        self._streams = [torch.cuda.Stream(device=device) for _ in range(2)]
+        return ([torch.empty((slab, d), dtype=dtype, device=device) for _ in range(self.world)], self._cur)
+
+    def start(self, cur, slots):
+        import torch
+
+        arrivals = []
+        if self.world == 1:
+            return arrivals
+        which = 0 if cur.data_ptr() == self._cur[0].data_ptr() else 1
+        hdl = self._hdl[which]
+        hdl.barrier(channel=which)            # every rank's `cur` of this layer is complete (stream-ordered)
+        ready = torch.cuda.Event()
+        ready.record()
+        for s in range(1, self.world):
+            src = (self.rank - s) % self.world
+            st = self._streams[s & 1]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                remote = hdl.get_buffer(src, self._shape, self._dtype)
+                slots[src].copy_(remote, non_blocking=True)          # peer -> local over NVLink (DMA)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            arrivals.append((src, (lambda e=ev: torch.cuda.current_stream().wait_event(e))))
+        return arrivals
+
+
+def propagate_sharded_overlap(plan: LightGCNShardPlan, block_spmm, E0_local, n_layers: int, exchange,
+                              rank: int):
+    """mean_{l=0..n_layers} L^l E0 on this rank's row block with the slab exchange overlapped with the
+    per-source-rank block products.  ``block_spmm(g, E_g [slab, d], acc)`` adds ``L[:, block g] @ E_g``
+    to ``acc`` (CUDA: ``SpmmGraph.spmm(..., acc=acc, acc_init=False)`` of the g-th column block from
+    :func:`split_column_blocks`)."""
+    import torch
+
+    slab, d = E0_local.shape
+    if not hasattr(exchange, "_bufs") or exchange._bufs[0][0].shape != (slab, d):
+        exchange._bufs = exchange.make_slabs(slab, d, E0_local.device, E0_local.dtype)
+    slots, curs = exchange._bufs
+    cur = curs[0]
+    cur.copy_(E0_local)
+    acc = E0_local.clone()
+    for layer in range(n_layers):
+        nxt = curs[(layer + 1) & 1]
+        arrivals = exchange.start(cur, slots)
+        nxt.zero_()
+        block_spmm(rank, cur, nxt)                       # own block: no communication needed
+        for src, wait in arrivals:
+            wait()
+            block_spmm(src, slots[src], nxt)
+        acc.add_(nxt)
+        cur = nxt
+    acc.div_(float(n_layers + 1))
+    return acc
+
+
+def block_spmm_fn(block_graphs):
+    """``block_spmm`` backed by the CUDA SpMM of the per-source-rank :class:`SpmmGraph` objects."""
+
+    def fn(g, E_block, acc):
+        if block_graphs[g].nnz:
+            block_graphs[g].spmm(E_block, out=None, acc=acc, acc_init=False, final_div=0.0)
+
+    return fn

@@ -67,11 +67,12 @@ def _check(sc, U, I, csr, users, K, n_oracle, min_ok_frac):
     np.testing.assert_array_equal(got_ids.cpu().numpy(), ids_e)
     np.testing.assert_array_equal(got_sc.cpu().numpy(), sc_e)
     # numpy oracle on a sample of the rows (heavy users first)
-    deg = csr.indptr[users + 1] - csr.indptr[users]
+    known = np.minimum(users, csr.n_users - 1)
+    deg = np.where(users < csr.n_users, csr.indptr[known + 1] - csr.indptr[known], 0)   # OOV row: no history
     pick = np.unique(np.concatenate([np.argsort(-deg)[: n_oracle // 4],
                                      np.random.default_rng(0).choice(len(users), n_oracle, replace=False)]))
     u_s = users[pick]
-    consumed = {int(u): csr.row(int(u)).tolist() for u in u_s if len(csr.row(int(u)))}
+    consumed = {int(u): csr.row(int(u)).tolist() for u in u_s if u < csr.n_users and len(csr.row(int(u)))}
     ref_ids, ref_sc = orc.recommend_from_embedding("rating", u_s.tolist(), K, U, I, N, consumed, True,
                                                    return_scores=True)
     full = orc.embed_scores(U, I, u_s, N)

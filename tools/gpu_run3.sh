@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+O=gpurun_out
+./tools/ubench/pipes > $O/r2_ubench_pipes.jsonl 2>&1
+VARIANTS="2:2.67:8192,12:2.67:8192,2:2.0:8192,12:2.0:8192,3:2.0:8192,2:2.0:16384" timeout 600 python tools/sweep_variants.py > $O/r2_variants_v3.jsonl 2> $O/r2_variants_v3.err; echo "rc=$?" >> $O/r2_variants_v3.err
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 3 -c 1 -o $O/r2_prof_sweep_v3 python tools/profile_embed.py --steps 3 --batch 8192 --pre-coef 2.0 > $O/r2_ncu_s3.log 2>&1
+cat $O/r2_ubench_pipes.jsonl
+cat $O/r2_variants_v3.jsonl | cut -c1-200
+tail -2 $O/r2_ncu_s3.log

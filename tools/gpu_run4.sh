@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+O=gpurun_out
+VARIANTS="2:2.0:8192,22:2.0:8192,32:2.0:8192,32:2.67:8192,32:1.6:8192,22:1.6:8192,32:2.0:16384" timeout 600 python tools/sweep_variants.py > $O/r2_variants_v4.jsonl 2> $O/r2_variants_v4.err; echo "rc=$?" >> $O/r2_variants_v4.err
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 3 -c 1 -o $O/r2_prof_sweep_v4 python tools/profile_embed.py --steps 3 --batch 8192 --pre-coef 2.0 --epi-warps 32 > $O/r2_ncu_s4.log 2>&1
+cat $O/r2_variants_v4.jsonl | cut -c1-200
+tail -2 $O/r2_ncu_s4.log; tail -3 $O/r2_variants_v4.err
