@@ -422,6 +422,93 @@ class _FeatModelBase:
     def max_grid_rows(self):
         return 1 << 22
 
+    def default_recs(self, n_rec=2000):
+        """Top-``min(n_rec, n_items)`` for the OOV user without the consumed filter — what
+        ``TfBase.fit`` stores as ``default_recs`` for cold-start users (``bases/tf_base.py:145-153``)."""
+        return self.recommend([self.n_users], min(int(n_rec), self.n_items), filter_consumed=False).flatten()
+
+    def recommend_dynamic(self, user_id, n_rec, data_info, user_feats=None, seq=None, filter_consumed=True,
+                          inner_id=False, return_scores=False):
+        """``recommend_tf_feat`` for ONE user with features / behaviour sequence supplied for this call
+        (``recommendation/recommend.py:39-54,81-105``, ``recommendation/preprocess.py:104-159``): the
+        user's feature columns are overridden in a per-row feature matrix of the N (user, item) rows
+        (``dynamic_feats.dynamic_feature_rows``; the device tables are not touched), a sequence model
+        reads the supplied sequence instead of the cached one."""
+        torch = self._torch
+        from .dynamic_feats import build_rec_seq, dynamic_feature_rows
+
+        if getattr(self, "has_multi_sparse", False) and user_feats:
+            raise NotImplementedError("feature overrides on layouts with multi-sparse fields")
+        if n_rec > self.n_items:
+            raise ValueError(f"`n_rec` {n_rec} exceeds num of items {self.n_items}")
+        u = int(user_id)
+        uid = torch.tensor([u], dtype=torch.int64, device=self.device)
+        N = self.n_items
+        layout = self.spec.layout
+        keep = None
+        if user_feats:
+            sp, de = dynamic_feature_rows(data_info, u, user_feats)
+            sr = _dev(sp, self.device, torch.int32)
+            dr = _dev(de, self.device, torch.float32)
+            layout = self.spec.with_rows(sr, dr)
+            keep = (sr, dr)
+        restore = None
+        if seq is not None and len(seq) > 0 and hasattr(self, "seqs"):
+            row, ln = build_rec_seq(seq, N, self.T, getattr(data_info, "item2id", None), inner_id)
+            restore = (self.seqs[u].clone(), self.lens[u].clone())
+            self.seqs[u] = torch.from_numpy(row[0]).to(self.device)
+            self.lens[u] = int(ln[0])
+        try:
+            if user_feats:          # explicit per-row features: the flat (user, item) grid
+                scores = self._forward(layout, uid, None, N, N).view(1, N).contiguous()
+            else:
+                scores = self.score_all_items(uid).contiguous()
+        finally:
+            if restore is not None:
+                self.seqs[u], self.lens[u] = restore
+        del keep
+        lib, stream = _lib.lib, _lib.current_stream()
+        if filter_consumed and self.csr.nnz > 0:
+            _lib.check(lib.b200_mask_consumed(_lib.ptr(scores), scores.stride(0), _lib.ptr(uid), 1, N, n_rec,
+                                              _lib.ptr(self.indptr_d), _lib.ptr(self.idx_d), self.csr.n_users, stream))
+        out_ids = torch.empty((1, n_rec), dtype=torch.int64, device=self.device)
+        out_sc = torch.empty((1, n_rec), dtype=torch.float32, device=self.device)
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(lib.b200_topk_rows_workspace_bytes(1, N, n_rec, ctypes.byref(nbytes)))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        _lib.check(lib.b200_topk_rows(_lib.ptr(scores), scores.stride(0), 1, N, n_rec, _lib.ptr(out_ids),
+                                      _lib.ptr(out_sc), _lib.ptr(ws), nbytes.value, stream))
+        ids = out_ids.cpu().numpy()
+        if return_scores:
+            sc = out_sc.cpu().numpy()
+            return ids, (1.0 / (1.0 + np.exp(-sc)) if self.task == "ranking" else sc)
+        return ids
+
+    def assign_oov(self, sparse_oov=None):
+        """``assign_tf_variables_oov`` (``bases/tf_base.py:310-353``) on the device tables, in place."""
+        torch = self._torch
+        with torch.no_grad():
+            for name, n in (("user_embeds", self.n_users), ("user_linear", self.n_users),
+                            ("item_embeds", self.n_items), ("item_linear", self.n_items)):
+                v = self.t.get(name)
+                if v is not None and v.shape[0] > n:
+                    v[n] = v[:n].mean(dim=0)
+            if sparse_oov is not None:
+                for name in ("sparse_embeds", "sparse_linear"):
+                    v = self.t.get(name)
+                    if v is None:
+                        continue
+                    start = 0
+                    for oov in [int(o) for o in sparse_oov]:
+                        if start >= oov:
+                            continue
+                        v[oov] = v[start:oov].mean(dim=0)
+                        start = oov + 1
+        for k in ("_item_part", "_item_side"):               # cached item-side partials depend on the tables
+            self.__dict__.pop(k, None)
+        if hasattr(self, "_rebuild_item_features"):
+            self._rebuild_item_features()
+
     # -- helpers -----------------------------------------------------------------------------------
     def _feat_forward(self, layout, users_d, items_d, R, grid_items, concat=None, pw=None, lin=None,
                       fm_out=None, head=None, row_offset=0, ssum=None, sqsum=None, lin_kernel=None, lin_bias=None):
@@ -753,14 +840,7 @@ class DIN(_SeqModelBase):
                  device=None):
         super().__init__(spec, weights, recent_seqs, recent_seq_lens, user_consumed, task, device)
         torch = self._torch
-        # item feature table G (combine_seq_features, concat mode; tfops/features.py:165-218), built once
-        parts = [self.t["item_embeds"]]
-        if self.spec.is_ is not None:
-            parts.append(self.t["sparse_embeds"][self.spec.is_.long()].reshape(self.n_items + 1, -1))
-        if self.spec.id_ is not None:
-            cols = torch.as_tensor(self.spec.item_dense_cols, device=self.device)
-            parts.append((self.spec.id_[:, :, None] * self.t["dense_embeds"][cols][None]).reshape(self.n_items + 1, -1))
-        self.G = torch.cat(parts, dim=1).contiguous()
+        self._rebuild_item_features()
         self.Kp = int(self.G.shape[1])
         self.extra = self.Kp
         att = weights["attention"]
@@ -768,6 +848,18 @@ class DIN(_SeqModelBase):
                         k2=_dev(np.asarray(att["k2"]).reshape(-1), self.device, torch.float32),
                         b2=float(np.asarray(att["b2"]).reshape(-1)[0]))
         self.mlp = self._upload_mlp(weights["mlp"])
+
+    def _rebuild_item_features(self):
+        """item feature table G (combine_seq_features, concat mode; tfops/features.py:165-218): built once
+        per set of tables (again after ``assign_oov``)."""
+        torch = self._torch
+        parts = [self.t["item_embeds"]]
+        if self.spec.is_ is not None:
+            parts.append(self.t["sparse_embeds"][self.spec.is_.long()].reshape(self.n_items + 1, -1))
+        if self.spec.id_ is not None:
+            cols = torch.as_tensor(self.spec.item_dense_cols, device=self.device)
+            parts.append((self.spec.id_[:, :, None] * self.t["dense_embeds"][cols][None]).reshape(self.n_items + 1, -1))
+        self.G = torch.cat(parts, dim=1).contiguous()
 
     # ---- hoisted all-items scoring (SURVEY.md 8d "a7 DIN all-items") ---------------------------------
     def _hoistable(self):

@@ -65,15 +65,19 @@ def recommend_tf_feat(model, user_ids, n_rec, user_feats, seq, filter_consumed, 
     (``process_tf_feat``) and runs the TF graph; here ``model.b200_engine`` — a
     :mod:`librecommender_b200.feat_models` engine (FM / DeepFM / DIN / YouTubeRanking) built from the
     model's saved variables — scores the implicit (user, item) grid on the GPU and the consumed
-    filter + top-K run on the score rows.  Single-user dynamic ``user_feats`` / ``seq`` overrides are
-    not served by the engine (the reference path stays responsible for them)."""
+    filter + top-K run on the score rows.  A single-user call with ``user_feats`` / ``seq`` goes through
+    ``engine.recommend_dynamic`` (explicit per-row feature matrix / replaced sequence row)."""
     from .. import _lib
 
     engine = getattr(model, "b200_engine", None)
     if engine is None:
         raise _lib.B200Error("recommend_tf_feat: attach a feat_models engine as `model.b200_engine` first")
-    if user_feats is not None or seq is not None:
-        raise NotImplementedError("dynamic user_feats / seq overrides are served by the reference path")
+    if user_feats is not None or (seq is not None and len(seq) > 0):
+        # single-user call with features / sequence supplied for this request (recommend.py:39-54)
+        if len(user_ids) != 1:
+            raise ValueError(f"Batch inference doesn't support assigning arbitrary features: {user_ids}")
+        return engine.recommend_dynamic(user_ids[0], n_rec, model.data_info, user_feats, seq, filter_consumed,
+                                        inner_id)
     if n_rec > model.n_items:
         raise ValueError(f"`n_rec` {n_rec} exceeds num of items {model.n_items}")
     if random_rec:

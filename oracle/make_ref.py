@@ -6,7 +6,8 @@ snapshot of this repository.  This script copies — byte for byte, nothing edit
 
 * ``/root/reference/libreco``                      (the Python package; ``*.py`` only: the Cython / Rust
   extensions are optional at import time, ``algorithms/als.py:137`` / ``bpr.py:311`` only warn), and
-* ``/root/reference/examples/sample_data/sample_movielens_rating.dat`` (C1's data set)
+* ``/root/reference/examples/sample_data/sample_movielens_rating.dat`` and ``sample_movielens_merged.csv``
+  (C1's data sets)
 
 into ``oracle/_ref/`` (git-ignored: reference sources never enter this repository's history; NOT
 gpurun-ignored: the directory ships with the snapshot like the built ``.so``).  ``oracle/ref_loader``
@@ -32,7 +33,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEST = os.path.join(HERE, "_ref")
 SRC_ROOT = os.environ.get("B200RECO_REFERENCE", "/root/reference")
-DATA_FILES = ["examples/sample_data/sample_movielens_rating.dat"]
+DATA_FILES = ["examples/sample_data/sample_movielens_rating.dat", "examples/sample_data/sample_movielens_merged.csv"]
 
 
 def _sha(path):
