@@ -77,12 +77,16 @@ int b200_score_rows_f32(const float* U, int64_t ldu, const int64_t* user_ids, in
  * Limits: d <= 256, K <= 288.
  * b200_recommend_embed_plan reports how a call of that shape will run: out[0] = 1 when the
  * speculative pre-pass (sweep<PRE> + guess_kernel) is used, out[1] item splits, out[2] item tiles
- * per split, out[3] user tiles, out[4] sampled tiles per split, out[5] TMA stages, out[6] epilogue
- * warps per TMEM lane quadrant, out[7] records per candidate list (n_out >= 8).
- * b200_recommend_embed_tune (process-wide, not thread-safe; 0 keeps a value): epilogue warps per
- * TMEM lane quadrant of the main pass (2 or 3) and the rank coefficient c of the speculative
+ * per split, out[3] user tiles, out[4] sampled tiles per split, out[5] TMA stages, out[6] = 10 x CTAs
+ * per cluster (2: every item tile is fetched from L2 once per pair of user tiles and TMA-multicast to
+ * both CTAs) + MMA groups per item tile, out[7] records per candidate list (n_out >= 8).
+ * b200_recommend_embed_tune (process-wide, not thread-safe; 0 keeps a value): organisation code =
+ * 100 x cluster size (1|2) + 10 x MMA groups per tile (1|2) + epilogue variant (3 vote-free group
+ * tests, 0 one vote per group; default 223), and the rank coefficient c of the speculative
  * threshold (about c * k_row items are expected above it). */
-int b200_recommend_embed_tune(int32_t epilogue_warps_per_quadrant, float pre_rank_coef);
+int b200_recommend_embed_tune(int32_t organisation_code, float pre_rank_coef);
+/* profiling diagnostics only (results are wrong while level > 0): ablate parts of the main pass */
+int b200_recommend_embed_debug(int32_t ablate_level);
 int b200_recommend_embed_plan(int64_t B, int64_t N, int32_t d, int32_t K, int32_t* out, int32_t n_out);
 int b200_embed_catalog_bytes(int64_t N, int32_t d, size_t* bytes);
 int b200_embed_catalog_prepare(const float* I, int64_t ldi, int64_t N, int32_t d, void* catalog,
@@ -359,6 +363,8 @@ int b200_l2_normalize_rows(float* x, int64_t ld, int64_t R, int32_t d, void* str
  *                     libreco/tfops/features.py:165-218); out[r,:Kp] = softmax_t(Dense1(sigmoid(
  *                     Dense16([q,k,q-k,q*k]))) * rsqrt(Kp), t < len) weighted sum of the keys
  *                     (libreco/layers/attention.py:45-64).  k1 [4Kp,16], b1 [16], k2 [16], b2.
+ *                     k1 == NULL selects the reference's use_tf_attention=True variant
+ *                     (attention.py:5-25: dot-product scores <q, k_t>, masked softmax, no weights).
  *                     Kp <= 128, T <= 256. */
 int b200_seq_pool(const float* E, int64_t lde, int32_t d, int64_t pad_index, const int32_t* seqs,
                   int64_t ld_seq, const int32_t* lens, int32_t T, const int64_t* users, int64_t R,

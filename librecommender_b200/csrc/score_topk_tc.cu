@@ -100,6 +100,8 @@ struct SweepParams {
   int32_t B_pad, m_tiles, n_splits, tiles_per_split, total_tiles, KB, nstage;
   int32_t n_pre_tiles;        // sampled tiles per split in the pre-pass
   int32_t capg, trig;         // records per list / uncounted records that trigger a compaction
+  int32_t ablate;             // diagnostics only (b200_recommend_embed_debug): 0 = normal operation
+  uint32_t hint_ns;           // suspend-time hint of the mbarrier waits
   const RowMeta* meta;        // [B_pad]
   uint32_t* row_tau_key;      // [B_pad]  running max of tau (order-preserving key)
   int32_t* row_status;        // [B_pad]  1 = needs the exact path
@@ -342,10 +344,17 @@ __device__ __forceinline__ void step_range(uint32_t tc, int j, int& first, int& 
   }
 }
 
-template <bool PRE, int W, int EPI>
+// CL = CTAs per thread-block cluster (1 or 2).  With CL = 2 the two CTAs of a cluster work on two
+// ADJACENT user tiles of the SAME item split in lock step: every item tile is fetched from L2 once
+// per cluster — each CTA loads half of it and the TMA multicasts that half into both CTAs' shared
+// memory — which halves the L2 -> SM traffic of the item table (the pass is L2-bandwidth bound
+// otherwise: 64 user tiles x 128 MB per launch at C2).  NH = MMA groups per item tile (2: two N=128
+// halves with their own accumulator barriers, 1: one N=256 group, the user tile is read from shared
+// memory once per k-step instead of twice).
+template <bool PRE, int W, int EPI, int CL, int NH>
 __global__ void __launch_bounds__(sweep_threads(W), 1)
 sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const SweepParams p) {
+             const __grid_constant__ CUtensorMap tmBh, const SweepParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B tiles
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -355,8 +364,13 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_units = p.m_tiles * p.n_splits;
+  // work units: (item split, user tile); a cluster takes CL adjacent user tiles of one split
+  const int crank = CL > 1 ? (int)ptx::cluster_ctarank() : 0;
+  const int cid = (int)blockIdx.x / CL, n_clusters = (int)gridDim.x / CL;
+  const int m_groups = p.m_tiles / CL;                    // host guarantees m_tiles % CL == 0
+  const int n_units = m_groups * p.n_splits;              // units per cluster-rank
   constexpr int STRIDE = PRE ? PRE_STRIDE : 1;
+  constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1u);
   // Warp roles.  The warp scheduler of an SM sub-partition prefers the HIGHEST warp id among its
   // ready warps, so the two single-lane roles that feed the tensor core (MMA issuer, TMA producer)
   // take the two highest warp ids: they are asleep on an mbarrier most of the time and must win the
@@ -364,12 +378,14 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   constexpr int WARP_MMA = 4 * W, WARP_TMA = 4 * W + 1;   // epilogue: warps 0 .. 4W-1 (quadrant = warp % 4)
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.nstage; ++s) { ptx::mbar_init(&ss->full[s], 1); ptx::mbar_init(&ss->empty[s], 1); }
+    // a shared-memory stage is written by the multicasts of all CL producers and may be refilled only
+    // when the MMAs of all CL CTAs have read it: `empty` collects one (multicast) commit per CTA
+    for (int s = 0; s < p.nstage; ++s) { ptx::mbar_init(&ss->full[s], 1); ptx::mbar_init(&ss->empty[s], CL); }
     for (int a = 0; a < 2; ++a)
       for (int hh = 0; hh < 2; ++hh) {
         ptx::mbar_init(&ss->tmem_full[a][hh], 1);
-        // one arrival per processed step: 4 lane quadrants x 2 steps per column half
-        ptx::mbar_init(&ss->tmem_empty[a][hh], 4 * (STEPS_PER_TILE / 2));
+        // one arrival per processed step: 4 lane quadrants x the steps of one MMA group
+        ptx::mbar_init(&ss->tmem_empty[a][hh], 4 * (STEPS_PER_TILE / NH));
       }
     ptx::mbar_init(&ss->a_full, 1);
     ptx::mbar_init(&ss->a_empty, 1);
@@ -383,6 +399,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();     // the peer's barriers exist before anything is multicast to them
   ptx::tc_fence_after();
   const uint32_t tmem_base = ss->tmem_base;
 
@@ -392,20 +409,27 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       uint32_t uiter = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++uiter) {
-        const int split = unit / p.m_tiles, m = unit % p.m_tiles;
+      for (int unit = cid; unit < n_units; unit += n_clusters, ++uiter) {
+        const int split = unit / m_groups, m = (unit % m_groups) * CL + crank;
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
-        ptx::mbar_wait_backoff(&ss->a_empty, (uiter & 1) ^ 1);
+        ptx::mbar_wait_hint(&ss->a_empty, (uiter & 1) ^ 1, p.hint_ns);
         ptx::mbar_arrive_expect_tx(&ss->a_full, (uint32_t)(p.KB * A_KB_BYTES));
         for (int kb = 0; kb < p.KB; ++kb)
           ptx::tma_load_2d(smemA + (size_t)kb * A_KB_BYTES, &tmA, &ss->a_full, kb * KBLK, m * TM);
         for (int t = t0; t < t1; t += STRIDE) {
-          ptx::mbar_wait_backoff(&ss->empty[stage], phase ^ 1);
+          ptx::mbar_wait_hint(&ss->empty[stage], phase ^ 1, p.hint_ns);
+          // the whole tile lands in THIS CTA's stage: its own share plus the peers' multicast shares
           ptx::mbar_arrive_expect_tx(&ss->full[stage], (uint32_t)(p.KB * B_KB_BYTES));
           uint8_t* dst = smemB + (size_t)stage * p.KB * B_KB_BYTES;
-          for (int kb = 0; kb < p.KB; ++kb)
-            ptx::tma_load_2d(dst + (size_t)kb * B_KB_BYTES, &tmB, &ss->full[stage], kb * KBLK, t * TN);
+          for (int kb = 0; kb < p.KB; ++kb) {
+            if (CL == 1) {
+              ptx::tma_load_2d(dst + (size_t)kb * B_KB_BYTES, &tmB, &ss->full[stage], kb * KBLK, t * TN);
+            } else {   // rows [crank * TN/CL, +TN/CL) of the tile, delivered to every CTA of the cluster
+              ptx::tma_load_2d_multicast(dst + (size_t)kb * B_KB_BYTES + (size_t)crank * (B_KB_BYTES / CL), &tmBh,
+                                         &ss->full[stage], kb * KBLK, t * TN + crank * (TN / CL), CL_MASK);
+            }
+          }
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         }
       }
@@ -413,7 +437,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(TM, TN / 2);
+      constexpr uint32_t idesc = ptx::umma_idesc_f16_f32(TM, TN / NH);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -421,24 +445,24 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       uint32_t uiter = 0;
       const uint32_t a_addr = ptx::smem_u32(smemA);
       const uint32_t b_addr = ptx::smem_u32(smemB);
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++uiter) {
-        const int split = unit / p.m_tiles;
+      for (int unit = cid; unit < n_units; unit += n_clusters, ++uiter) {
+        const int split = unit / m_groups;
         const int t0 = split * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
-        ptx::mbar_wait(&ss->a_full, uiter & 1);
+        ptx::mbar_wait_hint(&ss->a_full, uiter & 1, p.hint_ns);
         for (int t = t0; t < t1; t += STRIDE) {
-          ptx::mbar_wait(&ss->full[stage], phase);
-          // one N=128 MMA group per column half: each half of the accumulator has its own
-          // full / empty barrier pair, so its epilogue steps start as soon as that half is done
+          ptx::mbar_wait_hint(&ss->full[stage], phase, p.hint_ns);
+          // NH MMA groups per item tile, each with its own accumulator full / empty barrier pair, so the
+          // epilogue steps of a group start as soon as that group is done
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            ptx::mbar_wait(&ss->tmem_empty[acc][hh], acc_phase ^ 1);
+          for (int hh = 0; hh < NH; ++hh) {
+            ptx::mbar_wait_hint(&ss->tmem_empty[acc][hh], acc_phase ^ 1, p.hint_ns);
             ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN + hh * (TN / 2));
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN + hh * (TN / NH));
             for (int kb = 0; kb < p.KB; ++kb) {
               const uint64_t da = ptx::umma_desc_sw128_kmajor(a_addr + (uint32_t)(kb * A_KB_BYTES));
               const uint64_t db = ptx::umma_desc_sw128_kmajor(
-                  b_addr + (uint32_t)((stage * p.KB + kb) * B_KB_BYTES + hh * (TN / 2) * KBLK * 2));
+                  b_addr + (uint32_t)((stage * p.KB + kb) * B_KB_BYTES + hh * (TN / NH) * KBLK * 2));
 #pragma unroll
               for (int k4 = 0; k4 < KBLK / 16; ++k4) {
                 // advance 16 fp16 = 32 bytes inside the 128-byte swizzled row: +2 in the >>4 field
@@ -446,9 +470,11 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                               (uint32_t)((kb | k4) != 0));
               }
             }
-            ptx::umma_commit(&ss->tmem_full[acc][hh]);   // this half is ready for its epilogue steps
+            ptx::umma_commit(&ss->tmem_full[acc][hh]);   // this group is ready for its epilogue steps
           }
-          ptx::umma_commit(&ss->empty[stage]);           // smem stage reusable when these MMAs finish
+          // the shared-memory stage is reusable (in every CTA of the cluster) when these MMAs have read it
+          if (CL == 1) ptx::umma_commit(&ss->empty[stage]);
+          else ptx::umma_commit_multicast(&ss->empty[stage], CL_MASK);
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
@@ -464,8 +490,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t tc = 0;                        // running tile count of this CTA (accumulator stage / phase)
     const float pinf = __int_as_float(0x7f800000);
     const float ninf = __int_as_float(0xff800000);
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-      const int split = unit / p.m_tiles, m = unit % p.m_tiles;
+    for (int unit = cid; unit < n_units; unit += n_clusters) {
+      const int split = unit / m_groups, m = (unit % m_groups) * CL + crank;
       const int t0 = split * p.tiles_per_split;
       const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
       const int grow = m * TM + trow;
@@ -478,7 +504,8 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int t = t0; t < t1; t += STRIDE, ++ti, ++tc) {
           const int acc = (int)(tc & 1u);
           const uint32_t acc_phase = (tc >> 1) & 1u;
-          ptx::mbar_wait(&ss->tmem_full[acc][j], acc_phase);     // W_PRE == 2: warp j <-> column half j
+          constexpr int PH = NH == 2 ? 1 : 0;    // W_PRE == 2: warp j <-> column half j (group j when NH == 2)
+          ptx::mbar_wait_hint(&ss->tmem_full[acc][j * PH], acc_phase, p.hint_ns);
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + j * (TN / 2));
           float tm = ninf;
@@ -497,7 +524,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tm = fmaxf(tm, fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7])));
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][j]);
+            if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][j * PH]);
           }
           // tiles that contain zero-padded item rows would bias the estimate: drop them
           if ((int64_t)(t + 1) * TN > p.N) tm = ninf;
@@ -519,6 +546,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const uint32_t gk = __ldcg(p.row_tau_key + grow);
         if (gk != 0u) tau = key_to_float(gk);
       }
+      if (p.ablate >= 1) tau = pinf;   // diagnostics: nothing is ever collected (cold path only)
 
       // compaction of the lists flagged in `need` (warp-uniform mask)
       auto compact_flagged = [&](uint32_t need) {
@@ -562,11 +590,30 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         step_range<W>(tc, j, s_first, s_end, s_stride);
 #pragma unroll 1
         for (int s = s_first; s < s_end; s += s_stride) {   // ONE copy of the step body for every step
-          const int half = s >> 1;
-          ptx::mbar_wait(&ss->tmem_full[acc][half], acc_phase);
+          const int half = NH == 2 ? (s >> 1) : 0;
+          ptx::mbar_wait_hint(&ss->tmem_full[acc][half], acc_phase, p.hint_ns);
           ptx::tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + s * STEP);
           const int n_base = t * TN + s * STEP;
+          if (EPI == 9) {   // DIAGNOSTIC instantiation: the epilogue only hands the accumulator back (no read)
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
+            continue;
+          }
+          if (EPI == 8) {   // DIAGNOSTIC instantiation: tensor-memory read only (xor keeps the load alive)
+            uint32_t r[STEP];
+            ptx::tmem_ld_32x32b_x64(taddr, r);
+            ptx::tmem_ld_wait_regs64(r);
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
+            uint32_t x = 0;
+#pragma unroll
+            for (int c = 0; c < STEP; ++c) x ^= r[c];
+            if (x == 0x7fc00001u) my_b[0] = (int32_t)x;
+            continue;
+          }
           if (EPI != 1) {
             // ---- variants 0 / 2 / 3: every test and push on register-resident scores ------------------
             uint32_t r[STEP];
@@ -682,6 +729,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();     // no CTA leaves while a peer may still multicast to it
   if (warp == WARP_MMA) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
@@ -1143,13 +1191,17 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 
 // ---- tuning knobs (defaults compiled in; b200_recommend_embed_tune overrides them per process) ----
-static int g_epi_w = 2;            // epilogue warps per TMEM lane quadrant in the main pass: 2 or 3
-static int g_epi = 0;              // epilogue variant of the main pass (see sweep_kernel): 0 group tests, 1 step test
+static int g_epi = 3;              // epilogue variant of the main pass: 3 vote-free group tests, 0 one vote per group
+static int g_cluster = 2;          // 2 = pairs of user tiles share every item tile through TMA multicast, 1 = off
+static int g_nh = 2;               // MMA groups per item tile (2 x N=128 or 1 x N=256)
+static int g_ablate = 0;           // b200_recommend_embed_debug
+static int g_hint_ns = 20000;      // suspend-time hint of the mbarrier waits in the sweep kernels
 static float g_pre_coef = 2.67f;   // speculative rank target = g_pre_coef * k_row (+ 16 / sampled fraction)
 
 struct Plan {
   int B_pad, d_pad, KB, m_tiles, total_tiles, n_splits, tiles_per_split, nstage, n_pre_tiles;
   int W, n_lists, capg, trig;
+  int CL, NH;        // CTAs per cluster (TMA multicast of the item tiles), MMA groups per item tile
   bool use_pre;
   float pre_scale;   // g_pre_coef x sampled fraction of the item tiles (see prep_users_kernel)
   int64_t N_pad;
@@ -1163,11 +1215,14 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->KB = pl->d_pad / KBLK;
   B200_REQUIRE(pl->KB >= 1 && pl->KB <= MAX_KB, "fused scorer supports embed width <= %d (got %d)",
                MAX_KB * KBLK, d);
-  pl->B_pad = pad_to(B, TM);
+  // clusters of 2 CTAs take two adjacent user tiles: worth it from two user tiles on (B > 128)
+  pl->CL = (g_cluster == 2 && B > TM) ? 2 : 1;
+  pl->NH = g_nh;
+  pl->B_pad = pad_to(B, TM * pl->CL);
   pl->N_pad = (N + TN - 1) / TN * TN;
   pl->m_tiles = pl->B_pad / TM;
   pl->total_tiles = (int)(pl->N_pad / TN);
-  pl->W = g_epi_w;
+  pl->W = 2;
   // item splits: minimise makespan = waves * (tiles per split + per-unit overhead)
   const int ovh = 12;
   long best = -1;
@@ -1221,18 +1276,52 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   return 0;
 }
 
-template <bool PRE, int W, int EPI>
+template <bool PRE, int EPI, int CL, int NH>
 static int launch_sweep(int grid, const Plan& pl, cudaStream_t stream, const CUtensorMap& tmA,
-                        const CUtensorMap& tmB, const SweepParams& sp) {
+                        const CUtensorMap& tmB, const CUtensorMap& tmBh, const SweepParams& sp) {
+  constexpr int W = 2;
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel<PRE, W, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel<PRE, W, EPI, CL, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       227 * 1024));
     attr_set = true;
   }
-  sweep_kernel<PRE, W, EPI><<<grid, sweep_threads(W), pl.smem_bytes, stream>>>(tmA, tmB, sp);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)sweep_threads(W), 1, 1);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, sweep_kernel<PRE, W, EPI, CL, NH>, tmA, tmB, tmBh, sp));
   count_launch();
   return 0;
+}
+
+template <bool PRE>
+static int launch_sweep_dispatch(int grid, const Plan& pl, int epi, cudaStream_t stream, const CUtensorMap& tmA,
+                                 const CUtensorMap& tmB, const CUtensorMap& tmBh, const SweepParams& sp) {
+  // the pre-pass has one epilogue; the main pass: variant 3 (vote-free group tests) or 0 (one vote per group)
+  if (!PRE && (epi == 8 || epi == 9)) {   // diagnostic instantiations (no cluster, both MMA group counts)
+    if (epi == 8) return pl.NH == 2 ? launch_sweep<PRE, 8, 1, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
+                                    : launch_sweep<PRE, 8, 1, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
+    return pl.NH == 2 ? launch_sweep<PRE, 9, 1, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
+                      : launch_sweep<PRE, 9, 1, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
+  }
+  if (PRE || epi != 0) {
+    if (pl.CL == 2) return pl.NH == 2 ? launch_sweep<PRE, 3, 2, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
+                                      : launch_sweep<PRE, 3, 2, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
+    return pl.NH == 2 ? launch_sweep<PRE, 3, 1, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
+                      : launch_sweep<PRE, 3, 1, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
+  }
+  if (pl.CL == 2) return pl.NH == 2 ? launch_sweep<PRE, 0, 2, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
+                                    : launch_sweep<PRE, 0, 2, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
+  return pl.NH == 2 ? launch_sweep<PRE, 0, 1, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
+                    : launch_sweep<PRE, 0, 1, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
 }
 
 }  // namespace tc
@@ -1275,18 +1364,27 @@ extern "C" int b200_embed_catalog_prepare(const float* I, int64_t ldi, int64_t N
 }
 
 extern "C" int b200_recommend_embed_tune(int32_t epilogue_warps_per_quadrant, float pre_rank_coef) {
-  if (epilogue_warps_per_quadrant != 0) {   // W + 10 * (epilogue variant)
-    const int w = epilogue_warps_per_quadrant % 10, epi = epilogue_warps_per_quadrant / 10;
-    B200_REQUIRE(w >= 2 && w <= 4 && epi >= 0 && epi <= 3,
-                 "b200_recommend_embed_tune: epilogue warps per quadrant must be 2, 3 or 4 (+ 10 x variant 0..3)");
-    g_epi_w = w;
-    g_epi = epi;
+  if (epilogue_warps_per_quadrant != 0) {   // 100 * cluster size + 10 * MMA groups per tile + epilogue variant
+    const int cl = epilogue_warps_per_quadrant / 100, nh = (epilogue_warps_per_quadrant / 10) % 10,
+              epi = epilogue_warps_per_quadrant % 10;
+    B200_REQUIRE((cl == 1 || cl == 2) && (nh == 1 || nh == 2) && (epi == 0 || epi == 3 || ((epi == 8 || epi == 9) && cl == 1)),
+                 "b200_recommend_embed_tune: code = 100 * cluster (1|2) + 10 * MMA groups (1|2) + epilogue (0|3)");
+    g_cluster = cl; g_nh = nh; g_epi = epi;
   }
   if (pre_rank_coef != 0.f) {
     B200_REQUIRE(pre_rank_coef >= 1.0f && pre_rank_coef <= 16.f,
                  "b200_recommend_embed_tune: rank coefficient out of [1, 16]");
     g_pre_coef = pre_rank_coef;
   }
+  return 0;
+}
+
+// Diagnostics (profiling only; results are WRONG while level 1 is set): 1 = the main pass collects nothing.
+extern "C" int b200_recommend_embed_debug(int32_t ablate_level) {
+  // levels >= 100: suspend-time hint (ns) of the mbarrier waits of the sweep kernels = level - 100
+  if (ablate_level >= 100) { g_hint_ns = ablate_level - 100; return 0; }
+  B200_REQUIRE(ablate_level >= 0 && ablate_level <= 1, "b200_recommend_embed_debug: level 0..1 (or 100 + hint ns)");
+  g_ablate = ablate_level;
   return 0;
 }
 
@@ -1297,7 +1395,7 @@ extern "C" int b200_recommend_embed_plan(int64_t B, int64_t N, int32_t d, int32_
   Plan pl;
   if (int rc = make_plan(B, N, d, &pl)) return rc;
   out[0] = pl.use_pre ? 1 : 0; out[1] = pl.n_splits; out[2] = pl.tiles_per_split; out[3] = pl.m_tiles;
-  out[4] = pl.n_pre_tiles; out[5] = pl.nstage; out[6] = pl.W; out[7] = pl.capg;
+  out[4] = pl.n_pre_tiles; out[5] = pl.nstage; out[6] = pl.CL * 10 + pl.NH; out[7] = pl.capg;
   return 0;
 }
 
@@ -1348,9 +1446,10 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   // cnt and ghist are adjacent in the workspace: one memset
   B200_CUDA_OK(cudaMemsetAsync(cnt, 0, (pl.off_cs - pl.off_cnt), stream));
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmBh;
   if (int rc = make_tmap(&tmA, A, pl.B_pad, pl.d_pad, TM)) return rc;
   if (int rc = make_tmap(&tmB, Ih, pl.N_pad, pl.d_pad, TN)) return rc;
+  if (int rc = make_tmap(&tmBh, Ih, pl.N_pad, pl.d_pad, TN / 2)) return rc;   // per-CTA share of a tile (cluster of 2)
 
   SweepParams sp;
   sp.N = N; sp.B_pad = pl.B_pad; sp.m_tiles = pl.m_tiles; sp.n_splits = pl.n_splits;
@@ -1358,7 +1457,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   sp.nstage = pl.nstage; sp.n_pre_tiles = pl.n_pre_tiles; sp.capg = pl.capg; sp.trig = pl.trig;
   sp.meta = meta; sp.row_tau_key = tau;
   sp.row_status = status; sp.ghist = ghist; sp.cand_s = cand_s; sp.cand_b = cand_b; sp.cand_cnt = cnt;
-  sp.blockmax = bm;
+  sp.blockmax = bm; sp.ablate = g_ablate; sp.hint_ns = (uint32_t)g_hint_ns;
   const int n_units = pl.m_tiles * pl.n_splits;
   static int sm_count = 0;
   if (!sm_count) {
@@ -1366,28 +1465,19 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
     B200_CUDA_OK(cudaGetDevice(&dev));
     B200_CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = n_units < sm_count ? n_units : sm_count;
+  int grid = n_units < sm_count ? n_units : sm_count;
+  grid -= grid % pl.CL;                                    // whole clusters
 
   if (ev_sweep_start) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_start, stream));
   if (pl.use_pre) {
-    if (int rc = launch_sweep<true, W_PRE, 0>(grid, pl, stream, tmA, tmB, sp)) return rc;
+    if (int rc = launch_sweep_dispatch<true>(grid, pl, 3, stream, tmA, tmB, tmBh, sp)) return rc;
     guess_kernel<<<(unsigned)(pl.B_pad / 32), GUESS_THREADS, 0, stream>>>(
         bm, W_PRE * pl.n_splits * pl.n_pre_tiles, pl.B_pad, meta, tau, guess);
     count_launch();
   } else {
     B200_CUDA_OK(cudaMemsetAsync(guess, 0, (size_t)pl.B_pad * 4, stream));
   }
-  {
-    int rc;
-    // main-pass variants (b200_recommend_embed_tune): W = 2 with every epilogue variant, W = 3 / 4 with variant 0
-    if (pl.W == 3) rc = launch_sweep<false, 3, 0>(grid, pl, stream, tmA, tmB, sp);
-    else if (pl.W == 4) rc = launch_sweep<false, 4, 0>(grid, pl, stream, tmA, tmB, sp);
-    else if (g_epi == 1) rc = launch_sweep<false, 2, 1>(grid, pl, stream, tmA, tmB, sp);
-    else if (g_epi == 2) rc = launch_sweep<false, 2, 2>(grid, pl, stream, tmA, tmB, sp);
-    else if (g_epi == 3) rc = launch_sweep<false, 2, 3>(grid, pl, stream, tmA, tmB, sp);
-    else rc = launch_sweep<false, 2, 0>(grid, pl, stream, tmA, tmB, sp);
-    if (rc) return rc;
-  }
+  if (int rc = launch_sweep_dispatch<false>(grid, pl, g_epi, stream, tmA, tmB, tmBh, sp)) return rc;
   if (ev_sweep_stop) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_stop, stream));
 
   FinalizeParams fp;

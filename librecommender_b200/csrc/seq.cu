@@ -179,6 +179,65 @@ din_attention_kernel(const float* __restrict__ G, int64_t ldg, int Kp, const int
   }
 }
 
+// tf_attention (use_tf_attention=True; libreco/layers/attention.py:5-25 = tf.keras.layers.Attention(
+// use_scale=False) on [query] x keys with the sequence mask): a_t = <q, k_t>, masked positions get
+// -1e9 (their softmax weight underflows to exactly 0), out = sum_t softmax(a)_t k_t.  One warp per row.
+__global__ void __launch_bounds__(128)
+dot_attention_kernel(const float* __restrict__ G, int64_t ldg, int Kp, const int64_t* __restrict__ items,
+                     const int32_t* __restrict__ seqs, int64_t ld_seq, const int32_t* __restrict__ lens, int T,
+                     const int64_t* __restrict__ users, int64_t R, int64_t grid, int64_t off,
+                     float* __restrict__ out, int64_t ld_out) {
+  __shared__ float s_att[4][MAX_T];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 4 + wid;
+  if (r >= R) return;
+  const int64_t sr = seq_row_of(users, r, grid, off);
+  const int64_t item = grid > 0 ? (r + off) % grid : items[r];
+  const int32_t* s = seqs + sr * ld_seq;
+  const int len = min(max(lens[sr], 0), T);
+  const int TK = (Kp + 31) / 32;
+  float q[MAX_TK];
+#pragma unroll
+  for (int t = 0; t < MAX_TK; ++t) {
+    const int c = lane + t * 32;
+    q[t] = (t < TK && c < Kp) ? __ldg(G + item * ldg + c) : 0.f;
+  }
+  float amax = -3.0e38f;
+  for (int t = 0; t < len; ++t) {
+    const int64_t key = __ldg(s + t);
+    float a = 0.f;
+#pragma unroll
+    for (int tt = 0; tt < MAX_TK; ++tt) {
+      const int c = lane + tt * 32;
+      if (tt < TK && c < Kp) a = fmaf(q[tt], __ldg(G + key * ldg + c), a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) s_att[wid][t] = a;
+    amax = fmaxf(amax, a);
+  }
+  __syncwarp();
+  float den = 0.f;
+  for (int t = lane; t < len; t += 32) den += expf(s_att[wid][t] - amax);
+  den = warp_sum(den);
+  float acc[MAX_TK];
+#pragma unroll
+  for (int tt = 0; tt < MAX_TK; ++tt) acc[tt] = 0.f;
+  for (int t = 0; t < len; ++t) {
+    const int64_t key = __ldg(s + t);
+    const float p = expf(s_att[wid][t] - amax) / den;
+#pragma unroll
+    for (int tt = 0; tt < MAX_TK; ++tt) {
+      const int c = lane + tt * 32;
+      if (tt < TK && c < Kp) acc[tt] = fmaf(p, __ldg(G + key * ldg + c), acc[tt]);
+    }
+  }
+#pragma unroll
+  for (int tt = 0; tt < MAX_TK; ++tt) {
+    const int c = lane + tt * 32;
+    if (tt < TK && c < Kp) out[r * ld_out + c] = acc[tt];
+  }
+}
+
 // ---- DIN all-items scoring, hoisted (SURVEY.md 8d "a7 DIN all-items": per user one GEMM
 // [N, K'] x [K', 16 len] on the tensor cores instead of N x len re-associated mat-vecs) -------------
 // For ONE user the keys k_t are fixed and only the query q_n = G[n] varies:
@@ -313,11 +372,19 @@ extern "C" int b200_din_attention(const float* G, int64_t ldg, int32_t Kp, const
                                   const int64_t* users, int64_t R, int64_t grid_items,
                                   int64_t row_offset, const float* k1, const float* b1,
                                   const float* k2, float b2, float* out, int64_t ld_out, void* stream) {
-  B200_REQUIRE(G && seqs && lens && users && out && k1 && b1 && k2, "b200_din_attention: null pointer");
+  B200_REQUIRE(G && seqs && lens && users && out, "b200_din_attention: null pointer");
   B200_REQUIRE(grid_items > 0 || items, "b200_din_attention: item ids missing");
   B200_REQUIRE(Kp >= 1 && Kp <= 32 * MAX_TK, "b200_din_attention: feature width %d outside [1, %d]", Kp, 32 * MAX_TK);
   B200_REQUIRE(T >= 1 && T <= MAX_T, "b200_din_attention: sequence length %d outside [1, %d]", T, MAX_T);
   if (R == 0) return 0;
+  if (k1 == nullptr) {   // use_tf_attention=True: plain dot-product attention, no learned weights
+    dot_attention_kernel<<<(unsigned)ceil_div64(R, 4), 128, 0, (cudaStream_t)stream>>>(
+        G, ldg, Kp, items, seqs, ld_seq, lens, T, users, R, grid_items, row_offset, out, ld_out);
+    count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  B200_REQUIRE(b1 && k2, "b200_din_attention: attention MLP weights missing");
   AttW w; w.k1 = k1; w.b1 = b1; w.k2 = k2; w.b2 = b2;
   din_attention_kernel<<<(unsigned)ceil_div64(R, 4), 128, 0, (cudaStream_t)stream>>>(
       G, ldg, Kp, items, seqs, ld_seq, lens, T, users, R, grid_items, row_offset, w, out, ld_out);

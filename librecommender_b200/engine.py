@@ -131,7 +131,7 @@ class EmbedScorer:
         _lib.check(_lib.lib.b200_recommend_embed_plan(min(int(B), FUSED_ROWS_PER_CALL), self.n_items, self.d,
                                                       int(n_rec), out, 8))
         keys = ("use_pre", "n_splits", "tiles_per_split", "m_tiles", "n_pre_tiles", "tma_stages",
-                "epilogue_warps_per_quadrant", "records_per_list")
+                "cluster_x10_plus_mma_groups", "records_per_list")
         return dict(zip(keys, [int(v) for v in out]))
 
     def _fused_chunk(self, uid_chunk, n_rec, use_filter, out_ids, out_scores, status):

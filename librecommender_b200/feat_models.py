@@ -834,7 +834,9 @@ class YouTubeRanking(_SeqModelBase):
 
 
 class DIN(_SeqModelBase):
-    """libreco/algorithms/din.py:165-250 (inference, use_tf_attention=False)."""
+    """libreco/algorithms/din.py:165-250 (inference; ``use_tf_attention`` either way: with
+    ``weights["use_tf_attention"]`` the attention is the weight-free dot-product form of
+    ``layers/attention.py:5-25`` and all-items scoring runs on the flat (user, item) grid)."""
 
     def __init__(self, spec, weights, recent_seqs, recent_seq_lens, user_consumed=None, task="ranking",
                  device=None):
@@ -843,10 +845,15 @@ class DIN(_SeqModelBase):
         self._rebuild_item_features()
         self.Kp = int(self.G.shape[1])
         self.extra = self.Kp
-        att = weights["attention"]
-        self.att = dict(k1=_dev(att["k1"], self.device, torch.float32), b1=_dev(att["b1"], self.device, torch.float32),
-                        k2=_dev(np.asarray(att["k2"]).reshape(-1), self.device, torch.float32),
-                        b2=float(np.asarray(att["b2"]).reshape(-1)[0]))
+        # use_tf_attention=True (din.py:247-248, layers/attention.py:5-25): dot-product attention, no weights
+        self.use_tf_attention = bool(weights.get("use_tf_attention", False)) or weights.get("attention") is None
+        if self.use_tf_attention:
+            self.att = dict(k1=None, b1=None, k2=None, b2=0.0)
+        else:
+            att = weights["attention"]
+            self.att = dict(k1=_dev(att["k1"], self.device, torch.float32), b1=_dev(att["b1"], self.device, torch.float32),
+                            k2=_dev(np.asarray(att["k2"]).reshape(-1), self.device, torch.float32),
+                            b2=float(np.asarray(att["b2"]).reshape(-1)[0]))
         self.mlp = self._upload_mlp(weights["mlp"])
 
     def _rebuild_item_features(self):
@@ -866,7 +873,7 @@ class DIN(_SeqModelBase):
         dims = [w.shape[0] for w, _, _ in self.mlp]
         n = len(dims)
         return (self.K <= 64 and n in (2, 3) and dims[0] <= 256 and dims[1] <= 64 and (n == 2 or dims[2] <= 32)
-                and self.Kp % 4 == 0)
+                and self.Kp % 4 == 0 and not self.use_tf_attention)
 
     def _side_concat(self, which, ids_d):
         torch = self._torch

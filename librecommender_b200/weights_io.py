@@ -78,3 +78,89 @@ def save_default_recs(path, model_name, default_recs):
 
 def load_default_recs(path, model_name):
     return np.load(os.path.join(path, f"{model_name}_default_recs.npz"))["default_recs"]
+
+
+# ------------------------------------------------------------------------------------------------
+# TensorFlow auto-generated variable names of the un-named layers
+# ------------------------------------------------------------------------------------------------
+# The reference never names its heads: ``tf_dense(units=1)`` (layers/dense.py:52-80) becomes a
+# ``tf.keras.layers.Dense`` / ``tf.layers.dense`` whose variables TensorFlow names ``dense``,
+# ``dense_1``, ... in CREATION ORDER; ``tf.layers.batch_normalization`` likewise
+# (``batch_normalization``, ``batch_normalization_1``, ...), prefixed by the enclosing
+# ``tf.variable_scope`` — ``dense_nn`` opens ``<name>`` (default "mlp") and names its Dense layers
+# ``<name>_layer<i>`` (layers/dense.py:28-33).  The creation order per model is read off the graph
+# builders: fm.py:152-171, deepfm.py:158-174, din.py:205-218 (+ the "attention" dense_nn,
+# layers/attention.py:47-53), youtube_ranking.py:208-217, two_tower.py:400-409.  No TensorFlow exists in
+# this environment, so this table is RESTATED from TensorFlow's documented uniquifying rule and is
+# unverified against a real checkpoint; ``resolve_tf_names`` therefore checks every expected name AND
+# shape against the file and reports exactly what is missing instead of guessing.
+def _bn_names(prefix):
+    return {k: f"{prefix}/{v}:0" for k, v in (("gamma", "gamma"), ("beta", "beta"), ("mean", "moving_mean"),
+                                             ("var", "moving_variance"))}
+
+
+def _mlp_names(scope, n_layers, use_bn):
+    names = {"kernels": [f"{scope}/{scope}_layer{i}/kernel:0" for i in range(1, n_layers + 1)],
+             "biases": [f"{scope}/{scope}_layer{i}/bias:0" for i in range(1, n_layers + 1)]}
+    if use_bn:
+        names["bn_in"] = _bn_names(f"{scope}/batch_normalization")
+        names["bns"] = [_bn_names(f"{scope}/batch_normalization_{i}") for i in range(1, n_layers)]
+    return names
+
+
+def default_tf_names(model_name, n_hidden, use_bn, use_tf_attention=False):
+    """{engine weight key: TF variable name (or nested dict / list of names)} for the auto-named
+    variables of `model_name` in {"FM", "DeepFM", "DIN", "YouTubeRanking", "TwoTower"}."""
+    if model_name == "FM":
+        out = {"lin_kernel": "dense/kernel:0", "lin_bias": "dense/bias:0",
+               "pw_kernel": "dense_1/kernel:0", "pw_bias": "dense_1/bias:0"}
+        if use_bn:
+            out["fm_bn"] = _bn_names("batch_normalization")
+        return out
+    if model_name == "DeepFM":
+        return {"lin_kernel": "dense/kernel:0", "lin_bias": "dense/bias:0", "mlp": _mlp_names("mlp", n_hidden, use_bn),
+                "out_kernel": "dense_1/kernel:0", "out_bias": "dense_1/bias:0"}
+    if model_name == "DIN":
+        out = {"mlp": _mlp_names("mlp", n_hidden, use_bn), "out_kernel": "dense/kernel:0", "out_bias": "dense/bias:0"}
+        if not use_tf_attention:
+            out["attention"] = {"k1": "attention/attention_layer1/kernel:0", "b1": "attention/attention_layer1/bias:0",
+                                "k2": "attention/attention_layer2/kernel:0", "b2": "attention/attention_layer2/bias:0"}
+        return out
+    if model_name == "YouTubeRanking":
+        return {"mlp": _mlp_names("mlp", n_hidden, use_bn), "out_kernel": "dense/kernel:0", "out_bias": "dense/bias:0"}
+    if model_name == "TwoTower":
+        return {"user_tower": _mlp_names("user_tower", n_hidden, use_bn),
+                "item_tower": _mlp_names("item_tower", n_hidden, use_bn)}
+    raise ValueError(f"no TensorFlow name table for model `{model_name}`")
+
+
+def resolve_tf_names(npz, names):
+    """Read the (possibly nested) name table out of `npz`; a missing variable raises a ``KeyError`` that
+    lists the expected name and the names the file does contain."""
+    def take(n):
+        if isinstance(n, dict):
+            return {k: take(v) for k, v in n.items()}
+        if isinstance(n, list):
+            return [take(v) for v in n]
+        if n not in npz:
+            have = sorted(k for k in npz.files if not k.startswith("embedding/"))
+            raise KeyError(f"TF variable `{n}` not in the file; non-embedding variables present: {have}")
+        return np.asarray(npz[n])
+    return take(names)
+
+
+def load_reference_tf_model(path, model_name, arch, n_hidden, use_bn, use_tf_attention=False, extra_names=None):
+    """Engine weight dict of a model saved by the reference (``save_tf_variables``,
+    utils/save_load.py:70-98) WITHOUT a hand-written name map: the embedding-scope variables by their
+    fixed names, the heads / MLPs / batch-norms through :func:`default_tf_names` (override single entries
+    with `extra_names`)."""
+    from .feat_models import from_tf_variables
+
+    npz = np.load(os.path.join(path, f"{model_name}_tf_variables.npz"))
+    w = from_tf_variables(npz)
+    names = default_tf_names(arch, n_hidden, use_bn, use_tf_attention)
+    names.update(extra_names or {})
+    w.update(resolve_tf_names(npz, names))
+    if use_tf_attention:
+        w["use_tf_attention"] = True
+    return w

@@ -240,11 +240,29 @@ def din_attention(q, keys, lens, att, dtype=np.float32):
     return (p[:, :, None] * keys).sum(axis=1)
 
 
+def tf_attention(q, keys, lens, dtype=np.float32):
+    """attention.py:5-25 = tf.keras.layers.Attention(use_scale=False)([q[:, None], keys], mask=[None, m])
+    (third-party: Keras dot-product attention): scores <q, k_t>, masked positions -= 1e9, softmax over t,
+    output sum_t p_t k_t."""
+    B, T, _ = keys.shape
+    a = np.einsum("bk,btk->bt", q.astype(dtype), keys.astype(dtype))
+    mask = np.arange(T)[None, :] < np.asarray(lens).reshape(-1, 1)
+    a = a - dtype(1.0e9) * (~mask)
+    a = a - a.max(axis=1, keepdims=True)
+    p = np.exp(a)
+    p = p / p.sum(axis=1, keepdims=True)
+    return (p[:, :, None] * keys).sum(axis=1)
+
+
 def din_forward(w, spec, users, items, seqs, lens, sparse=None, dense=None, dtype=np.float32):
-    """din.py:182-218 — logits (use_tf_attention=False)."""
-    w = _cast(w, dtype)
+    """din.py:182-250 — logits; ``w["use_tf_attention"]`` selects tf_attention (din.py:247-248)."""
+    use_tf = bool(w.get("use_tf_attention", False))
+    w = _cast({k: v for k, v in w.items() if k != "use_tf_attention"}, dtype)
     G = item_feature_table(w, spec, dtype)
-    att_out = din_attention(G[items], G[seqs], lens, w["attention"], dtype)
+    if use_tf:
+        att_out = tf_attention(G[items], G[seqs], lens, dtype)
+    else:
+        att_out = din_attention(G[items], G[seqs], lens, w["attention"], dtype)
     parts = [w["user_embeds"][users], w["item_embeds"][items]]
     if sparse is not None:
         parts.append(w["sparse_embeds"][sparse].reshape(len(users), -1))

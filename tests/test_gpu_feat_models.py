@@ -140,6 +140,35 @@ def test_din_logits(use_bn):
     _close(model.logits(users, items).cpu().numpy()[ok], ref64[ok], 1e-5)
 
 
+def test_din_use_tf_attention():
+    """use_tf_attention=True (din.py:247-248): weight-free dot-product attention; predict rows and the
+    all-items grid agree with the restatement of tf.keras.layers.Attention(use_scale=False)."""
+    from librecommender_b200.feat_models import DIN
+    from oracle import ranking as orc
+    from oracle import tf_models as tm
+
+    rng, spec, consumed, seqs, lens = _seq_case(23)
+    w = tm.make_seq_weights(rng, spec, 16, (64, 32), True, din=True)
+    w["use_tf_attention"] = True
+    model = DIN(spec, w, seqs, lens, consumed)
+    assert model.use_tf_attention
+    users = rng.integers(0, 151, size=500)
+    items = rng.integers(0, 400, size=500)
+    sparse, dense = tm.row_features(spec, users, items)
+    ref64 = tm.din_forward(w, spec, users, items, seqs[users], np.maximum(lens[users], 0), sparse, dense,
+                           dtype=np.float64)
+    ok = lens[users] > 0
+    _close(model.logits(users, items).cpu().numpy()[ok], ref64[ok], 1e-5)
+    us = np.array([u for u in range(0, 150, 13) if lens[u] > 0])
+    N = spec["n_items"]
+    uu, ii = np.repeat(us, N), np.tile(np.arange(N), len(us))
+    sp, de = tm.row_features(spec, uu, ii)
+    preds = tm.din_forward(w, spec, uu, ii, seqs[uu], lens[uu], sp, de, dtype=np.float64).astype(np.float32)
+    got = model.recommend(us, 10, True)
+    ref = orc.rank_recommendations("ranking", us.tolist(), preds, 10, N, consumed, True)
+    assert orc.near_tie_mask(ref, got, preds.reshape(len(us), N), 1e-5).all()
+
+
 @pytest.mark.parametrize("hidden,hoisted", [((64, 32), True), ((128, 64, 32), True), ((300, 64, 32), False)])
 def test_youtube_ranking_logits_and_recommend(hidden, hoisted):
     """recommend goes through the hoisted all-items scorer when the MLP fits the pair kernel, else

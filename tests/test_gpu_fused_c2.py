@@ -2,7 +2,7 @@
 speculative pre-pass (``sweep_kernel<PRE>`` + ``guess_kernel`` + the status-3 check in
 ``finalize_kernel``) — C2's catalogue size (1 M items, d = 64, top-100, Zipf consumed lists with
 500-item users), a wider embedding with a ragged last tile / short last split, embeddings far from
-unit scale, and the 3-warps-per-quadrant epilogue variant.
+unit scale, and the kernel-organisation variants (cluster multicast on / off, MMA groups, epilogue).
 
 Contract (reference: libreco/recommendation/recommend.py:57-78 + ranking.py:10-56):
 * rows the fused path accepts (status 0) equal the exact materialised path BIT FOR BIT (ids and
@@ -121,8 +121,11 @@ def test_wide_embedding_ragged_catalogue_and_scale():
     _check(sc, U, I, csr, users, K, n_oracle=96, min_ok_frac=0.97)
 
 
-def test_three_warps_per_quadrant_variant():
-    """The W = 3 epilogue organisation (round-robin 64-column steps) gives the same answers."""
+@pytest.mark.parametrize("code", [123, 113, 213, 220])
+def test_kernel_organisation_variants(code):
+    """The tuning variants of the sweep give the same answers as the default (cluster of 2 with TMA
+    multicast, two MMA groups per tile, vote-free group tests = code 223): no cluster (1xx), one N=256
+    MMA group per tile (x1x), one vote per group (xx0)."""
     from librecommender_b200 import _lib
     from librecommender_b200.engine import EmbedScorer
 
@@ -132,9 +135,9 @@ def test_three_warps_per_quadrant_variant():
     sc = EmbedScorer(U, I, N, csr, n_users=n_users)
     users = np.random.default_rng(2).choice(n_users, size=2048, replace=False).astype(np.int64)
     try:
-        _lib.check(_lib.lib.b200_recommend_embed_tune(3, 0.0))
+        _lib.check(_lib.lib.b200_recommend_embed_tune(code, 0.0))
         plan = sc.fused_plan(len(users), K)
-        assert plan["use_pre"] == 1 and plan["epilogue_warps_per_quadrant"] == 3, plan
+        assert plan["use_pre"] == 1 and plan["cluster_x10_plus_mma_groups"] == code // 10, plan
         _check(sc, U, I, csr, users, K, n_oracle=64, min_ok_frac=0.97)
     finally:
-        _lib.check(_lib.lib.b200_recommend_embed_tune(2, 0.0))
+        _lib.check(_lib.lib.b200_recommend_embed_tune(223, 0.0))

@@ -62,3 +62,40 @@ def test_gather_and_scatter_rows_single_gpu():
     expect = full.clone().index_add_(0, ids, grads)
     assert float((t.local - expect).abs().max()) < 1e-4
     assert t.lookup(ids[:0]).shape == (0, 48)
+
+
+@pytest.mark.parametrize("G,d", [(1, 16), (2, 16), (4, 64), (3, 20), (8, 32)])
+def test_peer_gather_and_scatter_kernels_virtual_shards(G, d):
+    """b200_peer_gather_rows / b200_peer_scatter_add_rows with G shards that all live on THIS GPU: the
+    row -> (shard id % G, slot id / G) addressing, the vectorised and the generic paths, the float
+    atomics — exactly what runs over NVLink peer pointers when the shards belong to G GPUs."""
+    import ctypes
+
+    import torch
+
+    from librecommender_b200 import _lib
+
+    n_rows = 100_003
+    g = torch.Generator(device="cuda").manual_seed(G * 100 + d)
+    full = torch.randn(n_rows, d, device="cuda", generator=g)
+    rows_loc = -(-n_rows // G)
+    shards = []
+    for r in range(G):
+        s = torch.zeros(rows_loc, d, device="cuda")
+        part = full[r::G]
+        s[: part.shape[0]] = part
+        shards.append(s)
+    ptrs = (ctypes.c_void_p * G)(*[s.data_ptr() for s in shards])
+    ids = torch.randint(0, n_rows, (300_001,), device="cuda", generator=g)
+    out = torch.empty(ids.numel(), d, device="cuda")
+    _lib.check(_lib.lib.b200_peer_gather_rows(ptrs, G, d, d, _lib.ptr(ids), ids.numel(), _lib.ptr(out), d,
+                                              _lib.current_stream()))
+    assert torch.equal(out, full[ids])
+    grads = torch.randn(ids.numel(), d, device="cuda", generator=g)
+    _lib.check(_lib.lib.b200_peer_scatter_add_rows(ptrs, G, d, d, _lib.ptr(ids), ids.numel(), _lib.ptr(grads), d,
+                                                   _lib.current_stream()))
+    expect = full.clone().index_add_(0, ids, grads)
+    got = torch.empty_like(full)
+    for r in range(G):
+        got[r::G] = shards[r][: full[r::G].shape[0]]
+    assert float((got - expect).abs().max()) < 2e-4

@@ -45,3 +45,57 @@ def test_reference_loader_reads_our_default_recs(tmp_path):
 
     io.save_default_recs(str(tmp_path), "m", np.arange(2000))
     np.testing.assert_array_equal(ref_load(str(tmp_path), "m"), np.arange(2000))
+
+
+@pytest.mark.parametrize("arch,n_hidden,use_bn", [("FM", 0, True), ("DeepFM", 3, True), ("DeepFM", 2, False),
+                                                   ("DIN", 3, True), ("YouTubeRanking", 2, True), ("TwoTower", 2, True)])
+def test_auto_named_tf_variables_resolve_without_hand_written_map(tmp_path, arch, n_hidden, use_bn):
+    """A ``*_tf_variables.npz`` laid out with TensorFlow's creation-order names loads into the engine
+    weight structure with no name map from the caller; a missing variable is reported by name."""
+    from librecommender_b200 import weights_io as io
+
+    rng = np.random.default_rng(0)
+    names = io.default_tf_names(arch, n_hidden, use_bn)
+    flat = {}
+
+    def fill(n):
+        if isinstance(n, dict):
+            return {k: fill(v) for k, v in n.items()}
+        if isinstance(n, list):
+            return [fill(v) for v in n]
+        flat[n] = rng.standard_normal((3, 2)).astype(np.float32)
+        return flat[n]
+
+    expect = fill(names)
+    assert len(set(flat)) == len(flat)                                   # every variable has its own name
+    flat["embedding/user_embeds_var:0"] = rng.standard_normal((5, 4)).astype(np.float32)
+    flat["embedding/item_embeds_var:0"] = rng.standard_normal((6, 4)).astype(np.float32)
+    np.savez(os.path.join(tmp_path, "m_tf_variables.npz"), **flat)
+    w = io.load_reference_tf_model(str(tmp_path), "m", arch, n_hidden, use_bn)
+
+    def same(a, b):
+        if isinstance(a, dict):
+            assert set(a) == set(b)
+            for k in a:
+                same(a[k], b[k])
+        elif isinstance(a, list):
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                same(x, y)
+        else:
+            np.testing.assert_array_equal(a, b)
+
+    for k in names:
+        same(expect[k], w[k])
+    np.testing.assert_array_equal(w["user_embeds"], flat["embedding/user_embeds_var:0"])
+    # the name table follows the creation order of the reference's graph builders
+    if arch == "DeepFM" and use_bn:
+        assert names["mlp"]["bn_in"]["gamma"] == "mlp/batch_normalization/gamma:0"
+        assert names["mlp"]["kernels"][1] == "mlp/mlp_layer2/kernel:0"
+        assert names["mlp"]["bns"][0]["mean"] == "mlp/batch_normalization_1/moving_mean:0"
+        assert names["out_kernel"] == "dense_1/kernel:0" and names["lin_kernel"] == "dense/kernel:0"
+    some = next(n for n in flat if not n.startswith("embedding/"))
+    del flat[some]
+    np.savez(os.path.join(tmp_path, "bad_tf_variables.npz"), **flat)
+    with pytest.raises(KeyError, match=some.replace("/", "/")):
+        io.load_reference_tf_model(str(tmp_path), "bad", arch, n_hidden, use_bn)

@@ -27,27 +27,34 @@ def main():
     import librecommender_b200.engine as eng
 
     sc = EmbedScorer(U, I, args.items, ConsumedCSR.from_device_tensors(indptr, idx), n_users=args.users, device=dev)
-    variants = [(w, c, b) for b in (8192, 16384) for w in (2, 3, 4) for c in (2.67,)] + [(2, 2.0, 8192), (4, 2.0, 8192), (3, 2.0, 8192)]
+    variants = [(w, 2.0, b) for b in (8192, 16384) for w in (223, 213, 123, 113)]
     if os.environ.get("VARIANTS"):
         variants = [tuple(float(x) if "." in x else int(x) for x in v.split(":")) for v in os.environ["VARIANTS"].split(",")]
     rng = np.random.default_rng(5)
     steps, warm = 12, 3
     ref_ids = None
-    for w, c, b in variants:
+    for var in variants:
+        w, c, b = var[:3]
+        ablate = int(var[3]) if len(var) > 3 else 0
+        hint = int(var[4]) if len(var) > 4 else 20000
+        _lib.check(_lib.lib.b200_recommend_embed_debug(100 + hint))
+        _lib.check(_lib.lib.b200_recommend_embed_debug(ablate))
         _lib.check(_lib.lib.b200_recommend_embed_tune(int(w), float(c)))
         eng.FUSED_ROWS_PER_CALL = int(b)
         batches = [torch.from_numpy(rng.choice(args.users, size=int(b), replace=False).astype(np.int64)).to(dev)
                    for _ in range(steps + warm)]
+        run = (lambda bt: sc.recommend_fused(bt, args.topk, True, False)[0]) if ablate else \
+            (lambda bt: sc.recommend_device(bt, args.topk, True, False))
         for i in range(warm):
-            sc.recommend_device(batches[i], args.topk, True, False)
+            run(batches[i])
         torch.cuda.synchronize()
         sc.events = []
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fb = 0
         for i in range(warm, warm + steps):
-            out = sc.recommend_device(batches[i], args.topk, True, False)
-            fb += sc.last_fallback_rows
+            out = run(batches[i])
+            fb += sc.last_fallback_rows if not ablate else 0
         e1.record()
         torch.cuda.synchronize()
         sweep = float(np.mean([a.elapsed_time(z) for a, z in sc.events]))
@@ -57,7 +64,7 @@ def main():
         # parity spot check of the last batch against the exact path (256 rows)
         ex = sc.recommend_exact(batches[-1][:256], args.topk, True, False)
         same = bool((out[:256] == ex).all())
-        print(json.dumps({"W": w, "coef": c, "rows_per_launch": b, "sweep_ms": sweep, "step_ms_sync": step,
+        print(json.dumps({"ablate": ablate, "hint_ns": hint, "W": w, "coef": c, "rows_per_launch": b, "sweep_ms": sweep, "step_ms_sync": step,
                           "tflops": flops / sweep / 1e9, "users_per_s_sync": b / step * 1e3,
                           "fallback_rows": fb, "ids_equal_exact_256": same, "plan": sc.fused_plan(b, args.topk)}),
               flush=True)
