@@ -98,8 +98,8 @@ def test_recommend_tf_feat_requires_engine_and_validates():
     with pytest.raises(_lib.B200Error):
         recommend_tf_feat(model, [0], 5, None, None, True, False)
     model.b200_engine = object()
-    with pytest.raises(NotImplementedError):
-        recommend_tf_feat(model, 0, 5, {"sex": "F"}, None, True, False)
+    with pytest.raises(ValueError, match="Batch inference"):        # overrides are single-user only (recommend.py:39-54)
+        recommend_tf_feat(model, [0, 1], 5, {"sex": "F"}, None, True, False)
     with pytest.raises(ValueError, match="exceeds num of items"):
         recommend_tf_feat(model, [0], 11, None, None, True, False)
 
