@@ -52,7 +52,8 @@ constexpr int TM = 128;        // users per tile (UMMA M)
 constexpr int TN = 256;        // items per tile (UMMA N)
 constexpr int KBLK = 64;       // fp16 per 128-byte swizzled row
 constexpr int CAPG_MAX = 256;  // candidate GROUP records per (row, list), upper limit (runtime capg <= this)
-constexpr int GW = 8;          // a record = the 8 coarse scores of one 8-column group + its first item id
+constexpr int GW = 8;          // a record = the 8 coarse scores of one 8-column group + its first item id ...
+constexpr int REC = 12;        // ... in 12 words (48 bytes: two 16-byte score halves, the id, padding)
 constexpr int NB = 1024;       // bins of the per-row global coarse-score histogram
 constexpr int STEP = 64;       // accumulator columns per epilogue step (one tcgen05.ld.32x32b.x64)
 constexpr int STEPS_PER_TILE = TN / STEP;   // 4
@@ -106,8 +107,7 @@ struct SweepParams {
   uint32_t* row_tau_key;      // [B_pad]  running max of tau (order-preserving key)
   int32_t* row_status;        // [B_pad]  1 = needs the exact path
   uint32_t* ghist;            // [B_pad][NB]  coarse-score histogram of every counted candidate
-  float* cand_s;              // [W*n_splits][B_pad][capg][GW]  group records: 8 coarse scores ...
-  int32_t* cand_b;            // [W*n_splits][B_pad][capg]      ... and the item id of the first column
+  float* cand_r;              // [W*n_splits][B_pad][capg][REC]  group records: 8 coarse scores + first item id
   int32_t* cand_cnt;          // [W*n_splits][B_pad]            records per list
   float* blockmax;            // [W_PRE*n_splits][n_pre_tiles][B_pad]   (pre-pass output)
 };
@@ -240,7 +240,7 @@ __device__ __forceinline__ int score_bin(float s, float R, float inv_w) {
 
 // Warp-cooperative compaction of one candidate list of one row (rare in the main pass: the
 // speculative threshold keeps the lists short; this is the rigorous safety net and the normal
-// mode when no pre-pass ran).  A list holds GROUP records (8 scores + first item id).
+// mode when no pre-pass ran).  A list holds GROUP records (8 scores + first item id, REC words).
 //  1. every element >= tau_old of every record pushed since the previous compaction is counted
 //     ONCE into the row's global coarse-score histogram (shared by all lists / CTAs of the row);
 //  2. the histogram is read back: the highest bin whose suffix count reaches k gives a rigorous
@@ -248,7 +248,7 @@ __device__ __forceinline__ int score_bin(float s, float R, float inv_w) {
 //     (counts are a subset of the items at or above each edge), tau = edge - eps2;
 //  3. the list is rewritten keeping the records whose maximum is >= tau.
 // Records live in registers (CAPG_MAX/32 per lane).  Returns the new count; *tau_out = new tau.
-__device__ __noinline__ int compact_row(float* __restrict__ ls, int32_t* __restrict__ lb, int n,
+__device__ __noinline__ int compact_row(float* __restrict__ ls, int n,
                                            int n_counted, int k, float eps2, float R, float tau_old,
                                            uint32_t* __restrict__ gh, int lane, int32_t n_items,
                                            float* tau_out) {
@@ -262,9 +262,9 @@ __device__ __noinline__ int compact_row(float* __restrict__ ls, int32_t* __restr
     e0[j] = e1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     bs[j] = 0;
     if (i < n) {
-      e0[j] = *reinterpret_cast<const float4*>(ls + (size_t)i * GW);
-      e1[j] = *reinterpret_cast<const float4*>(ls + (size_t)i * GW + 4);
-      bs[j] = lb[i];
+      e0[j] = *reinterpret_cast<const float4*>(ls + (size_t)i * REC);
+      e1[j] = *reinterpret_cast<const float4*>(ls + (size_t)i * REC + 4);
+      bs[j] = reinterpret_cast<const int32_t*>(ls)[(size_t)i * REC + 8];
     }
   }
 #pragma unroll
@@ -322,9 +322,9 @@ __device__ __noinline__ int compact_row(float* __restrict__ ls, int32_t* __restr
     const uint32_t kb = __ballot_sync(0xffffffffu, keep);
     if (keep) {
       const int pos = w + __popc(kb & ((1u << lane) - 1u));
-      *reinterpret_cast<float4*>(ls + (size_t)pos * GW) = e0[j];
-      *reinterpret_cast<float4*>(ls + (size_t)pos * GW + 4) = e1[j];
-      lb[pos] = bs[j];
+      *reinterpret_cast<float4*>(ls + (size_t)pos * REC) = e0[j];
+      *reinterpret_cast<float4*>(ls + (size_t)pos * REC + 4) = e1[j];
+      reinterpret_cast<int32_t*>(ls)[(size_t)pos * REC + 8] = bs[j];
     }
     w += __popc(kb);
   }
@@ -333,16 +333,6 @@ __device__ __noinline__ int compact_row(float* __restrict__ ls, int32_t* __restr
 }
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-
-// Steps of running tile `tc` that warp `j` of its quadrant handles: s = first, first + stride, ... < end
-template <int W>
-__device__ __forceinline__ void step_range(uint32_t tc, int j, int& first, int& end, int& stride) {
-  if (W == 2) { first = 2 * j; end = 2 * j + 2; stride = 1; }
-  else if (W == 4) { first = j; end = j + 1; stride = 1; }
-  else {   // W == 3: step s of running tile tc has running index 4 tc + s, and 4 tc mod 3 == tc mod 3
-    first = (j + 3 - (int)(tc % 3u)) % 3; end = STEPS_PER_TILE; stride = 3;
-  }
-}
 
 // CL = CTAs per thread-block cluster (1 or 2).  With CL = 2 the two CTAs of a cluster work on two
 // ADJACENT user tiles of the SAME item split in lock step: every item tile is fetched from L2 once
@@ -537,8 +527,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // ---- main pass ----
       const RowMeta meta = p.meta[grow];
       const int64_t list0 = (int64_t)list_id * p.B_pad + (m * TM + q * 32);  // lane 0's slot
-      float* my_s = p.cand_s + (list0 + lane) * (int64_t)(p.capg * GW);
-      int32_t* my_b = p.cand_b + (list0 + lane) * (int64_t)p.capg;
+      float* my_r = p.cand_r + (list0 + lane) * (int64_t)(p.capg * REC);
       bool active = meta.active != 0;
       float tau = active ? ninf : pinf;
       int cnt = 0, n_counted = 0;
@@ -560,8 +549,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const float s_R = __shfl_sync(0xffffffffu, meta.R, src);
           const float s_tau = __shfl_sync(0xffffffffu, tau, src);
           float new_tau;
-          const int w = compact_row(p.cand_s + (list0 + src) * (int64_t)(p.capg * GW),
-                                    p.cand_b + (list0 + src) * (int64_t)p.capg, s_cnt, s_cntd, s_k, s_e, s_R,
+          const int w = compact_row(p.cand_r + (list0 + src) * (int64_t)(p.capg * REC), s_cnt, s_cntd, s_k, s_e, s_R,
                                     s_tau, p.ghist + (int64_t)(m * TM + q * 32 + src) * NB, lane, (int32_t)p.N,
                                     &new_tau);
           if (lane == src) {
@@ -570,7 +558,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             // also pick up what other lists of this row published meanwhile
             tau = fmaxf(new_tau, key_to_float(max(__ldcg(p.row_tau_key + grow), 1u)));
             atomicMax(p.row_tau_key + grow, float_to_key(new_tau));
-            if (w > p.capg - 16) {  // too many near-ties to bound: hand the row to the exact path
+            if (w > p.capg - 32) {  // too many near-ties to bound: hand the row to the exact path
               active = false;
               tau = pinf;
               cnt = 0;
@@ -583,147 +571,98 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
       // Zero-padded item rows of the last tile (ids >= N, coarse score exactly 0) may be collected when
       // tau <= 0; compact_row and finalize_kernel ignore ids >= N, so the sweep needs no tail code.
+      // Every warp owns two adjacent 64-column steps of every tile (W = 2).
       for (int t = t0; t < t1; ++t, ++tc) {
         const int acc = (int)(tc & 1u);
         const uint32_t acc_phase = (tc >> 1) & 1u;
-        int s_first, s_end, s_stride;
-        step_range<W>(tc, j, s_first, s_end, s_stride);
-#pragma unroll 1
-        for (int s = s_first; s < s_end; s += s_stride) {   // ONE copy of the step body for every step
-          const int half = NH == 2 ? (s >> 1) : 0;
-          ptx::mbar_wait_hint(&ss->tmem_full[acc][half], acc_phase, p.hint_ns);
+        const int cnt0 = cnt;
+        if (NH == 1) {   // one MMA group per tile: one wait, the accumulator goes back after the second read
+          ptx::mbar_wait_hint(&ss->tmem_full[acc][0], acc_phase, p.hint_ns);
           ptx::tc_fence_after();
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int s = 2 * j + i;
+          if (NH == 2 && i == 0) {   // group j of the tile belongs to warp j alone
+            ptx::mbar_wait_hint(&ss->tmem_full[acc][j], acc_phase, p.hint_ns);
+            ptx::tc_fence_after();
+          }
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + s * STEP);
           const int n_base = t * TN + s * STEP;
           if (EPI == 9) {   // DIAGNOSTIC instantiation: the epilogue only hands the accumulator back (no read)
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
+            if (i == 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_cnt(&ss->tmem_empty[acc][NH == 2 ? j : 0], 2);
+            }
             continue;
           }
-          if (EPI == 8) {   // DIAGNOSTIC instantiation: tensor-memory read only (xor keeps the load alive)
-            uint32_t r[STEP];
-            ptx::tmem_ld_32x32b_x64(taddr, r);
-            ptx::tmem_ld_wait_regs64(r);
+          uint32_t r[STEP];
+          ptx::tmem_ld_32x32b_x64(taddr, r);
+          ptx::tmem_ld_wait_regs64(r);
+          if (i == 1) {   // both reads of this warp are done: the MMA issuer may reuse the accumulator
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
+            if (lane == 0) ptx::mbar_arrive_cnt(&ss->tmem_empty[acc][NH == 2 ? j : 0], 2);
+          }
+          if (EPI == 8) {   // DIAGNOSTIC instantiation: tensor-memory read only (xor keeps the load alive)
             uint32_t x = 0;
 #pragma unroll
             for (int c = 0; c < STEP; ++c) x ^= r[c];
-            if (x == 0x7fc00001u) my_b[0] = (int32_t)x;
+            if (x == 0x7fc00001u) my_r[0] = __uint_as_float(x);
             continue;
           }
-          if (EPI != 1) {
-            // ---- variants 0 / 2 / 3: every test and push on register-resident scores ------------------
-            uint32_t r[STEP];
-            ptx::tmem_ld_32x32b_x64(taddr, r);
-            ptx::tmem_ld_wait_regs64(r);
-            // the accumulator columns of this step are in registers: hand them back to the MMA issuer now
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
-            float g[STEP / 8];
+          float g[STEP / 8];
 #pragma unroll
-            for (int gq = 0; gq < STEP / 8; ++gq) {
-              const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
-              const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
-              g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
-            }
-            auto push_group = [&](int gq) {   // this lane's group gq goes to its candidate list WHOLE
-              float4* dst = reinterpret_cast<float4*>(my_s + (size_t)cnt * GW);
-              dst[0] = make_float4(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]),
-                                   __uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
-              dst[1] = make_float4(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]),
-                                   __uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
-              my_b[cnt] = n_base + gq * 8;
-              ++cnt;
-            };
-            if (EPI == 0) {
-              // variant 0: warp-uniform tests, one vote per 8-column group (cold group: 3 instructions)
-              bool pushed = false;
+          for (int gq = 0; gq < STEP / 8; ++gq) {
+            const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
+            const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+            g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
+          }
+          if (EPI == 5) {
+            // ONE warp vote per 64-column step on its maximum (cold step: max tree + 7 instructions); a hot
+            // step writes every 8-column group that reaches tau in its lane as ONE 48-byte record (8 coarse
+            // scores + the first item id) with PREDICATED stores — no branches: lanes / groups without a hit
+            // issue the stores with a false predicate.  finalize_kernel sorts out which of the 8 scores count.
+            const float mm = fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]));
+            if (__any_sync(0xffffffffu, mm >= tau)) {
 #pragma unroll
               for (int gq = 0; gq < STEP / 8; ++gq) {
-                if (__any_sync(0xffffffffu, g[gq] >= tau)) {
-                  if (g[gq] >= tau) push_group(gq);
-                  pushed = true;
-                }
+                float* dst = my_r + (size_t)cnt * REC;
+                const int32_t idv = n_base + gq * 8;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "setp.ge.f32 p, %0, %1;\n\t"
+                    "@p st.global.v4.b32 [%2], {%3, %4, %5, %6};\n\t"
+                    "@p st.global.v4.b32 [%2+16], {%7, %8, %9, %10};\n\t"
+                    "@p st.global.b32 [%2+32], %11;\n\t}"
+                    ::"f"(g[gq]), "f"(tau), "l"(dst), "r"(r[gq * 8 + 0]), "r"(r[gq * 8 + 1]), "r"(r[gq * 8 + 2]),
+                    "r"(r[gq * 8 + 3]), "r"(r[gq * 8 + 4]), "r"(r[gq * 8 + 5]), "r"(r[gq * 8 + 6]),
+                    "r"(r[gq * 8 + 7]), "r"(idv)
+                    : "memory");
+                cnt += (g[gq] >= tau) ? 1 : 0;
               }
-              if (pushed)   // warp-uniform
-                compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > p.trig) || (cnt > p.capg - 8)));
-            } else if (EPI == 2) {
-              // variant 2: ONE vote per 64-column step; hot steps build the per-lane group mask, OR-reduce
-              // it (REDUX) and run the pushes under independent uniform tests
-              const float mm = fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]));
-              if (__any_sync(0xffffffffu, mm >= tau)) {
-                uint32_t hm = 0;
-#pragma unroll
-                for (int gq = 0; gq < STEP / 8; ++gq) hm |= (g[gq] >= tau) ? (1u << gq) : 0u;
-                const uint32_t any = __reduce_or_sync(0xffffffffu, hm);
-#pragma unroll
-                for (int gq = 0; gq < STEP / 8; ++gq)
-                  if (any & (1u << gq))
-                    if (hm & (1u << gq)) push_group(gq);
-                compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > p.trig) || (cnt > p.capg - 8)));
-              }
-            } else {
-              // variant 3: no votes at all in the group tests: divergent per-lane branches straight from the
-              // compare (the hardware skips a push block no lane takes); one vote per step for the overflow check
-              const int cnt0 = cnt;
-#pragma unroll
-              for (int gq = 0; gq < STEP / 8; ++gq)
-                if (g[gq] >= tau) push_group(gq);
-              if (__any_sync(0xffffffffu, cnt != cnt0))
-                compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > p.trig) || (cnt > p.capg - 8)));
             }
-            continue;
-          }
-          // ---- variant 1: one test per step, hot groups re-read from tensor memory ------------------
-          float g[STEP / 8];
-          {
-            uint32_t r[STEP];
-            ptx::tmem_ld_32x32b_x64(taddr, r);
-            ptx::tmem_ld_wait_regs64(r);
+          } else {
+            // variant 3: group tests as divergent per-lane branches straight from the compare
 #pragma unroll
             for (int gq = 0; gq < STEP / 8; ++gq) {
-              const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
-              const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
-              g[gq] = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
-            }
-          }   // the 64 accumulator values are dead from here on: only the 8 group maxima stay in registers
-          // ONE warp-uniform test per 64-column step (cold steps: max tree + 3 instructions).
-          const float mm = fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]));
-          if (__any_sync(0xffffffffu, mm >= tau)) {
-            // hot step: per-lane mask of the 8-column groups at or above tau, OR-reduced over the warp
-            // (one REDUX).  Every group that is hot in some lane is RE-READ from tensor memory (8 columns,
-            // warp-uniform dynamic address) and pushed WHOLE by the lanes it is hot in (two 16-byte stores
-            // + its first item id); finalize_kernel sorts out which of its 8 scores are candidates.
-            uint32_t hm = 0;
-#pragma unroll
-            for (int gq = 0; gq < STEP / 8; ++gq) hm |= (g[gq] >= tau) ? (1u << gq) : 0u;
-            uint32_t any = __reduce_or_sync(0xffffffffu, hm);
-#pragma unroll 1
-            while (any) {
-              const int gq = __ffs(any) - 1;
-              any &= any - 1;
-              uint32_t v[8];
-              ptx::tmem_ld_32x32b_x8(taddr + (uint32_t)(gq * 8), v);
-              ptx::tmem_ld_wait_regs8(v);
-              if ((hm >> gq) & 1u) {
-                float4* dst = reinterpret_cast<float4*>(my_s + (size_t)cnt * GW);
-                dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-                dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-                my_b[cnt] = n_base + gq * 8;
+              if (g[gq] >= tau) {
+                float4* dst = reinterpret_cast<float4*>(my_r + (size_t)cnt * REC);
+                dst[0] = make_float4(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]),
+                                     __uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
+                dst[1] = make_float4(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]),
+                                     __uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
+                reinterpret_cast<int32_t*>(dst)[8] = n_base + gq * 8;
                 ++cnt;
               }
             }
-            compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > p.trig) || (cnt > p.capg - 8)));
           }
-          // this step's accumulator columns are no longer needed: hand them back to the MMA issuer
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&ss->tmem_empty[acc][half]);
         }
+        // one overflow / compaction check per TILE (a tile adds at most 16 records to a list)
+        if (EPI != 8 && EPI != 9)
+          if (__any_sync(0xffffffffu, cnt != cnt0))
+            compact_flagged(__ballot_sync(0xffffffffu, (cnt - n_counted > p.trig) || (cnt > p.capg - 24)));
       }
       p.cand_cnt[list0 + lane] = cnt;
     }
@@ -812,8 +751,7 @@ struct FinalizeParams {
   int32_t* row_status;
   const uint32_t* row_tau_key;     // [B_pad] final threshold of the row (speculative start or rigorous raises)
   const uint32_t* tau_guess_key;   // [B_pad] speculative threshold used by the main pass (0 = none)
-  const float* cand_s;
-  const int32_t* cand_b;
+  const float* cand_r;
   const int32_t* cand_cnt;
   const float* U; int64_t ldu;
   const float* I; int64_t ldi;
@@ -896,10 +834,10 @@ finalize_kernel(const FinalizeParams p) {
           }
           const int j = g - s_off[lo];
           const int64_t slot = (int64_t)lo * p.B_pad + row;
-          const float4* ls = reinterpret_cast<const float4*>(p.cand_s + slot * (int64_t)(p.capg * GW)) + 2 * j;
+          const float4* ls = reinterpret_cast<const float4*>(p.cand_r + (slot * (int64_t)p.capg + j) * REC);
           a[q] = __ldcs(ls);
           b[q] = __ldcs(ls + 1);
-          base[q] = __ldcs(p.cand_b + slot * (int64_t)p.capg + j);
+          base[q] = __ldcs(reinterpret_cast<const int32_t*>(ls + 2));
         }
       }
 #pragma unroll
@@ -932,11 +870,11 @@ finalize_kernel(const FinalizeParams p) {
       for (int s = 0; s < p.n_lists; ++s) {
         const int64_t slot = (int64_t)s * p.B_pad + row;
         const int n = p.cand_cnt[slot];
-        const float* ls = p.cand_s + slot * (int64_t)(p.capg * GW);
-        const int32_t* lb = p.cand_b + slot * (int64_t)p.capg;
+        const float* ls = p.cand_r + slot * (int64_t)(p.capg * REC);
         for (int i = tid; i < n * GW; i += FIN_THREADS) {
-          const float v = ls[i];
-          if (v >= low && (int64_t)(lb[i / GW] + (i % GW)) < p.N) f(v, lb[i / GW] + (i % GW));
+          const float v = ls[(i / GW) * REC + (i % GW)];
+          const int32_t id = reinterpret_cast<const int32_t*>(ls)[(i / GW) * REC + 8] + (i % GW);
+          if (v >= low && (int64_t)id < p.N) f(v, id);
         }
       }
     }
@@ -1191,9 +1129,9 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 
 // ---- tuning knobs (defaults compiled in; b200_recommend_embed_tune overrides them per process) ----
-static int g_epi = 3;              // epilogue variant of the main pass: 3 vote-free group tests, 0 one vote per group
+static int g_epi = 5;              // epilogue variant of the main pass: 5 step vote + predicated stores, 3 divergent group tests
 static int g_cluster = 2;          // 2 = pairs of user tiles share every item tile through TMA multicast, 1 = off
-static int g_nh = 2;               // MMA groups per item tile (2 x N=128 or 1 x N=256)
+static int g_nh = 1;               // MMA groups per item tile (1 x N=256; 2 x N=128 re-reads the user tile: ~2x slower)
 static int g_ablate = 0;           // b200_recommend_embed_debug
 static int g_hint_ns = 20000;      // suspend-time hint of the mbarrier waits in the sweep kernels
 static float g_pre_coef = 2.67f;   // speculative rank target = g_pre_coef * k_row (+ 16 / sampled fraction)
@@ -1207,7 +1145,7 @@ struct Plan {
   int64_t N_pad;
   size_t smem_bytes;
   // workspace offsets
-  size_t off_A, off_meta, off_tau, off_guess, off_status, off_cnt, off_hist, off_cs, off_cb, off_bm, total;
+  size_t off_A, off_meta, off_tau, off_guess, off_status, off_cnt, off_hist, off_cs, off_bm, total;
 };
 
 static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
@@ -1269,17 +1207,15 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->off_status = off; off += al256((size_t)pl->B_pad * 4);
   pl->off_cnt = off; off += al256((size_t)pl->n_lists * pl->B_pad * 4);
   pl->off_hist = off; off += al256((size_t)pl->B_pad * NB * 4);
-  pl->off_cs = off; off += al256((size_t)pl->n_lists * pl->B_pad * pl->capg * GW * 4);
-  pl->off_cb = off; off += al256((size_t)pl->n_lists * pl->B_pad * pl->capg * 4);
+  pl->off_cs = off; off += al256((size_t)pl->n_lists * pl->B_pad * pl->capg * REC * 4);
   pl->off_bm = off; off += al256((size_t)W_PRE * pl->n_splits * pl->n_pre_tiles * pl->B_pad * 4);
   pl->total = off + 256;
   return 0;
 }
 
-template <bool PRE, int EPI, int CL, int NH>
+template <bool PRE, int W, int EPI, int CL, int NH>
 static int launch_sweep(int grid, const Plan& pl, cudaStream_t stream, const CUtensorMap& tmA,
                         const CUtensorMap& tmB, const CUtensorMap& tmBh, const SweepParams& sp) {
-  constexpr int W = 2;
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA_OK(cudaFuncSetAttribute(sweep_kernel<PRE, W, EPI, CL, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1302,26 +1238,31 @@ static int launch_sweep(int grid, const Plan& pl, cudaStream_t stream, const CUt
   return 0;
 }
 
-template <bool PRE>
-static int launch_sweep_dispatch(int grid, const Plan& pl, int epi, cudaStream_t stream, const CUtensorMap& tmA,
-                                 const CUtensorMap& tmB, const CUtensorMap& tmBh, const SweepParams& sp) {
-  // the pre-pass has one epilogue; the main pass: variant 3 (vote-free group tests) or 0 (one vote per group)
-  if (!PRE && (epi == 8 || epi == 9)) {   // diagnostic instantiations (no cluster, both MMA group counts)
-    if (epi == 8) return pl.NH == 2 ? launch_sweep<PRE, 8, 1, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
-                                    : launch_sweep<PRE, 8, 1, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
-    return pl.NH == 2 ? launch_sweep<PRE, 9, 1, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
-                      : launch_sweep<PRE, 9, 1, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
+// organisation = (epilogue warps per quadrant W, epilogue variant, cluster size CL, MMA groups NH); the
+// instantiated combinations are the default (W 2, variant 3, CL 2, NH 1) and its A/B neighbours
+static int launch_pre_dispatch(int grid, const Plan& pl, cudaStream_t stream, const CUtensorMap& tmA,
+                               const CUtensorMap& tmB, const CUtensorMap& tmBh, const SweepParams& sp) {
+  // the pre-pass has one epilogue (2 warps per quadrant, block maxima only)
+  if (pl.CL == 2) {
+    if (pl.NH == 1) return launch_sweep<true, 2, 3, 2, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
+    return launch_sweep<true, 2, 3, 2, 2>(grid, pl, stream, tmA, tmB, tmBh, sp);
   }
-  if (PRE || epi != 0) {
-    if (pl.CL == 2) return pl.NH == 2 ? launch_sweep<PRE, 3, 2, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
-                                      : launch_sweep<PRE, 3, 2, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
-    return pl.NH == 2 ? launch_sweep<PRE, 3, 1, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
-                      : launch_sweep<PRE, 3, 1, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
-  }
-  if (pl.CL == 2) return pl.NH == 2 ? launch_sweep<PRE, 0, 2, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
-                                    : launch_sweep<PRE, 0, 2, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
-  return pl.NH == 2 ? launch_sweep<PRE, 0, 1, 2>(grid, pl, stream, tmA, tmB, tmBh, sp)
-                    : launch_sweep<PRE, 0, 1, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
+  if (pl.NH == 1) return launch_sweep<true, 2, 3, 1, 1>(grid, pl, stream, tmA, tmB, tmBh, sp);
+  return launch_sweep<true, 2, 3, 1, 2>(grid, pl, stream, tmA, tmB, tmBh, sp);
+}
+
+static int launch_main_dispatch(int grid, const Plan& pl, int epi, cudaStream_t stream, const CUtensorMap& tmA,
+                                const CUtensorMap& tmB, const CUtensorMap& tmBh, const SweepParams& sp) {
+#define B200_SWEEP(E_, C_, N_) return launch_sweep<false, 2, E_, C_, N_>(grid, pl, stream, tmA, tmB, tmBh, sp)
+  // default: variant 5 (one vote per step + predicated record stores), one N=256 MMA group per tile,
+  // clusters of 2; the other instantiations are A/B points and diagnostics
+  if (epi == 8) { if (pl.NH == 2) B200_SWEEP(8, 1, 2); B200_SWEEP(8, 1, 1); }
+  if (epi == 9) { if (pl.NH == 2) B200_SWEEP(9, 1, 2); B200_SWEEP(9, 1, 1); }
+  if (pl.NH == 2) { if (pl.CL == 2) B200_SWEEP(5, 2, 2); B200_SWEEP(5, 1, 2); }
+  if (epi == 3) { if (pl.CL == 2) B200_SWEEP(3, 2, 1); B200_SWEEP(3, 1, 1); }
+  if (pl.CL == 2) B200_SWEEP(5, 2, 1);
+  B200_SWEEP(5, 1, 1);
+#undef B200_SWEEP
 }
 
 }  // namespace tc
@@ -1364,11 +1305,12 @@ extern "C" int b200_embed_catalog_prepare(const float* I, int64_t ldi, int64_t N
 }
 
 extern "C" int b200_recommend_embed_tune(int32_t epilogue_warps_per_quadrant, float pre_rank_coef) {
-  if (epilogue_warps_per_quadrant != 0) {   // 100 * cluster size + 10 * MMA groups per tile + epilogue variant
-    const int cl = epilogue_warps_per_quadrant / 100, nh = (epilogue_warps_per_quadrant / 10) % 10,
-              epi = epilogue_warps_per_quadrant % 10;
-    B200_REQUIRE((cl == 1 || cl == 2) && (nh == 1 || nh == 2) && (epi == 0 || epi == 3 || ((epi == 8 || epi == 9) && cl == 1)),
-                 "b200_recommend_embed_tune: code = 100 * cluster (1|2) + 10 * MMA groups (1|2) + epilogue (0|3)");
+  if (epilogue_warps_per_quadrant != 0) {   // organisation code: 100 * cluster size + 10 * MMA groups per tile + epilogue variant
+    const int code = epilogue_warps_per_quadrant % 1000;
+    const int cl = (code / 100) % 10, nh = (code / 10) % 10, epi = code % 10;
+    B200_REQUIRE((cl == 1 || cl == 2) && (nh == 1 || nh == 2) &&
+                     (epi == 3 || epi == 5 || ((epi == 8 || epi == 9) && cl == 1)),
+                 "b200_recommend_embed_tune: code = 100 * cluster (1|2) + 10 * MMA groups (1|2) + epilogue (3|5)");
     g_cluster = cl; g_nh = nh; g_epi = epi;
   }
   if (pre_rank_coef != 0.f) {
@@ -1433,8 +1375,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   int32_t* status = (int32_t*)(ws + pl.off_status);
   int32_t* cnt = (int32_t*)(ws + pl.off_cnt);
   uint32_t* ghist = (uint32_t*)(ws + pl.off_hist);
-  float* cand_s = (float*)(ws + pl.off_cs);
-  int32_t* cand_b = (int32_t*)(ws + pl.off_cb);
+  float* cand_r = (float*)(ws + pl.off_cs);
   float* bm = (float*)(ws + pl.off_bm);
   const CatalogHeader* hdr = (const CatalogHeader*)catalog;
   const __half* Ih = (const __half*)((const char*)catalog + 256);
@@ -1456,7 +1397,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   sp.tiles_per_split = pl.tiles_per_split; sp.total_tiles = pl.total_tiles; sp.KB = pl.KB;
   sp.nstage = pl.nstage; sp.n_pre_tiles = pl.n_pre_tiles; sp.capg = pl.capg; sp.trig = pl.trig;
   sp.meta = meta; sp.row_tau_key = tau;
-  sp.row_status = status; sp.ghist = ghist; sp.cand_s = cand_s; sp.cand_b = cand_b; sp.cand_cnt = cnt;
+  sp.row_status = status; sp.ghist = ghist; sp.cand_r = cand_r; sp.cand_cnt = cnt;
   sp.blockmax = bm; sp.ablate = g_ablate; sp.hint_ns = (uint32_t)g_hint_ns;
   const int n_units = pl.m_tiles * pl.n_splits;
   static int sm_count = 0;
@@ -1470,20 +1411,20 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
 
   if (ev_sweep_start) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_start, stream));
   if (pl.use_pre) {
-    if (int rc = launch_sweep_dispatch<true>(grid, pl, 3, stream, tmA, tmB, tmBh, sp)) return rc;
+    if (int rc = launch_pre_dispatch(grid, pl, stream, tmA, tmB, tmBh, sp)) return rc;
     guess_kernel<<<(unsigned)(pl.B_pad / 32), GUESS_THREADS, 0, stream>>>(
         bm, W_PRE * pl.n_splits * pl.n_pre_tiles, pl.B_pad, meta, tau, guess);
     count_launch();
   } else {
     B200_CUDA_OK(cudaMemsetAsync(guess, 0, (size_t)pl.B_pad * 4, stream));
   }
-  if (int rc = launch_sweep_dispatch<false>(grid, pl, g_epi, stream, tmA, tmB, tmBh, sp)) return rc;
+  if (int rc = launch_main_dispatch(grid, pl, g_epi, stream, tmA, tmB, tmBh, sp)) return rc;
   if (ev_sweep_stop) B200_CUDA_OK(cudaEventRecord((cudaEvent_t)ev_sweep_stop, stream));
 
   FinalizeParams fp;
   fp.B = B; fp.N = N; fp.B_pad = pl.B_pad; fp.n_lists = pl.n_lists; fp.K = K; fp.d = d; fp.capg = pl.capg;
   fp.meta = meta; fp.row_status = status; fp.row_tau_key = tau; fp.tau_guess_key = guess;
-  fp.cand_s = cand_s; fp.cand_b = cand_b; fp.cand_cnt = cnt;
+  fp.cand_r = cand_r; fp.cand_cnt = cnt;
   fp.U = U; fp.ldu = ldu; fp.I = I; fp.ldi = ldi; fp.user_ids = user_ids; fp.indptr = indptr;
   fp.idx = idx; fp.out_ids = out_ids; fp.out_scores = out_scores;
   finalize_kernel<<<(unsigned)B, FIN_THREADS, 0, stream>>>(fp);

@@ -253,6 +253,12 @@ class EmbedScorer:
         n_rec = int(n_rec)
         if isinstance(user_ids, torch.Tensor):
             uid_h = user_ids.to(torch.int64)
+        elif isinstance(user_ids, list):
+            # the reference passes a python list of inner ids: array.array's C loop is the fastest way in
+            import array
+
+            uid_h = torch.frombuffer(array.array("q", user_ids), dtype=torch.int64) if user_ids else \
+                torch.zeros(0, dtype=torch.int64)
         else:
             uid_h = torch.as_tensor(np.asarray(user_ids, dtype=np.int64))
         uid_d = uid_h.to(self.device, non_blocking=True)

@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+O=gpurun_out
+VARIANTS="213:2.0:8192,214:2.0:8192,114:2.0:8192,214:1.6:8192,214:2.0:16384,214:2.0:8192:1" timeout 500 python tools/sweep_variants.py > $O/r2_variants_v12.jsonl 2> $O/r2_variants_v12.err; echo "rc=$?" >> $O/r2_variants_v12.err
+cat $O/r2_variants_v12.jsonl | cut -c1-200
+tail -3 $O/r2_variants_v12.err
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 3 -c 1 -o $O/r2_prof_sweep_v12_e3 python tools/profile_embed.py --steps 3 --batch 8192 --pre-coef 2.0 --epi-warps 213 > $O/r2_ncu_s12a.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:sweep_kernel -s 3 -c 1 -o $O/r2_prof_sweep_v12_e4 python tools/profile_embed.py --steps 3 --batch 8192 --pre-coef 2.0 --epi-warps 214 > $O/r2_ncu_s12b.log 2>&1
+tail -2 $O/r2_ncu_s12a.log $O/r2_ncu_s12b.log

@@ -27,7 +27,7 @@ def main():
     import librecommender_b200.engine as eng
 
     sc = EmbedScorer(U, I, args.items, ConsumedCSR.from_device_tensors(indptr, idx), n_users=args.users, device=dev)
-    variants = [(w, 2.0, b) for b in (8192, 16384) for w in (223, 213, 123, 113)]
+    variants = [(w, 2.0, b) for b in (8192, 16384) for w in (215, 115, 213, 225)]
     if os.environ.get("VARIANTS"):
         variants = [tuple(float(x) if "." in x else int(x) for x in v.split(":")) for v in os.environ["VARIANTS"].split(",")]
     rng = np.random.default_rng(5)
