@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", default="auto", choices=["auto", "exact"])
     ap.add_argument("--no-secondary", action="store_true", help="skip the collective legs at N > 1")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configuration: c2 (default, the headline line); c1/c3/c4/c5 = the other "
+                         "configurations on one GPU (librecommender_b200/bench_configs.py)")
     ap.add_argument("--epi-warps", type=int, default=0, help="tuning: epilogue warps per TMEM quadrant (2|3)")
     ap.add_argument("--pre-coef", type=float, default=0.0, help="tuning: speculative rank coefficient")
     return ap.parse_args()
@@ -256,6 +259,13 @@ def main():
         return 0                                   # rank 0 alone runs the CPU arm
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    if args.config != "c2":
+        if rank != 0 or args.impl != "b200":
+            return 0
+        from librecommender_b200 import bench_configs
+
+        print(json.dumps(bench_configs.CONFIGS[args.config](args, ROOT, ClockSampler(local_rank))))
+        return 0
     if distributed and args.impl == "b200":
         import torch.distributed as dist
 

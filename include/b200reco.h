@@ -81,8 +81,8 @@ int b200_score_rows_f32(const float* U, int64_t ldu, const int64_t* user_ids, in
  * per cluster (2: every item tile is fetched from L2 once per pair of user tiles and TMA-multicast to
  * both CTAs) + MMA groups per item tile, out[7] records per candidate list (n_out >= 8).
  * b200_recommend_embed_tune (process-wide, not thread-safe; 0 keeps a value): organisation code =
- * 100 x cluster size (1|2) + 10 x MMA groups per tile (1|2) + epilogue variant (5: one warp vote per
- * 64-column step + predicated record stores, 3: divergent group tests; default 215), and the rank
+ * 100 x cluster size (1|2) + 10 x MMA groups per tile (1|2) + epilogue variant (3: divergent per-lane
+ * group tests, 5: one warp vote per 64-column step + predicated record stores; default 213), and the rank
  * coefficient c of the speculative threshold (about c * k_row items are expected above it). */
 int b200_recommend_embed_tune(int32_t organisation_code, float pre_rank_coef);
 /* profiling diagnostics only (results are wrong while level > 0): ablate parts of the main pass */

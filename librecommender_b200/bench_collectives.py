@@ -112,12 +112,13 @@ def _lookup(rank, world, dev, max_over_ranks, barrier):
     for name, n_rows, d, n_ids in (("deepfm_k16", 40_000_000, 16, 819_200), ("din_k64", 8_000_000, 64, 2_000_000)):
         rows_loc = -(-n_rows // world)
         # shard content is a cheap function of the global row id, so every rank can check its lookups
-        slot = torch.arange(rows_loc, device=dev, dtype=torch.float32)
-        gid = slot * world + rank
-        local = (gid[:, None] * 1e-3 + torch.arange(d, device=dev, dtype=torch.float32)[None, :]).contiguous()
+        # (integers below 2^24 only: exactly representable in fp32 whatever the row id)
+        gid = torch.arange(rows_loc, device=dev, dtype=torch.int64) * world + rank
+        cols = torch.arange(d, device=dev, dtype=torch.float32)[None, :]
+        local = ((gid % 65521).to(torch.float32)[:, None] + 0.5 * cols).contiguous()
         g = torch.Generator(device=dev).manual_seed(100 + rank)
         ids = torch.randint(0, n_rows, (n_ids,), device=dev, generator=g)
-        expect = ids.to(torch.float32)[:, None] * 1e-3 + torch.arange(d, device=dev, dtype=torch.float32)[None, :]
+        expect = (ids % 65521).to(torch.float32)[:, None] + 0.5 * cols
         cross = n_ids * (world - 1) / world * (d * 4)            # row bytes that must arrive over NVLink
         leg = {"rows": n_rows, "d": d, "ids_per_gpu": n_ids, "nvlink_row_bytes_per_gpu": cross}
         nccl = RowShardedTable(local, n_rows)

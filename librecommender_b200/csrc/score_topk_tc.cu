@@ -1129,7 +1129,7 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 
 // ---- tuning knobs (defaults compiled in; b200_recommend_embed_tune overrides them per process) ----
-static int g_epi = 5;              // epilogue variant of the main pass: 5 step vote + predicated stores, 3 divergent group tests
+static int g_epi = 3;              // epilogue variant of the main pass: 3 divergent group tests (measured best), 5 step vote + predicated stores
 static int g_cluster = 2;          // 2 = pairs of user tiles share every item tile through TMA multicast, 1 = off
 static int g_nh = 1;               // MMA groups per item tile (1 x N=256; 2 x N=128 re-reads the user tile: ~2x slower)
 static int g_ablate = 0;           // b200_recommend_embed_debug
@@ -1254,14 +1254,14 @@ static int launch_pre_dispatch(int grid, const Plan& pl, cudaStream_t stream, co
 static int launch_main_dispatch(int grid, const Plan& pl, int epi, cudaStream_t stream, const CUtensorMap& tmA,
                                 const CUtensorMap& tmB, const CUtensorMap& tmBh, const SweepParams& sp) {
 #define B200_SWEEP(E_, C_, N_) return launch_sweep<false, 2, E_, C_, N_>(grid, pl, stream, tmA, tmB, tmBh, sp)
-  // default: variant 5 (one vote per step + predicated record stores), one N=256 MMA group per tile,
-  // clusters of 2; the other instantiations are A/B points and diagnostics
+  // default: variant 3 (divergent per-lane group tests), one N=256 MMA group per tile, clusters of 2;
+  // the other instantiations are A/B points and diagnostics
   if (epi == 8) { if (pl.NH == 2) B200_SWEEP(8, 1, 2); B200_SWEEP(8, 1, 1); }
   if (epi == 9) { if (pl.NH == 2) B200_SWEEP(9, 1, 2); B200_SWEEP(9, 1, 1); }
-  if (pl.NH == 2) { if (pl.CL == 2) B200_SWEEP(5, 2, 2); B200_SWEEP(5, 1, 2); }
-  if (epi == 3) { if (pl.CL == 2) B200_SWEEP(3, 2, 1); B200_SWEEP(3, 1, 1); }
-  if (pl.CL == 2) B200_SWEEP(5, 2, 1);
-  B200_SWEEP(5, 1, 1);
+  if (pl.NH == 2) { if (pl.CL == 2) B200_SWEEP(3, 2, 2); B200_SWEEP(3, 1, 2); }
+  if (epi == 5) { if (pl.CL == 2) B200_SWEEP(5, 2, 1); B200_SWEEP(5, 1, 1); }
+  if (pl.CL == 2) B200_SWEEP(3, 2, 1);
+  B200_SWEEP(3, 1, 1);
 #undef B200_SWEEP
 }
 
