@@ -85,8 +85,13 @@ class ConsumedCSR:
     def device(self, device):
         import torch
 
-        key = str(device)
+        dv = torch.device(device)
+        if dv.type == "cuda" and dv.index is None:       # "cuda" and "cuda:<current>" are the same residency
+            dv = torch.device("cuda", torch.cuda.current_device())
+        key = str(dv)
         if key not in self._dev:
+            if self.indptr is None:
+                raise ValueError(f"device-only CSR lives on {list(self._dev)}, asked for {key}")
             idx = self.idx if len(self.idx) else np.zeros(1, dtype=np.int32)
             self._dev[key] = (
                 torch.from_numpy(self.indptr).to(device),

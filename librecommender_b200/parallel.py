@@ -507,3 +507,20 @@ def block_spmm_fn(block_graphs):
             block_graphs[g].spmm(E_block, out=None, acc=acc, acc_init=False, final_div=0.0)
 
     return fn
+
+
+# ------------------------------------------------------------------------------------------------
+# OOV rows of sharded tables: the mean row (assign_embedding_oov,
+# bases/embed_base.py:257-265; assign_tf_variables_oov, bases/tf_base.py:310-353) of a table whose rows
+# live on several ranks = local partial sums + ONE all-reduce.
+# ------------------------------------------------------------------------------------------------
+def sharded_mean_row(local_rows, n_local_valid: int, n_rows_global: int, group=None):
+    """Mean over the `n_rows_global` real rows of a table sharded over the ranks; `local_rows[:n_local_valid]`
+    are this rank's real rows (shard padding and the OOV slot itself excluded).  Accumulates in float64."""
+    import torch
+    import torch.distributed as dist
+
+    part = local_rows[:n_local_valid].sum(dim=0, dtype=torch.float64)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(part, group=group)
+    return (part / float(n_rows_global)).to(local_rows.dtype)

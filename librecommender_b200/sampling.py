@@ -101,14 +101,30 @@ def collator_seed(seed: int) -> int:
 # ----------------------------------------------------------------------------------------------
 # fast mode (device)
 # ----------------------------------------------------------------------------------------------
+def rank_stream_seed(seed: int, rank: int) -> int:
+    """Philox key of rank `rank` (stream id = (seed, rank, step)): rank 0 keeps the
+    single-process stream, every other rank gets a key a splitmix64 step away, so data-parallel ranks
+    never draw the same negatives for the same step."""
+    if rank == 0:
+        return int(seed)
+    z = (int(seed) + (rank * 0x9E3779B97F4A7C15)) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return int((z ^ (z >> 31)) & 0x7FFFFFFFFFFFFFFF)
+
+
 class DeviceNegativeSampler:
     def __init__(self, n_items, user_consumed=None, n_users=None, neg_probs=None, seed=42,
-                 tolerance=10, device=None):
+                 tolerance=10, device=None, rank=None):
         import torch
 
         self.device = device if device is not None else _lib.require_cuda()
         self.n_items = int(n_items)
-        self.seed = int(collator_seed(seed))
+        if rank is None:   # one process per GPU: the data-parallel rank selects the stream
+            rank = torch.distributed.get_rank() if (torch.distributed.is_available()
+                                                    and torch.distributed.is_initialized()) else 0
+        self.rank = int(rank)
+        self.seed = rank_stream_seed(int(collator_seed(seed)), self.rank)
         self.tolerance = int(tolerance)
         self.step = 0
         self.indptr = self.idx_sorted = None

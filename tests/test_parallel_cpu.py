@@ -70,3 +70,39 @@ def test_shard_bounds_balanced():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _worker_mean(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from librecommender_b200.parallel import sharded_mean_row
+
+    full = torch.from_numpy(np.random.default_rng(0).standard_normal((101, 6)).astype(np.float32))
+    local = full[rank::world].contiguous()
+    q.put((rank, sharded_mean_row(local, local.shape[0], 101).numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_oov_mean_row_gloo_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_mean, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = np.random.default_rng(0).standard_normal((101, 6)).astype(np.float32)
+    for _, m in res:
+        np.testing.assert_allclose(m, full.mean(axis=0), rtol=1e-6, atol=1e-7)
+
+
+def test_per_rank_sampler_streams_differ():
+    from librecommender_b200.sampling import rank_stream_seed
+
+    seeds = [rank_stream_seed(462, r) for r in range(8)]
+    assert seeds[0] == 462 and len(set(seeds)) == 8 and all(0 <= s < 2 ** 63 for s in seeds)
