@@ -174,8 +174,10 @@ typedef struct {       /* TF scope "embedding" (SURVEY.md Appendix C), fp32, row
  *   lin    [R]                 Dense1(concat of linear features) + bias (fm.py:156)
  *   fm_out [R]                 lin + elu(Dense1(BN(pw)))               (fm.py:165-170); BN folded
  *                              to scale/shift (inference), bn_scale NULL = use_bn False */
-/* process-wide switch (A/B measurements, tests): 1 = the bulk-copy (TMA) staged persistent gather for
- * eligible shapes (K % 4 == 0, K <= 32, >= 2048 rows), 0 = the register-gather kernels only. */
+/* process-wide switch (A/B measurements, tests).  bit 0: 1 = the bulk-copy (TMA) staged persistent gather for
+ * eligible shapes (K % 4 == 0, K <= 32, >= 2048 rows), 0 = the register-gather kernels only.
+ * bit 1: 1 = the older lane-per-field register kernel instead of the field-group kernel (K in {4,8,16,32}).
+ * bit 2: 1 = never the cp.async staged variant of the field-group kernel (default for >= 4096 rows). */
 int b200_feat_forward_tune(int32_t use_tma_staging);
 int b200_feat_forward(const b200_feat_layout* layout, const b200_feat_tables* tables,
                       const int64_t* users, const int64_t* items, int64_t R, int64_t grid_items,
@@ -307,6 +309,11 @@ int b200_deepfm_head_forward(const float* lin, const float* lin_bias, const floa
 int b200_deepfm_head_backward(const float* dlogit, const float* out_kernel, int32_t K, int32_t H, int64_t R,
                               float* dlin, float* dpw, int64_t lddpw, float* ddeep, int64_t lddeep,
                               void* stream);
+
+/* Backward of b200_l2_normalize_rows: x = the rows BEFORE normalisation, dy = gradient of the
+ * normalised rows; dx may alias dy. */
+int b200_l2_normalize_backward(const float* x, int64_t ldx, const float* dy, int64_t lddy, int64_t R, int32_t d,
+                               float* dx, int64_t lddx, void* stream);
 
 /* tf.train.AdamOptimizer over a WHOLE variable (what _apply_sparse_shared does for embedding
  * variables: m, v decayed everywhere, every row updated): lr_t = lr sqrt(1-b2^t)/(1-b1^t),

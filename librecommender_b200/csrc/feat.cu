@@ -14,6 +14,7 @@
 // HBM-bound gather: per row (2+F_s) random reads of 4K (+4) bytes.  One sub-warp of
 // lpr = min(32, pow2 >= K) lanes per row, lanes stride the embedding width; field indices are
 // loaded cooperatively and broadcast by shuffle, 4 gathers in flight.
+#include <algorithm>
 #include "common.cuh"
 #include "feat_common.cuh"
 #include "../../include/b200reco.h"
@@ -283,6 +284,359 @@ feat_forward_lanefield_kernel(const b200_feat_layout L, const b200_feat_tables T
   if (o.lin && lane == 0) o.lin[r] = lin_acc;
 }
 
+// ---- fast path for K in {4, 8, 16, 32}: one warp per row, K/4 LANES PER FIELD (a "field group" of 32/(K/4)
+// fields per warp instruction).  Every warp-level load reads 32/(K/4) whole embedding rows with 16 B per lane
+// (one L1 wavefront per 128 B instead of one per lane), every warp-level store writes 512 contiguous bytes of
+// the concatenated row, and the field sums need log2(32/(K/4)) shuffle steps on 8 values instead of a 32-lane
+// reduction of 2K values.  Field metadata (side, column, head weight) is staged once per block in shared
+// memory — indexing the by-value layout struct with a per-lane field number serialises in the constant cache.
+// U steps are resolved (index loads) and then gathered together: U row reads in flight per lane.
+// Measured ceiling for this access pattern (tools/ubench/gather.cu): 64-B random rows 2.7 TB/s from HBM,
+// 5.7 TB/s when the table mostly fits the 126 MB L2.
+template <int K4>
+__global__ void __launch_bounds__(256, 3)
+feat_forward_fieldgroup_kernel(const b200_feat_layout L, const b200_feat_tables T,
+                               const int64_t* __restrict__ users, const int64_t* __restrict__ items,
+                               int64_t R, int64_t grid_items, int64_t row_offset, Out o, Head h) {
+  constexpr int K = K4 * 4;
+  constexpr int FPW = 32 / K4;                 // fields per warp instruction
+  constexpr int U = 8;                         // steps in flight
+  constexpr int MAXF = 2 + 2 * B200_MAX_FIELDS;
+  __shared__ int32_t sh_code[MAXF];            // kind | column << 3
+  __shared__ int32_t sh_drow[MAXF];            // dense fields: row of dense_embeds / dense_linear
+  __shared__ float sh_link[MAXF];              // Dense(1) weight of the field's linear feature
+  const int n_id = ((L.id_mask & 1) ? 1 : 0) + ((L.id_mask & 2) ? 1 : 0);
+  const int F = n_id + L.n_sparse + L.n_dense;
+  const bool want_lin = (o.lin != nullptr) || (o.fm_out != nullptr);
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    int kind, col = 0, drow = 0;
+    if (f < n_id) kind = ((L.id_mask & 1) && f == 0) ? 0 : 1;
+    else if (f < n_id + L.n_sparse) {
+      const int fs = f - n_id;
+      if (L.sparse_rows) { kind = 4; col = fs; }
+      else { kind = L.sparse_side[fs] == 0 ? 2 : 3; col = L.sparse_col[fs]; }
+    } else {
+      const int fd = f - n_id - L.n_sparse;
+      drow = L.dense_embed_row[fd];
+      if (L.dense_rows) { kind = 7; col = fd; }
+      else { kind = L.dense_side[fd] == 0 ? 5 : 6; col = L.dense_col[fd]; }
+    }
+    sh_code[f] = kind | (col << 3);
+    sh_drow[f] = drow;
+    sh_link[f] = want_lin ? h.lin_kernel[f] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int fg = lane / K4, q = lane % K4;
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < R; r += n_warps) {
+    int64_t u, it;
+    if (grid_items > 0) { const int64_t rg = r + row_offset; u = users[rg / grid_items]; it = rg % grid_items; }
+    else { u = users[r]; it = items[r]; }
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s;
+    float lin_acc = 0.f;
+    for (int f0 = 0; f0 < F; f0 += FPW * U) {
+      const float4* src[U];
+      float scale[U];
+      // phase 1: source row of this lane's field in each of the U steps (the index loads go out together)
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int f = f0 + j * FPW + fg;
+        src[j] = nullptr;
+        scale[j] = 1.f;
+        if (f < F) {
+          const int code = sh_code[f];
+          const int kind = code & 7, col = code >> 3;
+          const float* rowp;
+          float lw = 0.f;
+          if (kind < 2) {
+            rowp = kind == 0 ? T.user_embeds + u * K : T.item_embeds + it * K;
+            if (want_lin) lw = kind == 0 ? __ldg(T.user_linear + u) : __ldg(T.item_linear + it);
+          } else if (kind < 5) {
+            const int32_t* ip = kind == 2 ? L.user_sparse_unique + u * L.ld_us + col
+                              : kind == 3 ? L.item_sparse_unique + it * L.ld_is + col
+                                          : L.sparse_rows + r * L.ld_sparse_rows + col;
+            const int32_t idx = __ldg(ip);
+            rowp = T.sparse_embeds + (int64_t)idx * K;
+            if (want_lin) lw = __ldg(T.sparse_linear + idx);
+          } else {
+            const float* xp = kind == 5 ? L.user_dense_unique + u * L.ld_ud + col
+                            : kind == 6 ? L.item_dense_unique + it * L.ld_id + col
+                                        : L.dense_rows + r * L.ld_dense_rows + col;
+            const float x = __ldg(xp);
+            const int drow = sh_drow[f];
+            rowp = T.dense_embeds + (int64_t)drow * K;
+            scale[j] = x;
+            if (want_lin) lw = __ldg(T.dense_linear + drow) * x;
+          }
+          if (want_lin && q == 0) lin_acc = fmaf(lw, sh_link[f], lin_acc);
+          src[j] = reinterpret_cast<const float4*>(rowp) + q;
+        }
+      }
+      // phase 2: U row reads in flight (16 B per lane, K/4 lanes per row)
+      float4 e[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) e[j] = src[j] ? __ldg(src[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // phase 3: sums + the concatenated row
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        if (!src[j]) continue;
+        float4 v = e[j];
+        v.x *= scale[j]; v.y *= scale[j]; v.z *= scale[j]; v.w *= scale[j];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y);
+        s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+        if (o.concat) {
+          const int f = f0 + j * FPW + fg;
+          *reinterpret_cast<float4*>(o.concat + r * o.ld_concat + (int64_t)f * K + q * 4) = v;
+        }
+      }
+    }
+    if (!o.pw && !o.fm_out && !o.lin && !o.ssum) continue;
+    // sum over the field groups: lanes with equal q hold the same 4 embedding columns
+#pragma unroll
+    for (int off = K4; off < 32; off <<= 1) {
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+      s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
+      s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+    }
+    const float sv[4] = {s.x, s.y, s.z, s.w};
+    const float s2v[4] = {s2.x, s2.y, s2.z, s2.w};
+    float head_acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int k = q * 4 + c;
+      const float pw = 0.5f * (sv[c] * sv[c] - s2v[c]);
+      if (fg == 0) {
+        if (o.pw) o.pw[r * o.ld_pw + k] = pw;
+        if (o.ssum) { o.ssum[r * o.ld_s + k] = sv[c]; o.sqsum[r * o.ld_s + k] = s2v[c]; }
+      }
+      if (o.fm_out) {
+        const float z = h.bn_scale ? fmaf(pw, h.bn_scale[k], h.bn_shift[k]) : pw;
+        head_acc = fmaf(z, h.pw_kernel[k], head_acc);
+      }
+    }
+    if (want_lin) lin_acc = warp_sum(lin_acc) + h.lin_bias;
+    if (o.fm_out) {
+#pragma unroll
+      for (int off = 1; off < K4; off <<= 1) head_acc += __shfl_xor_sync(0xffffffffu, head_acc, off);
+      head_acc += h.pw_bias;
+      if (lane == 0) o.fm_out[r] = lin_acc + (head_acc > 0.f ? head_acc : expm1f(head_acc));
+    }
+    if (o.lin && lane == 0) o.lin[r] = lin_acc;
+  }
+}
+
+// ---- large row counts, K in {4, 8, 16, 32}: the field-group layout above with the row gathers staged through
+// shared memory by cp.async (LDGSTS, 16 B per lane — the SAME request pattern as the register gather, but the
+// landing zone is shared memory instead of registers, so a warp keeps TWO whole rows of gathers in flight and the
+// index loads of a third).  ncu of the register kernel (profiles/r02_feat_fieldgroup_ncu.txt): 12 of 18 stall
+// cycles per issue are long-scoreboard, issue slots 33 % busy, DRAM 18 % — latency bound on the dependent chain
+// ids -> feature index -> embedding row.  Pipeline per warp, rows k = 0, 1, ...:
+//     iteration k:  G(k+1) address generation from the indices loaded one iteration ago + cp.async of every field
+//                   I(k+2) index loads into registers          (ids of row k+3 prefetched)
+//                   wait for the copies of row k, consume them from shared memory (every lane reads back exactly
+//                   the 16 bytes it copied itself: no cross-lane hand-off), sums, concat store, row outputs
+// One UBLKCP bulk copy per 64-byte row was measured 5.7x slower than register gathers (feat_tma.cu): the bulk-copy
+// engine is the wrong tool for rows this small; LDGSTS keeps the LSU's 8-rows-per-instruction coalescing.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int ASYNC_MAXS = 16;   // steps (warp-level gathers) per row the staged kernel holds in registers
+
+template <int K4>
+__global__ void __launch_bounds__(256)
+feat_forward_async_kernel(const b200_feat_layout L, const b200_feat_tables T,
+                          const int64_t* __restrict__ users, const int64_t* __restrict__ items,
+                          int64_t R, int64_t grid_items, int64_t row_offset, Out o, Head h, int NS) {
+  constexpr int K = K4 * 4;
+  constexpr int FPW = 32 / K4;
+  constexpr int MAXS = ASYNC_MAXS;
+  extern __shared__ float4 dyn_smem[];
+  const int wpb = blockDim.x >> 5;
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int fg = lane / K4, q = lane % K4;
+  const int n_id = ((L.id_mask & 1) ? 1 : 0) + ((L.id_mask & 2) ? 1 : 0);
+  const int F = n_id + L.n_sparse + L.n_dense;
+  const bool want_lin = (o.lin != nullptr) || (o.fm_out != nullptr);
+  // dynamic shared memory: [wpb][2][NS][32] float4 rings | [wpb][2][NS * FPW] scales | code[F] | drow[F] | link[F]
+  float4* ring = dyn_smem + (size_t)wib * 2 * NS * 32;
+  float* sx_all = reinterpret_cast<float*>(dyn_smem + (size_t)wpb * 2 * NS * 32);
+  float* sx = sx_all + (size_t)wib * 2 * NS * FPW;
+  int32_t* sh_code = reinterpret_cast<int32_t*>(sx_all + (size_t)wpb * 2 * NS * FPW);
+  int32_t* sh_drow = sh_code + F;
+  float* sh_link = reinterpret_cast<float*>(sh_drow + F);
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    int kind, col = 0, drow = 0;
+    if (f < n_id) kind = ((L.id_mask & 1) && f == 0) ? 0 : 1;
+    else if (f < n_id + L.n_sparse) {
+      const int fs = f - n_id;
+      if (L.sparse_rows) { kind = 4; col = fs; }
+      else { kind = L.sparse_side[fs] == 0 ? 2 : 3; col = L.sparse_col[fs]; }
+    } else {
+      const int fd = f - n_id - L.n_sparse;
+      drow = L.dense_embed_row[fd];
+      if (L.dense_rows) { kind = 7; col = fd; }
+      else { kind = L.dense_side[fd] == 0 ? 5 : 6; col = L.dense_col[fd]; }
+    }
+    sh_code[f] = kind | (col << 3);
+    sh_drow[f] = drow;
+    sh_link[f] = want_lin ? h.lin_kernel[f] : 0.f;
+  }
+  __syncthreads();
+
+  const int64_t n_warps = (int64_t)gridDim.x * wpb;
+  const int64_t w0 = (int64_t)blockIdx.x * wpb + wib;
+  auto load_ids = [&](int64_t r, int64_t& u, int64_t& it) {
+    u = 0; it = 0;
+    if (r < R) {
+      if (grid_items > 0) { const int64_t rg = r + row_offset; u = users[rg / grid_items]; it = rg % grid_items; }
+      else { u = users[r]; it = items[r]; }
+    }
+  };
+  int32_t raw[MAXS];
+  // I: feature index (sparse) / value bits (dense) of every step of row r
+  auto load_indices = [&](int64_t r, int64_t u, int64_t it) {
+#pragma unroll
+    for (int j = 0; j < MAXS; ++j) {
+      raw[j] = 0;
+      const int f = j * FPW + fg;
+      if (j < NS && f < F) {
+        const int code = sh_code[f];
+        const int kind = code & 7, col = code >> 3;
+        if (kind >= 2 && kind < 5) {
+          const int32_t* ip = kind == 2 ? L.user_sparse_unique + u * L.ld_us + col
+                            : kind == 3 ? L.item_sparse_unique + it * L.ld_is + col
+                                        : L.sparse_rows + r * L.ld_sparse_rows + col;
+          raw[j] = __ldg(ip);
+        } else if (kind >= 5) {
+          const float* xp = kind == 5 ? L.user_dense_unique + u * L.ld_ud + col
+                          : kind == 6 ? L.item_dense_unique + it * L.ld_id + col
+                                      : L.dense_rows + r * L.ld_dense_rows + col;
+          raw[j] = __float_as_int(__ldg(xp));
+        }
+      }
+    }
+  };
+
+  int64_t ua, ita, ub, itb, uc, itc;       // ids of rows k+1, k+2, k+3
+  load_ids(w0, ua, ita);
+  load_ids(w0 + n_warps, ub, itb);
+  load_ids(w0 + 2 * n_warps, uc, itc);
+  if (w0 < R) load_indices(w0, ua, ita);
+  float lin_cur = 0.f;
+  for (int64_t k = -1;; ++k) {
+    const int64_t r_cur = w0 + k * n_warps, r_nx = r_cur + n_warps, r_nx2 = r_nx + n_warps;
+    if (k >= 0 && r_cur >= R) break;
+    __syncwarp();
+    const int nb = (int)((k + 1) & 1);
+    // ---- G(k+1): addresses from raw[], asynchronous copies into ring[nb]
+    float lwn[MAXS];
+    if (r_nx < R) {
+#pragma unroll
+      for (int j = 0; j < MAXS; ++j) {
+        lwn[j] = 0.f;
+        const int f = j * FPW + fg;
+        if (j < NS && f < F) {
+          const int code = sh_code[f];
+          const int kind = code & 7;
+          const float* rowp;
+          float scale = 1.f;
+          if (kind < 2) {
+            rowp = kind == 0 ? T.user_embeds + ua * K : T.item_embeds + ita * K;
+            if (want_lin && q == 0) lwn[j] = kind == 0 ? __ldg(T.user_linear + ua) : __ldg(T.item_linear + ita);
+          } else if (kind < 5) {
+            rowp = T.sparse_embeds + (int64_t)raw[j] * K;
+            if (want_lin && q == 0) lwn[j] = __ldg(T.sparse_linear + raw[j]);
+          } else {
+            const int drow = sh_drow[f];
+            scale = __int_as_float(raw[j]);
+            rowp = T.dense_embeds + (int64_t)drow * K;
+            if (want_lin && q == 0) lwn[j] = __ldg(T.dense_linear + drow) * scale;
+          }
+          cp_async16(ring + ((size_t)nb * NS + j) * 32 + lane, reinterpret_cast<const float4*>(rowp) + q);
+          if (q == 0) sx[(nb * NS + j) * FPW + fg] = scale;
+        }
+      }
+    }
+    cp_async_commit();
+    // ---- I(k+2) and the ids of row k+3
+    if (r_nx2 < R) load_indices(r_nx2, ub, itb);
+    ua = ub; ita = itb; ub = uc; itb = itc;
+    load_ids(r_nx2 + 2 * n_warps, uc, itc);
+    // ---- row k has landed (everything but the newest group)
+    cp_async_wait<1>();
+    if (k >= 0) {
+      const int cb = (int)(k & 1);
+      const int64_t r = r_cur;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s;
+#pragma unroll
+      for (int j = 0; j < MAXS; ++j) {
+        const int f = j * FPW + fg;
+        if (j < NS && f < F) {
+          float4 v = ring[((size_t)cb * NS + j) * 32 + lane];
+          const float sc = sx[(cb * NS + j) * FPW + fg];
+          v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+          s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y);
+          s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+          if (o.concat) *reinterpret_cast<float4*>(o.concat + r * o.ld_concat + (int64_t)f * K + q * 4) = v;
+        }
+      }
+      if (o.pw || o.fm_out || o.lin || o.ssum) {
+#pragma unroll
+        for (int off = K4; off < 32; off <<= 1) {
+          s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+          s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+          s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
+          s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+        }
+        const float sv[4] = {s.x, s.y, s.z, s.w};
+        const float s2v[4] = {s2.x, s2.y, s2.z, s2.w};
+        float head_acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int kk = q * 4 + c;
+          const float pw = 0.5f * (sv[c] * sv[c] - s2v[c]);
+          if (fg == 0) {
+            if (o.pw) o.pw[r * o.ld_pw + kk] = pw;
+            if (o.ssum) { o.ssum[r * o.ld_s + kk] = sv[c]; o.sqsum[r * o.ld_s + kk] = s2v[c]; }
+          }
+          if (o.fm_out) {
+            const float z = h.bn_scale ? fmaf(pw, h.bn_scale[kk], h.bn_shift[kk]) : pw;
+            head_acc = fmaf(z, h.pw_kernel[kk], head_acc);
+          }
+        }
+        float lin_acc = 0.f;
+        if (want_lin) lin_acc = warp_sum(lin_cur) + h.lin_bias;
+        if (o.fm_out) {
+#pragma unroll
+          for (int off = 1; off < K4; off <<= 1) head_acc += __shfl_xor_sync(0xffffffffu, head_acc, off);
+          head_acc += h.pw_bias;
+          if (lane == 0) o.fm_out[r] = lin_acc + (head_acc > 0.f ? head_acc : expm1f(head_acc));
+        }
+        if (o.lin && lane == 0) o.lin[r] = lin_acc;
+      }
+    }
+    // linear-term partial of row k+1 (its weights were requested at the top of this iteration)
+    lin_cur = 0.f;
+    if (want_lin && q == 0 && r_nx < R) {
+#pragma unroll
+      for (int j = 0; j < MAXS; ++j) {
+        const int f = j * FPW + fg;
+        if (j < NS && f < F) lin_cur = fmaf(lwn[j], sh_link[f], lin_cur);
+      }
+    }
+    if (r_nx >= R) { cp_async_wait<0>(); break; }
+  }
+}
+
 // y[r, n] = act(sum_k x[r,k] * Wt[n,k] + b[n]) — 64x64x16 register-tiled SIMT GEMM (fp32, exact fma chain)
 constexpr int LM = 64, LN = 64, LK = 16;
 __global__ void __launch_bounds__(256)
@@ -379,11 +733,15 @@ __global__ void l2_normalize_kernel(float* __restrict__ x, int64_t ld, int64_t R
 using namespace b200;
 using namespace b200::feat;
 
+static int g_feat_kernel = 0;   // b200_feat_forward_tune bit 1: 0 = field-group kernel (default), 1 = lane-per-field kernel (A/B)
+static int g_feat_no_async = 0; // b200_feat_forward_tune bit 2: 1 = never use the cp.async staged kernel (A/B)
 static int g_feat_tma = 0;   // b200_feat_forward_tune: 1 = bulk-copy (TMA) staged kernel where eligible, 0 = register kernels
                              // (default: one UBLKCP per 64-byte row measured 5.7x SLOWER than the register gather, profiles/)
 
 extern "C" int b200_feat_forward_tune(int32_t use_tma_staging) {
-  g_feat_tma = use_tma_staging ? 1 : 0;
+  g_feat_tma = (use_tma_staging & 1) ? 1 : 0;
+  g_feat_kernel = (use_tma_staging & 2) ? 1 : 0;
+  g_feat_no_async = (use_tma_staging & 4) ? 1 : 0;
   return 0;
 }
 
@@ -422,7 +780,60 @@ extern "C" int b200_feat_forward(const b200_feat_layout* L, const b200_feat_tabl
     if (rc < 0) return rc;
     if (rc == 1) return 0;
   }
-  if (fast) {
+  const int K4v = K / 4;
+  const bool group_ok = fast && g_feat_kernel == 0 && (K4v == 1 || K4v == 2 || K4v == 4 || K4v == 8);
+  if (group_ok && !g_feat_no_async && R >= 4096) {
+    // cp.async staged kernel: two rows of gathers in flight per warp; warps per CTA and CTAs per SM chosen so
+    // that the rings fill the SM's shared memory
+    const int FPW = 32 / K4v;
+    const int n_id = ((L->id_mask & 1) ? 1 : 0) + ((L->id_mask & 2) ? 1 : 0);
+    const int F = n_id + L->n_sparse + L->n_dense;
+    const int NS = (F + FPW - 1) / FPW;
+    if (NS <= ASYNC_MAXS) {
+      const size_t per_warp = (size_t)2 * NS * 512 + (size_t)2 * NS * FPW * 4;
+      const size_t meta = (size_t)F * 12;
+      int best_w = 0, best_wpb = 0, best_nb = 0;
+      for (int wpb = 8; wpb >= 2; --wpb) {
+        const size_t per_block = wpb * per_warp + meta + 1024;
+        int nb = (int)((size_t)(228 * 1024) / per_block);
+        nb = std::min(nb, 16 / wpb);             // ~126 registers per thread: 16 warps per SM
+        if (nb * wpb > best_w) { best_w = nb * wpb; best_wpb = wpb; best_nb = nb; }
+      }
+      if (best_w >= 8) {
+        const size_t dyn = best_wpb * per_warp + meta;
+        const int64_t blocks_needed = ceil_div64(R, best_wpb);
+        const unsigned blocks = (unsigned)std::min<int64_t>(blocks_needed, (int64_t)148 * best_nb);
+        cudaStream_t st = (cudaStream_t)stream;
+        auto launch = [&](auto kern) -> int {
+          B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+          kern<<<blocks, best_wpb * 32, dyn, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h, NS);
+          return 0;
+        };
+        int rc;
+        switch (K4v) {
+          case 1: rc = launch(feat_forward_async_kernel<1>); break;
+          case 2: rc = launch(feat_forward_async_kernel<2>); break;
+          case 4: rc = launch(feat_forward_async_kernel<4>); break;
+          default: rc = launch(feat_forward_async_kernel<8>); break;
+        }
+        if (rc) return rc;
+        count_launch();
+        B200_CUDA_OK(cudaGetLastError());
+        return 0;
+      }
+    }
+  }
+  if (group_ok) {
+    // field-group kernel: persistent over rows (the per-block metadata staging is paid once per CTA)
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(R, 8), (int64_t)148 * 3);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (K4v) {
+      case 1: feat_forward_fieldgroup_kernel<1><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+      case 2: feat_forward_fieldgroup_kernel<2><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+      case 4: feat_forward_fieldgroup_kernel<4><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+      default: feat_forward_fieldgroup_kernel<8><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h); break;
+    }
+  } else if (fast) {
     const unsigned blocks = (unsigned)ceil_div64(R * 32, 256);
     cudaStream_t st = (cudaStream_t)stream;
     switch (K / 4) {

@@ -163,7 +163,7 @@ __global__ void prep_items_kernel(const float* __restrict__ I, int64_t ldi, int6
 
 __global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
                                   const int64_t* __restrict__ user_ids, int64_t B, int B_pad, int d,
-                                  int d_pad, int K, int64_t N, int filter, float pre_scale,
+                                  int d_pad, int K, int64_t N, int filter, float pre_scale, int pre_margin,
                                   const int64_t* __restrict__ indptr, int64_t n_users,
                                   const CatalogHeader* __restrict__ hdr,
                                   __half* __restrict__ A, RowMeta* __restrict__ meta,
@@ -211,7 +211,7 @@ __global__ void prep_users_kernel(const float* __restrict__ U, int64_t ldu,
     // speculative threshold = pre_k-th largest SAMPLED block maximum: about pre_k / f items of the
     // whole catalogue lie above it (f = sampled fraction); pre_scale = c * f keeps that at
     // >= c * k_row + 16 / f
-    m.pre_k = 16 + (int32_t)ceilf(pre_scale * (float)m.k_row);
+    m.pre_k = pre_margin + (int32_t)ceilf(pre_scale * (float)m.k_row);
     m.active = real;
     meta[row] = m;
     row_tau_key[row] = 0u;  // below every finite float
@@ -1134,7 +1134,8 @@ static int g_cluster = 2;          // 2 = pairs of user tiles share every item t
 static int g_nh = 1;               // MMA groups per item tile (1 x N=256; 2 x N=128 re-reads the user tile: ~2x slower)
 static int g_ablate = 0;           // b200_recommend_embed_debug
 static int g_hint_ns = 20000;      // suspend-time hint of the mbarrier waits in the sweep kernels
-static float g_pre_coef = 2.67f;   // speculative rank target = g_pre_coef * k_row (+ 16 / sampled fraction)
+static int g_pre_margin = 12;      // additive part of the speculative rank: pre_k = margin + coef * f * k_row sampled block maxima
+static float g_pre_coef = 2.0f;    // speculative rank target = g_pre_coef * k_row (+ 16 / sampled fraction)
 
 struct Plan {
   int B_pad, d_pad, KB, m_tiles, total_tiles, n_splits, tiles_per_split, nstage, n_pre_tiles;
@@ -1324,6 +1325,8 @@ extern "C" int b200_recommend_embed_tune(int32_t epilogue_warps_per_quadrant, fl
 // Diagnostics (profiling only; results are WRONG while level 1 is set): 1 = the main pass collects nothing.
 extern "C" int b200_recommend_embed_debug(int32_t ablate_level) {
   // levels >= 100: suspend-time hint (ns) of the mbarrier waits of the sweep kernels = level - 100
+  // levels -1 .. -64: additive margin of the speculative rank (pre_k = margin + coef * f * k_row) = -level
+  if (ablate_level < 0 && ablate_level >= -64) { g_pre_margin = -ablate_level; return 0; }
   if (ablate_level >= 100) { g_hint_ns = ablate_level - 100; return 0; }
   B200_REQUIRE(ablate_level >= 0 && ablate_level <= 1, "b200_recommend_embed_debug: level 0..1 (or 100 + hint ns)");
   g_ablate = ablate_level;
@@ -1381,7 +1384,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   const __half* Ih = (const __half*)((const char*)catalog + 256);
 
   prep_users_kernel<<<(unsigned)ceil_div64((int64_t)pl.B_pad * 32, 256), 256, 0, stream>>>(
-      U, ldu, user_ids, B, pl.B_pad, d, pl.d_pad, K, N, filter, pl.pre_scale, indptr, n_users, hdr, A, meta,
+      U, ldu, user_ids, B, pl.B_pad, d, pl.d_pad, K, N, filter, pl.pre_scale, g_pre_margin, indptr, n_users, hdr, A, meta,
       tau, status);
   count_launch();
   // cnt and ghist are adjacent in the workspace: one memset

@@ -341,6 +341,30 @@ __global__ void deepfm_head_backward_kernel(const float* __restrict__ dlogit, co
   else ddeep[r * ldd + (c - 1 - K)] = v;
 }
 
+
+// backward of tf.linalg.l2_normalize (y = x rsqrt(max(|x|^2, 1e-12))): dx = r (dy - y <y, dy>) above the clamp
+__global__ void l2_normalize_backward_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy,
+                                             int64_t lddy, int64_t R, int d, float* __restrict__ dx, int64_t lddx) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  float ss = 0.f, xd = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const float v = x[r * ldx + k];
+    ss = fmaf(v, v, ss);
+    xd = fmaf(v, dy[r * lddy + k], xd);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    xd += __shfl_xor_sync(0xffffffffu, xd, o);
+  }
+  const bool clamped = ss < 1e-12f;
+  const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+  const float c = clamped ? 0.f : xd * inv * inv * inv;      // <y, dy> r / |x| ... = <x, dy> r^3
+  for (int k = lane; k < d; k += 32) dx[r * lddx + k] = dy[r * lddy + k] * inv - x[r * ldx + k] * c;
+}
+
 }  // namespace train
 }  // namespace b200
 
@@ -487,6 +511,17 @@ extern "C" int b200_feat_backward(const b200_feat_layout* layout, const b200_fea
   const int64_t warps = ceil_div64(R, 32 / lpr);
   feat_backward_kernel<<<(unsigned)ceil_div64(warps * 32, 256), 256, shm, (cudaStream_t)stream>>>(
       *layout, *tables, users, items, R, dpw, ld_dpw, S, ld_s, dconcat, ld_dconcat, dlogit, lin_kernel, G, lpr);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200_l2_normalize_backward(const float* x, int64_t ldx, const float* dy, int64_t lddy, int64_t R,
+                                          int32_t d, float* dx, int64_t lddx, void* stream) {
+  B200_REQUIRE(x && dy && dx, "b200_l2_normalize_backward: null pointer");
+  if (R == 0) return 0;
+  l2_normalize_backward_kernel<<<(unsigned)ceil_div64(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, dy, lddy, R,
+                                                                                                   d, dx, lddx);
   B200_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -346,3 +346,227 @@ class DeepFMTrainer:
             mlp["bns"] = [bn(i + 1) for i in range(n - 1)]
         w["mlp"] = mlp
         return w
+
+
+class TwoTowerTrainer:
+    """TwoTower training step on the device, in-batch softmax loss (the reference's default):
+    ``libreco/algorithms/two_tower.py:306-346,400-410`` (both towers, ``dense_nn`` in training mode, optional
+    ``tf.linalg.l2_normalize``), ``tfops/loss.py:71-75`` + ``two_tower.py:458-479`` (``U V^T / temperature -
+    log Q``, optional accidental-hit mask, mean sparse softmax CE with the diagonal as labels), TF-Adam.
+
+        per tower: K1 gather (b200_feat_forward, tower layout) -> BN/Dense/ReLU stack (b200_bn_train_forward,
+        b200_linear_*) -> b200_l2_normalize_rows;  S = U V^T (b200_linear_*) -> b200_softmax_inbatch_loss
+        (S becomes dS) -> dU = dS V, dV = dS^T U -> b200_l2_normalize_backward -> stack backward ->
+        b200_feat_backward (scatter into the SHARED sparse / dense tables) -> b200_adam_dense
+
+    ``weights``: layout of ``feat_models.TwoTower`` / ``synthetic.make_two_tower_weights``.  ``temperature``
+    must be positive (the learned-temperature variant, ``temperature <= 0``, is not built)."""
+
+    _T = ("user_embeds", "item_embeds", "sparse_embeds", "dense_embeds")
+
+    def __init__(self, spec, weights, use_bn=True, norm_embed=False, temperature=1.0, remove_accidental_hits=False,
+                 lr=1e-3, epsilon=1e-5, device=None):
+        import torch
+
+        from .feat_models import FeatLayoutStruct
+
+        if temperature <= 0:
+            raise ValueError("learned temperature (temperature <= 0) is not supported")
+        self._torch = torch
+        K = int(weights["user_embeds"].shape[1])
+        self.spec = spec if isinstance(spec, FeatSpec) else FeatSpec(spec, K, device)
+        self.device, self.K = self.spec.device, K
+        self.use_bn, self.norm_embed = bool(use_bn), bool(norm_embed)
+        self.temperature, self.remove_hits = float(temperature), bool(remove_accidental_hits)
+        self.lr, self.epsilon, self.t = float(lr), float(epsilon), 0
+        f32 = torch.float32
+        p = {k: _dev(weights[k], self.device, f32).clone() for k in self._T if weights.get(k) is not None}
+        self.moving, self.n_layers, self.layouts, self.widths = {}, {}, {}, {}
+        for which, mask in (("user", 1), ("item", 2)):
+            mlp = weights[f"{which}_tower"]
+            n = self.n_layers[which] = len(mlp["kernels"])
+            for i in range(n):
+                p[f"{which}_Wt{i}"] = _dev(np.ascontiguousarray(np.asarray(mlp["kernels"][i]).T), self.device, f32).clone()
+                p[f"{which}_b{i}"] = _dev(mlp["biases"][i], self.device, f32).clone()
+            if self.use_bn:
+                for j, bn in enumerate([mlp.get("bn_in")] + list(mlp.get("bns") or [])):
+                    p[f"{which}_bn{j}_gamma"] = _dev(bn["gamma"], self.device, f32).clone()
+                    p[f"{which}_bn{j}_beta"] = _dev(bn["beta"], self.device, f32).clone()
+                    self.moving[f"{which}_bn{j}"] = (_dev(bn["mean"], self.device, f32).clone(),
+                                                     _dev(bn["var"], self.device, f32).clone())
+            L = FeatLayoutStruct.from_buffer_copy(self.spec.layout)
+            L.id_mask = mask
+            scols = self.spec.user_sparse_cols if which == "user" else self.spec.item_sparse_cols
+            dcols = self.spec.user_dense_cols if which == "user" else self.spec.item_dense_cols
+            L.n_sparse, L.n_dense = len(scols), len(dcols)
+            for f in range(len(scols)):
+                L.sparse_side[f], L.sparse_col[f] = (0 if which == "user" else 1), f
+            for f in range(len(dcols)):
+                L.dense_side[f], L.dense_col[f] = (0 if which == "user" else 1), f
+                L.dense_embed_row[f] = dcols[f]
+            self.layouts[which] = L
+            self.widths[which] = (1 + len(scols) + len(dcols)) * K
+        self.params = p
+        self.grads = {k: torch.zeros_like(v) for k, v in p.items()}
+        self.m = {k: torch.zeros_like(v) for k, v in p.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in p.items()}
+        T = FeatTablesStruct()
+        for k in self._T:
+            setattr(T, k, p[k].data_ptr() if k in p else None)
+        self.tables = T
+        self._lws = torch.empty(int(_lib.lib.b200_loss_workspace_bytes()), dtype=torch.uint8, device=self.device)
+
+    # ---- batch-norm / reductions (same kernels as DeepFMTrainer) -----------------------------------
+    def _bn_forward(self, x, name):
+        torch = self._torch
+        p = self.params
+        R, C = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=self.device)
+        var = torch.empty(C, dtype=torch.float32, device=self.device)
+        mm, mv = self.moving[name]
+        _lib.check(_lib.lib.b200_bn_train_forward(
+            _lib.ptr(x), x.stride(0), R, C, _lib.ptr(p[f"{name}_gamma"]), _lib.ptr(p[f"{name}_beta"]), BN_EPS,
+            BN_MOMENTUM, _lib.ptr(y), y.stride(0), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(mm), _lib.ptr(mv),
+            _lib.current_stream()))
+        return y, (mean, var)
+
+    def _bn_backward(self, dy, x, stats, name, relu_mask):
+        torch = self._torch
+        p, g = self.params, self.grads
+        R, C = x.shape
+        dx = torch.empty_like(x)
+        ws = torch.empty(C * 2, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib.b200_bn_train_backward(
+            _lib.ptr(dy), dy.stride(0), _lib.ptr(x), x.stride(0), R, C, _lib.ptr(stats[0]), _lib.ptr(stats[1]),
+            _lib.ptr(p[f"{name}_gamma"]), BN_EPS, 1 if relu_mask else 0, _lib.ptr(dx), dx.stride(0),
+            _lib.ptr(g[f"{name}_gamma"]), _lib.ptr(g[f"{name}_beta"]), _lib.ptr(ws), ws.numel() * 8,
+            _lib.current_stream()))
+        return dx
+
+    def _col_sum(self, X, out):
+        _lib.check(_lib.lib.b200_col_reduce(_lib.ptr(X), X.stride(0), X.shape[0], X.shape[1], None, None, 0,
+                                            _lib.ptr(out), _lib.current_stream()))
+
+    # ---- one tower ----------------------------------------------------------------------------------
+    def tower_forward(self, which, ids_d):
+        from .feat_models import linear
+
+        torch = self._torch
+        p = self.params
+        n = int(ids_d.numel())
+        x = torch.empty((n, self.widths[which]), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.b200_feat_forward(
+            ctypes.byref(self.layouts[which]), ctypes.byref(self.tables), _lib.ptr(ids_d), _lib.ptr(ids_d), n, 0, 0,
+            _lib.ptr(x), x.stride(0), None, 0, None, None, None, 0.0, None, None, None, 0.0,
+            None, None, 0, _lib.current_stream()))
+        c = dict(ids=ids_d, concat=x, bn_stats={}, dense_in=[], relu_out=[])
+        a = x
+        if self.use_bn:
+            a, c["bn_stats"][0] = self._bn_forward(a, f"{which}_bn0")
+        L = self.n_layers[which]
+        for i in range(L):
+            last = i == L - 1
+            c["dense_in"].append(a)
+            a = linear(a, p[f"{which}_Wt{i}"], p[f"{which}_b{i}"], not last, cache_split=False)
+            if not last:
+                c["relu_out"].append(a)
+                if self.use_bn:
+                    a, c["bn_stats"][i + 1] = self._bn_forward(a, f"{which}_bn{i + 1}")
+        if self.norm_embed:
+            c["pre_norm"] = a
+            a = a.clone()
+            _lib.check(_lib.lib.b200_l2_normalize_rows(_lib.ptr(a), a.stride(0), n, a.shape[1], _lib.current_stream()))
+        c["out"] = a
+        return c
+
+    def tower_backward(self, which, c, da):
+        from .feat_models import linear
+
+        torch = self._torch
+        lib, st, p, g = _lib.lib, _lib.current_stream(), self.params, self.grads
+        n = int(c["ids"].numel())
+        da = da.contiguous()
+        if self.norm_embed:
+            x = c["pre_norm"]
+            _lib.check(lib.b200_l2_normalize_backward(_lib.ptr(x), x.stride(0), _lib.ptr(da), da.stride(0), n,
+                                                      x.shape[1], _lib.ptr(da), da.stride(0), st))
+        L = self.n_layers[which]
+        for i in range(L - 1, -1, -1):
+            if i != L - 1:
+                r_out = c["relu_out"][i]
+                if self.use_bn:
+                    da = self._bn_backward(da, r_out, c["bn_stats"][i + 1], f"{which}_bn{i + 1}", True)
+                else:
+                    dh = torch.empty_like(da)
+                    _lib.check(lib.b200_relu_backward(_lib.ptr(da), _lib.ptr(r_out), da.numel(), _lib.ptr(dh), st))
+                    da = dh
+            x = c["dense_in"][i]
+            da = da.contiguous()
+            g[f"{which}_Wt{i}"] += linear(da.t().contiguous(), x.t().contiguous(), None, False, cache_split=False)
+            self._col_sum(da, g[f"{which}_b{i}"])
+            da = linear(da, p[f"{which}_Wt{i}"].t().contiguous(), None, False, cache_split=False)
+        dconcat = self._bn_backward(da, c["concat"], c["bn_stats"][0], f"{which}_bn0", False) if self.use_bn else da
+        gp = lambda k: _lib.ptr(g[k]) if k in g else None      # noqa: E731
+        _lib.check(lib.b200_feat_backward(
+            ctypes.byref(self.layouts[which]), ctypes.byref(self.tables), _lib.ptr(c["ids"]), _lib.ptr(c["ids"]), n,
+            None, 0, None, 0, _lib.ptr(dconcat), dconcat.stride(0), None, None,
+            gp("user_embeds"), gp("item_embeds"), gp("sparse_embeds"), gp("dense_embeds"), None, None, None, None,
+            None, st))
+
+    # ---- loss / step --------------------------------------------------------------------------------
+    def forward_backward(self, users_d, items_d, correction_d=None):
+        """Loss (device scalar) with every gradient buffer filled.  ``correction_d``: item_corrections[items]
+        of the batch (``two_tower.py:425-435``, ``tf_feed_dicts.py:121-122``) or None (use_correction=False)."""
+        from .feat_models import linear
+
+        torch = self._torch
+        lib, st = _lib.lib, _lib.current_stream()
+        cu = self.tower_forward("user", users_d)
+        ci = self.tower_forward("item", items_d)
+        U, V = cu["out"], ci["out"]
+        B = int(U.shape[0])
+        S = linear(U, V, None, False, cache_split=False)          # [B, B] = U V^T
+        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        corr = correction_d.to(torch.float32).contiguous() if correction_d is not None else None
+        _lib.check(lib.b200_softmax_inbatch_loss(_lib.ptr(S), S.stride(0), B, self.temperature, _lib.ptr(corr),
+                                                 _lib.ptr(items_d) if self.remove_hits else None, 1, _lib.ptr(loss),
+                                                 _lib.ptr(self._lws), self._lws.numel(), st))
+        dU = linear(S, V.t().contiguous(), None, False, cache_split=False)
+        dV = linear(S.t().contiguous(), U.t().contiguous(), None, False, cache_split=False)
+        self.tower_backward("user", cu, dU)
+        self.tower_backward("item", ci, dV)
+        self._last = (U, V)
+        return loss
+
+    def step(self, users_d, items_d, correction_d=None):
+        torch = self._torch
+        users_d = users_d.to(torch.int64).contiguous()
+        items_d = items_d.to(torch.int64).contiguous()
+        loss = self.forward_backward(users_d, items_d, correction_d)
+        self.t += 1
+        lib, st = _lib.lib, _lib.current_stream()
+        for k, v in self.params.items():
+            _lib.check(lib.b200_adam_dense(_lib.ptr(v), _lib.ptr(self.m[k]), _lib.ptr(self.v[k]), _lib.ptr(self.grads[k]),
+                                           v.numel(), self.lr, BETA1, BETA2, self.epsilon, self.t, st))
+        self._last = None
+        return loss
+
+    def export_weights(self):
+        p = self.params
+        w = {k: p[k].cpu().numpy() for k in self._T if k in p}
+        for which in ("user", "item"):
+            n = self.n_layers[which]
+            mlp = dict(kernels=[p[f"{which}_Wt{i}"].t().contiguous().cpu().numpy() for i in range(n)],
+                       biases=[p[f"{which}_b{i}"].cpu().numpy() for i in range(n)])
+            if self.use_bn:
+                def bn(j, which=which):
+                    mm, mv = self.moving[f"{which}_bn{j}"]
+                    return dict(gamma=p[f"{which}_bn{j}_gamma"].cpu().numpy(), beta=p[f"{which}_bn{j}_beta"].cpu().numpy(),
+                                mean=mm.cpu().numpy(), var=mv.cpu().numpy())
+                mlp["bn_in"] = bn(0)
+                mlp["bns"] = [bn(i + 1) for i in range(n - 1)]
+            w[f"{which}_tower"] = mlp
+        w["user_dense_cols"] = list(self.spec.user_dense_cols)
+        w["item_dense_cols"] = list(self.spec.item_dense_cols)
+        return w

@@ -135,7 +135,9 @@ def bench_feat():
     fm = FM(spec, wfm)
     out = torch.empty(R, dtype=torch.float32, device="cuda")
     ref_concat = None
-    for tma, tag in ((0, "register gather (lane per field)"), (1, "TMA-staged persistent (cp.async.bulk ring)")):
+    for tma, tag in ((0, "cp.async staged, K/4 lanes per field (default)"), (4, "register gather, K/4 lanes per field"),
+                     (2, "register gather, lane per field"),
+                     (1, "TMA-staged persistent (cp.async.bulk ring)")):
         _lib.check(_lib.lib.b200_feat_forward_tune(tma))
         ms = timeit(lambda: model._feat_forward(model.spec.layout, users, items, R, 0, concat=concat, pw=pw, lin=lin))
         emit(f"feat_forward gather+FM (DeepFM C3 row shape, writes deep input) [{tag}]", ms,
@@ -144,11 +146,12 @@ def bench_feat():
         if ref_concat is None:
             ref_concat, ref_pw, ref_lin = concat[:4096].clone(), pw[:4096].clone(), lin[:4096].clone()
         else:   # the two kernels must agree (concat bit-for-bit: pure copies; sums to rounding)
-            print(json.dumps({"check": "tma vs register kernel", "concat_equal": bool(torch.equal(concat[:4096], ref_concat)),
+            print(json.dumps({"check": f"variant {tma} vs default kernel", "concat_equal": bool(torch.equal(concat[:4096], ref_concat)),
                               "pw_max_abs_diff": float((pw[:4096] - ref_pw).abs().max()),
                               "lin_max_abs_diff": float((lin[:4096] - ref_lin).abs().max())}), flush=True)
         ms = timeit(lambda: fm._feat_forward(fm.spec.layout, users, items, R, 0, fm_out=out, head=fm.head))
         emit(f"feat_forward FM fused head (no intermediate) [{tag}]", ms, read + R * 4, {"rows": R, "tma": tma})
+    _lib.check(_lib.lib.b200_feat_forward_tune(0))
     ms = timeit(lambda: model.logits(users[:1 << 18].cpu().numpy(), items[:1 << 18].cpu().numpy()), iters=3)
     print(json.dumps({"kernel": "DeepFM predict rows/s (gather + fp32 MLP 1792-128-64-32)", "rows_per_s": (1 << 18) / (ms * 1e-3)}))
     # all-items scoring + top-100 (recommend_user of the TfBase models), hoisted kernels

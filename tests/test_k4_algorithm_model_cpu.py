@@ -57,7 +57,7 @@ def model_row(u, I, consumed, K, stride=2, block=16, guess_scale=1.0, stats=None
     tau = -np.inf
     if len(sampled) * 1 >= 16:
         f = len(sampled) / max(n_blocks, 1)
-        pre_k = 16 + int(np.ceil(2.67 * f * k_row))
+        pre_k = 12 + int(np.ceil(2.0 * f * k_row))        # g_pre_margin, g_pre_coef of score_topk_tc.cu
         bm = np.sort([coarse[b * block:(b + 1) * block].max() for b in sampled])[::-1]
         if len(bm) >= pre_k:
             tau = bm[pre_k - 1] * guess_scale if bm[pre_k - 1] > 0 else bm[pre_k - 1] / guess_scale

@@ -37,6 +37,10 @@ def main():
         w, c, b = var[:3]
         ablate = int(var[3]) if len(var) > 3 else 0
         hint = int(var[4]) if len(var) > 4 else 20000
+        margin = 16
+        if ablate < 0:                      # negative 4th field = additive margin of the speculative rank
+            margin, ablate = -ablate, 0
+        _lib.check(_lib.lib.b200_recommend_embed_debug(-margin))
         _lib.check(_lib.lib.b200_recommend_embed_debug(100 + hint))
         _lib.check(_lib.lib.b200_recommend_embed_debug(ablate))
         _lib.check(_lib.lib.b200_recommend_embed_tune(int(w), float(c)))
@@ -64,7 +68,7 @@ def main():
         # parity spot check of the last batch against the exact path (256 rows)
         ex = sc.recommend_exact(batches[-1][:256], args.topk, True, False)
         same = bool((out[:256] == ex).all())
-        print(json.dumps({"ablate": ablate, "hint_ns": hint, "W": w, "coef": c, "rows_per_launch": b, "sweep_ms": sweep, "step_ms_sync": step,
+        print(json.dumps({"ablate": ablate, "margin": margin, "hint_ns": hint, "W": w, "coef": c, "rows_per_launch": b, "sweep_ms": sweep, "step_ms_sync": step,
                           "tflops": flops / sweep / 1e9, "users_per_s_sync": b / step * 1e3,
                           "fallback_rows": fb, "ids_equal_exact_256": same, "plan": sc.fused_plan(b, args.topk)}),
               flush=True)
