@@ -177,7 +177,8 @@ typedef struct {       /* TF scope "embedding" (SURVEY.md Appendix C), fp32, row
 /* process-wide switch (A/B measurements, tests).  bit 0: 1 = the bulk-copy (TMA) staged persistent gather for
  * eligible shapes (K % 4 == 0, K <= 32, >= 2048 rows), 0 = the register-gather kernels only.
  * bit 1: 1 = the older lane-per-field register kernel instead of the field-group kernel (K in {4,8,16,32}).
- * bit 2: 1 = never the cp.async staged variant of the field-group kernel (default for >= 4096 rows). */
+ * bit 2: 1 = plain field-group kernel also for >= 4096 rows (default there: its software-pipelined variant).
+ * bit 3: 1 = the cp.async (LDGSTS) shared-memory staged variant instead of the software-pipelined one. */
 int b200_feat_forward_tune(int32_t use_tma_staging);
 int b200_feat_forward(const b200_feat_layout* layout, const b200_feat_tables* tables,
                       const int64_t* users, const int64_t* items, int64_t R, int64_t grid_items,

@@ -428,6 +428,229 @@ feat_forward_fieldgroup_kernel(const b200_feat_layout L, const b200_feat_tables 
   }
 }
 
+// ---- software-pipelined register gather (default for >= 4096 rows, K in {4, 8, 16, 32}, <= 16 steps per row):
+// the field-group layout with (a) the index loads of the NEXT batch of 8 steps issued while the row gathers of the
+// current batch are in flight — the dependent chain ids -> feature index -> embedding row costs one memory round
+// trip per batch instead of two (ncu of the unpipelined kernel: 68 % of the stall cycles long-scoreboard, DRAM at
+// 18 %) — and (b) the per-(lane, step) field metadata decoded ONCE into registers: a step whose 32/K4 fields are
+// all sparse ("pure", warp-uniform) is a load of the packed column, one 64-bit multiply-add and the gather.
+template <int K4>
+__global__ void __launch_bounds__(256, 2)
+feat_forward_pipe_kernel(const b200_feat_layout L, const b200_feat_tables T,
+                         const int64_t* __restrict__ users, const int64_t* __restrict__ items,
+                         int64_t R, int64_t grid_items, int64_t row_offset, Out o, Head h, int NS) {
+  constexpr int K = K4 * 4;
+  constexpr int FPW = 32 / K4;
+  constexpr int U = 8;                          // steps per batch
+  constexpr int MAXF = 2 + 2 * B200_MAX_FIELDS;
+  __shared__ int32_t sh_code[MAXF];
+  __shared__ int32_t sh_drow[MAXF];
+  __shared__ float sh_link[MAXF + 32];
+  const int lane = threadIdx.x & 31;
+  const int fg = lane / K4, q = lane % K4;
+  const int n_id = ((L.id_mask & 1) ? 1 : 0) + ((L.id_mask & 2) ? 1 : 0);
+  const int F = n_id + L.n_sparse + L.n_dense;
+  const bool want_lin = (o.lin != nullptr) || (o.fm_out != nullptr);
+  for (int f = threadIdx.x; f < NS * FPW; f += blockDim.x) {
+    if (f >= F) { sh_link[f] = 0.f; continue; }
+    int kind, col = 0, drow = 0;
+    if (f < n_id) kind = ((L.id_mask & 1) && f == 0) ? 0 : 1;
+    else if (f < n_id + L.n_sparse) {
+      const int fs = f - n_id;
+      kind = L.sparse_side[fs] == 0 ? 2 : 3;
+      col = L.sparse_col[fs];
+    } else {
+      const int fd = f - n_id - L.n_sparse;
+      drow = L.dense_embed_row[fd];
+      kind = L.dense_side[fd] == 0 ? 5 : 6;
+      col = L.dense_col[fd];
+    }
+    sh_code[f] = kind | (col << 3);
+    sh_drow[f] = drow;
+    sh_link[f] = want_lin ? h.lin_kernel[f] : 0.f;
+  }
+  __syncthreads();
+  const float* my_link = sh_link + fg;          // + j * FPW per step
+
+  uint32_t colpack[4] = {0u, 0u, 0u, 0u};       // column of (lane, step j) in its side's unique table, 8 bits each
+  uint32_t side_mask = 0, pure = 0;
+#pragma unroll
+  for (int j = 0; j < 2 * U; ++j) {
+    const int f = j * FPW + fg;
+    bool sparse_f = false;
+    if (j < NS && f < F) {
+      const int code = sh_code[f];
+      const int kind = code & 7, col = code >> 3;
+      if (kind == 2 || kind == 3) {
+        sparse_f = true;
+        colpack[j / 4] |= (uint32_t)col << (8 * (j % 4));
+        if (kind == 3) side_mask |= 1u << j;
+      }
+    }
+    if (__all_sync(0xffffffffu, sparse_f)) pure |= 1u << j;
+  }
+  const float4* tbl_q = reinterpret_cast<const float4*>(T.sparse_embeds) + q;
+
+  auto load_ids = [&](int64_t r, int64_t& u, int64_t& it) {
+    u = 0; it = 0;
+    if (r < R) {
+      if (grid_items > 0) { const int64_t rg = r + row_offset; u = users[rg / grid_items]; it = rg % grid_items; }
+      else { u = users[r]; it = items[r]; }
+    }
+  };
+  // index (sparse) / value bits (dense) of the 8 steps [J0, J0 + 8) of the row with ids (u, it)
+  auto load_indices = [&](int32_t (&raw)[U], const int J0, int64_t u, int64_t it) {
+    const int32_t* pu = L.user_sparse_unique + u * L.ld_us;
+    const int32_t* pi = L.item_sparse_unique + it * L.ld_is;
+#pragma unroll
+    for (int jj = 0; jj < U; ++jj) {
+      const int j = J0 + jj;
+      raw[jj] = 0;
+      if (j >= NS) continue;
+      const int col = (colpack[j / 4] >> (8 * (j % 4))) & 255u;
+      if ((pure >> j) & 1u) {
+        raw[jj] = __ldg((((side_mask >> j) & 1u) ? pi : pu) + col);
+      } else {
+        const int f = j * FPW + fg;
+        if (f < F) {
+          const int code = sh_code[f];
+          const int kind = code & 7;
+          if (kind == 2 || kind == 3) raw[jj] = __ldg((kind == 3 ? pi : pu) + col);
+          else if (kind >= 5) {
+            const int dcol = code >> 3;
+            const float* xp = kind == 5 ? L.user_dense_unique + u * L.ld_ud + dcol : L.item_dense_unique + it * L.ld_id + dcol;
+            raw[jj] = __float_as_int(__ldg(xp));
+          }
+        }
+      }
+    }
+  };
+
+  float4 s, s2;
+  float lin_acc;
+  float4 e[U];
+  float lw[U];
+  // phase A: row gathers (+ linear weights) of the steps [J0, J0 + 8) from their indices
+  auto gather = [&](const int32_t (&raw)[U], const int J0, int64_t u, int64_t it) {
+#pragma unroll
+    for (int jj = 0; jj < U; ++jj) {
+      const int j = J0 + jj;
+      e[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+      lw[jj] = 0.f;
+      if (j >= NS) continue;
+      if ((pure >> j) & 1u) {
+        e[jj] = __ldg(tbl_q + (int64_t)raw[jj] * K4);
+        if (want_lin) lw[jj] = __ldg(T.sparse_linear + raw[jj]);
+      } else {
+        const int f = j * FPW + fg;
+        if (f < F) {
+          const int kind = sh_code[f] & 7;
+          if (kind < 2) {
+            e[jj] = __ldg(reinterpret_cast<const float4*>(kind == 0 ? T.user_embeds + u * K : T.item_embeds + it * K) + q);
+            if (want_lin) lw[jj] = kind == 0 ? __ldg(T.user_linear + u) : __ldg(T.item_linear + it);
+          } else if (kind < 5) {
+            e[jj] = __ldg(tbl_q + (int64_t)raw[jj] * K4);
+            if (want_lin) lw[jj] = __ldg(T.sparse_linear + raw[jj]);
+          } else {
+            const int drow = sh_drow[f];
+            e[jj] = __ldg(reinterpret_cast<const float4*>(T.dense_embeds + (int64_t)drow * K) + q);
+            if (want_lin) lw[jj] = __ldg(T.dense_linear + drow);
+          }
+        }
+      }
+    }
+  };
+  // phase C: sums, linear term, concatenated row
+  auto consume = [&](const int32_t (&raw)[U], const int J0, float* crow) {
+#pragma unroll
+    for (int jj = 0; jj < U; ++jj) {
+      const int j = J0 + jj;
+      if (j >= NS) continue;
+      const bool is_pure = (pure >> j) & 1u;
+      const int f = j * FPW + fg;
+      if (!is_pure && f >= F) continue;
+      float4 v = e[jj];
+      float l = lw[jj];
+      if (!is_pure && (sh_code[f] & 7) >= 5) {
+        const float sc = __int_as_float(raw[jj]);
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        l *= sc;
+      }
+      if (want_lin) lin_acc = fmaf(l, my_link[j * FPW], lin_acc);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y);
+      s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+      if (crow) *reinterpret_cast<float4*>(crow + j * 128) = v;
+    }
+  };
+
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int64_t u, it, un, itn, un2, itn2;      // ids of the current row, the next one and the one after
+  load_ids(r, u, it);
+  load_ids(r + n_warps, un, itn);
+  load_ids(r + 2 * n_warps, un2, itn2);
+  int32_t rawA[U], rawB[U];
+  if (r < R) load_indices(rawA, 0, u, it);
+  const bool two = NS > U;
+  for (; r < R; r += n_warps) {
+    const bool has_next = r + n_warps < R;
+    s = make_float4(0.f, 0.f, 0.f, 0.f);
+    s2 = s;
+    lin_acc = 0.f;
+    float* crow = o.concat ? o.concat + r * o.ld_concat + lane * 4 : nullptr;   // + j * 128 floats per step
+    // ---- batch 0: gathers of steps 0..7 | indices of the next batch | consume
+    gather(rawA, 0, u, it);
+    if (two) load_indices(rawB, U, u, it);
+    else if (has_next) load_indices(rawB, 0, un, itn);
+    consume(rawA, 0, crow);
+    if (two) {
+      // ---- batch 1: gathers of steps 8..15 | indices of the next row's first batch | consume
+      gather(rawB, U, u, it);
+      if (has_next) load_indices(rawA, 0, un, itn);
+      consume(rawB, U, crow);
+    } else {
+#pragma unroll
+      for (int jj = 0; jj < U; ++jj) rawA[jj] = rawB[jj];
+    }
+    u = un; it = itn; un = un2; itn = itn2;
+    load_ids(r + 3 * n_warps, un2, itn2);
+    if (!o.pw && !o.fm_out && !o.lin && !o.ssum) continue;
+#pragma unroll
+    for (int off = K4; off < 32; off <<= 1) {
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+      s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
+      s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+      lin_acc += __shfl_xor_sync(0xffffffffu, lin_acc, off);     // the K4 lanes of a field hold copies
+    }
+    lin_acc += h.lin_bias;
+    const float sv[4] = {s.x, s.y, s.z, s.w};
+    const float s2v[4] = {s2.x, s2.y, s2.z, s2.w};
+    float head_acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int kk = q * 4 + c;
+      const float pw = 0.5f * (sv[c] * sv[c] - s2v[c]);
+      if (fg == 0) {
+        if (o.pw) o.pw[r * o.ld_pw + kk] = pw;
+        if (o.ssum) { o.ssum[r * o.ld_s + kk] = sv[c]; o.sqsum[r * o.ld_s + kk] = s2v[c]; }
+      }
+      if (o.fm_out) {
+        const float z = h.bn_scale ? fmaf(pw, h.bn_scale[kk], h.bn_shift[kk]) : pw;
+        head_acc = fmaf(z, h.pw_kernel[kk], head_acc);
+      }
+    }
+    if (o.fm_out) {
+#pragma unroll
+      for (int off = 1; off < K4; off <<= 1) head_acc += __shfl_xor_sync(0xffffffffu, head_acc, off);
+      head_acc += h.pw_bias;
+      if (lane == 0) o.fm_out[r] = lin_acc + (head_acc > 0.f ? head_acc : expm1f(head_acc));
+    }
+    if (o.lin && lane == 0) o.lin[r] = lin_acc;
+  }
+}
+
 // ---- large row counts, K in {4, 8, 16, 32}: the field-group layout above with the row gathers staged through
 // shared memory by cp.async (LDGSTS, 16 B per lane — the SAME request pattern as the register gather, but the
 // landing zone is shared memory instead of registers, so a warp keeps TWO whole rows of gathers in flight and the
@@ -450,8 +673,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 constexpr int ASYNC_MAXS = 16;   // steps (warp-level gathers) per row the staged kernel holds in registers
 
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
 template <int K4>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 feat_forward_async_kernel(const b200_feat_layout L, const b200_feat_tables T,
                           const int64_t* __restrict__ users, const int64_t* __restrict__ items,
                           int64_t R, int64_t grid_items, int64_t row_offset, Out o, Head h, int NS) {
@@ -465,31 +693,60 @@ feat_forward_async_kernel(const b200_feat_layout L, const b200_feat_tables T,
   const int n_id = ((L.id_mask & 1) ? 1 : 0) + ((L.id_mask & 2) ? 1 : 0);
   const int F = n_id + L.n_sparse + L.n_dense;
   const bool want_lin = (o.lin != nullptr) || (o.fm_out != nullptr);
-  // dynamic shared memory: [wpb][2][NS][32] float4 rings | [wpb][2][NS * FPW] scales | code[F] | drow[F] | link[F]
-  float4* ring = dyn_smem + (size_t)wib * 2 * NS * 32;
-  float* sx_all = reinterpret_cast<float*>(dyn_smem + (size_t)wpb * 2 * NS * 32);
-  float* sx = sx_all + (size_t)wib * 2 * NS * FPW;
-  int32_t* sh_code = reinterpret_cast<int32_t*>(sx_all + (size_t)wpb * 2 * NS * FPW);
+  // dynamic shared memory: [wpb][2][NS][32] float4 rings | [wpb][2][NS*FPW] scales | [wpb][2][NS*FPW] linear
+  // weights | code[F] | drow[F] | link[NS*FPW]
+  float4* ring = dyn_smem + (size_t)wib * 2 * NS * 32 + lane;          // this lane's 16-byte column of the ring
+  float* aux = reinterpret_cast<float*>(dyn_smem + (size_t)wpb * 2 * NS * 32);
+  float* sx = aux + (size_t)wib * 2 * NS * FPW + fg;                   // this lane's field column
+  float* slw = aux + (size_t)(wpb + wib) * 2 * NS * FPW + fg;
+  int32_t* sh_code = reinterpret_cast<int32_t*>(aux + (size_t)2 * wpb * 2 * NS * FPW);
   int32_t* sh_drow = sh_code + F;
-  float* sh_link = reinterpret_cast<float*>(sh_drow + F);
-  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+  float* sh_link = reinterpret_cast<float*>(sh_drow + F);              // [NS * FPW], 0 past F
+  for (int f = threadIdx.x; f < NS * FPW; f += blockDim.x) {
+    if (f >= F) { sh_link[f] = 0.f; continue; }
     int kind, col = 0, drow = 0;
     if (f < n_id) kind = ((L.id_mask & 1) && f == 0) ? 0 : 1;
     else if (f < n_id + L.n_sparse) {
       const int fs = f - n_id;
-      if (L.sparse_rows) { kind = 4; col = fs; }
-      else { kind = L.sparse_side[fs] == 0 ? 2 : 3; col = L.sparse_col[fs]; }
+      kind = L.sparse_side[fs] == 0 ? 2 : 3;
+      col = L.sparse_col[fs];
     } else {
       const int fd = f - n_id - L.n_sparse;
       drow = L.dense_embed_row[fd];
-      if (L.dense_rows) { kind = 7; col = fd; }
-      else { kind = L.dense_side[fd] == 0 ? 5 : 6; col = L.dense_col[fd]; }
+      kind = L.dense_side[fd] == 0 ? 5 : 6;
+      col = L.dense_col[fd];
     }
     sh_code[f] = kind | (col << 3);
     sh_drow[f] = drow;
     sh_link[f] = want_lin ? h.lin_kernel[f] : 0.f;
   }
   __syncthreads();
+  const float* my_link = sh_link + fg;                                 // + j * FPW per step
+
+  // ---- per-lane step descriptors (the field of (lane, step j) is the same for every row): a step whose 32/K4
+  // fields are ALL sparse ("pure", warp-uniform) needs only its column in the side's unique table (8 bits,
+  // packed four to a register) and one side bit; mixed steps (ids, dense fields, the ragged last step) take the
+  // generic path through the shared-memory metadata.
+  uint32_t colpack[MAXS / 4];
+  uint32_t side_mask = 0, pure = 0;
+#pragma unroll
+  for (int j = 0; j < MAXS / 4; ++j) colpack[j] = 0;
+#pragma unroll
+  for (int j = 0; j < MAXS; ++j) {
+    const int f = j * FPW + fg;
+    bool sparse_f = false;
+    if (j < NS && f < F) {
+      const int code = sh_code[f];
+      const int kind = code & 7, col = code >> 3;
+      if (kind == 2 || kind == 3) {
+        sparse_f = true;
+        colpack[j / 4] |= (uint32_t)col << (8 * (j % 4));
+        if (kind == 3) side_mask |= 1u << j;
+      }
+    }
+    if (__all_sync(0xffffffffu, sparse_f)) pure |= 1u << j;
+  }
+  const float* tbl_q = T.sparse_embeds + q * 4;
 
   const int64_t n_warps = (int64_t)gridDim.x * wpb;
   const int64_t w0 = (int64_t)blockIdx.x * wpb + wib;
@@ -501,25 +758,28 @@ feat_forward_async_kernel(const b200_feat_layout L, const b200_feat_tables T,
     }
   };
   int32_t raw[MAXS];
-  // I: feature index (sparse) / value bits (dense) of every step of row r
-  auto load_indices = [&](int64_t r, int64_t u, int64_t it) {
+  // I: feature index (sparse) / value bits (dense) of every step of a row with ids (u, it)
+  auto load_indices = [&](int64_t u, int64_t it) {
+    const int32_t* pu = L.user_sparse_unique + u * L.ld_us;
+    const int32_t* pi = L.item_sparse_unique + it * L.ld_is;
 #pragma unroll
     for (int j = 0; j < MAXS; ++j) {
-      raw[j] = 0;
-      const int f = j * FPW + fg;
-      if (j < NS && f < F) {
-        const int code = sh_code[f];
-        const int kind = code & 7, col = code >> 3;
-        if (kind >= 2 && kind < 5) {
-          const int32_t* ip = kind == 2 ? L.user_sparse_unique + u * L.ld_us + col
-                            : kind == 3 ? L.item_sparse_unique + it * L.ld_is + col
-                                        : L.sparse_rows + r * L.ld_sparse_rows + col;
-          raw[j] = __ldg(ip);
-        } else if (kind >= 5) {
-          const float* xp = kind == 5 ? L.user_dense_unique + u * L.ld_ud + col
-                          : kind == 6 ? L.item_dense_unique + it * L.ld_id + col
-                                      : L.dense_rows + r * L.ld_dense_rows + col;
-          raw[j] = __float_as_int(__ldg(xp));
+      if (j >= NS) continue;
+      const int col = (colpack[j / 4] >> (8 * (j % 4))) & 255u;
+      if ((pure >> j) & 1u) {
+        raw[j] = __ldg((((side_mask >> j) & 1u) ? pi : pu) + col);
+      } else {
+        raw[j] = 0;
+        const int f = j * FPW + fg;
+        if (f < F) {
+          const int code = sh_code[f];
+          const int kind = code & 7;
+          if (kind == 2 || kind == 3) raw[j] = __ldg((kind == 3 ? pi : pu) + col);
+          else if (kind >= 5) {
+            const int dcol = code >> 3;
+            const float* xp = kind == 5 ? L.user_dense_unique + u * L.ld_ud + dcol : L.item_dense_unique + it * L.ld_id + dcol;
+            raw[j] = __float_as_int(__ldg(xp));
+          }
         }
       }
     }
@@ -529,65 +789,79 @@ feat_forward_async_kernel(const b200_feat_layout L, const b200_feat_tables T,
   load_ids(w0, ua, ita);
   load_ids(w0 + n_warps, ub, itb);
   load_ids(w0 + 2 * n_warps, uc, itc);
-  if (w0 < R) load_indices(w0, ua, ita);
-  float lin_cur = 0.f;
+  if (w0 < R) load_indices(ua, ita);
   for (int64_t k = -1;; ++k) {
     const int64_t r_cur = w0 + k * n_warps, r_nx = r_cur + n_warps, r_nx2 = r_nx + n_warps;
     if (k >= 0 && r_cur >= R) break;
     __syncwarp();
     const int nb = (int)((k + 1) & 1);
-    // ---- G(k+1): addresses from raw[], asynchronous copies into ring[nb]
-    float lwn[MAXS];
+    // ---- G(k+1): addresses from raw[], asynchronous copies (rows AND linear weights) into buffer nb
     if (r_nx < R) {
+      float4* dst = ring + (size_t)nb * NS * 32;
+      float* dlw = slw + (size_t)nb * NS * FPW;
+      float* dsx = sx + (size_t)nb * NS * FPW;
 #pragma unroll
       for (int j = 0; j < MAXS; ++j) {
-        lwn[j] = 0.f;
-        const int f = j * FPW + fg;
-        if (j < NS && f < F) {
-          const int code = sh_code[f];
-          const int kind = code & 7;
-          const float* rowp;
-          float scale = 1.f;
-          if (kind < 2) {
-            rowp = kind == 0 ? T.user_embeds + ua * K : T.item_embeds + ita * K;
-            if (want_lin && q == 0) lwn[j] = kind == 0 ? __ldg(T.user_linear + ua) : __ldg(T.item_linear + ita);
-          } else if (kind < 5) {
-            rowp = T.sparse_embeds + (int64_t)raw[j] * K;
-            if (want_lin && q == 0) lwn[j] = __ldg(T.sparse_linear + raw[j]);
-          } else {
-            const int drow = sh_drow[f];
-            scale = __int_as_float(raw[j]);
-            rowp = T.dense_embeds + (int64_t)drow * K;
-            if (want_lin && q == 0) lwn[j] = __ldg(T.dense_linear + drow) * scale;
+        if (j >= NS) continue;
+        if ((pure >> j) & 1u) {
+          cp_async16(dst + j * 32, tbl_q + (int64_t)raw[j] * K);
+          if (want_lin && q == 0) cp_async4(dlw + j * FPW, T.sparse_linear + raw[j]);
+        } else {
+          const int f = j * FPW + fg;
+          if (f < F) {
+            const int kind = sh_code[f] & 7;
+            const float* rowp;
+            float scale = 1.f;
+            if (kind < 2) {
+              rowp = kind == 0 ? T.user_embeds + ua * K : T.item_embeds + ita * K;
+              if (want_lin && q == 0) cp_async4(dlw + j * FPW, kind == 0 ? T.user_linear + ua : T.item_linear + ita);
+            } else if (kind < 5) {
+              rowp = T.sparse_embeds + (int64_t)raw[j] * K;
+              if (want_lin && q == 0) cp_async4(dlw + j * FPW, T.sparse_linear + raw[j]);
+            } else {
+              const int drow = sh_drow[f];
+              scale = __int_as_float(raw[j]);
+              rowp = T.dense_embeds + (int64_t)drow * K;
+              if (want_lin && q == 0) dlw[j * FPW] = __ldg(T.dense_linear + drow) * scale;
+            }
+            cp_async16(dst + j * 32, rowp + q * 4);
+            if (q == 0) dsx[j * FPW] = scale;
           }
-          cp_async16(ring + ((size_t)nb * NS + j) * 32 + lane, reinterpret_cast<const float4*>(rowp) + q);
-          if (q == 0) sx[(nb * NS + j) * FPW + fg] = scale;
         }
       }
     }
     cp_async_commit();
     // ---- I(k+2) and the ids of row k+3
-    if (r_nx2 < R) load_indices(r_nx2, ub, itb);
+    if (r_nx2 < R) load_indices(ub, itb);
     ua = ub; ita = itb; ub = uc; itb = itc;
     load_ids(r_nx2 + 2 * n_warps, uc, itc);
     // ---- row k has landed (everything but the newest group)
     cp_async_wait<1>();
     if (k >= 0) {
+      __syncwarp();          // scales / linear weights of the quad's lane 0 are read by all its lanes
       const int cb = (int)(k & 1);
       const int64_t r = r_cur;
+      const float4* src = ring + (size_t)cb * NS * 32;
+      const float* csx = sx + (size_t)cb * NS * FPW;
+      const float* clw = slw + (size_t)cb * NS * FPW;
+      float* crow = o.concat ? o.concat + r * o.ld_concat + lane * 4 : nullptr;   // + j * 128 floats per step
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s;
+      float lin_acc = 0.f;
 #pragma unroll
       for (int j = 0; j < MAXS; ++j) {
-        const int f = j * FPW + fg;
-        if (j < NS && f < F) {
-          float4 v = ring[((size_t)cb * NS + j) * 32 + lane];
-          const float sc = sx[(cb * NS + j) * FPW + fg];
+        if (j >= NS) continue;
+        const bool is_pure = (pure >> j) & 1u;
+        if (!is_pure && j * FPW + fg >= F) continue;
+        float4 v = src[j * 32];
+        if (!is_pure) {
+          const float sc = csx[j * FPW];
           v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
-          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-          s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y);
-          s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
-          if (o.concat) *reinterpret_cast<float4*>(o.concat + r * o.ld_concat + (int64_t)f * K + q * 4) = v;
         }
+        if (want_lin) lin_acc = fmaf(clw[j * FPW], my_link[j * FPW], lin_acc);   // same value in the K4 lanes of a field
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y);
+        s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+        if (crow) *reinterpret_cast<float4*>(crow + j * 128) = v;
       }
       if (o.pw || o.fm_out || o.lin || o.ssum) {
 #pragma unroll
@@ -596,7 +870,9 @@ feat_forward_async_kernel(const b200_feat_layout L, const b200_feat_tables T,
           s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
           s2.x += __shfl_xor_sync(0xffffffffu, s2.x, off); s2.y += __shfl_xor_sync(0xffffffffu, s2.y, off);
           s2.z += __shfl_xor_sync(0xffffffffu, s2.z, off); s2.w += __shfl_xor_sync(0xffffffffu, s2.w, off);
+          lin_acc += __shfl_xor_sync(0xffffffffu, lin_acc, off);       // over the field groups (q lanes hold copies)
         }
+        lin_acc += h.lin_bias;
         const float sv[4] = {s.x, s.y, s.z, s.w};
         const float s2v[4] = {s2.x, s2.y, s2.z, s2.w};
         float head_acc = 0.f;
@@ -613,8 +889,6 @@ feat_forward_async_kernel(const b200_feat_layout L, const b200_feat_tables T,
             head_acc = fmaf(z, h.pw_kernel[kk], head_acc);
           }
         }
-        float lin_acc = 0.f;
-        if (want_lin) lin_acc = warp_sum(lin_cur) + h.lin_bias;
         if (o.fm_out) {
 #pragma unroll
           for (int off = 1; off < K4; off <<= 1) head_acc += __shfl_xor_sync(0xffffffffu, head_acc, off);
@@ -622,15 +896,6 @@ feat_forward_async_kernel(const b200_feat_layout L, const b200_feat_tables T,
           if (lane == 0) o.fm_out[r] = lin_acc + (head_acc > 0.f ? head_acc : expm1f(head_acc));
         }
         if (o.lin && lane == 0) o.lin[r] = lin_acc;
-      }
-    }
-    // linear-term partial of row k+1 (its weights were requested at the top of this iteration)
-    lin_cur = 0.f;
-    if (want_lin && q == 0 && r_nx < R) {
-#pragma unroll
-      for (int j = 0; j < MAXS; ++j) {
-        const int f = j * FPW + fg;
-        if (j < NS && f < F) lin_cur = fmaf(lwn[j], sh_link[f], lin_cur);
       }
     }
     if (r_nx >= R) { cp_async_wait<0>(); break; }
@@ -734,7 +999,8 @@ using namespace b200;
 using namespace b200::feat;
 
 static int g_feat_kernel = 0;   // b200_feat_forward_tune bit 1: 0 = field-group kernel (default), 1 = lane-per-field kernel (A/B)
-static int g_feat_no_async = 0; // b200_feat_forward_tune bit 2: 1 = never use the cp.async staged kernel (A/B)
+static int g_feat_no_async = 0; // b200_feat_forward_tune bit 2: 1 = neither the pipelined nor the cp.async staged kernel (A/B)
+static int g_feat_async = 0;    // bit 3: 1 = the cp.async staged kernel instead of the software-pipelined register kernel
 static int g_feat_tma = 0;   // b200_feat_forward_tune: 1 = bulk-copy (TMA) staged kernel where eligible, 0 = register kernels
                              // (default: one UBLKCP per 64-byte row measured 5.7x SLOWER than the register gather, profiles/)
 
@@ -742,6 +1008,7 @@ extern "C" int b200_feat_forward_tune(int32_t use_tma_staging) {
   g_feat_tma = (use_tma_staging & 1) ? 1 : 0;
   g_feat_kernel = (use_tma_staging & 2) ? 1 : 0;
   g_feat_no_async = (use_tma_staging & 4) ? 1 : 0;
+  g_feat_async = (use_tma_staging & 8) ? 1 : 0;
   return 0;
 }
 
@@ -782,7 +1049,27 @@ extern "C" int b200_feat_forward(const b200_feat_layout* L, const b200_feat_tabl
   }
   const int K4v = K / 4;
   const bool group_ok = fast && g_feat_kernel == 0 && (K4v == 1 || K4v == 2 || K4v == 4 || K4v == 8);
-  if (group_ok && !g_feat_no_async && R >= 4096) {
+  const bool staged_ok = group_ok && !g_feat_no_async && R >= 4096 && !L->sparse_rows && !L->dense_rows;
+  if (staged_ok && !g_feat_async) {
+    // software-pipelined register gather (default for large row counts)
+    const int FPW = 32 / K4v;
+    const int n_id = ((L->id_mask & 1) ? 1 : 0) + ((L->id_mask & 2) ? 1 : 0);
+    const int NS = (n_id + L->n_sparse + L->n_dense + FPW - 1) / FPW;
+    if (NS <= 16) {
+      const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(R, 8), (int64_t)148 * 2);
+      cudaStream_t st = (cudaStream_t)stream;
+      switch (K4v) {
+        case 1: feat_forward_pipe_kernel<1><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h, NS); break;
+        case 2: feat_forward_pipe_kernel<2><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h, NS); break;
+        case 4: feat_forward_pipe_kernel<4><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h, NS); break;
+        default: feat_forward_pipe_kernel<8><<<blocks, 256, 0, st>>>(*L, *T, users, items, R, grid_items, row_offset, o, h, NS); break;
+      }
+      count_launch();
+      B200_CUDA_OK(cudaGetLastError());
+      return 0;
+    }
+  }
+  if (staged_ok && g_feat_async) {
     // cp.async staged kernel: two rows of gathers in flight per warp; warps per CTA and CTAs per SM chosen so
     // that the rings fill the SM's shared memory
     const int FPW = 32 / K4v;
@@ -790,8 +1077,8 @@ extern "C" int b200_feat_forward(const b200_feat_layout* L, const b200_feat_tabl
     const int F = n_id + L->n_sparse + L->n_dense;
     const int NS = (F + FPW - 1) / FPW;
     if (NS <= ASYNC_MAXS) {
-      const size_t per_warp = (size_t)2 * NS * 512 + (size_t)2 * NS * FPW * 4;
-      const size_t meta = (size_t)F * 12;
+      const size_t per_warp = (size_t)2 * NS * 512 + (size_t)2 * 2 * NS * FPW * 4;   // rings + scales + linear weights
+      const size_t meta = (size_t)F * 8 + (size_t)NS * FPW * 4;
       int best_w = 0, best_wpb = 0, best_nb = 0;
       for (int wpb = 8; wpb >= 2; --wpb) {
         const size_t per_block = wpb * per_warp + meta + 1024;

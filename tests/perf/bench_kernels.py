@@ -135,7 +135,8 @@ def bench_feat():
     fm = FM(spec, wfm)
     out = torch.empty(R, dtype=torch.float32, device="cuda")
     ref_concat = None
-    for tma, tag in ((0, "cp.async staged, K/4 lanes per field (default)"), (4, "register gather, K/4 lanes per field"),
+    for tma, tag in ((0, "software-pipelined register gather, K/4 lanes per field (default)"),
+                     (8, "cp.async staged, K/4 lanes per field"), (4, "register gather, K/4 lanes per field"),
                      (2, "register gather, lane per field"),
                      (1, "TMA-staged persistent (cp.async.bulk ring)")):
         _lib.check(_lib.lib.b200_feat_forward_tune(tma))

@@ -1,5 +1,5 @@
-"""K1 (b200_feat_forward) kernel variants against the oracle's field embeddings: the cp.async staged field-group
-kernel (default for >= 4096 rows), the register field-group kernel, the lane-per-field kernel and — for a K the fast
+"""K1 (b200_feat_forward) kernel variants against the oracle's field embeddings: the software-pipelined field-group
+kernel (default for >= 4096 rows), its cp.async staged variant, the plain field-group kernel, the lane-per-field kernel and — for a K the fast
 paths do not take — the generic kernel.  Concatenated rows must be bit-exact (pure copies / one multiply), the FM
 sums agree to fp32 summation order; the three fast variants must agree with each other bit-for-bit on the copies.
 Covers K in {4, 8, 16, 32, 12}, row counts that are no multiple of anything, tower layouts (one id field),
@@ -9,7 +9,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-TUNES = {"async": 0, "fieldgroup": 4, "lanefield": 2}
+TUNES = {"pipe": 0, "async": 8, "fieldgroup": 4, "lanefield": 2}
 
 
 def _run(model, layout, users_d, items_d, R, K, F, grid_items=0, want_concat=True):
@@ -97,6 +97,7 @@ def test_tower_layout_and_grid_mode(which):
     for name, v in got.items():
         assert np.abs(v - ref).max() <= 3e-5 * max(1.0, np.abs(ref).max()), name
     np.testing.assert_array_equal(got["async"], got["fieldgroup"])
+    np.testing.assert_array_equal(got["pipe"], got["fieldgroup"])
     if which == "user":
         return
     # grid mode: 3 users x all 700 items of a smaller FM (rows = 3 * 700 < 4096 -> register kernel) and
