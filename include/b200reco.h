@@ -377,6 +377,11 @@ int b200_l2_normalize_rows(float* x, int64_t ld, int64_t R, int32_t d, void* str
 int b200_seq_pool(const float* E, int64_t lde, int32_t d, int64_t pad_index, const int32_t* seqs,
                   int64_t ld_seq, const int32_t* lens, int32_t T, const int64_t* users, int64_t R,
                   int64_t grid_items, int64_t row_offset, float* out, int64_t ld_out, void* stream);
+/* Backward of b200_seq_pool (training of the sequence models): g_embeds[seq_t, :d] += dout[r, :d] / sqrt(len)
+ * for every non-pad position of row r's sequence (row of users[r] in seqs / lens); float atomics. */
+int b200_seq_pool_backward(const float* dout, int64_t ld_dout, int32_t d, int64_t pad_index, const int32_t* seqs,
+                           int64_t ld_seq, const int32_t* lens, int32_t T, const int64_t* users, int64_t R,
+                           float* g_embeds, int64_t ld_g, void* stream);
 int b200_din_attention(const float* G, int64_t ldg, int32_t Kp, const int64_t* items,
                        const int32_t* seqs, int64_t ld_seq, const int32_t* lens, int32_t T,
                        const int64_t* users, int64_t R, int64_t grid_items, int64_t row_offset,

@@ -5,7 +5,8 @@
   synthetic bipartite graph (Zipf item popularity, Poisson(50) user degrees), rows sharded over the
   N GPUs, slab exchange per layer — (a) one NCCL all-gather per layer then SpMM, (b) the exchange
   overlapped with per-source-rank block SpMMs, slabs pulled over NVLink peer memory by the copy
-  engines (falls back to an NCCL send/recv ring when symmetric memory is unavailable).  Strong
+  engines (falls back to an NCCL send/recv ring when symmetric memory is unavailable), (c) two
+  products per layer: the own column block while the slabs travel, the rest in one product.  Strong
   scaling: ``efficiency = t_single / (N * t_N)`` with the single-GPU time measured in the same run.
 * ``row_sharded_lookup``: DeepFM-shaped (K = 16) and DIN-shaped (K' = 64) row gathers from a table
   sharded ``row % N`` — (a) NCCL path (index all-to-all, local gather, row all-to-all), (b) ONE
@@ -40,8 +41,9 @@ def _lightgcn(rank, world, dev, max_over_ranks, barrier, n_users=2_000_000, n_it
 
     from .consumed import ConsumedCSR
     from .lightgcn import SpmmGraph, build_laplacian_csr, propagate
-    from .parallel import (LightGCNShardPlan, PeerPullExchange, RingExchange, block_spmm_fn, gather_embeddings,
-                           propagate_sharded, propagate_sharded_overlap, sharded_spmm_fn, split_column_blocks)
+    from .parallel import (LightGCNShardPlan, PeerPullExchange, RingExchange, acc_spmm_fn, block_spmm_fn,
+                           gather_embeddings, propagate_sharded, propagate_sharded_overlap,
+                           propagate_sharded_two_phase, sharded_spmm_fn, split_column_blocks, split_local_remote)
 
     g = torch.Generator(device=dev).manual_seed(5)
     deg = torch.clamp(torch.poisson(torch.full((n_users,), 50.0, device=dev), generator=g), 1, 2000).long()
@@ -92,8 +94,20 @@ def _lightgcn(rank, world, dev, max_over_ranks, barrier, n_users=2_000_000, n_it
         return propagate_sharded_overlap(plan, block_spmm_fn(blocks), E0_loc, n_layers, exchange, rank)
 
     out["ms_overlapped"] = _timed(run_overlap, 5, max_over_ranks, barrier)
+    # (c) two products per layer: the own column block while the slabs travel, every other block in one product
+    own, rest = split_local_remote(lptr, lcol, lval, plan.slab, rank)
+    g_own, g_rest = SpmmGraph(*own), SpmmGraph(*rest)
+
+    def run_two_phase():
+        return propagate_sharded_two_phase(plan, acc_spmm_fn(g_own), acc_spmm_fn(g_rest), E0_loc, n_layers, exchange,
+                                           rank)
+
+    ue, ie = gather_embeddings(plan, run_two_phase())
+    out["two_phase_max_abs_err"] = float((torch.cat([ue, ie]) - ref).abs().max())
+    out["ms_two_phase"] = _timed(run_two_phase, 5, max_over_ranks, barrier)
     out["ms_single_gpu"] = _timed(lambda: propagate(full_graph, E0, n_layers), 3, max_over_ranks, barrier)
-    best = min(out["ms_overlapped"], out["ms_allgather_then_spmm"])
+    best = min(out["ms_overlapped"], out["ms_allgather_then_spmm"], out["ms_two_phase"])
+    out["efficiency_two_phase"] = out["ms_single_gpu"] / (world * out["ms_two_phase"])
     out["efficiency_overlapped"] = out["ms_single_gpu"] / (world * out["ms_overlapped"])
     out["efficiency_allgather"] = out["ms_single_gpu"] / (world * out["ms_allgather_then_spmm"])
     # algorithmic bytes per layer over all ranks: nnz (4 col + 4 val + 4 d gathered row) + rows (4 d + 8)

@@ -50,6 +50,30 @@ seq_pool_kernel(const float* __restrict__ E, int64_t lde, int d, int64_t pad_ind
   }
 }
 
+// backward of seq_pool: g[seq_t, :] += dout[r, :] / sqrt(len) for every non-pad position (float atomics)
+__global__ void __launch_bounds__(256)
+seq_pool_backward_kernel(const float* __restrict__ dout, int64_t ld_dout, int d, int64_t pad_index,
+                         const int32_t* __restrict__ seqs, int64_t ld_seq, const int32_t* __restrict__ lens, int T,
+                         const int64_t* __restrict__ users, int64_t R, float* __restrict__ g, int64_t ldg) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int64_t sr = seq_row_of(users, r, 0, 0);
+  const int32_t* s = seqs + sr * ld_seq;
+  const float len = (float)lens[sr];
+  if (!(len > 0.f)) return;                                        // div_no_nan: the output (and its gradient) is 0
+  const float inv = 1.0f / sqrtf(len);
+  for (int k0 = 0; k0 < d; k0 += 32) {
+    const int k = k0 + lane;
+    if (k >= d) continue;
+    const float v = dout[r * ld_dout + k] * inv;
+    for (int t = 0; t < T; ++t) {
+      const int32_t it = __ldg(s + t);
+      if (it != pad_index) atomicAdd(g + (int64_t)it * ldg + k, v);
+    }
+  }
+}
+
 struct AttW {
   const float* k1;   // [4K', 16] row-major (Dense(16) kernel; rows: q | k | q-k | q*k)
   const float* b1;   // [16]
@@ -362,6 +386,19 @@ extern "C" int b200_seq_pool(const float* E, int64_t lde, int32_t d, int64_t pad
   if (R == 0) return 0;
   seq_pool_kernel<<<(unsigned)ceil_div64(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       E, lde, d, pad_index, seqs, ld_seq, lens, T, users, R, grid_items, row_offset, out, ld_out);
+  count_launch();
+  B200_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b200_seq_pool_backward(const float* dout, int64_t ld_dout, int32_t d, int64_t pad_index,
+                                      const int32_t* seqs, int64_t ld_seq, const int32_t* lens, int32_t T,
+                                      const int64_t* users, int64_t R, float* g_embeds, int64_t ld_g,
+                                      void* stream) {
+  B200_REQUIRE(dout && seqs && lens && users && g_embeds, "b200_seq_pool_backward: null pointer");
+  if (R == 0) return 0;
+  seq_pool_backward_kernel<<<(unsigned)ceil_div64(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      dout, ld_dout, d, pad_index, seqs, ld_seq, lens, T, users, R, g_embeds, ld_g);
   count_launch();
   B200_CUDA_OK(cudaGetLastError());
   return 0;

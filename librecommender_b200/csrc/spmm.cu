@@ -231,27 +231,53 @@ spmm_long_chunks_kernel(const Args a, const int32_t* __restrict__ chunk_row,
   }
 }
 
-// ordered reduction of the partials of each long row (warp per row)
-__global__ void __launch_bounds__(256)
+// reduction of the partials of each long row in a FIXED order (deterministic): one CTA per row, warp w adds the
+// chunks c = w, w + 8, ... into two alternating accumulators (two loads in flight per lane), warp 0 then adds the
+// 8 x 2 partial sums in order.  (A single warp per row made the most popular item — ~2 M nnz = ~2000 chunks on a
+// Zipf graph — a serial chain of ~2000 dependent loads that did not shrink when the rows were sharded: the
+// sharded propagation's strong-scaling efficiency was 0.44 at 4 GPUs because of it.)
+constexpr int RED_WARPS = 8;
+__global__ void __launch_bounds__(RED_WARPS * 32)
 spmm_long_reduce_kernel(const Args a, const int32_t* __restrict__ long_rows,
                         const int64_t* __restrict__ long_chunk_ptr, int64_t n_long,
                         const float* __restrict__ partials) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  __shared__ float sh[RED_WARPS][2][32 * MAX_T];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t w = blockIdx.x;
   if (w >= n_long) return;
   Args b = a;
   b.lpr = 32;
   b.T = (a.d + 31) / 32;
   const int64_t r = long_rows[w];
-  float sum[MAX_T];
+  float s0[MAX_T], s1[MAX_T];
 #pragma unroll
-  for (int t = 0; t < MAX_T; ++t) sum[t] = 0.f;
-  for (int64_t c = long_chunk_ptr[w]; c < long_chunk_ptr[w + 1]; ++c) {
+  for (int t = 0; t < MAX_T; ++t) { s0[t] = 0.f; s1[t] = 0.f; }
+  const int64_t c_beg = long_chunk_ptr[w], c_end = long_chunk_ptr[w + 1];
+  for (int64_t c = c_beg + wid; c < c_end; c += 2 * RED_WARPS) {
+    const int64_t c2 = c + RED_WARPS;
 #pragma unroll
     for (int t = 0; t < MAX_T; ++t) {
       const int cc = lane + t * 32;
-      if (t < b.T && cc < a.d) sum[t] += partials[c * a.d + cc];
+      if (t < b.T && cc < a.d) {
+        s0[t] += partials[c * a.d + cc];
+        if (c2 < c_end) s1[t] += partials[c2 * a.d + cc];
+      }
     }
+  }
+#pragma unroll
+  for (int t = 0; t < MAX_T; ++t) {
+    sh[wid][0][lane + t * 32] = s0[t];
+    sh[wid][1][lane + t * 32] = s1[t];
+  }
+  __syncthreads();
+  if (wid != 0) return;
+  float sum[MAX_T];
+#pragma unroll
+  for (int t = 0; t < MAX_T; ++t) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < RED_WARPS; ++q) { v += sh[q][0][lane + t * 32]; v += sh[q][1][lane + t * 32]; }
+    sum[t] = v;
   }
   row_epilogue(b, r, lane, sum);
 }
@@ -309,7 +335,7 @@ extern "C" int b200_spmm_csr(const int64_t* indptr, const int32_t* col, const fl
     }
   }
   if (n_long > 0) {
-    spmm_long_reduce_kernel<<<(unsigned)ceil_div64(n_long * 32, 256), 256, 0, stream>>>(
+    spmm_long_reduce_kernel<<<(unsigned)n_long, RED_WARPS * 32, 0, stream>>>(
         a, long_rows, long_chunk_ptr, n_long, partials);
     count_launch();
   }

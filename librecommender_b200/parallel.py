@@ -421,7 +421,8 @@ class RingExchange:
         """(list of G receive buffers, 2 ping-pong `cur` buffers)."""
         import torch
 
-        return ([torch.empty((slab, d), dtype=dtype, device=device) for _ in range(self.world)],
+        self.gathered = torch.zeros((self.world * slab, d), dtype=dtype, device=device)     # slot g = rank g's slab
+        return ([self.gathered[g * slab:(g + 1) * slab] for g in range(self.world)],
                 [torch.empty((slab, d), dtype=dtype, device=device) for _ in range(2)])
 
 
@@ -444,7 +445,8 @@ class PeerPullExchange:
         self._hdl = [symm.rendezvous(t, grp) for t in self._cur]
         self._shape, self._dtype = (slab, d), dtype
         self._streams = [torch.cuda.Stream(device=device) for _ in range(2)]
-        return ([torch.empty((slab, d), dtype=dtype, device=device) for _ in range(self.world)], self._cur)
+        self.gathered = torch.zeros((self.world * slab, d), dtype=dtype, device=device)     # slot g = rank g's slab
+        return ([self.gathered[g * slab:(g + 1) * slab] for g in range(self.world)], self._cur)
 
     def start(self, cur, slots):
         import torch
@@ -497,6 +499,64 @@ def propagate_sharded_overlap(plan: LightGCNShardPlan, block_spmm, E0_local, n_l
         cur = nxt
     acc.div_(float(n_layers + 1))
     return acc
+
+
+def split_local_remote(lptr, lcol, lval, slab: int, rank: int):
+    """Local CSR (columns in the gathered layout) -> (own-block CSR with block-local columns, CSR of every OTHER
+    block with the gathered-layout columns kept).  Two products per layer instead of one per source rank: the
+    own block needs no communication and runs while the peers' slabs arrive; the rest runs once over the
+    gathered buffer.  In-row order preserved."""
+    import torch
+
+    dev = lptr.device
+    n_rows = lptr.numel() - 1
+    deg = lptr[1:] - lptr[:-1]
+    rows = torch.repeat_interleave(torch.arange(n_rows, device=dev), deg)
+    own = (lcol.to(torch.int64) // slab) == rank
+    out = []
+    for mask, shift in ((own, rank * slab), (~own, 0)):
+        sel = torch.nonzero(mask).flatten()
+        ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+        ptr[1:] = torch.cumsum(torch.bincount(rows[sel], minlength=n_rows), 0)
+        out.append((ptr, (lcol[sel].to(torch.int64) - shift).to(torch.int32).contiguous(), lval[sel].contiguous()))
+    return out[0], out[1]
+
+
+def propagate_sharded_two_phase(plan: LightGCNShardPlan, local_spmm, remote_spmm, E0_local, n_layers: int,
+                                exchange, rank: int):
+    """mean_{l=0..n_layers} L^l E0 on this rank's row block, two products per layer: ``local_spmm(E_own [slab, d],
+    acc)`` adds the own column block while the peers' slabs are in flight, ``remote_spmm(gathered [G * slab, d],
+    acc)`` adds every other block once they have all arrived (CSRs from :func:`split_local_remote`)."""
+    slab, d = E0_local.shape
+    if not hasattr(exchange, "_bufs") or exchange._bufs[0][0].shape != (slab, d):
+        exchange._bufs = exchange.make_slabs(slab, d, E0_local.device, E0_local.dtype)
+    slots, curs = exchange._bufs
+    cur = curs[0]
+    cur.copy_(E0_local)
+    acc = E0_local.clone()
+    for layer in range(n_layers):
+        nxt = curs[(layer + 1) & 1]
+        arrivals = exchange.start(cur, slots)
+        nxt.zero_()
+        local_spmm(cur, nxt)
+        for _, wait in arrivals:
+            wait()
+        if arrivals:
+            remote_spmm(exchange.gathered, nxt)
+        acc.add_(nxt)
+        cur = nxt
+    acc.div_(float(n_layers + 1))
+    return acc
+
+
+def acc_spmm_fn(graph):
+    """``E, acc -> acc += L_part @ E`` backed by the CUDA SpMM of one :class:`SpmmGraph`."""
+
+    def fn(E, acc):
+        if graph.nnz:
+            graph.spmm(E, out=None, acc=acc, acc_init=False, final_div=0.0)
+
+    return fn
 
 
 def block_spmm_fn(block_graphs):

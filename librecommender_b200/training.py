@@ -348,7 +348,134 @@ class DeepFMTrainer:
         return w
 
 
-class TwoTowerTrainer:
+class _StackTrainer:
+    """Shared pieces of the trainers built on ``dense_nn`` stacks (``libreco/layers/dense.py:12-49``, training mode):
+    parameters ``{prefix}Wt{i}`` [dout, din], ``{prefix}b{i}``, ``{prefix}bn{j}_gamma|beta`` (+ moving statistics),
+    forward / backward of one stack on the library kernels, TF-Adam over every variable."""
+
+    def _init_stack(self, prefix, mlp, p):
+        torch = self._torch
+        f32 = torch.float32
+        n = len(mlp["kernels"])
+        for i in range(n):
+            p[f"{prefix}Wt{i}"] = _dev(np.ascontiguousarray(np.asarray(mlp["kernels"][i]).T), self.device, f32).clone()
+            p[f"{prefix}b{i}"] = _dev(mlp["biases"][i], self.device, f32).clone()
+        if self.use_bn:
+            for j, bn in enumerate([mlp.get("bn_in")] + list(mlp.get("bns") or [])):
+                p[f"{prefix}bn{j}_gamma"] = _dev(bn["gamma"], self.device, f32).clone()
+                p[f"{prefix}bn{j}_beta"] = _dev(bn["beta"], self.device, f32).clone()
+                self.moving[f"{prefix}bn{j}"] = (_dev(bn["mean"], self.device, f32).clone(),
+                                                 _dev(bn["var"], self.device, f32).clone())
+        return n
+
+    def _finish_init(self, p):
+        torch = self._torch
+        self.params = p
+        self.grads = {k: torch.zeros_like(v) for k, v in p.items()}
+        self.m = {k: torch.zeros_like(v) for k, v in p.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in p.items()}
+        T = FeatTablesStruct()
+        for k in ("user_embeds", "item_embeds", "sparse_embeds", "dense_embeds"):
+            setattr(T, k, p[k].data_ptr() if k in p else None)
+        self.tables = T
+        self._lws = torch.empty(int(_lib.lib.b200_loss_workspace_bytes()), dtype=torch.uint8, device=self.device)
+
+    def _bn_forward(self, x, name):
+        torch = self._torch
+        p = self.params
+        R, C = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=self.device)
+        var = torch.empty(C, dtype=torch.float32, device=self.device)
+        mm, mv = self.moving[name]
+        _lib.check(_lib.lib.b200_bn_train_forward(
+            _lib.ptr(x), x.stride(0), R, C, _lib.ptr(p[f"{name}_gamma"]), _lib.ptr(p[f"{name}_beta"]), BN_EPS,
+            BN_MOMENTUM, _lib.ptr(y), y.stride(0), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(mm), _lib.ptr(mv),
+            _lib.current_stream()))
+        return y, (mean, var)
+
+    def _bn_backward(self, dy, x, stats, name, relu_mask):
+        torch = self._torch
+        p, g = self.params, self.grads
+        R, C = x.shape
+        dx = torch.empty_like(x)
+        ws = torch.empty(C * 2, dtype=torch.float64, device=self.device)
+        _lib.check(_lib.lib.b200_bn_train_backward(
+            _lib.ptr(dy), dy.stride(0), _lib.ptr(x), x.stride(0), R, C, _lib.ptr(stats[0]), _lib.ptr(stats[1]),
+            _lib.ptr(p[f"{name}_gamma"]), BN_EPS, 1 if relu_mask else 0, _lib.ptr(dx), dx.stride(0),
+            _lib.ptr(g[f"{name}_gamma"]), _lib.ptr(g[f"{name}_beta"]), _lib.ptr(ws), ws.numel() * 8,
+            _lib.current_stream()))
+        return dx
+
+    def _col_sum(self, X, out, wrow=None):
+        X2 = X if X.dim() == 2 else X.view(-1, 1)
+        _lib.check(_lib.lib.b200_col_reduce(_lib.ptr(X2), X2.stride(0), X2.shape[0], X2.shape[1], _lib.ptr(wrow), None, 0,
+                                            _lib.ptr(out), _lib.current_stream()))
+
+    def _stack_forward(self, prefix, n_layers, x):
+        """BN(input) -> [Dense -> ReLU -> BN] x (L-1) -> Dense with batch statistics; returns (out, cache)."""
+        from .feat_models import linear
+
+        p = self.params
+        c = dict(concat=x, bn_stats={}, dense_in=[], relu_out=[])
+        a = x
+        if self.use_bn:
+            a, c["bn_stats"][0] = self._bn_forward(a, f"{prefix}bn0")
+        for i in range(n_layers):
+            last = i == n_layers - 1
+            c["dense_in"].append(a)
+            a = linear(a, p[f"{prefix}Wt{i}"], p[f"{prefix}b{i}"], not last, cache_split=False)
+            if not last:
+                c["relu_out"].append(a)
+                if self.use_bn:
+                    a, c["bn_stats"][i + 1] = self._bn_forward(a, f"{prefix}bn{i + 1}")
+        return a, c
+
+    def _stack_backward(self, prefix, n_layers, c, da):
+        """Gradients of the stack's variables ADDED into ``self.grads``; returns d loss / d input."""
+        from .feat_models import linear
+
+        torch = self._torch
+        lib, st, p, g = _lib.lib, _lib.current_stream(), self.params, self.grads
+        da = da.contiguous()
+        for i in range(n_layers - 1, -1, -1):
+            if i != n_layers - 1:
+                r_out = c["relu_out"][i]
+                if self.use_bn:
+                    da = self._bn_backward(da, r_out, c["bn_stats"][i + 1], f"{prefix}bn{i + 1}", True)
+                else:
+                    dh = torch.empty_like(da)
+                    _lib.check(lib.b200_relu_backward(_lib.ptr(da), _lib.ptr(r_out), da.numel(), _lib.ptr(dh), st))
+                    da = dh
+            x = c["dense_in"][i]
+            da = da.contiguous()
+            g[f"{prefix}Wt{i}"] += linear(da.t().contiguous(), x.t().contiguous(), None, False, cache_split=False)
+            self._col_sum(da, g[f"{prefix}b{i}"])
+            da = linear(da, p[f"{prefix}Wt{i}"].t().contiguous(), None, False, cache_split=False)
+        return self._bn_backward(da, c["concat"], c["bn_stats"][0], f"{prefix}bn0", False) if self.use_bn else da
+
+    def _adam_all(self):
+        self.t += 1
+        lib, st = _lib.lib, _lib.current_stream()
+        for k, v in self.params.items():
+            _lib.check(lib.b200_adam_dense(_lib.ptr(v), _lib.ptr(self.m[k]), _lib.ptr(self.v[k]), _lib.ptr(self.grads[k]),
+                                           v.numel(), self.lr, BETA1, BETA2, self.epsilon, self.t, st))
+
+    def _export_stack(self, prefix, n):
+        p = self.params
+        mlp = dict(kernels=[p[f"{prefix}Wt{i}"].t().contiguous().cpu().numpy() for i in range(n)],
+                   biases=[p[f"{prefix}b{i}"].cpu().numpy() for i in range(n)])
+        if self.use_bn:
+            def bn(j):
+                mm, mv = self.moving[f"{prefix}bn{j}"]
+                return dict(gamma=p[f"{prefix}bn{j}_gamma"].cpu().numpy(), beta=p[f"{prefix}bn{j}_beta"].cpu().numpy(),
+                            mean=mm.cpu().numpy(), var=mv.cpu().numpy())
+            mlp["bn_in"] = bn(0)
+            mlp["bns"] = [bn(i + 1) for i in range(n - 1)]
+        return mlp
+
+
+class TwoTowerTrainer(_StackTrainer):
     """TwoTower training step on the device, in-batch softmax loss (the reference's default):
     ``libreco/algorithms/two_tower.py:306-346,400-410`` (both towers, ``dense_nn`` in training mode, optional
     ``tf.linalg.l2_normalize``), ``tfops/loss.py:71-75`` + ``two_tower.py:458-479`` (``U V^T / temperature -
@@ -383,17 +510,7 @@ class TwoTowerTrainer:
         p = {k: _dev(weights[k], self.device, f32).clone() for k in self._T if weights.get(k) is not None}
         self.moving, self.n_layers, self.layouts, self.widths = {}, {}, {}, {}
         for which, mask in (("user", 1), ("item", 2)):
-            mlp = weights[f"{which}_tower"]
-            n = self.n_layers[which] = len(mlp["kernels"])
-            for i in range(n):
-                p[f"{which}_Wt{i}"] = _dev(np.ascontiguousarray(np.asarray(mlp["kernels"][i]).T), self.device, f32).clone()
-                p[f"{which}_b{i}"] = _dev(mlp["biases"][i], self.device, f32).clone()
-            if self.use_bn:
-                for j, bn in enumerate([mlp.get("bn_in")] + list(mlp.get("bns") or [])):
-                    p[f"{which}_bn{j}_gamma"] = _dev(bn["gamma"], self.device, f32).clone()
-                    p[f"{which}_bn{j}_beta"] = _dev(bn["beta"], self.device, f32).clone()
-                    self.moving[f"{which}_bn{j}"] = (_dev(bn["mean"], self.device, f32).clone(),
-                                                     _dev(bn["var"], self.device, f32).clone())
+            self.n_layers[which] = self._init_stack(f"{which}_", weights[f"{which}_tower"], p)
             L = FeatLayoutStruct.from_buffer_copy(self.spec.layout)
             L.id_mask = mask
             scols = self.spec.user_sparse_cols if which == "user" else self.spec.item_sparse_cols
@@ -406,73 +523,19 @@ class TwoTowerTrainer:
                 L.dense_embed_row[f] = dcols[f]
             self.layouts[which] = L
             self.widths[which] = (1 + len(scols) + len(dcols)) * K
-        self.params = p
-        self.grads = {k: torch.zeros_like(v) for k, v in p.items()}
-        self.m = {k: torch.zeros_like(v) for k, v in p.items()}
-        self.v = {k: torch.zeros_like(v) for k, v in p.items()}
-        T = FeatTablesStruct()
-        for k in self._T:
-            setattr(T, k, p[k].data_ptr() if k in p else None)
-        self.tables = T
-        self._lws = torch.empty(int(_lib.lib.b200_loss_workspace_bytes()), dtype=torch.uint8, device=self.device)
-
-    # ---- batch-norm / reductions (same kernels as DeepFMTrainer) -----------------------------------
-    def _bn_forward(self, x, name):
-        torch = self._torch
-        p = self.params
-        R, C = x.shape
-        y = torch.empty_like(x)
-        mean = torch.empty(C, dtype=torch.float32, device=self.device)
-        var = torch.empty(C, dtype=torch.float32, device=self.device)
-        mm, mv = self.moving[name]
-        _lib.check(_lib.lib.b200_bn_train_forward(
-            _lib.ptr(x), x.stride(0), R, C, _lib.ptr(p[f"{name}_gamma"]), _lib.ptr(p[f"{name}_beta"]), BN_EPS,
-            BN_MOMENTUM, _lib.ptr(y), y.stride(0), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(mm), _lib.ptr(mv),
-            _lib.current_stream()))
-        return y, (mean, var)
-
-    def _bn_backward(self, dy, x, stats, name, relu_mask):
-        torch = self._torch
-        p, g = self.params, self.grads
-        R, C = x.shape
-        dx = torch.empty_like(x)
-        ws = torch.empty(C * 2, dtype=torch.float64, device=self.device)
-        _lib.check(_lib.lib.b200_bn_train_backward(
-            _lib.ptr(dy), dy.stride(0), _lib.ptr(x), x.stride(0), R, C, _lib.ptr(stats[0]), _lib.ptr(stats[1]),
-            _lib.ptr(p[f"{name}_gamma"]), BN_EPS, 1 if relu_mask else 0, _lib.ptr(dx), dx.stride(0),
-            _lib.ptr(g[f"{name}_gamma"]), _lib.ptr(g[f"{name}_beta"]), _lib.ptr(ws), ws.numel() * 8,
-            _lib.current_stream()))
-        return dx
-
-    def _col_sum(self, X, out):
-        _lib.check(_lib.lib.b200_col_reduce(_lib.ptr(X), X.stride(0), X.shape[0], X.shape[1], None, None, 0,
-                                            _lib.ptr(out), _lib.current_stream()))
+        self._finish_init(p)
 
     # ---- one tower ----------------------------------------------------------------------------------
     def tower_forward(self, which, ids_d):
-        from .feat_models import linear
-
         torch = self._torch
-        p = self.params
         n = int(ids_d.numel())
         x = torch.empty((n, self.widths[which]), dtype=torch.float32, device=self.device)
         _lib.check(_lib.lib.b200_feat_forward(
             ctypes.byref(self.layouts[which]), ctypes.byref(self.tables), _lib.ptr(ids_d), _lib.ptr(ids_d), n, 0, 0,
             _lib.ptr(x), x.stride(0), None, 0, None, None, None, 0.0, None, None, None, 0.0,
             None, None, 0, _lib.current_stream()))
-        c = dict(ids=ids_d, concat=x, bn_stats={}, dense_in=[], relu_out=[])
-        a = x
-        if self.use_bn:
-            a, c["bn_stats"][0] = self._bn_forward(a, f"{which}_bn0")
-        L = self.n_layers[which]
-        for i in range(L):
-            last = i == L - 1
-            c["dense_in"].append(a)
-            a = linear(a, p[f"{which}_Wt{i}"], p[f"{which}_b{i}"], not last, cache_split=False)
-            if not last:
-                c["relu_out"].append(a)
-                if self.use_bn:
-                    a, c["bn_stats"][i + 1] = self._bn_forward(a, f"{which}_bn{i + 1}")
+        a, c = self._stack_forward(f"{which}_", self.n_layers[which], x)
+        c["ids"] = ids_d
         if self.norm_embed:
             c["pre_norm"] = a
             a = a.clone()
@@ -481,32 +544,14 @@ class TwoTowerTrainer:
         return c
 
     def tower_backward(self, which, c, da):
-        from .feat_models import linear
-
-        torch = self._torch
-        lib, st, p, g = _lib.lib, _lib.current_stream(), self.params, self.grads
+        lib, st, g = _lib.lib, _lib.current_stream(), self.grads
         n = int(c["ids"].numel())
         da = da.contiguous()
         if self.norm_embed:
             x = c["pre_norm"]
             _lib.check(lib.b200_l2_normalize_backward(_lib.ptr(x), x.stride(0), _lib.ptr(da), da.stride(0), n,
                                                       x.shape[1], _lib.ptr(da), da.stride(0), st))
-        L = self.n_layers[which]
-        for i in range(L - 1, -1, -1):
-            if i != L - 1:
-                r_out = c["relu_out"][i]
-                if self.use_bn:
-                    da = self._bn_backward(da, r_out, c["bn_stats"][i + 1], f"{which}_bn{i + 1}", True)
-                else:
-                    dh = torch.empty_like(da)
-                    _lib.check(lib.b200_relu_backward(_lib.ptr(da), _lib.ptr(r_out), da.numel(), _lib.ptr(dh), st))
-                    da = dh
-            x = c["dense_in"][i]
-            da = da.contiguous()
-            g[f"{which}_Wt{i}"] += linear(da.t().contiguous(), x.t().contiguous(), None, False, cache_split=False)
-            self._col_sum(da, g[f"{which}_b{i}"])
-            da = linear(da, p[f"{which}_Wt{i}"].t().contiguous(), None, False, cache_split=False)
-        dconcat = self._bn_backward(da, c["concat"], c["bn_stats"][0], f"{which}_bn0", False) if self.use_bn else da
+        dconcat = self._stack_backward(f"{which}_", self.n_layers[which], c, da)
         gp = lambda k: _lib.ptr(g[k]) if k in g else None      # noqa: E731
         _lib.check(lib.b200_feat_backward(
             ctypes.byref(self.layouts[which]), ctypes.byref(self.tables), _lib.ptr(c["ids"]), _lib.ptr(c["ids"]), n,
@@ -544,11 +589,7 @@ class TwoTowerTrainer:
         users_d = users_d.to(torch.int64).contiguous()
         items_d = items_d.to(torch.int64).contiguous()
         loss = self.forward_backward(users_d, items_d, correction_d)
-        self.t += 1
-        lib, st = _lib.lib, _lib.current_stream()
-        for k, v in self.params.items():
-            _lib.check(lib.b200_adam_dense(_lib.ptr(v), _lib.ptr(self.m[k]), _lib.ptr(self.v[k]), _lib.ptr(self.grads[k]),
-                                           v.numel(), self.lr, BETA1, BETA2, self.epsilon, self.t, st))
+        self._adam_all()
         self._last = None
         return loss
 
@@ -556,17 +597,119 @@ class TwoTowerTrainer:
         p = self.params
         w = {k: p[k].cpu().numpy() for k in self._T if k in p}
         for which in ("user", "item"):
-            n = self.n_layers[which]
-            mlp = dict(kernels=[p[f"{which}_Wt{i}"].t().contiguous().cpu().numpy() for i in range(n)],
-                       biases=[p[f"{which}_b{i}"].cpu().numpy() for i in range(n)])
-            if self.use_bn:
-                def bn(j, which=which):
-                    mm, mv = self.moving[f"{which}_bn{j}"]
-                    return dict(gamma=p[f"{which}_bn{j}_gamma"].cpu().numpy(), beta=p[f"{which}_bn{j}_beta"].cpu().numpy(),
-                                mean=mm.cpu().numpy(), var=mv.cpu().numpy())
-                mlp["bn_in"] = bn(0)
-                mlp["bns"] = [bn(i + 1) for i in range(n - 1)]
-            w[f"{which}_tower"] = mlp
+            w[f"{which}_tower"] = self._export_stack(f"{which}_", self.n_layers[which])
         w["user_dense_cols"] = list(self.spec.user_dense_cols)
         w["item_dense_cols"] = list(self.spec.item_dense_cols)
+        return w
+
+
+class YouTubeRankingTrainer(_StackTrainer):
+    """YouTubeRanking training step on the device: ``libreco/algorithms/youtube_ranking.py:167-218`` in training
+    mode (concat(user, item, pooled behaviour sequence, sparse, dense) -> ``dense_nn`` -> Dense(1)), mean sigmoid
+    CE, TF-Adam.  The batch carries one behaviour sequence per ROW (``seqs`` [R, T] padded with ``n_items``,
+    ``lens`` [R]; ``libreco/batch/sequence.py:75-91``).
+
+        K1 gather (b200_feat_forward) + b200_seq_pool -> stack forward -> b200_concat_dense -> b200_pointwise_loss
+        -> stack backward -> b200_feat_backward (field gradients) + b200_seq_pool_backward (sequence gradient into
+        the item-embedding table) -> b200_adam_dense
+
+    Internally the pooled block sits AFTER the F field blocks (the inference engine's layout); the first kernel and
+    the input batch-norm are permuted on the way in and out (``feat_models.permute_mlp_input``)."""
+
+    _T = ("user_embeds", "item_embeds", "sparse_embeds", "dense_embeds")
+
+    def __init__(self, spec, weights, use_bn=True, lr=1e-3, epsilon=1e-5, device=None):
+        import torch
+
+        from .feat_models import permute_mlp_input
+
+        self._torch = torch
+        K = int(weights["user_embeds"].shape[1])
+        self.spec = spec if isinstance(spec, FeatSpec) else FeatSpec(spec, K, device)
+        self.device, self.K = self.spec.device, K
+        self.F = 2 + self.spec.n_sparse + self.spec.n_dense
+        self.n_items = self.spec.n_items
+        self.use_bn, self.lr, self.epsilon, self.t = bool(use_bn), float(lr), float(epsilon), 0
+        f32 = torch.float32
+        F = self.F
+        self.perm = np.concatenate([np.arange(0, 2 * K), np.arange(3 * K, (F + 1) * K), np.arange(2 * K, 3 * K)])
+        p = {k: _dev(weights[k], self.device, f32).clone() for k in self._T if weights.get(k) is not None}
+        self.moving = {}
+        self.n_layers = self._init_stack("", permute_mlp_input(weights["mlp"], self.perm), p)
+        p["out_kernel"] = _dev(np.asarray(weights["out_kernel"]).reshape(-1), self.device, f32).clone()
+        p["out_bias"] = _dev(np.asarray(weights["out_bias"]).reshape(1), self.device, f32).clone()
+        self._finish_init(p)
+
+    def forward(self, users_d, items_d, seqs_d, lens_d):
+        torch = self._torch
+        lib, st, p, K, F = _lib.lib, _lib.current_stream(), self.params, self.K, self.F
+        R = int(users_d.numel())
+        x = torch.empty((R, (F + 1) * K), dtype=torch.float32, device=self.device)
+        _lib.check(lib.b200_feat_forward(
+            ctypes.byref(self.spec.layout), ctypes.byref(self.tables), _lib.ptr(users_d), _lib.ptr(items_d), R, 0, 0,
+            _lib.ptr(x), x.stride(0), None, 0, None, None, None, 0.0, None, None, None, 0.0, None, None, 0, st))
+        rows = torch.arange(R, dtype=torch.int64, device=self.device)
+        pooled = x[:, F * K:]
+        E = p["item_embeds"]
+        _lib.check(lib.b200_seq_pool(_lib.ptr(E), E.stride(0), K, self.n_items, _lib.ptr(seqs_d), seqs_d.stride(0),
+                                     _lib.ptr(lens_d), seqs_d.shape[1], _lib.ptr(rows), R, 0, 0, _lib.ptr(pooled),
+                                     pooled.stride(0), st))
+        h, c = self._stack_forward("", self.n_layers, x)
+        logit = torch.empty(R, dtype=torch.float32, device=self.device)
+        _lib.check(lib.b200_concat_dense(_lib.ptr(h), h.stride(0), h.shape[1], None, 0, 0, None, 0, 0,
+                                         _lib.ptr(p["out_kernel"]), 0.0, R, _lib.ptr(logit), st))
+        logit += p["out_bias"]                      # device scalar add (the bias is a trainable variable)
+        c.update(R=R, users=users_d, items=items_d, seqs=seqs_d, lens=lens_d, rows=rows, h=h, logit=logit)
+        self._cache = c
+        return logit
+
+    def backward(self, labels_d):
+        from .feat_models import linear
+
+        torch = self._torch
+        lib, st, p, g, K, F = _lib.lib, _lib.current_stream(), self.params, self.grads, self.K, self.F
+        c = self._cache
+        R = c["R"]
+        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        dlogit = torch.empty(R, dtype=torch.float32, device=self.device)
+        _lib.check(lib.b200_pointwise_loss(_lib.ptr(c["logit"]), _lib.ptr(labels_d), R, 0, 0.25, 2.0, _lib.ptr(loss),
+                                           _lib.ptr(dlogit), _lib.ptr(self._lws), self._lws.numel(), st))
+        self._col_sum(c["h"], g["out_kernel"], dlogit)
+        self._col_sum(dlogit, g["out_bias"])
+        # d h = dlogit (x) out_kernel: the Dense(1) transposed, on the library's dense kernel (din = 1)
+        da = linear(dlogit.view(R, 1), p["out_kernel"].view(-1, 1), None, False, cache_split=False)
+        dx = self._stack_backward("", self.n_layers, c, da)
+        gp = lambda k: _lib.ptr(g[k]) if k in g else None      # noqa: E731
+        _lib.check(lib.b200_feat_backward(
+            ctypes.byref(self.spec.layout), ctypes.byref(self.tables), _lib.ptr(c["users"]), _lib.ptr(c["items"]), R,
+            None, 0, None, 0, _lib.ptr(dx), dx.stride(0), None, None,
+            gp("user_embeds"), gp("item_embeds"), gp("sparse_embeds"), gp("dense_embeds"), None, None, None, None,
+            None, st))
+        dpool = dx[:, F * K:]
+        ge = g["item_embeds"]
+        _lib.check(lib.b200_seq_pool_backward(_lib.ptr(dpool), dpool.stride(0), K, self.n_items, _lib.ptr(c["seqs"]),
+                                              c["seqs"].stride(0), _lib.ptr(c["lens"]), c["seqs"].shape[1],
+                                              _lib.ptr(c["rows"]), R, _lib.ptr(ge), ge.stride(0), st))
+        return loss
+
+    def step(self, users_d, items_d, seqs_d, lens_d, labels_d):
+        torch = self._torch
+        self.forward(users_d.to(torch.int64).contiguous(), items_d.to(torch.int64).contiguous(),
+                     seqs_d.to(torch.int32).contiguous(), lens_d.to(torch.int32).contiguous())
+        loss = self.backward(labels_d.to(torch.float32).contiguous())
+        self._adam_all()
+        self._cache = None
+        return loss
+
+    def export_weights(self):
+        p = self.params
+        w = {k: p[k].cpu().numpy() for k in self._T if k in p}
+        mlp = self._export_stack("", self.n_layers)
+        inv = np.argsort(self.perm)
+        mlp["kernels"][0] = mlp["kernels"][0][inv]
+        if self.use_bn:
+            mlp["bn_in"] = {k: v[inv] for k, v in mlp["bn_in"].items()}
+        w["mlp"] = mlp
+        w["out_kernel"] = p["out_kernel"].cpu().numpy()
+        w["out_bias"] = np.float32(p["out_bias"].cpu().numpy()[0])
         return w

@@ -193,3 +193,61 @@ def test_split_column_blocks_preserves_rows_and_order():
             assert c.numel() == 0 or int(c.max()) < plan.slab
             blk = torch.sparse_csr_tensor(p, c.to(torch.int64), v, size=(plan.slab, plan.slab)).to_dense()
             np.testing.assert_array_equal(blk.numpy(), dense[:, g * plan.slab:(g + 1) * plan.slab].numpy())
+
+
+# ---- two-phase variant: own block while the slabs travel, every other block in ONE product (gloo) -------------
+def _worker_two_phase(rank, world, port, n_users, n_items, d, n_layers, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from librecommender_b200.parallel import (LightGCNShardPlan, RingExchange, gather_embeddings,
+                                              propagate_sharded_two_phase, split_local_remote)
+
+    _, L = _graph(0, n_users, n_items)
+    E0 = torch.from_numpy(np.random.default_rng(1).standard_normal((n_users + n_items, d)).astype(np.float32))
+    plan = LightGCNShardPlan(n_users, n_items, world)
+    lptr, lcol, lval = plan.shard_csr(torch.from_numpy(L.indptr.astype(np.int64)),
+                                      torch.from_numpy(L.indices.astype(np.int32)),
+                                      torch.from_numpy(L.data.astype(np.float32)), rank)
+    (p0, c0, v0), (p1, c1, v1) = split_local_remote(lptr, lcol, lval, plan.slab, rank)
+    own = torch.sparse_csr_tensor(p0, c0.to(torch.int64), v0, size=(plan.slab, plan.slab))
+    rest = torch.sparse_csr_tensor(p1, c1.to(torch.int64), v1, size=(plan.slab, world * plan.slab))
+
+    def local_spmm(E, acc):
+        acc += own @ E
+
+    def remote_spmm(G, acc):
+        acc += rest @ G
+
+    ex = RingExchange(world, rank)
+    out_local = propagate_sharded_two_phase(plan, local_spmm, remote_spmm, plan.scatter_rows(E0, rank), n_layers, ex,
+                                            rank)
+    ue, ie = gather_embeddings(plan, out_local)
+    q.put((rank, ue.numpy(), ie.numpy(), int(v0.numel()) + int(v1.numel()),
+           bool(c1.numel() == 0 or ((c1.to(torch.int64) // plan.slab) != rank).all())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_two_phase_propagation_matches_oracle_gloo(world):
+    from oracle import lightgcn as ol
+
+    n_users, n_items, port, d, n_layers = 37, 23, _free_port(), 8, 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_two_phase, args=(r, world, port, n_users, n_items, d, n_layers, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _, L = _graph(0, n_users, n_items)
+    E0 = np.random.default_rng(1).standard_normal((n_users + n_items, d)).astype(np.float32)
+    ref = np.concatenate(ol.propagate(L, E0[:n_users], E0[n_users:], n_layers))
+    assert sum(r[3] for r in res) == L.nnz                          # own + rest tile the matrix
+    for rank, ue, ie, _, rest_has_no_own_columns in res:
+        assert rest_has_no_own_columns
+        np.testing.assert_allclose(np.concatenate([ue, ie]), ref, rtol=1e-5, atol=1e-6)

@@ -78,6 +78,23 @@ def main():
         return float(t)
 
     ms_sharded = timed(run_sharded)
+    # two products per layer (own block while the slabs are pulled over NVLink peer memory, the rest in one)
+    err_two, ms_two = None, None
+    if world > 1:
+        from librecommender_b200.parallel import (PeerPullExchange, acc_spmm_fn, propagate_sharded_two_phase,
+                                                  split_local_remote)
+
+        lptr, lcol, lval = plan.shard_csr(ip, col, val, rank)
+        own, rest = split_local_remote(lptr, lcol, lval, plan.slab, rank)
+        g_own, g_rest = SpmmGraph(*own), SpmmGraph(*rest)
+        ex = PeerPullExchange(world, rank)
+
+        def run_two():
+            return propagate_sharded_two_phase(plan, acc_spmm_fn(g_own), acc_spmm_fn(g_rest), E0_loc, n_layers, ex, rank)
+
+        ue2, ie2 = gather_embeddings(plan, run_two())
+        err_two = float((torch.cat([ue2, ie2]) - ref).abs().max())
+        ms_two = timed(run_two)
     ms_single = timed(lambda: propagate(full_graph, E0, n_layers))
     nnz_l = torch.tensor([lg.nnz], device=dev)
     nnz_all = [torch.zeros_like(nnz_l) for _ in range(world)]
@@ -91,9 +108,11 @@ def main():
                           "max_abs_err_vs_single_gpu": err, "ref_scale": scale,
                           "nnz_per_rank": [int(x) for x in nnz_all],
                           "ms_sharded_3_layers": ms_sharded, "ms_single_gpu_3_layers": ms_single,
-                          "speedup": ms_single / ms_sharded,
+                          "speedup": ms_single / ms_sharded, "two_phase_max_abs_err": err_two,
+                          "ms_two_phase_3_layers": ms_two,
                           "allgather_bytes_per_layer_per_rank": plan.world * plan.slab * d * 4}), flush=True)
     assert err <= 1e-6 * max(scale, 1.0), (err, scale)
+    assert err_two is None or err_two <= 1e-5 * max(scale, 1.0), (err_two, scale)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
