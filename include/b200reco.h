@@ -322,6 +322,13 @@ int b200_l2_normalize_backward(const float* x, int64_t ldx, const float* dy, int
 int b200_adam_dense(float* param, float* m, float* v, float* grad, int64_t n, float lr, float beta1,
                     float beta2, float eps, int64_t step, void* stream);
 
+/* The same update for a CAPTURED (CUDA graph) training step: b200_adam_begin_step increments the device step
+ * counter and writes lr_t = lr sqrt(1-b2^t)/(1-b1^t) (double arithmetic) to lr_t_dev once per step;
+ * b200_adam_dense_dev reads it — nothing about the step number is baked into the launch parameters. */
+int b200_adam_begin_step(int64_t* step_dev, float lr, float beta1, float beta2, float* lr_t_dev, void* stream);
+int b200_adam_dense_dev(float* param, float* m, float* v, float* grad, int64_t n, const float* lr_t_dev, float beta1,
+                        float beta2, float eps, void* stream);
+
 /* ---- training losses: value + gradient w.r.t. the scores in one pass ------
  * All reductions are two-stage and deterministic.  `workspace` >= b200_loss_workspace_bytes().
  * `loss_out` is a device scalar.  Gradient outputs may be NULL. */

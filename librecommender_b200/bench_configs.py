@@ -86,7 +86,9 @@ def c3(args, root, sampler):
     B = 8192
     tu, ti = users[:B].contiguous(), items[:B].contiguous()
     labels = torch.as_tensor((rng.random(B) < 1 / 6).astype(np.float32)).cuda()
-    ms_t = _timeit(lambda: tr.step(tu, ti, labels), iters=20, warm=5)
+    ms_eager = _timeit(lambda: tr.step(tu, ti, labels), iters=20, warm=5)
+    # the same step captured once into a CUDA graph and replayed (launch-bound when issued from Python)
+    ms_t = _timeit(lambda: tr.step_graph(tu, ti, labels), iters=20, warm=5)
     clocks = sampler.stop()
     peaks = _peaks(root)
     peak = float(peaks.get("hbm_gbs", 6650.0))
@@ -102,7 +104,9 @@ def c3(args, root, sampler):
     return _line("training-step interactions/sec (DeepFM)", B / (ms_t * 1e-3), "interactions/s", 20, 5, ms_t, config,
                  roofline, None, clocks,
                  {"predict_rows_per_s": (1 << 18) / (ms_p * 1e-3), "gather_rows_per_s": R / (ms_g * 1e-3),
-                  "gpu_launches": int(_lib.launch_count())})
+                  "ms_per_step_eager_launches": ms_eager, "step": "CUDA graph replay (step_graph)",
+                  "kernels_per_captured_step": int(getattr(tr, "graph_launches_per_step", 0)),
+                  "gpu_launches": int(_lib.launch_count()) + 25 * int(getattr(tr, "graph_launches_per_step", 0))})
 
 
 def c4(args, root, sampler):

@@ -14,6 +14,7 @@
 //                       variables every row touches (dense-field rows, Dense(1) kernel of the linear term)
 //   adam_dense          TF-Adam over a whole variable: m, v decayed everywhere, var updated everywhere
 //                       (what _apply_sparse_shared does for IndexedSlices gradients), gradient zeroed
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "feat_common.cuh"
 #include "../../include/b200reco.h"
@@ -252,32 +253,73 @@ __global__ void adam_dense_kernel(float* __restrict__ p, float* __restrict__ m, 
 
 // ---- generic pieces for the MLP tails (dense_nn in training mode, libreco/layers/dense.py:12-49) ----
 
-// out[k] = sum_r (w ? w[r] : 1) * X[r,k] * (Y ? Y[r,k] : 1): 32 columns x 8 row lanes per block,
-// coalesced along the columns, double accumulation, fixed reduction order (deterministic).
-__global__ void __launch_bounds__(256)
+// out[k] = sum_r (w ? w[r] : 1) * X[r,k] * (Y ? Y[r,k] : 1): 32 columns x 16 row lanes per CTA, a CLUSTER of
+// COLRED_CL CTAs along the rows (thread-block cluster + distributed shared memory: CTA 0 adds the other CTAs'
+// partial sums straight out of their shared memory, no global scratch, no atomics), 4 independent accumulators
+// per thread, double accumulation, fixed reduction order (deterministic).  The first version ran ONE CTA per 32
+// columns with a 1024-deep dependent loop: 155 us per call, 41 % of a DeepFM training step.
+constexpr int COLRED_CL = 8;
+constexpr int COLRED_TY = 16;
+__global__ void __launch_bounds__(32 * COLRED_TY)
 col_reduce_kernel(const float* __restrict__ X, int64_t ldx, int64_t R, int K, const float* __restrict__ w,
                   const float* __restrict__ Y, int64_t ldy, double* __restrict__ out_d, float* __restrict__ out_f) {
-  __shared__ double sh[8][33];
+  namespace cg = cooperative_groups;
+  __shared__ double sh[COLRED_TY][33];
+  __shared__ double tot[32];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();          // position along the rows
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + tx;
-  double s = 0.0;
+  const int lanes = COLRED_CL * COLRED_TY;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   if (k < K) {
-    for (int64_t r = ty; r < R; r += 8) {
+    auto term = [&](int64_t r) -> double {
       double v = (double)X[r * ldx + k];
       if (Y) v *= (double)Y[r * ldy + k];
       if (w) v *= (double)w[r];
-      s += v;
+      return v;
+    };
+    int64_t r = crank * COLRED_TY + ty;
+    for (; r + 3 * lanes < R; r += 4 * lanes) {
+      const double v0 = term(r), v1 = term(r + lanes), v2 = term(r + 2 * lanes), v3 = term(r + 3 * lanes);
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
     }
+    for (; r < R; r += lanes) a0 += term(r);
   }
-  sh[ty][tx] = s;
+  sh[ty][tx] = (a0 + a1) + (a2 + a3);
   __syncthreads();
-  if (ty == 0 && k < K) {
+  if (ty == 0) {
     double t = 0.0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) t += sh[j][tx];
+    for (int j = 0; j < COLRED_TY; ++j) t += sh[j][tx];
+    tot[tx] = t;
+  }
+  cluster.sync();
+  if (crank == 0 && ty == 0 && k < K) {
+    double t = 0.0;
+    for (int c = 0; c < COLRED_CL; ++c) t += *cluster.map_shared_rank(&tot[tx], c);
     if (out_d) out_d[k] = t;
     if (out_f) out_f[k] += (float)t;
   }
+  cluster.sync();                                          // keep every CTA's shared memory alive until it was read
+}
+
+static int launch_col_reduce(const float* X, int64_t ldx, int64_t R, int K, const float* w, const float* Y, int64_t ldy,
+                             double* out_d, float* out_f, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((K + 31) / 32), COLRED_CL, 1);
+  cfg.blockDim = dim3(32 * COLRED_TY, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = COLRED_CL;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA_OK(cudaLaunchKernelEx(&cfg, col_reduce_kernel, X, ldx, R, K, w, Y, ldy, out_d, out_f));
+  return 0;
 }
 
 // BN backward with batch statistics.  s1 = sum dy, s2 = sum dy * x (workspace, doubles).
@@ -365,6 +407,30 @@ __global__ void l2_normalize_backward_kernel(const float* __restrict__ x, int64_
   for (int k = lane; k < d; k += 32) dx[r * lddx + k] = dy[r * lddy + k] * inv - x[r * ldx + k] * c;
 }
 
+
+// CUDA-graph friendly Adam: the step counter and the bias-corrected step size live on the device, so a captured
+// training step can be replayed (a host-computed lr_t would be baked into the graph at capture time)
+__global__ void adam_begin_step_kernel(long long* __restrict__ step, float lr, float b1, float b2, float* __restrict__ lr_t) {
+  const long long t = *step + 1;
+  *step = t;
+  *lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+}
+
+__global__ void adam_dense_dev_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                      float* __restrict__ g, int64_t n, const float* __restrict__ lr_t_dev, float b1,
+                                      float b2, float eps) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lr_t = __ldg(lr_t_dev);
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  g[i] = 0.f;
+}
+
 }  // namespace train
 }  // namespace b200
 
@@ -375,7 +441,7 @@ extern "C" int b200_col_reduce(const float* X, int64_t ldx, int64_t R, int32_t K
                                const float* Y, int64_t ldy, float* out, void* stream) {
   B200_REQUIRE(X && out && K > 0, "b200_col_reduce: bad arguments");
   if (R == 0) return 0;
-  col_reduce_kernel<<<(unsigned)((K + 31) / 32), 256, 0, (cudaStream_t)stream>>>(X, ldx, R, K, wrow, Y, ldy, nullptr, out);
+  if (launch_col_reduce(X, ldx, R, K, wrow, Y, ldy, nullptr, out, (cudaStream_t)stream)) return 1;
   B200_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -391,9 +457,8 @@ extern "C" int b200_bn_train_backward(const float* dy, int64_t lddy, const float
   cudaStream_t st = (cudaStream_t)stream;
   double* s1 = (double*)workspace;
   double* s2 = s1 + K;
-  const unsigned gb = (unsigned)((K + 31) / 32);
-  col_reduce_kernel<<<gb, 256, 0, st>>>(dy, lddy, R, K, nullptr, nullptr, 0, s1, nullptr);
-  col_reduce_kernel<<<gb, 256, 0, st>>>(dy, lddy, R, K, nullptr, x, ldx, s2, nullptr);
+  if (launch_col_reduce(dy, lddy, R, K, nullptr, nullptr, 0, s1, nullptr, st)) return 1;
+  if (launch_col_reduce(dy, lddy, R, K, nullptr, x, ldx, s2, nullptr, st)) return 1;
   bn_backward_apply_kernel<<<(unsigned)ceil_div64(R * K, 256), 256, 0, st>>>(
       dy, lddy, x, ldx, R, K, batch_mean, batch_var, gamma, eps, relu_mask, s1, s2, dx, lddx, g_gamma, g_beta);
   B200_CUDA_OK(cudaGetLastError());
@@ -536,6 +601,26 @@ extern "C" int b200_adam_dense(float* param, float* m, float* v, float* grad, in
   const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) / (1.0 - pow((double)beta1, (double)step));
   adam_dense_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(param, m, v, grad, n, (float)lr_t,
                                                                                      beta1, beta2, eps);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200_adam_begin_step(int64_t* step_dev, float lr, float beta1, float beta2, float* lr_t_dev, void* stream) {
+  B200_REQUIRE(step_dev && lr_t_dev, "b200_adam_begin_step: null pointer");
+  adam_begin_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(step_dev), lr, beta1, beta2,
+                                                            lr_t_dev);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200_adam_dense_dev(float* param, float* m, float* v, float* grad, int64_t n, const float* lr_t_dev,
+                                   float beta1, float beta2, float eps, void* stream) {
+  B200_REQUIRE(param && m && v && grad && lr_t_dev, "b200_adam_dense_dev: null pointer");
+  if (n == 0) return 0;
+  adam_dense_dev_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(param, m, v, grad, n, lr_t_dev,
+                                                                                       beta1, beta2, eps);
   B200_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -67,6 +67,8 @@ def _dev(x, device, dtype):
 LINEAR_IMPL = "auto"
 TC_MIN_DIN = 64
 TC_MIN_ROWS = 4096
+TC_MIN_MACS = 1 << 27
+TC_LONG_K = 1024        # long reductions (weight gradients over the batch) starve the SIMT kernel's few CTAs
 
 
 _SPLIT_CACHE = {}
@@ -99,7 +101,10 @@ def linear(x, Wt, b, relu, cache_split=True):
     y = torch.empty((R, dout), dtype=torch.float32, device=x.device)
     bp = _lib.ptr(b) if b is not None else None
     aligned = x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and x.stride(1) == 1 and Wt.stride(1) == 1
-    use_tc = LINEAR_IMPL == "tf32x3" or (LINEAR_IMPL == "auto" and din >= TC_MIN_DIN and R >= TC_MIN_ROWS)
+    # few output rows but a long reduction (the weight gradients dWt = dY^T X of the training steps: 128 x 1792
+    # outputs over 8192 rows) would run on a handful of SIMT CTAs: send those to the tensor-core kernel too
+    use_tc = LINEAR_IMPL == "tf32x3" or (LINEAR_IMPL == "auto" and din >= TC_MIN_DIN and
+                                         (R >= TC_MIN_ROWS or din >= TC_LONG_K or R * din * dout >= TC_MIN_MACS))
     w_ok = cache_split or (Wt.stride(0) % 4 == 0 and Wt.data_ptr() % 16 == 0)
     if use_tc and aligned and w_ok:
         ws = split_weights(Wt) if cache_split else None

@@ -30,7 +30,66 @@ _TABLES = ("user_embeds", "item_embeds", "sparse_embeds", "dense_embeds",
            "user_linear", "item_linear", "sparse_linear", "dense_linear")
 
 
-class FMTrainer:
+def _adam_update(tr):
+    """TF-Adam over every variable of trainer ``tr`` with the step counter and the bias-corrected step size ON THE
+    DEVICE (``b200_adam_begin_step`` / ``b200_adam_dense_dev``): the same launches work eagerly and inside a
+    captured CUDA graph."""
+    torch = tr._torch
+    if getattr(tr, "_step_dev", None) is None:
+        tr._step_dev = torch.full((1,), int(tr.t), dtype=torch.int64, device=tr.device)
+        tr._lr_t = torch.zeros(1, dtype=torch.float32, device=tr.device)
+    lib, st = _lib.lib, _lib.current_stream()
+    _lib.check(lib.b200_adam_begin_step(_lib.ptr(tr._step_dev), tr.lr, BETA1, BETA2, _lib.ptr(tr._lr_t), st))
+    for k, v in tr.params.items():
+        _lib.check(lib.b200_adam_dense_dev(_lib.ptr(v), _lib.ptr(tr.m[k]), _lib.ptr(tr.v[k]), _lib.ptr(tr.grads[k]),
+                                           v.numel(), _lib.ptr(tr._lr_t), BETA1, BETA2, tr.epsilon, st))
+    tr.t += 1
+
+
+def _weight_grad(dy, x):
+    """dWt [dout, din] = dY^T X on the library's dense kernel.  The kernel tiles the OUTPUT rows over the SMs, so
+    the product is taken in the orientation with more output rows (din > dout: (X^T dY)^T) — the reduction runs
+    over the batch either way."""
+    from .feat_models import linear
+
+    dyt, xt = dy.t().contiguous(), x.t().contiguous()
+    if xt.shape[0] > dyt.shape[0]:
+        return linear(xt, dyt, None, False, cache_split=False).t()
+    return linear(dyt, xt, None, False, cache_split=False)
+
+
+class _GraphedStep:
+    """``step_graph(*device tensors)``: the trainer's ``step`` captured ONCE per input shape into a CUDA graph and
+    replayed — a step is ~100 small launches (gather, BN, dense layers, reductions, one Adam launch per variable),
+    launch-bound when issued one by one from Python.  Inputs are copied into static buffers; the returned loss
+    is a static device scalar, valid until the next replay.  Semantics are those of ``step``."""
+
+    def step_graph(self, *inputs):
+        torch = self._torch
+        graphs = self.__dict__.setdefault("_graphs", {})
+        key = tuple(None if x is None else (tuple(x.shape), x.dtype) for x in inputs)
+        ent = graphs.get(key)
+        if ent is None:
+            if getattr(self, "_step_dev", None) is None:          # allocate the device counters outside the capture
+                self._step_dev = torch.full((1,), int(self.t), dtype=torch.int64, device=self.device)
+                self._lr_t = torch.zeros(1, dtype=torch.float32, device=self.device)
+            static = [None if x is None else x.detach().clone() for x in inputs]
+            graph = torch.cuda.CUDAGraph()
+            launches0 = int(_lib.lib.b200_launch_count())
+            with torch.cuda.graph(graph):
+                loss = self.step(*static)          # recorded, not executed (the host counter `t` advances here)
+            ent = graphs[key] = (graph, static, loss, int(_lib.lib.b200_launch_count()) - launches0)
+        else:
+            for s_, x in zip(ent[1], inputs):
+                if s_ is not None:
+                    s_.copy_(x, non_blocking=True)
+            self.t += 1
+        ent[0].replay()
+        self.graph_launches_per_step = ent[3]      # this library's kernels inside one replay
+        return ent[2]
+
+
+class FMTrainer(_GraphedStep):
     """Owns the FM variables of ``fm.py`` (scope "embedding" tables + the two Dense(1) heads + BN),
     their Adam slots and gradient buffers.  ``weights`` uses the inference layout of
     ``feat_models.FM`` / ``oracle.tf_models.make_fm_weights``."""
@@ -130,10 +189,7 @@ class FMTrainer:
             _lib.ptr(b["dpw"]), K, _lib.ptr(b["S"]), K, None, 0, _lib.ptr(b["dlogit"]), _lib.ptr(p["lin_kernel"]),
             gp("user_embeds"), gp("item_embeds"), gp("sparse_embeds"), gp("dense_embeds"), gp("user_linear"),
             gp("item_linear"), gp("sparse_linear"), gp("dense_linear"), gp("lin_kernel"), st))
-        self.t += 1
-        for k in p:
-            _lib.check(lib.b200_adam_dense(_lib.ptr(p[k]), _lib.ptr(self.m[k]), _lib.ptr(self.v[k]), _lib.ptr(g[k]),
-                                           p[k].numel(), self.lr, BETA1, BETA2, self.epsilon, self.t, st))
+        _adam_update(self)
         return b["loss"]
 
     def export_weights(self):
@@ -148,7 +204,7 @@ class FMTrainer:
         return w
 
 
-class DeepFMTrainer:
+class DeepFMTrainer(_GraphedStep):
     """DeepFM training step on the device: ``libreco/algorithms/deepfm.py:143-175`` with
     ``dense_nn`` in training mode (``libreco/layers/dense.py:12-49``: BN(input) -> [Dense -> ReLU ->
     BN] x (L-1) -> Dense, no dropout = the reference's default), mean sigmoid CE, TF-Adam.
@@ -302,7 +358,7 @@ class DeepFMTrainer:
             x = c["dense_in"][i]
             da = da.contiguous()
             # dWt [dout, din] = dY^T X ; db = column sums of dY ; dX = dY Wt
-            g[f"Wt{i}"] += linear(da.t().contiguous(), x.t().contiguous(), None, False, cache_split=False)
+            g[f"Wt{i}"] += _weight_grad(da, x)
             self._col_reduce(da, g[f"b{i}"])
             da = linear(da, p[f"Wt{i}"].t().contiguous(), None, False, cache_split=False)
         dconcat = self._bn_backward(da, c["concat"], c["bn_stats"][0], 0, False) if self.use_bn else da
@@ -322,11 +378,7 @@ class DeepFMTrainer:
         self.forward(users_d, items_d)
         self._cache["users"], self._cache["items"] = users_d, items_d
         loss = self.backward(labels_d)
-        self.t += 1
-        lib, st = _lib.lib, _lib.current_stream()
-        for k, v in self.params.items():
-            _lib.check(lib.b200_adam_dense(_lib.ptr(v), _lib.ptr(self.m[k]), _lib.ptr(self.v[k]), _lib.ptr(self.grads[k]),
-                                           v.numel(), self.lr, BETA1, BETA2, self.epsilon, self.t, st))
+        _adam_update(self)
         self._cache = None
         return loss
 
@@ -348,7 +400,7 @@ class DeepFMTrainer:
         return w
 
 
-class _StackTrainer:
+class _StackTrainer(_GraphedStep):
     """Shared pieces of the trainers built on ``dense_nn`` stacks (``libreco/layers/dense.py:12-49``, training mode):
     parameters ``{prefix}Wt{i}`` [dout, din], ``{prefix}b{i}``, ``{prefix}bn{j}_gamma|beta`` (+ moving statistics),
     forward / backward of one stack on the library kernels, TF-Adam over every variable."""
@@ -449,17 +501,13 @@ class _StackTrainer:
                     da = dh
             x = c["dense_in"][i]
             da = da.contiguous()
-            g[f"{prefix}Wt{i}"] += linear(da.t().contiguous(), x.t().contiguous(), None, False, cache_split=False)
+            g[f"{prefix}Wt{i}"] += _weight_grad(da, x)
             self._col_sum(da, g[f"{prefix}b{i}"])
             da = linear(da, p[f"{prefix}Wt{i}"].t().contiguous(), None, False, cache_split=False)
         return self._bn_backward(da, c["concat"], c["bn_stats"][0], f"{prefix}bn0", False) if self.use_bn else da
 
     def _adam_all(self):
-        self.t += 1
-        lib, st = _lib.lib, _lib.current_stream()
-        for k, v in self.params.items():
-            _lib.check(lib.b200_adam_dense(_lib.ptr(v), _lib.ptr(self.m[k]), _lib.ptr(self.v[k]), _lib.ptr(self.grads[k]),
-                                           v.numel(), self.lr, BETA1, BETA2, self.epsilon, self.t, st))
+        _adam_update(self)
 
     def _export_stack(self, prefix, n):
         p = self.params

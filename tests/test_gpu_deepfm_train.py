@@ -91,3 +91,29 @@ def test_training_steps_match_oracle(use_bn):
     sparse, dense = tm.row_features(spec, users, items)
     ref = tm.deepfm_forward(dt_.export_weights(st), users, items, sparse, dense, dtype=np.float64)
     assert np.abs(got - ref).max() <= 3e-2 * max(1.0, np.abs(ref).max())
+
+
+def test_graph_replay_equals_eager_steps():
+    """step_graph (one CUDA-graph capture, then replays with the Adam step counter on the device) must produce
+    the same parameters as the eager step loop, for every trainer family."""
+    import torch
+
+    from librecommender_b200.training import DeepFMTrainer, FMTrainer
+    from oracle import tf_models as tm
+
+    spec, w, batches = _case(21, True, (64, 32))
+    rng = np.random.default_rng(0)
+    wf = tm.make_fm_weights(rng, spec, 16, True)
+    for cls, weights in ((DeepFMTrainer, w), (FMTrainer, wf)):
+        a = cls(spec, weights, use_bn=True, lr=1e-2)
+        b = cls(spec, weights, use_bn=True, lr=1e-2)
+        for users, items, labels in batches + batches:
+            u, i, y = torch.as_tensor(users).cuda(), torch.as_tensor(items).cuda(), torch.as_tensor(labels).cuda()
+            la = float(a.step(u, i, y))
+            lb = float(b.step_graph(u, i, y))
+            assert abs(la - lb) <= 1e-5 * max(1.0, abs(la)), (cls.__name__, la, lb)
+        assert a.t == b.t == 6 and int(b._step_dev.item()) == 6
+        assert b.graph_launches_per_step > 10
+        for k in a.params:
+            da = (a.params[k] - b.params[k]).abs().max().item()
+            assert da <= 2e-4, (cls.__name__, k, da)       # float atomics in the scatter: order differs run to run

@@ -111,3 +111,20 @@ def test_learned_temperature_is_refused():
     spec, w, _ = _case(1, False)
     with pytest.raises(ValueError, match="learned temperature"):
         TwoTowerTrainer(spec, w, use_bn=False, temperature=0.0)
+
+
+def test_graph_replay_equals_eager_steps():
+    import torch
+
+    from librecommender_b200.training import TwoTowerTrainer
+
+    spec, w, batches = _case(13, True)
+    a = TwoTowerTrainer(spec, w, use_bn=True, norm_embed=True, temperature=0.5, lr=1e-2)
+    b = TwoTowerTrainer(spec, w, use_bn=True, norm_embed=True, temperature=0.5, lr=1e-2)
+    for users, items, corr in batches + batches:
+        u, i, c = torch.as_tensor(users).cuda(), torch.as_tensor(items).cuda(), torch.as_tensor(corr).cuda()
+        la, lb = float(a.step(u, i, c)), float(b.step_graph(u, i, c))
+        assert abs(la - lb) <= 1e-5 * max(1.0, abs(la)), (la, lb)
+    assert a.t == b.t == 6
+    for k in a.params:
+        assert (a.params[k] - b.params[k]).abs().max().item() <= 2e-4, k
