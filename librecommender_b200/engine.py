@@ -9,6 +9,7 @@ runs on; tables are uploaded once per (array object) and cached.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -19,6 +20,28 @@ _SCORE_WS_BYTES = 1 << 30  # materialised-score workspace of the exact path
 FUSED_MAX_D = 256           # limits of b200_recommend_embed (include/b200reco.h)
 FUSED_MAX_K = 288
 FUSED_ROWS_PER_CALL = 16384
+NVTX = bool(int(os.environ.get("B200_NVTX", "0")))     # B200_NVTX=1: NVTX ranges around the phases of a recommend call
+
+
+class _nvtx:
+    """``with _nvtx("name"):`` — an NVTX range when B200_NVTX=1 (nsys / ncu --nvtx timelines), free otherwise."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            import torch
+
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if NVTX:
+            import torch
+
+            torch.cuda.nvtx.range_pop()
+        return False
+
 
 
 def _as_device_f32(x, device):
@@ -261,7 +284,8 @@ class EmbedScorer:
                 torch.zeros(0, dtype=torch.int64)
         else:
             uid_h = torch.as_tensor(np.asarray(user_ids, dtype=np.int64))
-        uid_d = uid_h.to(self.device, non_blocking=True)
+        with _nvtx("b200.recommend.h2d_ids"):
+            uid_d = uid_h.to(self.device, non_blocking=True)
         B = int(uid_d.numel())
         if path == "exact" or (path == "auto" and not self.fused_ok(n_rec)):
             res = self.recommend_exact(uid_d, n_rec, filter_consumed, return_scores)
@@ -283,15 +307,17 @@ class EmbedScorer:
             ev.record(main)
             res.setdefault("chunks", []).append((r0, r1, ev))
 
-        ids_d, sc_d, status_d = self.recommend_fused(uid_d, n_rec, filter_consumed, return_scores, on_chunk)
-        with torch.cuda.stream(side):
+        with _nvtx("b200.recommend.fused_kernels"):
+            ids_d, sc_d, status_d = self.recommend_fused(uid_d, n_rec, filter_consumed, return_scores, on_chunk)
+        with _nvtx("b200.recommend.d2h_results"), torch.cuda.stream(side):
             for r0, r1, ev in res.get("chunks", []):
                 side.wait_event(ev)
                 ids_slot[0][r0:r1].copy_(ids_d[r0:r1], non_blocking=True)
                 st_slot[0][r0:r1].copy_(status_d[r0:r1], non_blocking=True)
                 if return_scores:
                     sc_slot[0][r0:r1].copy_(sc_d[r0:r1], non_blocking=True)
-        side.synchronize()
+        with _nvtx("b200.recommend.sync"):
+            side.synchronize()
         for t in (ids_d, sc_d, status_d):            # the side stream used them: keep the allocator informed
             if t is not None:
                 t.record_stream(side)
@@ -301,7 +327,8 @@ class EmbedScorer:
         self.last_fallback_rows = int(len(bad))
         if len(bad):                       # rows the fused path could not prove: exact path
             bad_d = torch.as_tensor(bad, device=self.device)
-            fix = self.recommend_exact(uid_d[bad_d], n_rec, filter_consumed, return_scores)
+            with _nvtx("b200.recommend.exact_repair"):
+                fix = self.recommend_exact(uid_d[bad_d], n_rec, filter_consumed, return_scores)
             if return_scores:
                 ids[bad], scores[bad] = fix[0].cpu().numpy(), fix[1].cpu().numpy()
             else:
