@@ -415,6 +415,17 @@ int b200_din_attention_hoisted(const float* Z, int64_t ldz, int64_t N, const flo
                                const int32_t* seq, int32_t len, const float* k2, float b2, float* out,
                                int64_t ld_out, void* stream);
 
+/* The same per-user product with the attention's tail FUSED into the GEMM epilogue (DIN all-items):
+ * A[r, g] = sum_{j<16} dot_w16[j] * sigmoid((X Wt^T + bias)[r, 16 g + j]), g < dout / 16 — the [R, dout]
+ * pre-activations (16x the bytes of A) are never written.  Then b200_din_attention_from_logits:
+ * out[n, :Kp] = sum_t softmax_t((A[n, t] + b2) * rsqrt(Kp)) * G[seq[t], :Kp], t < len (1 <= len <= 64). */
+int b200_linear_tf32x3_sigmoid_dot(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
+                                   const float* Wsplit, const float* bias, int32_t din, int32_t dout,
+                                   const float* dot_w16, float* A, int64_t lda, void* stream);
+int b200_din_attention_from_logits(const float* A, int64_t lda, int64_t N, const float* G, int64_t ldg, int32_t Kp,
+                                   const int32_t* seq, int32_t len, float b2, float* out, int64_t ld_out,
+                                   void* stream);
+
 /* ---- a12: negative sampling (libreco/sampling/negatives.py:17-82; collators.py:138-166) ---
  * Counter-based (Philox4x32-10) device sampler; result = f(seed, step, index) only.
  * mode 0 random, 1 unconsumed (needs users + per-user SORTED consumed CSR), 2 popular (needs the

@@ -96,6 +96,10 @@ SIGNATURES = {
     "b200_mul_elementwise": (c_int, [_P, _P, c_int64, _P, _P]),
     "b200_ngcf_combine": (c_int, [_P, c_int64, _P, c_int64, c_int64, c_int32, c_float, _P, c_int64, _P]),
     "b200_din_user_weights": (c_int, [_P, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int64, _P, _P]),
+    "b200_linear_tf32x3_sigmoid_dot": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, _P, c_int32, c_int32, _P, _P, c_int64,
+                                               _P]),
+    "b200_din_attention_from_logits": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int32, _P, c_int32, c_float, _P,
+                                               c_int64, _P]),
     "b200_din_attention_hoisted": (c_int, [_P, c_int64, c_int64, _P, c_int64, c_int32, _P, c_int32, _P, c_float, _P,
                                            c_int64, _P]),
     "b200_sample_negatives": (c_int, [_P, _P, c_int64, c_int32, c_int64, c_int32, c_int32, c_uint64, c_uint64,

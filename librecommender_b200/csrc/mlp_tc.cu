@@ -38,6 +38,7 @@ struct Params {
   int64_t ldy;
   const float* bias;
   float* Y;
+  const float* dot_w;     // fused DIN epilogue: 16 weights of the Dense(1) on sigmoid(Dense(16)) (NULL = plain layer)
   int din, dout, n_pad, relu;
   int n_tiles, n_chunks, nstage;
 };
@@ -88,7 +89,7 @@ __global__ void split_weights_kernel(const float* __restrict__ W, int64_t ldw, i
 
 // WSPLIT: tmW / tmWlo address the pre-split weight copies; otherwise the splitters also split the
 // weight tile of every stage (self-contained call, more shared-memory traffic).
-template <bool WSPLIT>
+template <bool WSPLIT, bool DOT>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmWlo, const Params p) {
@@ -246,7 +247,29 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (acc == 0) acc_phase ^= 1;
       }
       const int64_t row = (int64_t)tile * TM + q * 32 + lane;
-      if (row < p.R) {
+      if (DOT && row < p.R) {
+        // fused attention epilogue (DIN all-items): per group of 16 columns ONE output
+        //   a[row, (col0 + 16 g) / 16] = sum_j dot_w[j] * sigmoid(y[16 g + j] + bias)
+        // the [R, dout] pre-activations (16x the bytes) are never written
+        const int ncol = min(p.dout - col0, NMAX);
+        float w2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w2[j] = __ldg(p.dot_w + j);
+        float* yd = p.Y + row * p.ldy + col0 / 16;
+#pragma unroll
+        for (int g = 0; g < NMAX / 16; ++g) {
+          if (g * 16 < ncol) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int c = g * 16 + j;
+              const float v = y[c] + (p.bias ? __ldg(p.bias + col0 + c) : 0.f);
+              a = fmaf(w2[j], 1.0f / (1.0f + expf(-v)), a);
+            }
+            yd[g] = a;
+          }
+        }
+      } else if (!DOT && row < p.R) {
         float* yr = p.Y + row * p.ldy + col0;
         const int ncol = min(p.dout - col0, NMAX);
         const bool vec = ((p.ldy & 3) == 0) && ((((uintptr_t)p.Y) & 15) == 0);
@@ -333,18 +356,38 @@ extern "C" int b200_linear_tf32x3_split_weights(const float* Wt, int64_t ldw, in
   return 0;
 }
 
+static int launch_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
+                                const float* Wsplit, const float* bias, int32_t din, int32_t dout,
+                                int32_t relu, const float* dot_w, float* Y, int64_t ldy, void* stream);
+
 extern "C" int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
                                   const float* Wsplit, const float* bias, int32_t din, int32_t dout,
                                   int32_t relu, float* Y, int64_t ldy, void* stream) {
+  B200_REQUIRE(ldy >= dout, "leading dimension too small");
+  return launch_linear_tf32x3(X, ldx, R, Wt, ldw, Wsplit, bias, din, dout, relu, nullptr, Y, ldy, stream);
+}
+
+extern "C" int b200_linear_tf32x3_sigmoid_dot(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
+                                              const float* Wsplit, const float* bias, int32_t din, int32_t dout,
+                                              const float* dot_w16, float* A, int64_t lda, void* stream) {
+  B200_REQUIRE(dot_w16 && A, "b200_linear_tf32x3_sigmoid_dot: null pointer");
+  B200_REQUIRE(dout % 16 == 0 && lda >= dout / 16, "b200_linear_tf32x3_sigmoid_dot: dout must be a multiple of 16, lda >= dout / 16");
+  return launch_linear_tf32x3(X, ldx, R, Wt, ldw, Wsplit, bias, din, dout, 0, dot_w16, A, lda, stream);
+}
+
+static int launch_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
+                                const float* Wsplit, const float* bias, int32_t din, int32_t dout,
+                                int32_t relu, const float* dot_w, float* Y, int64_t ldy, void* stream) {
   using namespace b200;
   using namespace b200::mlp;
   B200_REQUIRE(R >= 0 && din > 0 && dout > 0, "bad shape");
   B200_REQUIRE((ldx & 3) == 0 && ((uintptr_t)X & 15) == 0, "b200_linear_tf32x3 needs 16-byte aligned X rows (ldx % 4 == 0)");
   B200_REQUIRE(Wsplit ? (((uintptr_t)Wsplit & 15) == 0) : ((ldw & 3) == 0 && ((uintptr_t)Wt & 15) == 0),
                "b200_linear_tf32x3 needs 16-byte aligned weight rows (ldw % 4 == 0) or a split copy");
-  B200_REQUIRE(ldx >= din && (Wsplit || ldw >= din) && ldy >= dout, "leading dimension too small");
+  B200_REQUIRE(ldx >= din && (Wsplit || ldw >= din), "leading dimension too small");
   if (R == 0) return 0;
   Params p;
+  p.dot_w = dot_w;
   p.R = R;
   p.ldy = ldy;
   p.bias = bias;
@@ -372,10 +415,10 @@ extern "C" int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const 
 
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA_OK(cudaFuncSetAttribute(linear_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      220 * 1024));
-    B200_CUDA_OK(cudaFuncSetAttribute(linear_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      220 * 1024));
+    B200_CUDA_OK(cudaFuncSetAttribute(linear_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    B200_CUDA_OK(cudaFuncSetAttribute(linear_tf32x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    B200_CUDA_OK(cudaFuncSetAttribute(linear_tf32x3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    B200_CUDA_OK(cudaFuncSetAttribute(linear_tf32x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
   int dev = 0, sms = 148;
@@ -383,10 +426,15 @@ extern "C" int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int gy = (dout + NMAX - 1) / NMAX;
   const int gx = max(1, min(p.n_tiles, sms / gy));
-  if (Wsplit)
-    linear_tf32x3_kernel<true><<<dim3(gx, gy), THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, tmWlo, p);
-  else
-    linear_tf32x3_kernel<false><<<dim3(gx, gy), THREADS, smem, (cudaStream_t)stream>>>(tmX, tmW, tmWlo, p);
+  const dim3 grid(gx, gy);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dot_w) {
+    if (Wsplit) linear_tf32x3_kernel<true, true><<<grid, THREADS, smem, st>>>(tmX, tmW, tmWlo, p);
+    else linear_tf32x3_kernel<false, true><<<grid, THREADS, smem, st>>>(tmX, tmW, tmWlo, p);
+  } else {
+    if (Wsplit) linear_tf32x3_kernel<true, false><<<grid, THREADS, smem, st>>>(tmX, tmW, tmWlo, p);
+    else linear_tf32x3_kernel<false, false><<<grid, THREADS, smem, st>>>(tmX, tmW, tmWlo, p);
+  }
   B200_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

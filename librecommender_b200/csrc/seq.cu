@@ -13,6 +13,7 @@
 //   c_j    = b1_j + sum_c q_c * (W1q + W1d)[c][j]
 // (W1q/W1k/W1d/W1p = the four K'-row blocks of the Dense(16) kernel), so the per-key work is one
 // K' x 16 mat-vec held in registers; a 16-value butterfly reduction needs 16 shuffles.
+#include <algorithm>
 #include "common.cuh"
 #include "../../include/b200reco.h"
 
@@ -346,6 +347,53 @@ din_attention_hoisted_kernel(const float* __restrict__ Z, int64_t ldz, int64_t N
   }
 }
 
+
+// DIN all-items, second half: A[n, t] = Dense(1)(sigmoid(Dense(16)(...))) WITHOUT its bias, written by the fused
+// GEMM epilogue (b200_linear_tf32x3_sigmoid_dot).  One warp per item: lane t owns position t (two rounds for
+// T <= 64), softmax over the len positions, out = sum_t p_t k_t with the user's keys staged ONCE per CTA in
+// shared memory (they are the same for every item) and p_t broadcast by shuffle.
+__global__ void __launch_bounds__(256)
+din_attention_from_logits_kernel(const float* __restrict__ A, int64_t lda, int64_t N, const float* __restrict__ G,
+                                 int64_t ldg, int Kp, const int32_t* __restrict__ seq, int len, float b2,
+                                 float* __restrict__ out, int64_t ld_out) {
+  extern __shared__ float s_keys[];                      // [len][Kp]
+  for (int i = threadIdx.x; i < len * Kp; i += blockDim.x)
+    s_keys[i] = __ldg(G + (int64_t)__ldg(seq + i / Kp) * ldg + (i % Kp));
+  __syncthreads();
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float scale = rsqrtf((float)Kp);
+  const int TK = (Kp + 31) / 32;
+  for (int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + wid; n < N; n += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    const float* a = A + n * lda;
+    const float a0 = lane < len ? (__ldg(a + lane) + b2) * scale : -3.0e38f;
+    const float a1 = lane + 32 < len ? (__ldg(a + lane + 32) + b2) * scale : -3.0e38f;
+    float amax = fmaxf(a0, a1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    float e0 = lane < len ? expf(a0 - amax) : 0.f;
+    float e1 = lane + 32 < len ? expf(a1 - amax) : 0.f;
+    const float den = warp_sum(e0 + e1);
+    e0 /= den;
+    e1 /= den;
+    float acc[MAX_TK];
+#pragma unroll
+    for (int tt = 0; tt < MAX_TK; ++tt) acc[tt] = 0.f;
+    for (int t = 0; t < len; ++t) {
+      const float p = __shfl_sync(0xffffffffu, t < 32 ? e0 : e1, t & 31);
+#pragma unroll
+      for (int tt = 0; tt < MAX_TK; ++tt) {
+        const int c = lane + tt * 32;
+        if (tt < TK && c < Kp) acc[tt] = fmaf(p, s_keys[t * Kp + c], acc[tt]);
+      }
+    }
+#pragma unroll
+    for (int tt = 0; tt < MAX_TK; ++tt) {
+      const int c = lane + tt * 32;
+      if (tt < TK && c < Kp) out[n * ld_out + c] = acc[tt];
+    }
+  }
+}
+
 }  // namespace seq
 }  // namespace b200
 
@@ -373,6 +421,23 @@ extern "C" int b200_din_attention_hoisted(const float* Z, int64_t ldz, int64_t N
   if (N == 0) return 0;
   din_attention_hoisted_kernel<<<(unsigned)ceil_div64(N, 4), 128, 0, (cudaStream_t)stream>>>(
       Z, ldz, N, G, ldg, Kp, seq, len, k2, b2, out, ld_out);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200_din_attention_from_logits(const float* A, int64_t lda, int64_t N, const float* G, int64_t ldg,
+                                              int32_t Kp, const int32_t* seq, int32_t len, float b2, float* out,
+                                              int64_t ld_out, void* stream) {
+  B200_REQUIRE(A && G && seq && out, "b200_din_attention_from_logits: null pointer");
+  B200_REQUIRE(Kp >= 1 && Kp <= 32 * MAX_TK && len >= 1 && len <= 64 && len <= MAX_T,
+               "b200_din_attention_from_logits: bad shape");
+  if (N == 0) return 0;
+  const size_t smem = (size_t)len * Kp * 4;
+  B200_REQUIRE(smem <= 48 * 1024, "b200_din_attention_from_logits: keys do not fit shared memory");
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(N, 8), (int64_t)148 * 8);
+  din_attention_from_logits_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(A, lda, N, G, ldg, Kp, seq, len, b2, out,
+                                                                               ld_out);
   B200_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

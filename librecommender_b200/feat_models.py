@@ -68,6 +68,9 @@ LINEAR_IMPL = "auto"
 TC_MIN_DIN = 64
 TC_MIN_ROWS = 4096
 TC_MIN_MACS = 1 << 27
+DIN_FUSED_ATTENTION = False   # DIN all-items: sigmoid / Dense(1) fused into the attention GEMM's epilogue.  Measured
+# (profiles/r02_launches_din_*.csv): no gain — the fused GEMM 524 us + softmax kernel 242 us per user vs 359 + 395 us
+# for the [N, 16 len] round trip; the per-tile cost of the K = 64 product dominates either way.  Kept as a tested variant.
 TC_LONG_K = 1024        # long reductions (weight gradients over the batch) starve the SIMT kernel's few CTAs
 
 
@@ -925,16 +928,30 @@ class DIN(_SeqModelBase):
             ln = int(lens_h[r])
             seq = self.seqs[user_ids_d[r]]                                       # int32 [T] view (device)
             Z = None
+            fused = False
             if ln > 0:
                 Wt = torch.empty((16 * ln, Kp), dtype=torch.float32, device=self.device)
                 bias = torch.empty(16 * ln, dtype=torch.float32, device=self.device)
                 _lib.check(lib.b200_din_user_weights(_lib.ptr(self.G), self.G.stride(0), Kp, _lib.ptr(seq), ln,
                                                      _lib.ptr(self.att["k1"]), _lib.ptr(self.att["b1"]), _lib.ptr(Wt),
                                                      Wt.stride(0), _lib.ptr(bias), st))
-                Z = linear(Gn, Wt, bias, False, cache_split=False)               # [N, 16 ln]
-            _lib.check(lib.b200_din_attention_hoisted(
-                _lib.ptr(Z), Z.stride(0) if Z is not None else 0, N, _lib.ptr(self.G), self.G.stride(0), Kp,
-                _lib.ptr(seq), ln, _lib.ptr(self.att["k2"]), self.att["b2"], _lib.ptr(att), att.stride(0), st))
+                fused = (DIN_FUSED_ATTENTION and ln <= 64 and ln * Kp * 4 <= 48 * 1024 and Kp % 4 == 0
+                         and Gn.stride(0) % 4 == 0 and N >= TC_MIN_ROWS)
+                if fused:
+                    # sigmoid + Dense(1) in the GEMM's epilogue: [N, ln] logits instead of [N, 16 ln] pre-activations
+                    A = torch.empty((N, ln), dtype=torch.float32, device=self.device)
+                    _lib.check(lib.b200_linear_tf32x3_sigmoid_dot(
+                        _lib.ptr(Gn), Gn.stride(0), N, _lib.ptr(Wt), Wt.stride(0), None, _lib.ptr(bias), Kp, 16 * ln,
+                        _lib.ptr(self.att["k2"]), _lib.ptr(A), A.stride(0), st))
+                    _lib.check(lib.b200_din_attention_from_logits(
+                        _lib.ptr(A), A.stride(0), N, _lib.ptr(self.G), self.G.stride(0), Kp, _lib.ptr(seq), ln,
+                        self.att["b2"], _lib.ptr(att), att.stride(0), st))
+                else:
+                    Z = linear(Gn, Wt, bias, False, cache_split=False)           # [N, 16 ln]
+            if not fused:
+                _lib.check(lib.b200_din_attention_hoisted(
+                    _lib.ptr(Z), Z.stride(0) if Z is not None else 0, N, _lib.ptr(self.G), self.G.stride(0), Kp,
+                    _lib.ptr(seq), ln, _lib.ptr(self.att["k2"]), self.att["b2"], _lib.ptr(att), att.stride(0), st))
             Pi = self._item_part + linear(att, self._w_att, None, False)         # [N, H1]
             Pu = Pu_all[r:r + 1]
             _lib.check(lib.b200_deepfm_pair_scores(

@@ -292,3 +292,36 @@ def test_recommend_tf_feat_shim():
         assert not set(ids[r].tolist()) & set(consumed[u])
         assert not set(rnd[r].tolist()) & set(consumed[u])
         assert len(set(rnd[r].tolist())) == 10
+
+
+@pytest.mark.parametrize("T", [20, 50])
+def test_din_fused_attention_epilogue_equals_unfused_and_flat(T):
+    """Catalogue large enough for the tensor-core path (N >= 4096): the fused GEMM epilogue
+    (b200_linear_tf32x3_sigmoid_dot + b200_din_attention_from_logits) against the two-kernel hoisted form
+    ([N, 16 len] pre-activations + b200_din_attention_hoisted) and the per-row kernel on the flat grid."""
+    import torch
+
+    from librecommender_b200 import feat_models as fmods
+    from librecommender_b200.feat_models import DIN, recent_sequences
+    from oracle import tf_models as tm
+
+    rng = np.random.default_rng(41 + T)
+    n_users, n_items = 60, 5003
+    spec = tm.make_spec(rng, n_users, n_items, [9], [6, 13, 21], 1, 0)
+    consumed = {u: rng.choice(n_items, size=int(rng.integers(1, 70)), replace=False).tolist() for u in range(n_users - 1)}
+    seqs, lens = recent_sequences(consumed, n_users, n_items, T)       # the last user has no history
+    w = tm.make_seq_weights(rng, spec, 16, (128, 64, 32), True, din=True)
+    model = DIN(spec, w, seqs, lens, consumed)
+    assert model._hoistable() and model.Kp == 64
+    uid = torch.tensor([0, 7, n_users - 1, n_users, 33], device="cuda")
+    try:
+        fmods.DIN_FUSED_ATTENTION = True
+        fused = model.score_all_items(uid).cpu().numpy()
+        fmods.DIN_FUSED_ATTENTION = False
+        unfused = model.score_all_items(uid).cpu().numpy()
+    finally:
+        fmods.DIN_FUSED_ATTENTION = False
+    flat = fmods._FeatModelBase.score_all_items(model, uid).cpu().numpy()
+    scale = np.maximum(np.abs(flat), np.abs(flat).mean())
+    assert (np.abs(unfused - flat) <= 1e-5 * scale + 1e-6).all(), float(np.abs(unfused - flat).max())
+    assert (np.abs(fused - flat) <= 1e-5 * scale + 1e-6).all(), float(np.abs(fused - flat).max())
