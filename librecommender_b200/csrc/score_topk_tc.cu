@@ -99,6 +99,7 @@ struct RowMeta {
 struct SweepParams {
   int64_t N;
   int32_t B_pad, m_tiles, n_splits, tiles_per_split, total_tiles, KB, nstage;
+  int32_t kb_stages;          // 1: a ring stage holds ONE 64-wide k-block of an item tile (d_pad > 128), 0: the whole tile
   int32_t n_pre_tiles;        // sampled tiles per split in the pre-pass
   int32_t capg, trig;         // records per list / uncounted records that trigger a compaction
   int32_t ablate;             // diagnostics only (b200_recommend_embed_debug): 0 = normal operation
@@ -350,7 +351,7 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smemA = smem;                                  // KB * 16 KB
   uint8_t* smemB = smem + (size_t)p.KB * A_KB_BYTES;      // nstage * KB * 32 KB
-  SweepSmem* ss = (SweepSmem*)(smemB + (size_t)p.nstage * p.KB * B_KB_BYTES);
+  SweepSmem* ss = (SweepSmem*)(smemB + (size_t)p.nstage * (p.kb_stages ? 1 : p.KB) * B_KB_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -408,6 +409,22 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int kb = 0; kb < p.KB; ++kb)
           ptx::tma_load_2d(smemA + (size_t)kb * A_KB_BYTES, &tmA, &ss->a_full, kb * KBLK, m * TM);
         for (int t = t0; t < t1; t += STRIDE) {
+          if (p.kb_stages) {
+            // wide embeddings (d_pad > 128): one ring stage per 64-wide k-block, consumed block by block
+            for (int kb = 0; kb < p.KB; ++kb) {
+              ptx::mbar_wait_hint(&ss->empty[stage], phase ^ 1, p.hint_ns);
+              ptx::mbar_arrive_expect_tx(&ss->full[stage], (uint32_t)B_KB_BYTES);
+              uint8_t* dst = smemB + (size_t)stage * B_KB_BYTES;
+              if (CL == 1) {
+                ptx::tma_load_2d(dst, &tmB, &ss->full[stage], kb * KBLK, t * TN);
+              } else {
+                ptx::tma_load_2d_multicast(dst + (size_t)crank * (B_KB_BYTES / CL), &tmBh, &ss->full[stage], kb * KBLK,
+                                           t * TN + crank * (TN / CL), CL_MASK);
+              }
+              if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+            }
+            continue;
+          }
           ptx::mbar_wait_hint(&ss->empty[stage], phase ^ 1, p.hint_ns);
           // the whole tile lands in THIS CTA's stage: its own share plus the peers' multicast shares
           ptx::mbar_arrive_expect_tx(&ss->full[stage], (uint32_t)(p.KB * B_KB_BYTES));
@@ -441,6 +458,29 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int t1 = min(t0 + p.tiles_per_split, p.total_tiles);
         ptx::mbar_wait_hint(&ss->a_full, uiter & 1, p.hint_ns);
         for (int t = t0; t < t1; t += STRIDE) {
+          if (p.kb_stages) {
+            // k-block stages (NH == 1): the accumulator of the tile is built block by block, every stage is handed
+            // back as soon as its four MMAs have read it
+            ptx::mbar_wait_hint(&ss->tmem_empty[acc][0], acc_phase ^ 1, p.hint_ns);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
+            for (int kb = 0; kb < p.KB; ++kb) {
+              ptx::mbar_wait_hint(&ss->full[stage], phase, p.hint_ns);
+              ptx::tc_fence_after();
+              const uint64_t da = ptx::umma_desc_sw128_kmajor(a_addr + (uint32_t)(kb * A_KB_BYTES));
+              const uint64_t db = ptx::umma_desc_sw128_kmajor(b_addr + (uint32_t)(stage * B_KB_BYTES));
+#pragma unroll
+              for (int k4 = 0; k4 < KBLK / 16; ++k4)
+                ptx::umma_f16(d_tmem, da + (uint64_t)(k4 * 2), db + (uint64_t)(k4 * 2), idesc, (uint32_t)((kb | k4) != 0));
+              if (CL == 1) ptx::umma_commit(&ss->empty[stage]);
+              else ptx::umma_commit_multicast(&ss->empty[stage], CL_MASK);
+              if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+            }
+            ptx::umma_commit(&ss->tmem_full[acc][0]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+            continue;
+          }
           ptx::mbar_wait_hint(&ss->full[stage], phase, p.hint_ns);
           // NH MMA groups per item tile, each with its own accumulator full / empty barrier pair, so the
           // epilogue steps of a group start as soon as that group is done
@@ -1138,7 +1178,7 @@ static int g_pre_margin = 12;      // additive part of the speculative rank: pre
 static float g_pre_coef = 2.0f;    // speculative rank target = g_pre_coef * k_row (+ 16 / sampled fraction)
 
 struct Plan {
-  int B_pad, d_pad, KB, m_tiles, total_tiles, n_splits, tiles_per_split, nstage, n_pre_tiles;
+  int B_pad, d_pad, KB, m_tiles, total_tiles, n_splits, tiles_per_split, nstage, n_pre_tiles, kb_stages;
   int W, n_lists, capg, trig;
   int CL, NH;        // CTAs per cluster (TMA multicast of the item tiles), MMA groups per item tile
   bool use_pre;
@@ -1195,11 +1235,16 @@ static int make_plan(int64_t B, int64_t N, int d, Plan* pl) {
   pl->capg = (pl->use_pre && pl->n_lists >= 16) ? 128 : CAPG_MAX;
   pl->trig = pl->use_pre ? pl->capg : 96;
   const size_t budget = 227 * 1024 - 1024 /*align*/ - sizeof(SweepSmem) - (size_t)pl->KB * A_KB_BYTES;
-  int ns = (int)(budget / ((size_t)pl->KB * B_KB_BYTES));
-  if (ns > 6) ns = 6;
+  // d_pad <= 128: a ring stage = one whole 256-item tile (KB k-blocks); wider embeddings: one k-block per stage
+  // (a whole tile of d_pad = 256 is 128 KB: two of them do not fit beside the 64 KB user tile)
+  pl->kb_stages = pl->KB > 2;
+  B200_REQUIRE(!pl->kb_stages || pl->NH == 1, "the two-MMA-group organisation supports embed width <= 128 only");
+  const size_t stage_bytes = pl->kb_stages ? (size_t)B_KB_BYTES : (size_t)pl->KB * B_KB_BYTES;
+  int ns = (int)(budget / stage_bytes);
+  if (ns > (pl->kb_stages ? 8 : 6)) ns = pl->kb_stages ? 8 : 6;
   B200_REQUIRE(ns >= 2, "not enough shared memory for the item pipeline");
   pl->nstage = ns;
-  pl->smem_bytes = 1024 + (size_t)pl->KB * A_KB_BYTES + (size_t)ns * pl->KB * B_KB_BYTES + sizeof(SweepSmem);
+  pl->smem_bytes = 1024 + (size_t)pl->KB * A_KB_BYTES + (size_t)ns * stage_bytes + sizeof(SweepSmem);
   size_t off = 0;
   pl->off_A = off; off += al256((size_t)pl->B_pad * pl->d_pad * 2);
   pl->off_meta = off; off += al256((size_t)pl->B_pad * sizeof(RowMeta));
@@ -1398,7 +1443,7 @@ extern "C" int b200_recommend_embed(const float* U, int64_t ldu, const int64_t* 
   SweepParams sp;
   sp.N = N; sp.B_pad = pl.B_pad; sp.m_tiles = pl.m_tiles; sp.n_splits = pl.n_splits;
   sp.tiles_per_split = pl.tiles_per_split; sp.total_tiles = pl.total_tiles; sp.KB = pl.KB;
-  sp.nstage = pl.nstage; sp.n_pre_tiles = pl.n_pre_tiles; sp.capg = pl.capg; sp.trig = pl.trig;
+  sp.nstage = pl.nstage; sp.kb_stages = pl.kb_stages; sp.n_pre_tiles = pl.n_pre_tiles; sp.capg = pl.capg; sp.trig = pl.trig;
   sp.meta = meta; sp.row_tau_key = tau;
   sp.row_status = status; sp.ghist = ghist; sp.cand_r = cand_r; sp.cand_cnt = cnt;
   sp.blockmax = bm; sp.ablate = g_ablate; sp.hint_ns = (uint32_t)g_hint_ns;

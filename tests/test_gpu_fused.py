@@ -32,6 +32,8 @@ def _mk(seed, n_users, N, d, mean_c, normalise=True, scale=1.0):
     (64, 3231, 16, 10, 20, 64),        # C1-like catalogue, d padded 16 -> 64
     (300, 20000, 128, 50, 10, 257),    # two K blocks
     (50, 1000, 7, 5, 3, 50),           # odd width
+    (300, 30000, 160, 50, 10, 300),    # three K blocks: one ring stage per k-block (d_pad > 128)
+    (200, 25000, 256, 100, 20, 200),   # four K blocks, the widest supported embedding
 ])
 def test_fused_equals_exact_and_oracle(n_users, N, d, K, mean_c, B):
     import torch
