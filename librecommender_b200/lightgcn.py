@@ -111,6 +111,8 @@ class SpmmGraph:
         E = E.contiguous()
         d = int(E.shape[1])
         val = self.val if val is None else val
+        if out is None and acc is None:
+            out = torch.empty((self.n, d), dtype=torch.float32, device=self.device)
         part = self.partials(d)
         _lib.check(_lib.lib.b200_spmm_csr(
             _lib.ptr(self.indptr), _lib.ptr(self.col), _lib.ptr(val), self.n,

@@ -32,6 +32,10 @@ def _run(model, layout, users_d, items_d, R, K, F, grid_items=0, want_concat=Tru
     (4, [6] * 20, [9] * 25, 3, 3, 8191),                                                      # F = 53, K4 = 1
     (16, [13] * 60, [7] * 55, 4, 5, 4500),                                                    # F = 126: 16 steps
     (12, [7, 30, 12], [11, 5], 1, 1, 4200),                                                   # lane-per-field only
+    (32, [13] * 40, [7] * 38, 1, 1, 4100),                                                    # F = 82, K = 32: 21 steps > 16
+    (4, [6] * 60, [9] * 60, 5, 5, 4300),                                                      # F = 132 fields of 16 bytes
+    (8, [5] * 60, [4] * 60, 4, 4, 4097),                                                      # F = 130
+    (16, [9], [4], 0, 0, 5000),                                                               # F = 4: one ragged step
 ])
 def test_variants_match_oracle_and_each_other(K, us, its, nud, nid, R):
     import torch
