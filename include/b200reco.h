@@ -245,6 +245,14 @@ int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, 
                        const float* Wsplit, const float* bias, int32_t din, int32_t dout, int32_t relu,
                        float* Y, int64_t ldy, void* stream);
 
+/* Split-K form for products with few output tiles and a long reduction (the weight gradients dWt = dY^T X of
+ * the training steps: 1792 x 128 outputs over 8192 rows = 14 tiles): `splits` CTAs along the reduction per
+ * output tile write partial products into workspace (splits * R * dout floats), a second kernel adds them in a
+ * fixed order (+ bias, ReLU).  splits == 1 is b200_linear_tf32x3 without a pre-split weight copy. */
+int b200_linear_tf32x3_splitk(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw, const float* bias,
+                              int32_t din, int32_t dout, int32_t relu, int32_t splits, float* workspace,
+                              size_t workspace_bytes, float* Y, int64_t ldy, void* stream);
+
 /* ---- training step of the FM-family models (reference graph in training mode:
  * libreco/algorithms/fm.py:152-171, tf.layers.batch_normalization(training=True),
  * libreco/training/tf_trainer.py:112-123 tf.train.AdamOptimizer + BN update ops) --------------- */

@@ -61,6 +61,8 @@ SIGNATURES = {
     "b200_linear_tf32x3_split_weights": (c_int, [_P, c_int64, c_int32, c_int32, _P, _P]),
     "b200_linear_tf32x3": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, _P, c_int32, c_int32, c_int32, _P, c_int64,
                                    _P]),
+    "b200_linear_tf32x3_splitk": (c_int, [_P, c_int64, c_int64, _P, c_int64, _P, c_int32, c_int32, c_int32, c_int32, _P,
+                                          c_size_t, _P, c_int64, _P]),
     "b200_bn_train_forward": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, c_float, c_float, _P, c_int64, _P, _P, _P,
                                       _P, _P]),
     "b200_fm_head_forward": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P]),

@@ -41,6 +41,8 @@ struct Params {
   const float* dot_w;     // fused DIN epilogue: 16 weights of the Dense(1) on sigmoid(Dense(16)) (NULL = plain layer)
   int din, dout, n_pad, relu;
   int n_tiles, n_chunks, nstage;
+  int n_chunks_total;      // split-K: CTA z takes k-chunks [z * n_chunks, min((z + 1) * n_chunks, n_chunks_total))
+  int64_t split_stride;    //          and writes its partial product to Y + z * split_stride (no bias / ReLU)
 };
 
 struct Smem {
@@ -102,6 +104,8 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int col0 = blockIdx.y * NMAX;
+  const int kc_base = blockIdx.z * p.n_chunks;
+  const int kc_count = min(p.n_chunks, p.n_chunks_total - kc_base);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstage; ++s) {
@@ -132,13 +136,14 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int kc = 0; kc < p.n_chunks; ++kc) {
+        for (int kc = 0; kc < kc_count; ++kc) {
           ptx::mbar_wait(&ss->empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&ss->full[stage], (uint32_t)(A_BYTES + (WSPLIT ? 2 : 1) * b_bytes));
           uint8_t* st = smem + (size_t)stage * stage_bytes;
-          ptx::tma_load_2d(st, &tmX, &ss->full[stage], kc * KC, tile * TM);
-          ptx::tma_load_2d(st + 2 * A_BYTES, &tmW, &ss->full[stage], kc * KC, col0);
-          if (WSPLIT) ptx::tma_load_2d(st + 2 * A_BYTES + b_bytes, &tmWlo, &ss->full[stage], kc * KC, col0);
+          const int kx = (kc_base + kc) * KC;
+          ptx::tma_load_2d(st, &tmX, &ss->full[stage], kx, tile * TM);
+          ptx::tma_load_2d(st + 2 * A_BYTES, &tmW, &ss->full[stage], kx, col0);
+          if (WSPLIT) ptx::tma_load_2d(st + 2 * A_BYTES + b_bytes, &tmWlo, &ss->full[stage], kx, col0);
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
         }
       }
@@ -153,7 +158,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       uint32_t acc_phase = 0;
       const uint32_t s_addr = ptx::smem_u32(smem);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int kc = 0; kc < p.n_chunks; ++kc) {
+        for (int kc = 0; kc < kc_count; ++kc) {
           const int gpos = kc % GC;
           if (gpos == 0) {   // new accumulator group
             ptx::mbar_wait(&ss->tmem_empty[acc], acc_phase ^ 1);
@@ -179,7 +184,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           }
           ptx::umma_commit(&ss->empty[stage]);
           if (++stage == p.nstage) { stage = 0; phase ^= 1; }
-          if (gpos == GC - 1 || kc == p.n_chunks - 1) {
+          if (gpos == GC - 1 || kc == kc_count - 1) {
             ptx::umma_commit(&ss->tmem_full[acc]);
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
@@ -194,7 +199,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     uint32_t phase = 0;
     const int b_vec = b_bytes / 16;          // float4 per B tile
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      for (int kc = 0; kc < p.n_chunks; ++kc) {
+      for (int kc = 0; kc < kc_count; ++kc) {
         ptx::mbar_wait(&ss->full[stage], phase);
         uint8_t* st = smem + (size_t)stage * stage_bytes;
         float4* ah = (float4*)st;
@@ -217,7 +222,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int n_groups = (p.n_chunks + GC - 1) / GC;
+    const int n_groups = (kc_count + GC - 1) / GC;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       float y[NMAX];
 #pragma unroll
@@ -270,7 +275,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           }
         }
       } else if (!DOT && row < p.R) {
-        float* yr = p.Y + row * p.ldy + col0;
+        float* yr = p.Y + (int64_t)blockIdx.z * p.split_stride + row * p.ldy + col0;
         const int ncol = min(p.dout - col0, NMAX);
         const bool vec = ((p.ldy & 3) == 0) && ((((uintptr_t)p.Y) & 15) == 0);
 #pragma unroll
@@ -302,6 +307,20 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 4 * NMAX);
   }
+}
+
+
+// split-K: Y[r, c] = act(sum_z part[z][r, c] + bias[c]) in a fixed order (deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int64_t R, int dout,
+                                     const float* __restrict__ bias, int relu, float* __restrict__ Y, int64_t ldy) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * dout) return;
+  const int64_t r = i / dout;
+  const int c = (int)(i % dout);
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += part[(int64_t)z * R * dout + i];
+  if (bias) v += __ldg(bias + c);
+  Y[r * ldy + c] = relu ? fmaxf(v, 0.f) : v;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -358,7 +377,8 @@ extern "C" int b200_linear_tf32x3_split_weights(const float* Wt, int64_t ldw, in
 
 static int launch_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
                                 const float* Wsplit, const float* bias, int32_t din, int32_t dout,
-                                int32_t relu, const float* dot_w, float* Y, int64_t ldy, void* stream);
+                                int32_t relu, const float* dot_w, float* Y, int64_t ldy, void* stream,
+                                int splits = 1, float* workspace = nullptr);
 
 extern "C" int b200_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
                                   const float* Wsplit, const float* bias, int32_t din, int32_t dout,
@@ -375,9 +395,21 @@ extern "C" int b200_linear_tf32x3_sigmoid_dot(const float* X, int64_t ldx, int64
   return launch_linear_tf32x3(X, ldx, R, Wt, ldw, Wsplit, bias, din, dout, 0, dot_w16, A, lda, stream);
 }
 
+extern "C" int b200_linear_tf32x3_splitk(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
+                                         const float* bias, int32_t din, int32_t dout, int32_t relu, int32_t splits,
+                                         float* workspace, size_t workspace_bytes, float* Y, int64_t ldy, void* stream) {
+  B200_REQUIRE(splits >= 1 && splits <= 64, "b200_linear_tf32x3_splitk: splits outside [1, 64]");
+  B200_REQUIRE(ldy >= dout, "leading dimension too small");
+  B200_REQUIRE(splits == 1 || (workspace && workspace_bytes >= (size_t)splits * (size_t)R * (size_t)dout * 4),
+               "b200_linear_tf32x3_splitk: workspace too small (splits * R * dout floats)");
+  return launch_linear_tf32x3(X, ldx, R, Wt, ldw, nullptr, bias, din, dout, relu, nullptr, Y, ldy, stream, splits,
+                              workspace);
+}
+
 static int launch_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const float* Wt, int64_t ldw,
                                 const float* Wsplit, const float* bias, int32_t din, int32_t dout,
-                                int32_t relu, const float* dot_w, float* Y, int64_t ldy, void* stream) {
+                                int32_t relu, const float* dot_w, float* Y, int64_t ldy, void* stream,
+                                int splits, float* workspace) {
   using namespace b200;
   using namespace b200::mlp;
   B200_REQUIRE(R >= 0 && din > 0 && dout > 0, "bad shape");
@@ -397,7 +429,17 @@ static int launch_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const fl
   p.relu = relu;
   p.n_pad = dout >= NMAX ? NMAX : (dout + 31) / 32 * 32;
   p.n_tiles = (int)((R + TM - 1) / TM);
-  p.n_chunks = (din + KC - 1) / KC;
+  p.n_chunks_total = (din + KC - 1) / KC;
+  p.n_chunks = (p.n_chunks_total + splits - 1) / splits;
+  splits = (p.n_chunks_total + p.n_chunks - 1) / p.n_chunks;        // no empty split
+  p.split_stride = 0;
+  if (splits > 1) {   // partial products [splits][R, dout] into the workspace, bias / ReLU in the reduction
+    p.split_stride = R * (int64_t)dout;
+    p.Y = workspace;
+    p.ldy = dout;
+    p.bias = nullptr;
+    p.relu = 0;
+  }
   const int stage_bytes = 2 * A_BYTES + 2 * p.n_pad * KC * 4;
   p.nstage = min(MAXSTAGE, (200 * 1024) / stage_bytes);
   const size_t smem = (size_t)p.nstage * stage_bytes + sizeof(Smem) + 1024;
@@ -425,8 +467,8 @@ static int launch_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const fl
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int gy = (dout + NMAX - 1) / NMAX;
-  const int gx = max(1, min(p.n_tiles, sms / gy));
-  const dim3 grid(gx, gy);
+  const int gx = max(1, min(p.n_tiles, sms / (gy * splits)));
+  const dim3 grid(gx, gy, splits);
   cudaStream_t st = (cudaStream_t)stream;
   if (dot_w) {
     if (Wsplit) linear_tf32x3_kernel<true, true><<<grid, THREADS, smem, st>>>(tmX, tmW, tmWlo, p);
@@ -434,6 +476,11 @@ static int launch_linear_tf32x3(const float* X, int64_t ldx, int64_t R, const fl
   } else {
     if (Wsplit) linear_tf32x3_kernel<true, false><<<grid, THREADS, smem, st>>>(tmX, tmW, tmWlo, p);
     else linear_tf32x3_kernel<false, false><<<grid, THREADS, smem, st>>>(tmX, tmW, tmWlo, p);
+  }
+  if (splits > 1) {
+    const int64_t n = R * (int64_t)dout;
+    splitk_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(workspace, splits, R, dout, bias, relu, Y, ldy);
+    count_launch();
   }
   B200_CUDA_OK(cudaGetLastError());
   count_launch();

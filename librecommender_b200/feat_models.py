@@ -109,6 +109,17 @@ def linear(x, Wt, b, relu, cache_split=True):
     use_tc = LINEAR_IMPL == "tf32x3" or (LINEAR_IMPL == "auto" and din >= TC_MIN_DIN and
                                          (R >= TC_MIN_ROWS or din >= TC_LONG_K or R * din * dout >= TC_MIN_MACS))
     w_ok = cache_split or (Wt.stride(0) % 4 == 0 and Wt.data_ptr() % 16 == 0)
+    if use_tc and aligned and w_ok and not cache_split and din >= TC_LONG_K:
+        # few output tiles, long reduction: split the reduction over enough CTAs to fill the SMs
+        tiles = -(-R // 128) * -(-dout // 128)
+        splits = max(1, min(16, 148 // tiles, din // 256))
+        if splits > 1:
+            part = torch.empty(splits * R * dout, dtype=torch.float32, device=x.device)
+            _lib.check(_lib.lib.b200_linear_tf32x3_splitk(_lib.ptr(x), x.stride(0), R, _lib.ptr(Wt), Wt.stride(0), bp, din,
+                                                          dout, 1 if relu else 0, splits, _lib.ptr(part),
+                                                          part.numel() * 4, _lib.ptr(y), y.stride(0),
+                                                          _lib.current_stream()))
+            return y
     if use_tc and aligned and w_ok:
         ws = split_weights(Wt) if cache_split else None
         _lib.check(_lib.lib.b200_linear_tf32x3(_lib.ptr(x), x.stride(0), R, _lib.ptr(Wt), Wt.stride(0), _lib.ptr(ws), bp,

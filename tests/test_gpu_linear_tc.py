@@ -136,3 +136,41 @@ def test_deepfm_logits_with_forced_linear_impl(impl):
         fm.LINEAR_IMPL = old
     scale = np.maximum(np.abs(ref64), np.abs(ref64).mean())
     assert (np.abs(got - ref64) <= 1e-5 * scale + 1e-6).all(), float(np.abs(got - ref64).max())
+
+
+@pytest.mark.parametrize("R,din,dout,splits,relu,bias", [
+    (1792, 8192, 128, 10, False, False),    # the DeepFM first-layer weight gradient (X^T dY): 14 tiles x 10 splits
+    (128, 8192, 64, 16, False, False),      # one tile, 16 splits
+    (300, 1000, 200, 7, True, True),        # k tail (1000 = 31.25 chunks), ragged last split, bias + ReLU in the reduction
+    (129, 96, 32, 3, False, True),          # 3 chunks over 3 splits
+    (64, 4096, 10, 64, False, False),       # more splits than make sense: clipped to one chunk each
+])
+def test_linear_tf32x3_splitk_matches_fp64(R, din, dout, splits, relu, bias):
+    import torch
+
+    from librecommender_b200 import _lib
+
+    rng = np.random.default_rng(R + din + splits)
+    x = rng.standard_normal((R, din)).astype(np.float32)
+    Wt = (rng.standard_normal((dout, din)) / np.sqrt(din)).astype(np.float32)
+    b = rng.standard_normal(dout).astype(np.float32) if bias else None
+    xd, Wd = torch.from_numpy(x).cuda(), torch.from_numpy(Wt).cuda()
+    bd = torch.from_numpy(b).cuda() if bias else None
+    y = torch.full((R, dout), float("nan"), dtype=torch.float32, device="cuda")
+    ws = torch.empty(splits * R * dout, dtype=torch.float32, device="cuda")
+    outs = []
+    for _ in range(2):
+        _lib.check(_lib.lib.b200_linear_tf32x3_splitk(_lib.ptr(xd), xd.stride(0), R, _lib.ptr(Wd), Wd.stride(0),
+                                                      _lib.ptr(bd), din, dout, 1 if relu else 0, splits, _lib.ptr(ws),
+                                                      ws.numel() * 4, _lib.ptr(y), y.stride(0), _lib.current_stream()))
+        torch.cuda.synchronize()
+        outs.append(y.cpu().numpy().copy())
+    np.testing.assert_array_equal(outs[0], outs[1])                    # fixed reduction order
+    ref = x.astype(np.float64) @ Wt.astype(np.float64).T
+    mag = np.abs(x).astype(np.float64) @ np.abs(Wt).astype(np.float64).T
+    if bias:
+        ref = ref + b
+    if relu:
+        ref = np.maximum(ref, 0.0)
+    err = np.abs(outs[0] - ref) / (mag + 1e-30)
+    assert err.max() <= 2e-6, float(err.max())
