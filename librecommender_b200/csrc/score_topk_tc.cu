@@ -40,6 +40,7 @@
 // reference's filter rule applies (ranking.py:38), so removing consumed candidates still leaves
 // the exact top-K.  Rows that cannot be bounded (k_row too large, failed speculation, too many
 // near-ties) are flagged in row_status and re-run by the caller on the exact materialised path.
+#include <type_traits>
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 #include "../../include/b200reco.h"
@@ -801,7 +802,7 @@ struct FinalizeParams {
   float* out_scores;   // [B, K] or null
 };
 
-__global__ void __launch_bounds__(FIN_THREADS)
+__global__ void __launch_bounds__(FIN_THREADS, 5)
 finalize_kernel(const FinalizeParams p) {
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_prefix, s_krem;
@@ -1050,47 +1051,51 @@ finalize_kernel(const FinalizeParams p) {
     // e = tid + t * 256).  Partners inside the thread (j >= 256) are exchanged directly, partners
     // inside the warp (j < 32) with shuffles; only the stages with 32 <= j < 256 go through shared
     // memory (double-buffered: one barrier per such stage instead of one per stage).
-    constexpr int EPT = 2;
-    const int ept = P <= FIN_THREADS ? 1 : 2;
-    unsigned long long x[EPT];
+    // two instantiations: one element per thread (<= 256 candidates, the usual case: k_row ~ 150) and two
+    auto bitonic_regs = [&](auto ec) {
+      constexpr int EPT = decltype(ec)::value;
+      unsigned long long x[EPT];
 #pragma unroll
-    for (int t = 0; t < EPT; ++t) x[t] = (t < ept) ? mine[t] : 0ull;
-    int buf = 0;
+      for (int t = 0; t < EPT; ++t) x[t] = mine[t];
+      int buf = 0;
 #pragma unroll 1
-    for (int k = 2; k <= P; k <<= 1) {
+      for (int k = 2; k <= P; k <<= 1) {
 #pragma unroll 1
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        if (j >= FIN_THREADS) {          // only k = 512, j = 256: elements tid and tid + 256, descending
-          const unsigned long long a = x[0], b = x[1];
-          x[0] = a > b ? a : b;
-          x[1] = a > b ? b : a;
-          continue;
-        }
-        unsigned long long y[EPT];
-        if (j >= 32) {
-          unsigned long long* sb = c_sort + buf * (EPT * FIN_THREADS);
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          if (EPT == 2 && j >= FIN_THREADS) {   // only k = 512, j = 256: elements tid and tid + 256, descending
+            const unsigned long long a = x[0], b = x[EPT - 1];
+            x[0] = a > b ? a : b;
+            x[EPT - 1] = a > b ? b : a;
+            continue;
+          }
+          unsigned long long y[EPT];
+          if (j >= 32) {
+            unsigned long long* sb = c_sort + buf * (EPT * FIN_THREADS);
 #pragma unroll
-          for (int t = 0; t < EPT; ++t) if (t < ept) sb[t * FIN_THREADS + tid] = x[t];
-          __syncthreads();
+            for (int t = 0; t < EPT; ++t) sb[t * FIN_THREADS + tid] = x[t];
+            __syncthreads();
 #pragma unroll
-          for (int t = 0; t < EPT; ++t) if (t < ept) y[t] = sb[t * FIN_THREADS + (tid ^ j)];
-          buf ^= 1;
-        } else {
+            for (int t = 0; t < EPT; ++t) y[t] = sb[t * FIN_THREADS + (tid ^ j)];
+            buf ^= 1;
+          } else {
 #pragma unroll
-          for (int t = 0; t < EPT; ++t) y[t] = __shfl_xor_sync(0xffffffffu, x[t], j);
-        }
+            for (int t = 0; t < EPT; ++t) y[t] = __shfl_xor_sync(0xffffffffu, x[t], j);
+          }
 #pragma unroll
-        for (int t = 0; t < EPT; ++t) {
-          const int e = tid + t * FIN_THREADS;
-          const bool take_max = (((e & k) == 0) == ((e & j) == 0));   // descending blocks keep the max first
-          x[t] = take_max ? (x[t] > y[t] ? x[t] : y[t]) : (x[t] < y[t] ? x[t] : y[t]);
+          for (int t = 0; t < EPT; ++t) {
+            const int e = tid + t * FIN_THREADS;
+            const bool take_max = (((e & k) == 0) == ((e & j) == 0));   // descending blocks keep the max first
+            x[t] = take_max ? (x[t] > y[t] ? x[t] : y[t]) : (x[t] < y[t] ? x[t] : y[t]);
+          }
         }
       }
-    }
-    __syncthreads();
+      __syncthreads();
 #pragma unroll
-    for (int t = 0; t < EPT; ++t) if (t < ept) c_sort[t * FIN_THREADS + tid] = x[t];
-    __syncthreads();
+      for (int t = 0; t < EPT; ++t) c_sort[t * FIN_THREADS + tid] = x[t];
+      __syncthreads();
+    };
+    if (P <= FIN_THREADS) bitonic_regs(std::integral_constant<int, 1>{});
+    else bitonic_regs(std::integral_constant<int, 2>{});
   } else {
 #pragma unroll
     for (int t = 0; t < MAXC / FIN_THREADS; ++t) {

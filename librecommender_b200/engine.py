@@ -180,10 +180,13 @@ class EmbedScorer:
         if self.events is not None:
             self.events.append((e0, e1))
 
-    def recommend_fused(self, user_ids_d, n_rec, filter_consumed=True, return_scores=False, on_chunk=None):
+    def recommend_fused(self, user_ids_d, n_rec, filter_consumed=True, return_scores=False, on_chunk=None,
+                        before_chunk=None):
         """Tensor-core path (b200_recommend_embed).  Returns (ids, scores|None, status):
         rows with status != 0 hold -1 ids and must be re-run on the exact path.  ``on_chunk(r0, r1)``
-        is called after the kernels of rows [r0, r1) have been enqueued."""
+        is called after the kernels of rows [r0, r1) have been enqueued, ``before_chunk(r0, r1)`` just before
+        (the host seam fills ``user_ids_d[r0:r1]`` there, so converting the ids of chunk i+1 overlaps the kernels
+        of chunk i)."""
         torch = self._torch
         B = int(user_ids_d.numel())
         N = self.n_items
@@ -195,6 +198,8 @@ class EmbedScorer:
         use_filter = 1 if (filter_consumed and self.csr.nnz > 0) else 0
         for r0 in range(0, B, FUSED_ROWS_PER_CALL):
             r1 = min(B, r0 + FUSED_ROWS_PER_CALL)
+            if before_chunk is not None:
+                before_chunk(r0, r1)
             self._fused_chunk(user_ids_d[r0:r1], n_rec, use_filter, out_ids[r0:r1],
                               out_scores[r0:r1] if return_scores else None, status[r0:r1])
             if on_chunk is not None:
@@ -274,18 +279,32 @@ class EmbedScorer:
         ids, the kernels, one D2H of ids (+ the per-row status) and a single synchronisation."""
         torch = self._torch
         n_rec = int(n_rec)
-        if isinstance(user_ids, torch.Tensor):
-            uid_h = user_ids.to(torch.int64)
-        elif isinstance(user_ids, list):
-            # the reference passes a python list of inner ids: array.array's C loop is the fastest way in
+        fill = None
+        fused = not (path == "exact" or (path == "auto" and not self.fused_ok(n_rec)))
+        if isinstance(user_ids, list) and fused and len(user_ids) > FUSED_ROWS_PER_CALL:
+            # a long python list (the reference's calling convention): converted and uploaded chunk by chunk, the
+            # conversion of chunk i+1 runs while the kernels of chunk i execute
             import array
 
-            uid_h = torch.frombuffer(array.array("q", user_ids), dtype=torch.int64) if user_ids else \
-                torch.zeros(0, dtype=torch.int64)
+            uid_d = torch.empty(len(user_ids), dtype=torch.int64, device=self.device)
+
+            def fill(r0, r1, _lst=user_ids):
+                with _nvtx("b200.recommend.h2d_ids"):
+                    uid_d[r0:r1].copy_(torch.frombuffer(array.array("q", _lst[r0:r1]), dtype=torch.int64),
+                                       non_blocking=True)
         else:
-            uid_h = torch.as_tensor(np.asarray(user_ids, dtype=np.int64))
-        with _nvtx("b200.recommend.h2d_ids"):
-            uid_d = uid_h.to(self.device, non_blocking=True)
+            if isinstance(user_ids, torch.Tensor):
+                uid_h = user_ids.to(torch.int64)
+            elif isinstance(user_ids, list):
+                # the reference passes a python list of inner ids: array.array's C loop is the fastest way in
+                import array
+
+                uid_h = torch.frombuffer(array.array("q", user_ids), dtype=torch.int64) if user_ids else \
+                    torch.zeros(0, dtype=torch.int64)
+            else:
+                uid_h = torch.as_tensor(np.asarray(user_ids, dtype=np.int64))
+            with _nvtx("b200.recommend.h2d_ids"):
+                uid_d = uid_h.to(self.device, non_blocking=True)
         B = int(uid_d.numel())
         if path == "exact" or (path == "auto" and not self.fused_ok(n_rec)):
             res = self.recommend_exact(uid_d, n_rec, filter_consumed, return_scores)
@@ -308,7 +327,7 @@ class EmbedScorer:
             res.setdefault("chunks", []).append((r0, r1, ev))
 
         with _nvtx("b200.recommend.fused_kernels"):
-            ids_d, sc_d, status_d = self.recommend_fused(uid_d, n_rec, filter_consumed, return_scores, on_chunk)
+            ids_d, sc_d, status_d = self.recommend_fused(uid_d, n_rec, filter_consumed, return_scores, on_chunk, fill)
         with _nvtx("b200.recommend.d2h_results"), torch.cuda.stream(side):
             for r0, r1, ev in res.get("chunks", []):
                 side.wait_event(ev)

@@ -79,3 +79,25 @@ def test_mixed_magnitudes_and_duplicated_consumed_entries():
         c = rng.choice(N, size=30, replace=False).tolist()
         consumed[u] = c + c[:10]         # duplicates (the reference's lists may hold them)
     _run(U, I, N, consumed, list(range(n_users)), K, n_users)
+
+
+def test_long_python_list_is_converted_chunk_by_chunk_and_matches_array_input():
+    """> 16 384 users as a python list (the reference's calling convention): the host seam converts and uploads the
+    ids per launch chunk; the result must equal the one-shot numpy-array input and the exact path."""
+    import torch
+
+    from librecommender_b200.engine import EmbedScorer
+
+    rng = np.random.default_rng(21)
+    n_users, N, d, K = 60000, 6000, 32, 10
+    U = rng.standard_normal((n_users + 1, d)).astype(np.float32)
+    I = rng.standard_normal((N + 1, d)).astype(np.float32)
+    consumed = {int(u): rng.choice(N, size=8, replace=False).tolist() for u in rng.choice(n_users, 5000, replace=False)}
+    sc = EmbedScorer(U, I, N, consumed, n_users=n_users)
+    users = rng.integers(0, n_users + 1, 40001)
+    a = sc.recommend(users.tolist(), K, True, False)
+    b = sc.recommend(users, K, True, False)
+    np.testing.assert_array_equal(a, b)
+    e = sc.recommend_exact(torch.as_tensor(users).cuda(), K, True, False).cpu().numpy()
+    np.testing.assert_array_equal(a, e)
+    assert a.dtype == np.int64 and a.shape == (40001, K)
