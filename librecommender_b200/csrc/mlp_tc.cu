@@ -49,6 +49,9 @@ struct Smem {
   uint64_t full[MAXSTAGE], split[MAXSTAGE], empty[MAXSTAGE];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
+  uint32_t pad_[3];
+  float bias_s[NMAX];      // bias of this CTA's column block (0 past dout / without bias): the epilogue read 128
+                           // separate global words per thread and tile before — 27 % of the kernel's stall samples
 };
 
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
@@ -124,6 +127,10 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (warp == 1) {
     ptx::tmem_alloc(&ss->tmem_base, 4 * NMAX);
     ptx::tmem_relinquish();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + NMAX) {
+    const int c = threadIdx.x - 64;
+    ss->bias_s[c] = (p.bias && col0 + c < p.dout) ? __ldg(p.bias + col0 + c) : 0.f;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -268,7 +275,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int c = g * 16 + j;
-              const float v = y[c] + (p.bias ? __ldg(p.bias + col0 + c) : 0.f);
+              const float v = y[c] + ss->bias_s[c];
               a = fmaf(w2[j], 1.0f / (1.0f + expf(-v)), a);
             }
             yd[g] = a;
@@ -285,7 +292,7 @@ linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int c = c4 * 4 + i;
-              float v = y[c] + ((c < ncol && p.bias) ? __ldg(p.bias + col0 + c) : 0.f);
+              float v = y[c] + ss->bias_s[c];
               o[i] = p.relu ? fmaxf(v, 0.f) : v;
             }
             if (vec && c4 * 4 + 3 < ncol) {

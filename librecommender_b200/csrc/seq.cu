@@ -394,6 +394,87 @@ din_attention_from_logits_kernel(const float* __restrict__ A, int64_t lda, int64
   }
 }
 
+
+// DIN all-items, hoisted form, second kernel — v2.  The first version (one warp per item, two positions per 32-lane
+// load, a 4-step shuffle tree per pair of positions, softmax weights recomputed by every lane) was instruction
+// bound: 3660 warp instructions per item, issue slots 84 % busy (profiles/r02_din_attention_ncu.txt).  Here lane t
+// OWNS positions t and t + 32: it reads the 16 pre-activations of a position as four 16-byte loads (consecutive
+// lanes = consecutive 64 bytes), does the 16 sigmoids and the Dense(1) dot in registers — no shuffles —, the softmax
+// is one max / one sum over the warp, and the weighted key sum reads the user's keys from shared memory (staged once
+// per CTA, they are the same for every item) with p_t broadcast by shuffle.
+template <int TKC>
+__global__ void __launch_bounds__(256)
+din_attention_hoisted_v2_kernel(const float* __restrict__ Z, int64_t ldz, int64_t N, const float* __restrict__ G,
+                                int64_t ldg, int Kp, const int32_t* __restrict__ seq, int len,
+                                const float* __restrict__ k2, float b2, float* __restrict__ out, int64_t ld_out) {
+  extern __shared__ float s_keys[];                      // [len][Kp]
+  for (int i = threadIdx.x; i < len * Kp; i += blockDim.x)
+    s_keys[i] = __ldg(G + (int64_t)__ldg(seq + i / Kp) * ldg + (i % Kp));
+  __syncthreads();
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float scale = rsqrtf((float)Kp);
+  float w2[HID];
+#pragma unroll
+  for (int j = 0; j < HID; ++j) w2[j] = __ldg(k2 + j);
+  const int wpb = blockDim.x >> 5;
+  for (int64_t n = (int64_t)blockIdx.x * wpb + wid; n < N; n += (int64_t)gridDim.x * wpb) {
+    const float4* z4 = reinterpret_cast<const float4*>(Z + n * ldz);
+    float a[2];
+#pragma unroll
+    for (int rnd = 0; rnd < 2; ++rnd) {
+      const int t = lane + rnd * 32;
+      a[rnd] = -3.0e38f;
+      if (t < len) {
+        float4 v[HID / 4];
+#pragma unroll
+        for (int q = 0; q < HID / 4; ++q) v[q] = __ldg(z4 + t * (HID / 4) + q);
+        float d = 0.f;
+#pragma unroll
+        for (int q = 0; q < HID / 4; ++q) {
+          d = fmaf(w2[4 * q + 0], __frcp_rn(1.0f + expf(-v[q].x)), d);
+          d = fmaf(w2[4 * q + 1], __frcp_rn(1.0f + expf(-v[q].y)), d);
+          d = fmaf(w2[4 * q + 2], __frcp_rn(1.0f + expf(-v[q].z)), d);
+          d = fmaf(w2[4 * q + 3], __frcp_rn(1.0f + expf(-v[q].w)), d);
+        }
+        a[rnd] = (d + b2) * scale;
+      }
+    }
+    float amax = fmaxf(a[0], a[1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    float e0 = lane < len ? expf(a[0] - amax) : 0.f;
+    float e1 = lane + 32 < len ? expf(a[1] - amax) : 0.f;
+    const float den = warp_sum(e0 + e1);
+    e0 /= den;
+    e1 /= den;
+    float acc[TKC];
+#pragma unroll
+    for (int tt = 0; tt < TKC; ++tt) acc[tt] = 0.f;
+    const int l0 = min(len, 32);
+    for (int t = 0; t < l0; ++t) {
+      const float p = __shfl_sync(0xffffffffu, e0, t);
+#pragma unroll
+      for (int tt = 0; tt < TKC; ++tt) {
+        const int c = lane + tt * 32;
+        if (c < Kp) acc[tt] = fmaf(p, s_keys[t * Kp + c], acc[tt]);
+      }
+    }
+    for (int t = 32; t < len; ++t) {
+      const float p = __shfl_sync(0xffffffffu, e1, t - 32);
+#pragma unroll
+      for (int tt = 0; tt < TKC; ++tt) {
+        const int c = lane + tt * 32;
+        if (c < Kp) acc[tt] = fmaf(p, s_keys[t * Kp + c], acc[tt]);
+      }
+    }
+#pragma unroll
+    for (int tt = 0; tt < TKC; ++tt) {
+      const int c = lane + tt * 32;
+      if (c < Kp) out[n * ld_out + c] = acc[tt];
+    }
+  }
+}
+
 }  // namespace seq
 }  // namespace b200
 
@@ -419,6 +500,21 @@ extern "C" int b200_din_attention_hoisted(const float* Z, int64_t ldz, int64_t N
   B200_REQUIRE(G && seq && k2 && out && (Z || len == 0), "b200_din_attention_hoisted: null pointer");
   B200_REQUIRE(Kp >= 1 && Kp <= 32 * MAX_TK && len >= 0 && len <= MAX_T, "b200_din_attention_hoisted: bad shape");
   if (N == 0) return 0;
+  const bool z_ok = Z && (ldz % 4 == 0) && ((reinterpret_cast<uintptr_t>(Z) & 15) == 0);
+  if (len >= 1 && len <= 64 && z_ok && (size_t)len * Kp * 4 <= 48 * 1024 && N >= 1024) {
+    const size_t smem = (size_t)len * Kp * 4;
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(N, 8), (int64_t)148 * 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch ((Kp + 31) / 32) {
+      case 1: din_attention_hoisted_v2_kernel<1><<<blocks, 256, smem, st>>>(Z, ldz, N, G, ldg, Kp, seq, len, k2, b2, out, ld_out); break;
+      case 2: din_attention_hoisted_v2_kernel<2><<<blocks, 256, smem, st>>>(Z, ldz, N, G, ldg, Kp, seq, len, k2, b2, out, ld_out); break;
+      case 3: din_attention_hoisted_v2_kernel<3><<<blocks, 256, smem, st>>>(Z, ldz, N, G, ldg, Kp, seq, len, k2, b2, out, ld_out); break;
+      default: din_attention_hoisted_v2_kernel<4><<<blocks, 256, smem, st>>>(Z, ldz, N, G, ldg, Kp, seq, len, k2, b2, out, ld_out); break;
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+  }
   din_attention_hoisted_kernel<<<(unsigned)ceil_div64(N, 4), 128, 0, (cudaStream_t)stream>>>(
       Z, ldz, N, G, ldg, Kp, seq, len, k2, b2, out, ld_out);
   B200_CUDA_OK(cudaGetLastError());
