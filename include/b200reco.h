@@ -403,6 +403,16 @@ int b200_din_attention(const float* G, int64_t ldg, int32_t Kp, const int64_t* i
                        const float* k1, const float* b1, const float* k2, float b2, float* out,
                        int64_t ld_out, void* stream);
 
+/* Backward of b200_din_attention (paper attention, explicit pairs: row r = (items[r], sequence row users[r])):
+ * dout [R, Kp] = gradient of the attention output.  ADDS (float atomics) the gradient of the item feature rows
+ * into dG [n_items+1, Kp] (query row and every non-masked key row) and the gradients of the attention weights
+ * into g_k1 [4Kp, 16], g_b1 [16], g_k2 [16], g_b2 [1].  T <= 64; rows with length 0 contribute nothing. */
+int b200_din_attention_backward(const float* G, int64_t ldg, int32_t Kp, const int64_t* items, const int32_t* seqs,
+                                int64_t ld_seq, const int32_t* lens, int32_t T, const int64_t* users, int64_t R,
+                                const float* k1, const float* b1, const float* k2, float b2, const float* dout,
+                                int64_t ld_dout, float* dG, int64_t ld_dg, float* g_k1, float* g_b1, float* g_k2,
+                                float* g_b2, void* stream);
+
 /* NGCF layer pieces (libreco/algorithms/torch_modules/ngcf_module.py:100-121): the
  * propagation L E is b200_spmm_csr, the two Dense products are b200_linear_*; these are the
  * element-wise parts: out = a * b, and out[r] = normalize_2(leaky_relu(self[r] + pair[r], slope)). */

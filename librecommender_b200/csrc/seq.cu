@@ -475,6 +475,188 @@ din_attention_hoisted_v2_kernel(const float* __restrict__ Z, int64_t ldz, int64_
   }
 }
 
+
+// ---- DIN attention backward (training of DIN): gradient of out[r] = sum_t p_t k_t with
+// p = softmax_t((Dense1(sigmoid(Dense16([q, k_t, q - k_t, q * k_t]))) ) * rsqrt(K')) w.r.t. the item feature rows
+// (q = G[item], k_t = G[seq_t]) and the attention weights.  One warp per row, lanes own feature columns; the forward
+// quantities are recomputed (h_t kept in shared memory), the weight gradient uses
+//     sum_t dz_t (x) [q, k_t, q - k_t, q * k_t] = [q (x) A, B, q (x) A - B, q * B],  A = sum_t dz_t, B = sum_t k_t (x) dz_t
+// so a row costs 4 K' x 16 shared-memory accumulations instead of that per position; persistent CTAs flush their
+// [4 K', 16] accumulator with one global atomic per element at the end.
+constexpr int BWD_T = 64;        // positions per row this kernel keeps (sequence lengths above fall outside training use)
+template <int TKC>
+__global__ void __launch_bounds__(128)
+din_attention_backward_kernel(const float* __restrict__ G, int64_t ldg, int Kp, const int64_t* __restrict__ items,
+                              const int32_t* __restrict__ seqs, int64_t ld_seq, const int32_t* __restrict__ lens, int T,
+                              const int64_t* __restrict__ users, int64_t R, AttW w, const float* __restrict__ dout,
+                              int64_t ld_dout, float* __restrict__ dG, int64_t ld_dg, float* __restrict__ g_k1,
+                              float* __restrict__ g_b1, float* __restrict__ g_k2, float* __restrict__ g_b2) {
+  extern __shared__ float bsm[];
+  float* sW = bsm;                                        // [4 Kp][HID]
+  float* sh_all = sW + 4 * Kp * HID;                      // [4 warps][BWD_T][HID]
+  float* sa_all = sh_all + 4 * BWD_T * HID;               // [4][BWD_T]  logits, then p
+  float* sdp_all = sa_all + 4 * BWD_T;                    // [4][BWD_T]  <dout, k_t>
+  for (int i = threadIdx.x; i < 4 * Kp * HID; i += blockDim.x) sW[i] = 0.f;
+  __syncthreads();
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sh = sh_all + wid * BWD_T * HID;
+  float* sa = sa_all + wid * BWD_T;
+  float* sdp = sdp_all + wid * BWD_T;
+  const float scale = rsqrtf((float)Kp);
+  float k2r[HID], gk2[HID], gb1[HID];
+  float gb2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < HID; ++j) { k2r[j] = __ldg(w.k2 + j); gk2[j] = 0.f; gb1[j] = 0.f; }
+  for (int64_t r = (int64_t)blockIdx.x * 4 + wid; r < R; r += (int64_t)gridDim.x * 4) {
+    const int64_t sr = seq_row_of(users, r, 0, 0);
+    const int64_t item = items[r];
+    const int32_t* sq = seqs + sr * ld_seq;
+    const int len = min(min(max(lens[sr], 0), T), BWD_T);
+    if (len == 0) continue;                               // forward output is 0: no gradient
+    float q[TKC], dy[TKC], M[TKC][HID], cpart[HID];
+#pragma unroll
+    for (int j = 0; j < HID; ++j) cpart[j] = 0.f;
+#pragma unroll
+    for (int tt = 0; tt < TKC; ++tt) {
+      const int c = lane + tt * 32;
+      q[tt] = 0.f; dy[tt] = 0.f;
+      if (c < Kp) {
+        q[tt] = __ldg(G + item * ldg + c);
+        dy[tt] = __ldg(dout + r * ld_dout + c);
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
+          const float wq = __ldg(w.k1 + (int64_t)c * HID + j);
+          const float wk = __ldg(w.k1 + (int64_t)(Kp + c) * HID + j);
+          const float wd = __ldg(w.k1 + (int64_t)(2 * Kp + c) * HID + j);
+          const float wp = __ldg(w.k1 + (int64_t)(3 * Kp + c) * HID + j);
+          M[tt][j] = (wk - wd) + q[tt] * wp;
+          cpart[j] = fmaf(q[tt], wq + wd, cpart[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < HID; ++j) M[tt][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < HID; ++j) cpart[j] = warp_sum(cpart[j]) + __ldg(w.b1 + j);
+    // ---- forward recompute: h_t, logits, <dout, k_t>
+    float amax = -3.0e38f;
+    for (int t = 0; t < len; ++t) {
+      const int64_t key = __ldg(sq + t);
+      float part[HID];
+      float dp = 0.f;
+#pragma unroll
+      for (int j = 0; j < HID; ++j) part[j] = 0.f;
+#pragma unroll
+      for (int tt = 0; tt < TKC; ++tt) {
+        const int c = lane + tt * 32;
+        if (c < Kp) {
+          const float kv = __ldg(G + key * ldg + c);
+          dp = fmaf(dy[tt], kv, dp);
+#pragma unroll
+          for (int j = 0; j < HID; ++j) part[j] = fmaf(kv, M[tt][j], part[j]);
+        }
+      }
+      dp = warp_sum(dp);
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < HID; ++j) {
+        const float z = warp_sum(part[j]) + cpart[j];
+        const float hj = 1.0f / (1.0f + expf(-z));
+        if (lane == j) sh[t * HID + j] = hj;
+        a = fmaf(hj, k2r[j], a);
+      }
+      a = (a + w.b2) * scale;
+      if (lane == 0) { sa[t] = a; sdp[t] = dp; }
+      amax = fmaxf(amax, a);
+    }
+    __syncwarp();
+    float den = 0.f;
+    for (int t = lane; t < len; t += 32) den += expf(sa[t] - amax);
+    den = warp_sum(den);
+    float S = 0.f;
+    for (int t = lane; t < len; t += 32) {
+      const float pt = expf(sa[t] - amax) / den;
+      S = fmaf(pt, sdp[t], S);
+      sa[t] = pt;                                          // logits -> probabilities
+    }
+    S = warp_sum(S);
+    __syncwarp();
+    // ---- backward over the positions
+    float A[HID], B[TKC][HID];
+#pragma unroll
+    for (int j = 0; j < HID; ++j) A[j] = 0.f;
+#pragma unroll
+    for (int tt = 0; tt < TKC; ++tt)
+#pragma unroll
+      for (int j = 0; j < HID; ++j) B[tt][j] = 0.f;
+    for (int t = 0; t < len; ++t) {
+      const int64_t key = __ldg(sq + t);
+      const float pt = sa[t];
+      const float da = scale * pt * (sdp[t] - S);          // d loss / d (Dense1 output of position t)
+      gb2 += da;
+      float dz[HID];
+#pragma unroll
+      for (int j = 0; j < HID; ++j) {
+        const float hj = sh[t * HID + j];
+        gk2[j] = fmaf(da, hj, gk2[j]);
+        dz[j] = da * k2r[j] * hj * (1.0f - hj);
+        A[j] += dz[j];
+      }
+#pragma unroll
+      for (int tt = 0; tt < TKC; ++tt) {
+        const int c = lane + tt * 32;
+        if (c < Kp) {
+          const float kv = __ldg(G + key * ldg + c);
+          float dk = pt * dy[tt];
+#pragma unroll
+          for (int j = 0; j < HID; ++j) {
+            dk = fmaf(M[tt][j], dz[j], dk);
+            B[tt][j] = fmaf(kv, dz[j], B[tt][j]);
+          }
+          atomicAdd(dG + key * ld_dg + c, dk);
+        }
+      }
+    }
+    // ---- query gradient, weight gradients of this row
+#pragma unroll
+    for (int j = 0; j < HID; ++j) gb1[j] += A[j];
+#pragma unroll
+    for (int tt = 0; tt < TKC; ++tt) {
+      const int c = lane + tt * 32;
+      if (c < Kp) {
+        float dq = 0.f;
+#pragma unroll
+        for (int j = 0; j < HID; ++j) {
+          const float wq = __ldg(w.k1 + (int64_t)c * HID + j);
+          const float wd = __ldg(w.k1 + (int64_t)(2 * Kp + c) * HID + j);
+          const float wp = __ldg(w.k1 + (int64_t)(3 * Kp + c) * HID + j);
+          dq = fmaf(wq + wd, A[j], dq);
+          dq = fmaf(wp, B[tt][j], dq);
+          const float qa = q[tt] * A[j];
+          atomicAdd(sW + (0 * Kp + c) * HID + j, qa);
+          atomicAdd(sW + (1 * Kp + c) * HID + j, B[tt][j]);
+          atomicAdd(sW + (2 * Kp + c) * HID + j, qa - B[tt][j]);
+          atomicAdd(sW + (3 * Kp + c) * HID + j, q[tt] * B[tt][j]);
+        }
+        atomicAdd(dG + item * ld_dg + c, dq);
+      }
+    }
+    __syncwarp();
+  }
+  // every lane holds the same gk2 / gb1 / gb2 (computed redundantly): lane j publishes element j
+#pragma unroll
+  for (int j = 0; j < HID; ++j) {
+    if (lane == j) { atomicAdd(g_k2 + j, gk2[j]); atomicAdd(g_b1 + j, gb1[j]); }
+  }
+  if (lane == 0) atomicAdd(g_b2, gb2);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * Kp * HID; i += blockDim.x) {
+    const float v = sW[i];
+    if (v != 0.f) atomicAdd(g_k1 + i, v);
+  }
+}
+
 }  // namespace seq
 }  // namespace b200
 
@@ -534,6 +716,40 @@ extern "C" int b200_din_attention_from_logits(const float* A, int64_t lda, int64
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(N, 8), (int64_t)148 * 8);
   din_attention_from_logits_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(A, lda, N, G, ldg, Kp, seq, len, b2, out,
                                                                                ld_out);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200_din_attention_backward(const float* G, int64_t ldg, int32_t Kp, const int64_t* items,
+                                           const int32_t* seqs, int64_t ld_seq, const int32_t* lens, int32_t T,
+                                           const int64_t* users, int64_t R, const float* k1, const float* b1,
+                                           const float* k2, float b2, const float* dout, int64_t ld_dout, float* dG,
+                                           int64_t ld_dg, float* g_k1, float* g_b1, float* g_k2, float* g_b2,
+                                           void* stream) {
+  B200_REQUIRE(G && items && seqs && lens && users && k1 && b1 && k2 && dout && dG && g_k1 && g_b1 && g_k2 && g_b2,
+               "b200_din_attention_backward: null pointer");
+  B200_REQUIRE(Kp >= 1 && Kp <= 32 * MAX_TK, "b200_din_attention_backward: feature width %d outside [1, %d]", Kp, 32 * MAX_TK);
+  B200_REQUIRE(T >= 1 && T <= BWD_T, "b200_din_attention_backward: sequence length %d outside [1, %d]", T, BWD_T);
+  if (R == 0) return 0;
+  AttW w{k1, b1, k2, b2};
+  const size_t smem = ((size_t)4 * Kp * HID + (size_t)4 * BWD_T * HID + (size_t)8 * BWD_T) * 4;
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(R, 4), (int64_t)148 * 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto launch = [&](auto kern) -> int {
+    B200_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<blocks, 128, smem, st>>>(G, ldg, Kp, items, seqs, ld_seq, lens, T, users, R, w, dout, ld_dout, dG, ld_dg, g_k1,
+                                    g_b1, g_k2, g_b2);
+    return 0;
+  };
+  int rc;
+  switch ((Kp + 31) / 32) {
+    case 1: rc = launch(din_attention_backward_kernel<1>); break;
+    case 2: rc = launch(din_attention_backward_kernel<2>); break;
+    case 3: rc = launch(din_attention_backward_kernel<3>); break;
+    default: rc = launch(din_attention_backward_kernel<4>); break;
+  }
+  if (rc) return rc;
   B200_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

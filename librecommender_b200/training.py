@@ -761,3 +761,159 @@ class YouTubeRankingTrainer(_StackTrainer):
         w["out_kernel"] = p["out_kernel"].cpu().numpy()
         w["out_bias"] = np.float32(p["out_bias"].cpu().numpy()[0])
         return w
+
+
+class DINTrainer(_StackTrainer):
+    """DIN training step on the device: ``libreco/algorithms/din.py:165-250`` in training mode (paper attention,
+    ``libreco/layers/attention.py:28-64``; concat(user, item, sparse, dense, attention output) -> ``dense_nn`` ->
+    Dense(1)), mean sigmoid CE, TF-Adam.  One behaviour sequence per ROW (``seqs`` [R, T] padded with ``n_items``,
+    ``lens`` [R] >= 1, T <= 64).
+
+        item feature table G = [item emb | its sparse embs | value x dense embs] rebuilt from the CURRENT tables
+        (b200_gather_rows per item sparse field) -> K1 gather + b200_din_attention -> stack forward ->
+        b200_concat_dense -> b200_pointwise_loss -> stack backward -> b200_feat_backward (field gradients) +
+        b200_din_attention_backward (dG + attention weight gradients) -> dG folded back into the tables
+        (item-embedding block added, sparse blocks through b200_scatter_add_rows, dense blocks through
+        b200_col_reduce) -> b200_adam_dense_dev
+    """
+
+    _T = ("user_embeds", "item_embeds", "sparse_embeds", "dense_embeds")
+
+    def __init__(self, spec, weights, use_bn=True, lr=1e-3, epsilon=1e-5, device=None):
+        import torch
+
+        self._torch = torch
+        K = int(weights["user_embeds"].shape[1])
+        self.spec = spec if isinstance(spec, FeatSpec) else FeatSpec(spec, K, device)
+        self.device, self.K = self.spec.device, K
+        self.F = 2 + self.spec.n_sparse + self.spec.n_dense
+        self.n_items = self.spec.n_items
+        self.use_bn, self.lr, self.epsilon, self.t = bool(use_bn), float(lr), float(epsilon), 0
+        f32 = torch.float32
+        p = {k: _dev(weights[k], self.device, f32).clone() for k in self._T if weights.get(k) is not None}
+        self.moving = {}
+        self.n_layers = self._init_stack("", weights["mlp"], p)
+        p["out_kernel"] = _dev(np.asarray(weights["out_kernel"]).reshape(-1), self.device, f32).clone()
+        p["out_bias"] = _dev(np.asarray(weights["out_bias"]).reshape(1), self.device, f32).clone()
+        att = weights["attention"]
+        p["att_k1"] = _dev(att["k1"], self.device, f32).clone()
+        p["att_b1"] = _dev(att["b1"], self.device, f32).clone()
+        p["att_k2"] = _dev(np.asarray(att["k2"]).reshape(-1), self.device, f32).clone()
+        p["att_b2"] = _dev(np.asarray(att["b2"]).reshape(1), self.device, f32).clone()
+        self._b2_host = float(np.asarray(att["b2"]).reshape(-1)[0])      # Dense(1) bias enters the kernels by value
+        sp = self.spec
+        self._is = [sp.is_[:, j].to(torch.int64).contiguous() for j in range(sp.is_.shape[1])] if sp.is_ is not None else []
+        self._id = [sp.id_[:, j].contiguous() for j in range(sp.id_.shape[1])] if sp.id_ is not None else []
+        self._id_cols = list(sp.item_dense_cols)
+        self.Kp = K * (1 + len(self._is) + len(self._id))
+        self._finish_init(p)
+
+    def _build_G(self):
+        torch = self._torch
+        p, K, st = self.params, self.K, _lib.current_stream()
+        n = self.n_items + 1
+        G = torch.empty((n, self.Kp), dtype=torch.float32, device=self.device)
+        G[:, :K].copy_(p["item_embeds"][:n])
+        off = K
+        for idx in self._is:
+            blk = G[:, off:off + K]
+            _lib.check(_lib.lib.b200_gather_rows(_lib.ptr(p["sparse_embeds"]), K, K, _lib.ptr(idx), n, _lib.ptr(blk),
+                                                 G.stride(0), st))
+            off += K
+        for vals, col in zip(self._id, self._id_cols):
+            G[:, off:off + K] = vals[:, None] * p["dense_embeds"][col][None, :]
+            off += K
+        return G
+
+    def forward(self, users_d, items_d, seqs_d, lens_d):
+        torch = self._torch
+        lib, st, p, K, F, Kp = _lib.lib, _lib.current_stream(), self.params, self.K, self.F, self.Kp
+        R = int(users_d.numel())
+        T = int(seqs_d.shape[1])
+        G = self._build_G()
+        x = torch.empty((R, F * K + Kp), dtype=torch.float32, device=self.device)
+        _lib.check(lib.b200_feat_forward(
+            ctypes.byref(self.spec.layout), ctypes.byref(self.tables), _lib.ptr(users_d), _lib.ptr(items_d), R, 0, 0,
+            _lib.ptr(x), x.stride(0), None, 0, None, None, None, 0.0, None, None, None, 0.0, None, None, 0, st))
+        rows = torch.arange(R, dtype=torch.int64, device=self.device)
+        att_out = x[:, F * K:]
+        # the Dense(1) bias shifts every logit of a row alike: the softmax ignores it, its gradient is exactly 0 and
+        # TF-Adam never moves it — the initial value is passed by value, no device read
+        b2 = self._b2_host
+        _lib.check(lib.b200_din_attention(
+            _lib.ptr(G), G.stride(0), Kp, _lib.ptr(items_d), _lib.ptr(seqs_d), seqs_d.stride(0), _lib.ptr(lens_d), T,
+            _lib.ptr(rows), R, 0, 0, _lib.ptr(p["att_k1"]), _lib.ptr(p["att_b1"]), _lib.ptr(p["att_k2"]), b2,
+            _lib.ptr(att_out), att_out.stride(0), st))
+        h, c = self._stack_forward("", self.n_layers, x)
+        logit = torch.empty(R, dtype=torch.float32, device=self.device)
+        _lib.check(lib.b200_concat_dense(_lib.ptr(h), h.stride(0), h.shape[1], None, 0, 0, None, 0, 0,
+                                         _lib.ptr(p["out_kernel"]), 0.0, R, _lib.ptr(logit), st))
+        logit += p["out_bias"]
+        c.update(R=R, T=T, users=users_d, items=items_d, seqs=seqs_d, lens=lens_d, rows=rows, h=h, logit=logit, G=G, b2=b2)
+        self._cache = c
+        return logit
+
+    def backward(self, labels_d):
+        from .feat_models import linear
+
+        torch = self._torch
+        lib, st, p, g, K, F, Kp = _lib.lib, _lib.current_stream(), self.params, self.grads, self.K, self.F, self.Kp
+        c = self._cache
+        R = c["R"]
+        loss = torch.empty((), dtype=torch.float32, device=self.device)
+        dlogit = torch.empty(R, dtype=torch.float32, device=self.device)
+        _lib.check(lib.b200_pointwise_loss(_lib.ptr(c["logit"]), _lib.ptr(labels_d), R, 0, 0.25, 2.0, _lib.ptr(loss),
+                                           _lib.ptr(dlogit), _lib.ptr(self._lws), self._lws.numel(), st))
+        self._col_sum(c["h"], g["out_kernel"], dlogit)
+        self._col_sum(dlogit, g["out_bias"])
+        da = linear(dlogit.view(R, 1), p["out_kernel"].view(-1, 1), None, False, cache_split=False)
+        dx = self._stack_backward("", self.n_layers, c, da)
+        gp = lambda k: _lib.ptr(g[k]) if k in g else None      # noqa: E731
+        _lib.check(lib.b200_feat_backward(
+            ctypes.byref(self.spec.layout), ctypes.byref(self.tables), _lib.ptr(c["users"]), _lib.ptr(c["items"]), R,
+            None, 0, None, 0, _lib.ptr(dx), dx.stride(0), None, None,
+            gp("user_embeds"), gp("item_embeds"), gp("sparse_embeds"), gp("dense_embeds"), None, None, None, None,
+            None, st))
+        # ---- attention backward: gradient of the item feature table + the attention weights
+        G = c["G"]
+        n = self.n_items + 1
+        dG = torch.zeros((n, Kp), dtype=torch.float32, device=self.device)
+        datt = dx[:, F * K:]
+        _lib.check(lib.b200_din_attention_backward(
+            _lib.ptr(G), G.stride(0), Kp, _lib.ptr(c["items"]), _lib.ptr(c["seqs"]), c["seqs"].stride(0),
+            _lib.ptr(c["lens"]), c["T"], _lib.ptr(c["rows"]), R, _lib.ptr(p["att_k1"]), _lib.ptr(p["att_b1"]),
+            _lib.ptr(p["att_k2"]), c["b2"], _lib.ptr(datt), datt.stride(0), _lib.ptr(dG), dG.stride(0),
+            _lib.ptr(g["att_k1"]), _lib.ptr(g["att_b1"]), _lib.ptr(g["att_k2"]), _lib.ptr(g["att_b2"]), st))
+        # ---- dG back into the tables G was built from
+        g["item_embeds"][:n] += dG[:, :K]
+        off = K
+        for idx in self._is:
+            blk = dG[:, off:off + K]
+            _lib.check(lib.b200_scatter_add_rows(_lib.ptr(g["sparse_embeds"]), K, K, _lib.ptr(idx), n, _lib.ptr(blk),
+                                                 dG.stride(0), st))
+            off += K
+        for vals, col in zip(self._id, self._id_cols):
+            blk = dG[:, off:off + K]
+            _lib.check(lib.b200_col_reduce(_lib.ptr(blk), dG.stride(0), n, K, _lib.ptr(vals), None, 0,
+                                           _lib.ptr(g["dense_embeds"][col]), st))
+            off += K
+        return loss
+
+    def step(self, users_d, items_d, seqs_d, lens_d, labels_d):
+        torch = self._torch
+        self.forward(users_d.to(torch.int64).contiguous(), items_d.to(torch.int64).contiguous(),
+                     seqs_d.to(torch.int32).contiguous(), lens_d.to(torch.int32).contiguous())
+        loss = self.backward(labels_d.to(torch.float32).contiguous())
+        _adam_update(self)
+        self._cache = None
+        return loss
+
+    def export_weights(self):
+        p = self.params
+        w = {k: p[k].cpu().numpy() for k in self._T if k in p}
+        w["mlp"] = self._export_stack("", self.n_layers)
+        w["out_kernel"] = p["out_kernel"].cpu().numpy()
+        w["out_bias"] = np.float32(p["out_bias"].cpu().numpy()[0])
+        w["attention"] = dict(k1=p["att_k1"].cpu().numpy(), b1=p["att_b1"].cpu().numpy(), k2=p["att_k2"].cpu().numpy(),
+                              b2=np.float32(p["att_b2"].cpu().numpy()[0]))
+        return w
