@@ -332,8 +332,13 @@ int b200_adam_dense(float* param, float* m, float* v, float* grad, int64_t n, fl
 
 /* The same update for a CAPTURED (CUDA graph) training step: b200_adam_begin_step increments the device step
  * counter and writes lr_t = lr sqrt(1-b2^t)/(1-b1^t) (double arithmetic) to lr_t_dev once per step;
- * b200_adam_dense_dev reads it — nothing about the step number is baked into the launch parameters. */
-int b200_adam_begin_step(int64_t* step_dev, float lr, float beta1, float beta2, float* lr_t_dev, void* stream);
+ * b200_adam_dense_dev reads it — nothing about the step number is baked into the launch parameters.
+ * decay_steps > 0: lr is first multiplied by decay_rate ^ floor((t - 1) / decay_steps) (lr_decay=True:
+ * tf.train.exponential_decay, staircase, libreco/tfops/configs.py:38-45). */
+int b200_adam_begin_step(int64_t* step_dev, float lr, float beta1, float beta2, float decay_rate, int64_t decay_steps,
+                         float* lr_t_dev, void* stream);
+/* y += alpha * x — the L2 regulariser's gradient 2 reg w (tf.keras.regularizers.l2, tfops/configs.py:20-26). */
+int b200_axpy(float* y, const float* x, float alpha, int64_t n, void* stream);
 int b200_adam_dense_dev(float* param, float* m, float* v, float* grad, int64_t n, const float* lr_t_dev, float beta1,
                         float beta2, float eps, void* stream);
 

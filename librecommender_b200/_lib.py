@@ -78,7 +78,8 @@ SIGNATURES = {
     "b200_deepfm_head_forward": (c_int, [_P, _P, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, c_int64, _P, _P]),
     "b200_deepfm_head_backward": (c_int, [_P, _P, c_int32, c_int32, c_int64, _P, _P, c_int64, _P, c_int64, _P]),
     "b200_adam_dense": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, _P]),
-    "b200_adam_begin_step": (c_int, [_P, c_float, c_float, c_float, _P, _P]),
+    "b200_adam_begin_step": (c_int, [_P, c_float, c_float, c_float, c_float, c_int64, _P, _P]),
+    "b200_axpy": (c_int, [_P, _P, c_float, c_int64, _P]),
     "b200_adam_dense_dev": (c_int, [_P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, _P]),
     "b200_loss_workspace_bytes": (c_size_t, []),
     "b200_pointwise_loss": (c_int, [_P, _P, c_int64, c_int32, c_float, c_float, _P, _P, _P, c_size_t, _P]),

@@ -410,10 +410,21 @@ __global__ void l2_normalize_backward_kernel(const float* __restrict__ x, int64_
 
 // CUDA-graph friendly Adam: the step counter and the bias-corrected step size live on the device, so a captured
 // training step can be replayed (a host-computed lr_t would be baked into the graph at capture time)
-__global__ void adam_begin_step_kernel(long long* __restrict__ step, float lr, float b1, float b2, float* __restrict__ lr_t) {
+__global__ void adam_begin_step_kernel(long long* __restrict__ step, float lr, float b1, float b2, float decay_rate,
+                                       long long decay_steps, float* __restrict__ lr_t) {
   const long long t = *step + 1;
   *step = t;
-  *lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+  // tf.train.exponential_decay(lr, global_step, decay_steps, decay_rate, staircase=True): global_step counts the
+  // COMPLETED steps, i.e. t - 1 while step t runs (libreco/tfops/configs.py:38-45)
+  double lr_now = (double)lr;
+  if (decay_steps > 0) lr_now *= pow((double)decay_rate, (double)((t - 1) / decay_steps));
+  *lr_t = (float)(lr_now * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+}
+
+// y += alpha * x  (L2 regulariser: d (reg * sum w^2) / dw = 2 reg w added to the gradient buffers)
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float alpha, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaf(alpha, x[i], y[i]);
 }
 
 __global__ void adam_dense_dev_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
@@ -606,10 +617,20 @@ extern "C" int b200_adam_dense(float* param, float* m, float* v, float* grad, in
   return 0;
 }
 
-extern "C" int b200_adam_begin_step(int64_t* step_dev, float lr, float beta1, float beta2, float* lr_t_dev, void* stream) {
+extern "C" int b200_axpy(float* y, const float* x, float alpha, int64_t n, void* stream) {
+  B200_REQUIRE(y && x, "b200_axpy: null pointer");
+  if (n == 0) return 0;
+  axpy_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(y, x, alpha, n);
+  B200_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+extern "C" int b200_adam_begin_step(int64_t* step_dev, float lr, float beta1, float beta2, float decay_rate,
+                                    int64_t decay_steps, float* lr_t_dev, void* stream) {
   B200_REQUIRE(step_dev && lr_t_dev, "b200_adam_begin_step: null pointer");
   adam_begin_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(step_dev), lr, beta1, beta2,
-                                                            lr_t_dev);
+                                                            decay_rate, (long long)decay_steps, lr_t_dev);
   B200_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

@@ -29,6 +29,20 @@ BETA1, BETA2 = 0.9, 0.999
 _TABLES = ("user_embeds", "item_embeds", "sparse_embeds", "dense_embeds",
            "user_linear", "item_linear", "sparse_linear", "dense_linear")
 
+_REG_VARS = _TABLES      # tf.get_variable(..., regularizer=self.reg): deepfm.py:186-259, two_tower.py:258-285, din.py, ...
+
+
+def set_regularisation(tr, reg=None, lr_decay=False, decay_steps=0, decay_rate=0.96):
+    """``reg`` (``tf.keras.regularizers.l2(reg)`` on the embedding / linear tables: the optimised loss gains
+    ``reg * sum w^2``, the REPORTED loss stays the data loss) and ``lr_decay`` (``tf.train.exponential_decay``,
+    staircase, ``decay_steps`` = batches per epoch in the reference) for any trainer of this module."""
+    if reg is not None and not (isinstance(reg, float) and reg > 0.0):
+        raise ValueError("reg must be float and positive...")
+    tr.reg = float(reg) if reg else 0.0
+    tr.decay_steps = int(decay_steps) if lr_decay else 0
+    tr.decay_rate = float(decay_rate)
+    return tr
+
 
 def _adam_update(tr):
     """TF-Adam over every variable of trainer ``tr`` with the step counter and the bias-corrected step size ON THE
@@ -39,7 +53,14 @@ def _adam_update(tr):
         tr._step_dev = torch.full((1,), int(tr.t), dtype=torch.int64, device=tr.device)
         tr._lr_t = torch.zeros(1, dtype=torch.float32, device=tr.device)
     lib, st = _lib.lib, _lib.current_stream()
-    _lib.check(lib.b200_adam_begin_step(_lib.ptr(tr._step_dev), tr.lr, BETA1, BETA2, _lib.ptr(tr._lr_t), st))
+    reg = float(getattr(tr, "reg", 0.0) or 0.0)
+    if reg > 0.0:                 # L2 on the embedding / linear tables only (the variables built with regularizer=reg)
+        for k in _REG_VARS:
+            if k in tr.params:
+                _lib.check(lib.b200_axpy(_lib.ptr(tr.grads[k]), _lib.ptr(tr.params[k]), 2.0 * reg, tr.params[k].numel(), st))
+    decay_steps = int(getattr(tr, "decay_steps", 0) or 0)
+    _lib.check(lib.b200_adam_begin_step(_lib.ptr(tr._step_dev), tr.lr, BETA1, BETA2,
+                                        float(getattr(tr, "decay_rate", 0.96)), decay_steps, _lib.ptr(tr._lr_t), st))
     for k, v in tr.params.items():
         _lib.check(lib.b200_adam_dense_dev(_lib.ptr(v), _lib.ptr(tr.m[k]), _lib.ptr(tr.v[k]), _lib.ptr(tr.grads[k]),
                                            v.numel(), _lib.ptr(tr._lr_t), BETA1, BETA2, tr.epsilon, st))

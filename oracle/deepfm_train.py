@@ -136,10 +136,19 @@ def forward_backward(st, users, items, sparse, dense, labels):
     return loss, out, g, stats
 
 
-def train_step(st, users, items, sparse, dense, labels, lr, eps=1e-5):
+def train_step(st, users, items, sparse, dense, labels, lr, eps=1e-5, reg=0.0, decay_steps=0, decay_rate=0.96):
+    """``reg``: tf.keras.regularizers.l2 on the embedding / linear tables (deepfm.py:186-259; tfops/configs.py:20-26):
+    optimised loss = data loss + reg * sum w^2, the returned loss is the data loss (tf_trainer.py: sess.run(self.loss)).
+    ``decay_steps`` > 0: tf.train.exponential_decay(lr, global_step, decay_steps, decay_rate, staircase=True)."""
     p = st["params"]
     dt = p["user_embeds"].dtype
     loss, _, g, stats = forward_backward(st, users, items, sparse, dense, labels)
+    if reg:
+        for k in TABLES:
+            if k in p:
+                g[k] = g[k] + dt.type(2.0 * reg) * p[k]
+    if decay_steps:
+        lr = lr * decay_rate ** (st["t"] // decay_steps)          # global_step = completed steps
     st["t"] += 1
     t = st["t"]
     lr_t = dt.type(lr) * np.sqrt(1 - dt.type(B2) ** t) / (1 - dt.type(B1) ** t)

@@ -117,3 +117,37 @@ def test_graph_replay_equals_eager_steps():
         for k in a.params:
             da = (a.params[k] - b.params[k]).abs().max().item()
             assert da <= 2e-4, (cls.__name__, k, da)       # float atomics in the scatter: order differs run to run
+
+
+def test_l2_regulariser_and_lr_decay_match_oracle():
+    """set_regularisation: reg (2 reg w added to the table gradients) + staircase exponential lr decay, 5 steps."""
+    import torch
+
+    from librecommender_b200.training import DeepFMTrainer, set_regularisation
+    from oracle import deepfm_train as dt_
+    from oracle import tf_models as tm
+
+    spec, w, batches = _case(31, True, (64, 32))
+    lr, eps, reg = 1e-2, 1e-5, 3e-3
+    tr = set_regularisation(DeepFMTrainer(spec, w, use_bn=True, lr=lr, epsilon=eps), reg=reg, lr_decay=True,
+                            decay_steps=2, decay_rate=0.5)
+    plain = DeepFMTrainer(spec, w, use_bn=True, lr=lr, epsilon=eps)
+    st = dt_.init_state(w, True)
+    seq = batches + batches[:2]
+    for step, (users, items, labels) in enumerate(seq):
+        sparse, dense = tm.row_features(spec, users, items)
+        ref_loss = dt_.train_step(st, users, items, sparse, dense, labels, lr, eps, reg=reg, decay_steps=2, decay_rate=0.5)
+        u, i, y = torch.as_tensor(users).cuda(), torch.as_tensor(items).cuda(), torch.as_tensor(labels).cuda()
+        loss = tr.step(u, i, y)
+        plain.step(u, i, y)
+        assert abs(float(loss) - ref_loss) <= 2e-3 * max(1.0, abs(ref_loss)) * (step + 1), (step, float(loss), ref_loss)
+    moved = 0.0
+    for k, ref in _map_params(st["params"]).items():
+        got = tr.params[k].cpu().numpy().astype(np.float64).reshape(ref.shape)
+        # the decayed step sizes bound the total movement: lr (1 + 1 + .5 + .5 + .25) = 3.25 lr per weight
+        assert np.abs(got - ref).max() <= 0.12 * lr * 3.25, (k, float(np.abs(got - ref).max()))
+        assert np.median(np.abs(got - ref)) <= 0.01 * lr, (k, float(np.median(np.abs(got - ref))))
+        moved = max(moved, float((tr.params[k] - plain.params[k]).abs().max()))
+    assert moved > 0.5 * lr          # the regulariser + decay changed the trajectory
+    with pytest.raises(ValueError, match="reg must be float and positive"):
+        set_regularisation(plain, reg=-1.0)
