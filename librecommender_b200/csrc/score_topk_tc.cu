@@ -621,6 +621,50 @@ sweep_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ptx::mbar_wait_hint(&ss->tmem_full[acc][0], acc_phase, p.hint_ns);
           ptx::tc_fence_after();
         }
+        if (EPI == 6) {
+          // variant 6 (NH == 1): the warp's 128 columns as FOUR 32-column reads, double-buffered — the next read is
+          // issued right after the wait for the current one, so its tensor-memory latency runs under the max tree /
+          // group tests of the current 32 columns (tcgen05.wait::ld waits for ALL outstanding loads of the thread,
+          // hence issue-after-wait rather than two loads in flight).  Same 64 registers of read data as variant 3.
+          const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN + 2 * j * STEP);
+          const int nb = t * TN + 2 * j * STEP;
+          auto process32 = [&](const uint32_t (&r)[32], const int n_base) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+              const float a0 = fmax3(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]), __uint_as_float(r[gq * 8 + 2]));
+              const float a1 = fmax3(__uint_as_float(r[gq * 8 + 3]), __uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]));
+              const float gm = fmax3(a0, a1, fmaxf(__uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7])));
+              if (gm >= tau) {
+                float4* dst = reinterpret_cast<float4*>(my_r + (size_t)cnt * REC);
+                dst[0] = make_float4(__uint_as_float(r[gq * 8 + 0]), __uint_as_float(r[gq * 8 + 1]),
+                                     __uint_as_float(r[gq * 8 + 2]), __uint_as_float(r[gq * 8 + 3]));
+                dst[1] = make_float4(__uint_as_float(r[gq * 8 + 4]), __uint_as_float(r[gq * 8 + 5]),
+                                     __uint_as_float(r[gq * 8 + 6]), __uint_as_float(r[gq * 8 + 7]));
+                reinterpret_cast<int32_t*>(dst)[8] = n_base + gq * 8;
+                ++cnt;
+              }
+            }
+          };
+          uint32_t ra[32], rb[32];
+          ptx::tmem_ld_32x32b_x32(tb, ra);
+          ptx::tmem_ld_wait_regs(ra);
+          ptx::tmem_ld_32x32b_x32(tb + 32, rb);
+          process32(ra, nb);
+          __syncwarp();
+          ptx::tmem_ld_wait_regs(rb);
+          ptx::tmem_ld_32x32b_x32(tb + 64, ra);
+          process32(rb, nb + 32);
+          __syncwarp();
+          ptx::tmem_ld_wait_regs(ra);
+          ptx::tmem_ld_32x32b_x32(tb + 96, rb);
+          process32(ra, nb + 64);
+          __syncwarp();
+          ptx::tmem_ld_wait_regs(rb);
+          ptx::tc_fence_before();              // all four reads of this warp are done: the accumulator may be reused
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cnt(&ss->tmem_empty[acc][0], 2);
+          process32(rb, nb + 96);
+        } else
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int s = 2 * j + i;
@@ -1311,6 +1355,7 @@ static int launch_main_dispatch(int grid, const Plan& pl, int epi, cudaStream_t 
   if (epi == 9) { if (pl.NH == 2) B200_SWEEP(9, 1, 2); B200_SWEEP(9, 1, 1); }
   if (pl.NH == 2) { if (pl.CL == 2) B200_SWEEP(3, 2, 2); B200_SWEEP(3, 1, 2); }
   if (epi == 5) { if (pl.CL == 2) B200_SWEEP(5, 2, 1); B200_SWEEP(5, 1, 1); }
+  if (epi == 6) { if (pl.CL == 2) B200_SWEEP(6, 2, 1); B200_SWEEP(6, 1, 1); }
   if (pl.CL == 2) B200_SWEEP(3, 2, 1);
   B200_SWEEP(3, 1, 1);
 #undef B200_SWEEP
@@ -1360,8 +1405,8 @@ extern "C" int b200_recommend_embed_tune(int32_t epilogue_warps_per_quadrant, fl
     const int code = epilogue_warps_per_quadrant % 1000;
     const int cl = (code / 100) % 10, nh = (code / 10) % 10, epi = code % 10;
     B200_REQUIRE((cl == 1 || cl == 2) && (nh == 1 || nh == 2) &&
-                     (epi == 3 || epi == 5 || ((epi == 8 || epi == 9) && cl == 1)),
-                 "b200_recommend_embed_tune: code = 100 * cluster (1|2) + 10 * MMA groups (1|2) + epilogue (3|5)");
+                     (epi == 3 || epi == 5 || (epi == 6 && nh == 1) || ((epi == 8 || epi == 9) && cl == 1)),
+                 "b200_recommend_embed_tune: code = 100 * cluster (1|2) + 10 * MMA groups (1|2) + epilogue (3|5|6; 6 needs one MMA group)");
     g_cluster = cl; g_nh = nh; g_epi = epi;
   }
   if (pre_rank_coef != 0.f) {

@@ -121,7 +121,7 @@ def test_wide_embedding_ragged_catalogue_and_scale():
     _check(sc, U, I, csr, users, K, n_oracle=96, min_ok_frac=0.97)
 
 
-@pytest.mark.parametrize("code", [113, 215, 223, 125])
+@pytest.mark.parametrize("code", [113, 215, 223, 125, 216, 116])
 def test_kernel_organisation_variants(code):
     """The tuning variants of the sweep give the same answers as the default (code 213: cluster of 2 with
     TMA multicast, one N=256 MMA group per tile, divergent per-lane group tests): no cluster (1xx), two
