@@ -407,6 +407,9 @@ int b200_din_attention(const float* G, int64_t ldg, int32_t Kp, const int64_t* i
                        const int64_t* users, int64_t R, int64_t grid_items, int64_t row_offset,
                        const float* k1, const float* b1, const float* k2, float b2, float* out,
                        int64_t ld_out, void* stream);
+/* process-wide A/B switch (tests, measurements): 1 = the lane-owns-position kernel for T <= 64 and K' % 4 == 0
+ * (default), 0 = the first version everywhere. */
+int b200_din_attention_tune(int32_t use_v2);
 
 /* Backward of b200_din_attention (paper attention, explicit pairs: row r = (items[r], sequence row users[r])):
  * dout [R, Kp] = gradient of the attention output.  ADDS (float atomics) the gradient of the item feature rows

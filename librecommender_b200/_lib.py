@@ -94,6 +94,7 @@ SIGNATURES = {
                               _P, c_int64, _P]),
     "b200_seq_pool_backward": (c_int, [_P, c_int64, c_int32, c_int64, _P, c_int64, _P, c_int32, _P, c_int64, _P, c_int64,
                                        _P]),
+    "b200_din_attention_tune": (c_int, [c_int32]),
     "b200_din_attention_backward": (c_int, [_P, c_int64, c_int32, _P, _P, c_int64, _P, c_int32, _P, c_int64, _P, _P, _P,
                                             c_float, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P]),
     "b200_din_attention": (c_int, [_P, c_int64, c_int32, _P, _P, c_int64, _P, c_int32, _P, c_int64, c_int64, c_int64,

@@ -657,11 +657,134 @@ din_attention_backward_kernel(const float* __restrict__ G, int64_t ldg, int Kp, 
   }
 }
 
+
+// ---- din_attention, v2 (T <= 64, K' % 4 == 0): the per-row matrix M[c][j] = (Wk - Wd)[c][j] + q_c Wp[c][j] goes to
+// SHARED memory (K' x 16 floats per warp) and lane t OWNS position t (and t + 32): it streams its key row in
+// 16-byte pieces and does the 16 dot products against M with broadcast shared-memory reads — 16 FMAs per loaded
+// element, no shuffle butterflies (the first version: K'/32 x 16 FMAs and 31 shuffles + selects per position for the
+// whole warp).  Softmax = one max / one sum over the warp; the weighted key sum reads each key row once more,
+// coalesced, with p_t broadcast by shuffle.
+template <int TKC>
+__global__ void __launch_bounds__(128)
+din_attention_v2_kernel(const float* __restrict__ G, int64_t ldg, int Kp, const int64_t* __restrict__ items,
+                        const int32_t* __restrict__ seqs, int64_t ld_seq, const int32_t* __restrict__ lens, int T,
+                        const int64_t* __restrict__ users, int64_t R, int64_t grid, int64_t off, AttW w,
+                        float* __restrict__ out, int64_t ld_out) {
+  extern __shared__ float sM_all[];                       // [4 warps][Kp][HID]
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sM = sM_all + (size_t)wid * Kp * HID;
+  const float scale = rsqrtf((float)Kp);
+  float k2r[HID];
+#pragma unroll
+  for (int j = 0; j < HID; ++j) k2r[j] = __ldg(w.k2 + j);
+  for (int64_t r = (int64_t)blockIdx.x * 4 + wid; r < R; r += (int64_t)gridDim.x * 4) {
+    const int64_t sr = seq_row_of(users, r, grid, off);
+    const int64_t item = grid > 0 ? (r + off) % grid : items[r];
+    const int32_t* sq = seqs + sr * ld_seq;
+    const int len = min(max(lens[sr], 0), T);
+    // ---- M (shared) and c_j = <q, Wq + Wd> + b1 (every lane)
+    float cpart[HID];
+#pragma unroll
+    for (int j = 0; j < HID; ++j) cpart[j] = 0.f;
+    __syncwarp();                                          // the previous row's readers of sM are done
+#pragma unroll
+    for (int tt = 0; tt < TKC; ++tt) {
+      const int c = lane + tt * 32;
+      if (c < Kp) {
+        const float qc = __ldg(G + item * ldg + c);
+        const float4* wq4 = reinterpret_cast<const float4*>(w.k1 + (int64_t)c * HID);
+        const float4* wk4 = reinterpret_cast<const float4*>(w.k1 + (int64_t)(Kp + c) * HID);
+        const float4* wd4 = reinterpret_cast<const float4*>(w.k1 + (int64_t)(2 * Kp + c) * HID);
+        const float4* wp4 = reinterpret_cast<const float4*>(w.k1 + (int64_t)(3 * Kp + c) * HID);
+#pragma unroll
+        for (int j4 = 0; j4 < HID / 4; ++j4) {
+          const float4 a = __ldg(wq4 + j4), b = __ldg(wk4 + j4), d = __ldg(wd4 + j4), e = __ldg(wp4 + j4);
+          float4 m;
+          m.x = (b.x - d.x) + qc * e.x; m.y = (b.y - d.y) + qc * e.y;
+          m.z = (b.z - d.z) + qc * e.z; m.w = (b.w - d.w) + qc * e.w;
+          reinterpret_cast<float4*>(sM + c * HID)[j4] = m;
+          cpart[4 * j4 + 0] = fmaf(qc, a.x + d.x, cpart[4 * j4 + 0]);
+          cpart[4 * j4 + 1] = fmaf(qc, a.y + d.y, cpart[4 * j4 + 1]);
+          cpart[4 * j4 + 2] = fmaf(qc, a.z + d.z, cpart[4 * j4 + 2]);
+          cpart[4 * j4 + 3] = fmaf(qc, a.w + d.w, cpart[4 * j4 + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < HID; ++j) cpart[j] = warp_sum(cpart[j]) + __ldg(w.b1 + j);
+    __syncwarp();
+    // ---- logits: lane t owns positions t and t + 32
+    float a[2];
+#pragma unroll
+    for (int rnd = 0; rnd < 2; ++rnd) {
+      const int t = lane + rnd * 32;
+      a[rnd] = -3.0e38f;
+      if (t < len) {
+        const float4* k4 = reinterpret_cast<const float4*>(G + (int64_t)__ldg(sq + t) * ldg);
+        float z[HID];
+#pragma unroll
+        for (int j = 0; j < HID; ++j) z[j] = cpart[j];
+        for (int c4 = 0; c4 < Kp / 4; ++c4) {
+          const float4 kv = __ldg(k4 + c4);
+          const float kk[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4* m4 = reinterpret_cast<const float4*>(sM + (c4 * 4 + i) * HID);
+#pragma unroll
+            for (int j4 = 0; j4 < HID / 4; ++j4) {
+              const float4 m = m4[j4];                    // same address in every lane: a broadcast
+              z[4 * j4 + 0] = fmaf(kk[i], m.x, z[4 * j4 + 0]);
+              z[4 * j4 + 1] = fmaf(kk[i], m.y, z[4 * j4 + 1]);
+              z[4 * j4 + 2] = fmaf(kk[i], m.z, z[4 * j4 + 2]);
+              z[4 * j4 + 3] = fmaf(kk[i], m.w, z[4 * j4 + 3]);
+            }
+          }
+        }
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < HID; ++j) d = fmaf(k2r[j], __frcp_rn(1.0f + expf(-z[j])), d);
+        a[rnd] = (d + w.b2) * scale;
+      }
+    }
+    float amax = fmaxf(a[0], a[1]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    float e0 = lane < len ? expf(a[0] - amax) : 0.f;
+    float e1 = lane + 32 < len ? expf(a[1] - amax) : 0.f;
+    const float den = warp_sum(e0 + e1);
+    if (len > 0) { e0 /= den; e1 /= den; }
+    float acc[TKC];
+#pragma unroll
+    for (int tt = 0; tt < TKC; ++tt) acc[tt] = 0.f;
+    for (int t = 0; t < len; ++t) {
+      const float pt = __shfl_sync(0xffffffffu, t < 32 ? e0 : e1, t & 31);
+      const float* key = G + (int64_t)__ldg(sq + t) * ldg;
+#pragma unroll
+      for (int tt = 0; tt < TKC; ++tt) {
+        const int c = lane + tt * 32;
+        if (c < Kp) acc[tt] = fmaf(pt, __ldg(key + c), acc[tt]);
+      }
+    }
+#pragma unroll
+    for (int tt = 0; tt < TKC; ++tt) {
+      const int c = lane + tt * 32;
+      if (c < Kp) out[r * ld_out + c] = acc[tt];
+    }
+  }
+}
+
 }  // namespace seq
 }  // namespace b200
 
 using namespace b200;
 using namespace b200::seq;
+
+static int g_din_v2 = 1;     // b200_din_attention_tune: 1 = lane-owns-position kernel where eligible (default), 0 = first version
+
+extern "C" int b200_din_attention_tune(int32_t use_v2) {
+  g_din_v2 = use_v2 ? 1 : 0;
+  return 0;
+}
 
 extern "C" int b200_din_user_weights(const float* G, int64_t ldg, int32_t Kp, const int32_t* seq, int32_t len,
                                      const float* k1, const float* b1, float* Wt, int64_t ldw, float* bias,
@@ -800,6 +923,22 @@ extern "C" int b200_din_attention(const float* G, int64_t ldg, int32_t Kp, const
   }
   B200_REQUIRE(b1 && k2, "b200_din_attention: attention MLP weights missing");
   AttW w; w.k1 = k1; w.b1 = b1; w.k2 = k2; w.b2 = b2;
+  const bool v2_ok = g_din_v2 && T <= 64 && Kp % 4 == 0 && ldg % 4 == 0 && ((reinterpret_cast<uintptr_t>(G) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(k1) & 15) == 0);
+  if (v2_ok) {
+    const size_t smem = (size_t)4 * Kp * HID * 4;
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div64(R, 4), (int64_t)148 * 16);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch ((Kp + 31) / 32) {
+      case 1: din_attention_v2_kernel<1><<<blocks, 128, smem, st>>>(G, ldg, Kp, items, seqs, ld_seq, lens, T, users, R, grid_items, row_offset, w, out, ld_out); break;
+      case 2: din_attention_v2_kernel<2><<<blocks, 128, smem, st>>>(G, ldg, Kp, items, seqs, ld_seq, lens, T, users, R, grid_items, row_offset, w, out, ld_out); break;
+      case 3: din_attention_v2_kernel<3><<<blocks, 128, smem, st>>>(G, ldg, Kp, items, seqs, ld_seq, lens, T, users, R, grid_items, row_offset, w, out, ld_out); break;
+      default: din_attention_v2_kernel<4><<<blocks, 128, smem, st>>>(G, ldg, Kp, items, seqs, ld_seq, lens, T, users, R, grid_items, row_offset, w, out, ld_out); break;
+    }
+    count_launch();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   din_attention_kernel<<<(unsigned)ceil_div64(R, 4), 128, 0, (cudaStream_t)stream>>>(
       G, ldg, Kp, items, seqs, ld_seq, lens, T, users, R, grid_items, row_offset, w, out, ld_out);
   count_launch();

@@ -325,3 +325,35 @@ def test_din_fused_attention_epilogue_equals_unfused_and_flat(T):
     scale = np.maximum(np.abs(flat), np.abs(flat).mean())
     assert (np.abs(unfused - flat) <= 1e-5 * scale + 1e-6).all(), float(np.abs(unfused - flat).max())
     assert (np.abs(fused - flat) <= 1e-5 * scale + 1e-6).all(), float(np.abs(fused - flat).max())
+
+
+def test_din_attention_kernel_versions_agree():
+    """b200_din_attention: the lane-owns-position kernel (default) against the first version on explicit pairs and
+    on the all-items grid, incl. the user without history and T = 50."""
+    import torch
+
+    from librecommender_b200 import _lib
+    from librecommender_b200.feat_models import DIN, recent_sequences
+    from oracle import tf_models as tm
+
+    rng = np.random.default_rng(77)
+    n_users, n_items, T = 80, 700, 50
+    spec = tm.make_spec(rng, n_users, n_items, [9], [6, 13, 21], 1, 0)
+    consumed = {u: rng.choice(n_items, size=int(rng.integers(1, 90)), replace=False).tolist() for u in range(n_users - 1)}
+    seqs, lens = recent_sequences(consumed, n_users, n_items, T)
+    w = tm.make_seq_weights(rng, spec, 16, (64, 32), True, din=True)
+    model = DIN(spec, w, seqs, lens, consumed)
+    users, items = rng.integers(0, n_users + 1, 3000), rng.integers(0, n_items, 3000)
+    out = {}
+    try:
+        for v in (1, 0):
+            _lib.check(_lib.lib.b200_din_attention_tune(v))
+            out[v] = model.logits(users, items).cpu().numpy()
+    finally:
+        _lib.check(_lib.lib.b200_din_attention_tune(1))
+    sparse, dense = tm.row_features(spec, users, items)
+    ref = tm.din_forward(w, spec, users, items, seqs[users], lens[users], sparse, dense, dtype=np.float64)
+    ok = lens[users] > 0                                   # length 0: documented divergence (zeros vs uniform softmax)
+    scale = max(1.0, np.abs(ref).max())
+    assert np.abs(out[1] - out[0]).max() <= 1e-5 * scale
+    assert np.abs(out[1][ok] - ref[ok]).max() <= 1e-4 * scale
