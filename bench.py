@@ -7,7 +7,8 @@ TwoTower-style retrieval, 10 M users x 1 M items, embed 64, top-100, consumed fi
     torchrun --nproc-per-node N ... bench.py --gpus N ...     # one rank per GPU (users sharded)
 
 One JSON line on rank 0 (see the driver contract).  A "step" = one recommend call for a batch of
-`--batch` distinct users per rank (run as launches of <= 16384 users).  `value` is device-resident
+`--batch` distinct users per rank (device leg: launches of <= 32768 users; host seam: <= 16384, so that the
+D2H of a chunk and the id conversion of the next overlap kernels).  `value` is device-resident
 (user ids already in HBM, result left in HBM); `e2e` goes through the reference-facing seam
 `recommend_from_embedding(model, <python list of user ids>, n_rec, ...)` with HOST ids in and a
 fresh HOST int64[B, n_rec] array out.  For N > 1 the same run also times the two paths that DO have
@@ -275,7 +276,7 @@ def main():
                 f"top-{args.topk}, filter_consumed, batch {args.batch} users/step/GPU")
     config = {"workload": workload, "users": args.users, "items": args.items, "embed": args.dim,
               "n_rec": args.topk, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
-              "users_per_launch": min(args.batch, 16384),
+              "users_per_launch": {"device_leg": min(args.batch, 32768), "e2e_leg": min(args.batch, 16384)},
               "parallelism": f"users sharded x{world}, item table replicated, no data-path collective",
               "l2": "inputs larger than L2 (item table 256 MB fp32 + 128 MB fp16, user table 2.56 GB)",
               "device_leg": "2 steps in flight on one stream (async handle, check of step i after enqueue of i+1)",
@@ -433,7 +434,9 @@ def main():
         pass
     roofline = None
     if sweep_ms:
-        rows_per_launch = min(args.batch, 16384)
+        import librecommender_b200.engine as _eng
+
+        rows_per_launch = min(args.batch, _eng.FUSED_ROWS_PER_CALL)      # device leg: users per b200_recommend_embed launch
         flops = 2.0 * args.dim * args.items * rows_per_launch          # per launch (2*d*N per user)
         avg_ms = float(np.mean(sweep_ms))
         achieved = flops / (avg_ms * 1e-3) / 1e12
@@ -441,7 +444,9 @@ def main():
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "sweep_traffic.json")))
-            traffic = tr["dram_bytes_per_launch"]
+            # the capture is of a 16 384-user launch: scale to this run's users per launch (records and item-table
+            # passes both grow linearly with the user tiles)
+            traffic = tr["dram_bytes_per_launch"] * rows_per_launch / float(tr.get("users_per_launch", 16384))
         except Exception:
             pass
         roofline = {"bound": "tensor", "kernel": "b200::tc::sweep_kernel (PRE + guess + MAIN)", "achieved": achieved,

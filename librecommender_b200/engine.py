@@ -19,7 +19,8 @@ from .consumed import ConsumedCSR, as_csr
 _SCORE_WS_BYTES = 1 << 30  # materialised-score workspace of the exact path
 FUSED_MAX_D = 256           # limits of b200_recommend_embed (include/b200reco.h)
 FUSED_MAX_K = 288
-FUSED_ROWS_PER_CALL = 16384
+FUSED_ROWS_PER_CALL = 32768    # users per b200_recommend_embed launch on the device path (+3 % per user over 16384)
+HOST_ROWS_PER_CALL = 16384     # host seam: smaller launches so that a chunk's D2H / the next chunk's id conversion overlap kernels
 NVTX = bool(int(os.environ.get("B200_NVTX", "0")))     # B200_NVTX=1: NVTX ranges around the phases of a recommend call
 
 
@@ -181,7 +182,7 @@ class EmbedScorer:
             self.events.append((e0, e1))
 
     def recommend_fused(self, user_ids_d, n_rec, filter_consumed=True, return_scores=False, on_chunk=None,
-                        before_chunk=None):
+                        before_chunk=None, rows_per_call=None):
         """Tensor-core path (b200_recommend_embed).  Returns (ids, scores|None, status):
         rows with status != 0 hold -1 ids and must be re-run on the exact path.  ``on_chunk(r0, r1)``
         is called after the kernels of rows [r0, r1) have been enqueued, ``before_chunk(r0, r1)`` just before
@@ -196,8 +197,9 @@ class EmbedScorer:
         out_scores = torch.empty((B, n_rec), dtype=torch.float32, device=self.device) if return_scores else None
         status = torch.empty(B, dtype=torch.int32, device=self.device)
         use_filter = 1 if (filter_consumed and self.csr.nnz > 0) else 0
-        for r0 in range(0, B, FUSED_ROWS_PER_CALL):
-            r1 = min(B, r0 + FUSED_ROWS_PER_CALL)
+        step = int(rows_per_call or FUSED_ROWS_PER_CALL)
+        for r0 in range(0, B, step):
+            r1 = min(B, r0 + step)
             if before_chunk is not None:
                 before_chunk(r0, r1)
             self._fused_chunk(user_ids_d[r0:r1], n_rec, use_filter, out_ids[r0:r1],
@@ -281,7 +283,7 @@ class EmbedScorer:
         n_rec = int(n_rec)
         fill = None
         fused = not (path == "exact" or (path == "auto" and not self.fused_ok(n_rec)))
-        if isinstance(user_ids, list) and fused and len(user_ids) > FUSED_ROWS_PER_CALL:
+        if isinstance(user_ids, list) and fused and len(user_ids) > HOST_ROWS_PER_CALL:
             # a long python list (the reference's calling convention): converted and uploaded chunk by chunk, the
             # conversion of chunk i+1 runs while the kernels of chunk i execute
             import array
@@ -327,7 +329,8 @@ class EmbedScorer:
             res.setdefault("chunks", []).append((r0, r1, ev))
 
         with _nvtx("b200.recommend.fused_kernels"):
-            ids_d, sc_d, status_d = self.recommend_fused(uid_d, n_rec, filter_consumed, return_scores, on_chunk, fill)
+            ids_d, sc_d, status_d = self.recommend_fused(uid_d, n_rec, filter_consumed, return_scores, on_chunk, fill,
+                                                         rows_per_call=min(HOST_ROWS_PER_CALL, FUSED_ROWS_PER_CALL))
         with _nvtx("b200.recommend.d2h_results"), torch.cuda.stream(side):
             for r0, r1, ev in res.get("chunks", []):
                 side.wait_event(ev)
