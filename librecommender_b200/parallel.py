@@ -584,3 +584,109 @@ def sharded_mean_row(local_rows, n_local_valid: int, n_rows_global: int, group=N
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(part, group=group)
     return (part / float(n_rows_global)).to(local_rows.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# Item-sharded recommend (the variant for an item table larger than one GPU): the ITEMS are
+# split by id range, every rank scores all B users against its shard (the fused tensor-core path on the shard),
+# keeps its local top-K with exact scores, and ONE exchange step — an all-gather of (id, score)[B, K] — is followed
+# by a K-way merge on the device (b200_topk_rows over the G*K gathered candidates per row).  Exact scores do not
+# depend on the sharding and the candidates of a row arrive ordered (shard, score desc, id asc), so the merge
+# reproduces the single-GPU total order (score desc, item id asc) bit for bit.
+# ------------------------------------------------------------------------------------------------
+def restrict_consumed_to_shard(indptr, idx, item_lo: int, item_hi: int):
+    """Consumed CSR (numpy ``indptr int64[n_users+1]``, ``idx int32[nnz]``, global item ids, arrival order kept)
+    -> the same users' lists restricted to items in ``[item_lo, item_hi)`` with shard-local ids."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    idx = np.asarray(idx)
+    keep = (idx >= item_lo) & (idx < item_hi)
+    counts = np.add.reduceat(keep.astype(np.int64), indptr[:-1]) if len(idx) else np.zeros(len(indptr) - 1, np.int64)
+    counts[indptr[:-1] == indptr[1:]] = 0            # reduceat on an empty segment returns the next element
+    lptr = np.zeros(len(indptr), dtype=np.int64)
+    np.cumsum(counts, out=lptr[1:])
+    return lptr, (idx[keep] - item_lo).astype(np.int32)
+
+
+def merge_topk_shards(ids, scores, n_rec: int):
+    """``ids`` int64 ``[G, B, K]`` (global item ids, -1 = no candidate), ``scores`` fp32 ``[G, B, K]`` (device
+    tensors, each shard's rows sorted by (score desc, id asc)) -> ``(ids [B, n_rec], scores [B, n_rec])`` of the
+    merged order.  One b200_topk_rows over the ``G*K`` candidates of a row; positions index the concatenation
+    (shard-major), which is ascending in item id among equal scores."""
+    import ctypes
+
+    import torch
+
+    from . import _lib
+
+    G, B, K = ids.shape
+    cat_ids = ids.permute(1, 0, 2).reshape(B, G * K).contiguous()
+    cat_sc = scores.permute(1, 0, 2).reshape(B, G * K).contiguous().clone()
+    cat_sc[cat_ids < 0] = float("-inf")
+    ld = (G * K + 3) // 4 * 4
+    if ld != G * K:
+        pad = torch.full((B, ld), float("-inf"), dtype=torch.float32, device=cat_sc.device)
+        pad[:, :G * K] = cat_sc
+        cat_sc = pad
+    pos = torch.empty((B, n_rec), dtype=torch.int64, device=cat_sc.device)
+    out_sc = torch.empty((B, n_rec), dtype=torch.float32, device=cat_sc.device)
+    nbytes = ctypes.c_size_t(0)
+    _lib.check(_lib.lib.b200_topk_rows_workspace_bytes(B, G * K, n_rec, ctypes.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=cat_sc.device)
+    _lib.check(_lib.lib.b200_topk_rows(_lib.ptr(cat_sc), cat_sc.stride(0), B, G * K, n_rec, _lib.ptr(pos), _lib.ptr(out_sc),
+                                       _lib.ptr(ws), nbytes.value, _lib.current_stream()))
+    return torch.gather(cat_ids, 1, pos), out_sc
+
+
+class ItemShardScorer:
+    """One rank's shard ``I[item_lo:item_hi]`` of an item-sharded catalogue + the full user table; ``local_topk``
+    returns the shard's best ``n_rec`` items per user with GLOBAL ids and exact scores (the fused tensor-core path on
+    the shard, flagged rows repaired on the exact path as always)."""
+
+    def __init__(self, user_embeddings, item_shard, item_lo: int, consumed_indptr=None, consumed_idx=None,
+                 n_users=None, device=None):
+        from .consumed import ConsumedCSR
+        from .engine import EmbedScorer
+
+        self.item_lo = int(item_lo)
+        self.n_local = int(item_shard.shape[0])
+        csr, self.max_consumed = None, 0
+        if consumed_indptr is not None:
+            indptr = np.asarray(consumed_indptr, dtype=np.int64)
+            self.max_consumed = int((indptr[1:] - indptr[:-1]).max()) if len(indptr) > 1 else 0
+            lptr, lidx = restrict_consumed_to_shard(indptr, consumed_idx, self.item_lo, self.item_lo + self.n_local)
+            csr = ConsumedCSR(lptr, lidx)
+        # EmbedScorer wants an [n_items + 1, d] table (last row = the OOV item, never scored)
+        import torch
+
+        shard = torch.as_tensor(item_shard) if not isinstance(item_shard, torch.Tensor) else item_shard
+        pad = torch.zeros((1, shard.shape[1]), dtype=shard.dtype, device=shard.device)
+        self.scorer = EmbedScorer(user_embeddings, torch.cat([shard, pad], dim=0), self.n_local, csr, n_users=n_users,
+                                  device=device)
+
+    def local_topk(self, user_ids_d, n_rec: int):
+        if n_rec + self.max_consumed > self.n_local:
+            raise ValueError(f"item shard of {self.n_local} rows is too small for n_rec {n_rec} + {self.max_consumed} "
+                             "consumed items (the consumed-filter rule of ranking.py:38 is evaluated per shard)")
+        ids, scores = self.scorer.recommend_device(user_ids_d, n_rec, True, True)
+        return ids + self.item_lo, scores
+
+
+def recommend_item_sharded(shard: ItemShardScorer, user_ids_d, n_rec: int, group=None, all_gather=None, merge=None):
+    """All B users against this rank's item shard, all-gather of the ``(id, score)[B, n_rec]`` candidates, K-way merge:
+    every rank returns the global ``(ids [B, n_rec], scores [B, n_rec])``.  ``all_gather(t) -> [G, ...]`` defaults to
+    ``torch.distributed.all_gather_into_tensor`` (tests inject a stand-in to run several shards in one process);
+    ``merge`` defaults to :func:`merge_topk_shards` (CUDA; the gloo CPU test injects a numpy stand-in)."""
+    import torch
+    import torch.distributed as dist
+
+    ids, scores = shard.local_topk(user_ids_d, n_rec)
+    if all_gather is None:
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            return ids, scores
+
+        def all_gather(t):
+            out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(out, t.contiguous(), group=group)      # concatenated along dim 0 (nccl and gloo)
+            return out.view((world,) + tuple(t.shape))
+    return (merge or merge_topk_shards)(all_gather(ids), all_gather(scores), n_rec)

@@ -100,3 +100,41 @@ def test_peer_gather_and_scatter_kernels_virtual_shards(G, d):
     for r in range(G):
         got[r::G] = shards[r][: full[r::G].shape[0]]
     assert float((got - expect).abs().max()) < 2e-4
+
+
+@pytest.mark.parametrize("G", [2, 3])
+def test_item_sharded_recommend_virtual_shards_equals_single_gpu(G):
+    """SURVEY 8e row 1, item-sharded variant: G shards of the catalogue scored one after the other in ONE process
+    (the all-gather is a stack), merged with b200_topk_rows: ids and exact scores equal the single-scorer result."""
+    import numpy as np
+    import torch
+
+    from librecommender_b200.consumed import ConsumedCSR
+    from librecommender_b200.engine import EmbedScorer
+    from librecommender_b200.parallel import ItemShardScorer, merge_topk_shards, shard_bounds
+
+    rng = np.random.default_rng(G)
+    n_users, N, d, K = 500, 30001, 64, 100
+    U = rng.standard_normal((n_users + 1, d)).astype(np.float32)
+    I = rng.standard_normal((N + 1, d)).astype(np.float32)
+    I[7000] = I[12] ; I[20000] = I[12]; I[29999] = I[12]          # equal scores across shards: the id order must survive
+    consumed = {u: rng.choice(N, size=int(rng.integers(0, 60)), replace=False).tolist() for u in range(n_users)}
+    consumed = {u: c for u, c in consumed.items() if c}
+    csr = ConsumedCSR.from_dict(consumed, n_users)
+    full = EmbedScorer(U, I, N, csr, n_users=n_users)
+    users = torch.as_tensor(rng.integers(0, n_users + 1, 300)).cuda()
+    ref_ids, ref_sc = full.recommend_device(users, K, True, True)
+    ids_l, sc_l = [], []
+    for g in range(G):
+        lo, hi = shard_bounds(N, G, g)
+        sh = ItemShardScorer(U, torch.as_tensor(I[lo:hi]), lo, csr.indptr, csr.idx, n_users=n_users)
+        a, b = sh.local_topk(users, K)
+        ids_l.append(a)
+        sc_l.append(b)
+    ids, sc = merge_topk_shards(torch.stack(ids_l), torch.stack(sc_l), K)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ids.cpu().numpy(), ref_ids.cpu().numpy())
+    np.testing.assert_array_equal(sc.cpu().numpy(), ref_sc.cpu().numpy())
+    tiny = ItemShardScorer(U, torch.as_tensor(I[:120]), 0, csr.indptr, csr.idx, n_users=n_users)
+    with pytest.raises(ValueError, match="too small"):
+        tiny.local_topk(users, K)

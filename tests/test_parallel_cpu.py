@@ -106,3 +106,81 @@ def test_per_rank_sampler_streams_differ():
 
     seeds = [rank_stream_seed(462, r) for r in range(8)]
     assert seeds[0] == 462 and len(set(seeds)) == 8 and all(0 <= s < 2 ** 63 for s in seeds)
+
+
+def test_restrict_consumed_to_shard_keeps_order_and_translates_ids():
+    from librecommender_b200.parallel import restrict_consumed_to_shard
+
+    indptr = np.array([0, 4, 4, 7, 9], dtype=np.int64)                  # user 1 has no history
+    idx = np.array([50, 3, 120, 51, 7, 199, 100, 0, 99], dtype=np.int32)
+    lptr, lidx = restrict_consumed_to_shard(indptr, idx, 50, 150)
+    np.testing.assert_array_equal(lptr, [0, 3, 3, 4, 5])
+    np.testing.assert_array_equal(lidx, [0, 70, 1, 50, 49])             # arrival order kept, ids minus 50
+    lptr, lidx = restrict_consumed_to_shard(indptr, idx, 0, 50)
+    np.testing.assert_array_equal(lptr, [0, 1, 1, 2, 3])
+    np.testing.assert_array_equal(lidx, [3, 7, 0])
+    lptr, lidx = restrict_consumed_to_shard(np.array([0, 0], dtype=np.int64), np.zeros(0, np.int32), 0, 10)
+    np.testing.assert_array_equal(lptr, [0, 0])
+    assert lidx.size == 0
+
+
+def _worker_item_sharded(rank, world, port, q):
+    import os
+
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from librecommender_b200.parallel import recommend_item_sharded, shard_bounds
+
+    rng = np.random.default_rng(0)
+    n_users, N, d, K = 40, 300, 8, 7
+    U = rng.standard_normal((n_users, d)).astype(np.float32)
+    I = rng.standard_normal((N, d)).astype(np.float32)
+    lo, hi = shard_bounds(N, world, rank)
+
+    class Shard:                                  # stand-in for ItemShardScorer (numpy scores of this rank's items)
+        def local_topk(self, users, n_rec):
+            sc = U[users.numpy()] @ I[lo:hi].T
+            order = np.lexsort((np.broadcast_to(np.arange(hi - lo), sc.shape), -sc), axis=1)[:, :n_rec]
+            return torch.as_tensor(order + lo), torch.as_tensor(np.take_along_axis(sc, order, axis=1))
+
+    def merge(ids, scores, n_rec):                # stand-in for merge_topk_shards (the CUDA kernel)
+        G, B, K_ = ids.shape
+        ci = ids.permute(1, 0, 2).reshape(B, G * K_).numpy()
+        cs = scores.permute(1, 0, 2).reshape(B, G * K_).numpy()
+        order = np.lexsort((ci, -cs), axis=1)[:, :n_rec]
+        return torch.as_tensor(np.take_along_axis(ci, order, axis=1)), torch.as_tensor(np.take_along_axis(cs, order, axis=1))
+
+    users = torch.as_tensor(np.arange(0, n_users, 3))
+    ids, sc = recommend_item_sharded(Shard(), users, K, merge=merge)
+    full = U[users.numpy()] @ I.T
+    ref = np.lexsort((np.broadcast_to(np.arange(N), full.shape), -full), axis=1)[:, :K]
+    q.put((rank, bool((ids.numpy() == ref).all()), bool(np.allclose(sc.numpy(), np.take_along_axis(full, ref, axis=1)))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_item_sharded_recommend_gloo_world2():
+    """all-gather plumbing of recommend_item_sharded with numpy stand-ins for the shard scorer and the merge kernel."""
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_item_sharded, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ids_ok, sc_ok in res:
+        assert ids_ok and sc_ok, rank
