@@ -675,6 +675,27 @@ class DeepFM(_FeatModelBase):
         return max(1, (1 << 30) // (self.F * self.K * 4))
 
 
+def wide_deep_weights(user_wide, item_wide, sparse_wide, dense_wide, wide_kernel, wide_bias, user_deep, item_deep,
+                      sparse_deep, dense_deep, mlp, deep_kernel, deep_bias):
+    """WideDeep (``libreco/algorithms/wide_deep.py:150-262``) on the DeepFM engine: the wide term
+    ``Dense1(concat of the 1-d wide embeddings)`` IS DeepFM's linear term, the deep tower IS DeepFM's, and
+    ``output = wide_term + Dense1(deep)`` is DeepFM's head ``<[lin, pw, deep], w> + b`` with weight 1 on ``lin``, 0 on
+    the pairwise block and the ``deep_term`` kernel / bias on the rest.  Returns the weight dict :class:`DeepFM` takes
+    (variables named as in the reference: ``user_wide_var`` ... ``dense_deep_var``, ``wide_term`` / ``deep_term``)."""
+    K = int(np.asarray(user_deep).shape[1])
+    w = dict(user_embeds=user_deep, item_embeds=item_deep, user_linear=np.asarray(user_wide).reshape(-1),
+             item_linear=np.asarray(item_wide).reshape(-1), lin_kernel=np.asarray(wide_kernel).reshape(-1),
+             lin_bias=np.float32(np.asarray(wide_bias).reshape(-1)[0]), mlp=mlp,
+             out_kernel=np.concatenate([np.ones(1, np.float32), np.zeros(K, np.float32),
+                                        np.asarray(deep_kernel, dtype=np.float32).reshape(-1)]),
+             out_bias=np.float32(np.asarray(deep_bias).reshape(-1)[0]))
+    if sparse_deep is not None:
+        w["sparse_embeds"], w["sparse_linear"] = sparse_deep, np.asarray(sparse_wide).reshape(-1)
+    if dense_deep is not None:
+        w["dense_embeds"], w["dense_linear"] = dense_deep, np.asarray(dense_wide).reshape(-1)
+    return w
+
+
 def from_tf_variables(npz, names=None):
     """Map a reference ``<name>_tf_variables.npz`` (utils/save_load.py:70-80) to WEIGHT_KEYS.
     Embedding names are fixed by the reference code; the un-named

@@ -170,6 +170,27 @@ def deepfm_forward(w, users, items, sparse=None, dense=None, dtype=np.float32):
     return (cat @ w["out_kernel"].reshape(-1, 1) + w["out_bias"]).reshape(-1)
 
 
+def wide_deep_forward(wd, users, items, sparse=None, dense=None, dtype=np.float32):
+    """wide_deep.py:150-176 — logits.  ``wd``: the reference's variables (user_wide [n+1], ..., wide_kernel [F],
+    wide_bias, user_deep [n+1, K], ..., mlp, deep_kernel [H], deep_bias)."""
+    c = lambda x: np.asarray(x, dtype=dtype)      # noqa: E731
+    wide = [c(wd["user_wide"])[users][:, None], c(wd["item_wide"])[items][:, None]]
+    deep = [c(wd["user_deep"])[users][:, None, :], c(wd["item_deep"])[items][:, None, :]]
+    if sparse is not None:
+        wide.append(c(wd["sparse_wide"])[sparse])
+        deep.append(c(wd["sparse_deep"])[sparse])
+    if dense is not None:
+        x = dense.astype(dtype)
+        wide.append(x * c(wd["dense_wide"])[None, :])
+        deep.append(x[:, :, None] * c(wd["dense_deep"])[None, :, :])
+    wide = np.concatenate(wide, axis=1)
+    deep = np.concatenate(deep, axis=1)
+    wide_term = wide @ c(wd["wide_kernel"]).reshape(-1, 1) + dtype(wd["wide_bias"])
+    h = dense_nn(deep.reshape(len(users), -1), _cast(wd["mlp"], dtype))
+    deep_term = h @ c(wd["deep_kernel"]).reshape(-1, 1) + dtype(wd["deep_bias"])
+    return (wide_term + deep_term).reshape(-1)
+
+
 def tower_forward(w, ids, sparse, dense, which, norm, dtype=np.float32):
     """two_tower.py:306-346,400-410 — one tower over `ids` with that side's features."""
     w = _cast(w, dtype)

@@ -357,3 +357,36 @@ def test_din_attention_kernel_versions_agree():
     scale = max(1.0, np.abs(ref).max())
     assert np.abs(out[1] - out[0]).max() <= 1e-5 * scale
     assert np.abs(out[1][ok] - ref[ok]).max() <= 1e-4 * scale
+
+
+def test_wide_deep_runs_on_the_deepfm_engine():
+    """SURVEY 8f-4 adjacent model: WideDeep's variables mapped onto the DeepFM engine (feat_models.wide_deep_weights):
+    logits and the hoisted all-items recommend against the numpy restatement of wide_deep.py."""
+    from librecommender_b200.feat_models import DeepFM, wide_deep_weights
+    from oracle import ranking as orc
+    from oracle import tf_models as tm
+
+    rng = np.random.default_rng(17)
+    spec = tm.make_spec(rng, 120, 260, [7, 30], [11, 5, 40], 1, 2)
+    base = tm.make_deepfm_weights(rng, spec, 16, (64, 32), True)          # tables / MLP of the right shapes
+    H = 32
+    wd = dict(user_wide=base["user_linear"], item_wide=base["item_linear"], sparse_wide=base["sparse_linear"],
+              dense_wide=base["dense_linear"], wide_kernel=base["lin_kernel"], wide_bias=np.float32(0.03),
+              user_deep=base["user_embeds"], item_deep=base["item_embeds"], sparse_deep=base["sparse_embeds"],
+              dense_deep=base["dense_embeds"], mlp=base["mlp"],
+              deep_kernel=rng.standard_normal(H).astype(np.float32) * 0.3, deep_bias=np.float32(-0.02))
+    w = wide_deep_weights(**wd)
+    consumed = {u: rng.choice(260, size=6, replace=False).tolist() for u in range(120)}
+    model = DeepFM(spec, w, consumed)
+    users, items = rng.integers(0, 120, 700), rng.integers(0, 260, 700)
+    sparse, dense = tm.row_features(spec, users, items)
+    ref = tm.wide_deep_forward(wd, users, items, sparse, dense, dtype=np.float64)
+    got = model.logits(users, items).cpu().numpy()
+    _close(got, ref, 3e-5)
+    uid = np.arange(0, 120, 5)
+    got_ids = model.recommend(uid, 10, True)
+    all_u, all_i = np.repeat(uid, 260), np.tile(np.arange(260), len(uid))
+    sp, dn = tm.row_features(spec, all_u, all_i)
+    full = tm.wide_deep_forward(wd, all_u, all_i, sp, dn, dtype=np.float64).reshape(len(uid), 260)
+    ref_ids = orc.rank_recommendations("ranking", uid.tolist(), full.astype(np.float32).copy(), 10, 260, consumed, True)
+    assert orc.near_tie_mask(ref_ids, got_ids, full.astype(np.float32), 1e-5).all()
