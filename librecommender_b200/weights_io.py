@@ -164,3 +164,25 @@ def load_reference_tf_model(path, model_name, arch, n_hidden, use_bn, use_tf_att
     if use_tf_attention:
         w["use_tf_attention"] = True
     return w
+
+
+def load_reference_wide_deep(path, model_name, n_hidden, use_bn):
+    """Weight dict for :class:`feat_models.DeepFM` from a WideDeep model saved by the reference
+    (``<model_name>_tf_variables.npz``; variables of ``libreco/algorithms/wide_deep.py:150-262``: ``embedding/
+    {user,item,sparse,dense}_{wide,deep}_var``, ``wide_term``, the ``deep`` dense_nn stack, ``deep_term``) through
+    :func:`feat_models.wide_deep_weights`."""
+    from .feat_models import wide_deep_weights
+
+    npz = np.load(os.path.join(path, f"{model_name}_tf_variables.npz"))
+
+    def emb(name):
+        key = f"embedding/{name}:0"
+        return np.asarray(npz[key]) if key in npz else None
+
+    rest = resolve_tf_names(npz, {"mlp": _mlp_names("deep", n_hidden, use_bn), "wide_kernel": "wide_term/kernel:0",
+                                  "wide_bias": "wide_term/bias:0", "deep_kernel": "deep_term/kernel:0",
+                                  "deep_bias": "deep_term/bias:0"})
+    return wide_deep_weights(emb("user_wide_var"), emb("item_wide_var"), emb("sparse_wide_var"), emb("dense_wide_var"),
+                             rest["wide_kernel"], rest["wide_bias"], emb("user_deep_var"), emb("item_deep_var"),
+                             emb("sparse_deep_var"), emb("dense_deep_var"), rest["mlp"], rest["deep_kernel"],
+                             rest["deep_bias"])

@@ -24,3 +24,37 @@ def test_mapping_reproduces_wide_deep_logits():
     b = tm.deepfm_forward(w, users, items, sparse, dense, dtype=np.float64)
     np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-12)
     assert w["out_kernel"].shape == (1 + 8 + 8,) and w["out_kernel"][0] == 1.0 and (w["out_kernel"][1:9] == 0).all()
+
+
+def test_load_reference_wide_deep_from_npz(tmp_path):
+    """A synthetic ``<name>_tf_variables.npz`` with the reference's WideDeep variable names -> engine weights."""
+    from librecommender_b200.weights_io import load_reference_wide_deep
+
+    rng = np.random.default_rng(5)
+    spec = tm.make_spec(rng, 30, 40, [7], [11, 5], 1, 1)
+    base = tm.make_deepfm_weights(rng, spec, 8, (16, 8), True)
+    mlp = base["mlp"]
+    arrays = {"embedding/user_wide_var:0": base["user_linear"].reshape(-1, 1), "embedding/item_wide_var:0": base["item_linear"].reshape(-1, 1),
+              "embedding/sparse_wide_var:0": base["sparse_linear"].reshape(-1, 1), "embedding/dense_wide_var:0": base["dense_linear"].reshape(-1, 1),
+              "embedding/user_deep_var:0": base["user_embeds"], "embedding/item_deep_var:0": base["item_embeds"],
+              "embedding/sparse_deep_var:0": base["sparse_embeds"], "embedding/dense_deep_var:0": base["dense_embeds"],
+              "wide_term/kernel:0": base["lin_kernel"].reshape(-1, 1), "wide_term/bias:0": np.array([0.04], np.float32),
+              "deep_term/kernel:0": rng.standard_normal((8, 1)).astype(np.float32), "deep_term/bias:0": np.array([-0.01], np.float32)}
+    for i in range(2):
+        arrays[f"deep/deep_layer{i + 1}/kernel:0"] = mlp["kernels"][i]
+        arrays[f"deep/deep_layer{i + 1}/bias:0"] = mlp["biases"][i]
+    for j, bn in enumerate([mlp["bn_in"]] + list(mlp["bns"])):
+        scope = "deep/batch_normalization" + ("" if j == 0 else f"_{j}")
+        for k, v in (("gamma", bn["gamma"]), ("beta", bn["beta"]), ("moving_mean", bn["mean"]), ("moving_variance", bn["var"])):
+            arrays[f"{scope}/{k}:0"] = v
+    np.savez(tmp_path / "wd_tf_variables.npz", **arrays)
+    w = load_reference_wide_deep(str(tmp_path), "wd", 2, True)
+    users, items = rng.integers(0, 30, 100), rng.integers(0, 40, 100)
+    sparse, dense = tm.row_features(spec, users, items)
+    wd = dict(user_wide=base["user_linear"], item_wide=base["item_linear"], sparse_wide=base["sparse_linear"],
+              dense_wide=base["dense_linear"], wide_kernel=base["lin_kernel"], wide_bias=np.float32(0.04),
+              user_deep=base["user_embeds"], item_deep=base["item_embeds"], sparse_deep=base["sparse_embeds"],
+              dense_deep=base["dense_embeds"], mlp=mlp, deep_kernel=arrays["deep_term/kernel:0"].reshape(-1),
+              deep_bias=np.float32(-0.01))
+    np.testing.assert_allclose(tm.deepfm_forward(w, users, items, sparse, dense, dtype=np.float64),
+                               tm.wide_deep_forward(wd, users, items, sparse, dense, dtype=np.float64), rtol=1e-12, atol=1e-12)
