@@ -258,8 +258,11 @@ def main():
     distributed = world > 1
     if args.impl == "reference" and rank != 0:
         return 0                                   # rank 0 alone runs the CPU arm
-    torch.cuda.set_device(local_rank)
-    device = torch.device("cuda", local_rank)
+    if args.impl == "reference" and not torch.cuda.is_available():
+        device = torch.device("cpu")               # the CPU arm does not need a GPU (synthetic tables made on the host)
+    else:
+        torch.cuda.set_device(local_rank)
+        device = torch.device("cuda", local_rank)
     if args.config != "c2":
         if rank != 0 or args.impl != "b200":
             return 0
@@ -288,7 +291,8 @@ def main():
 
     U, I = make_tables(args, device)
     indptr, idx = make_consumed_csr(args, device)
-    torch.cuda.synchronize()
+    if device.type == "cuda":
+        torch.cuda.synchronize()
 
     if args.impl == "reference":
         try:   # torchrun exports OMP_NUM_THREADS=1: the CPU arm must still use every host thread
