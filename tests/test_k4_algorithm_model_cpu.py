@@ -8,8 +8,6 @@ guessed too high, heavy users with capped k_row)."""
 import numpy as np
 import pytest
 
-from oracle import ranking as orc
-
 ERR_COEF = 0.00097705
 KROW_MAX = 288
 
