@@ -1069,3 +1069,83 @@ class TwoTower:
             E = torch.cat(rows, dim=0)
             outs.append(torch.cat([E, E.mean(dim=0, keepdim=True)], dim=0))
         return outs[0], outs[1]
+
+
+class YouTubeRetrieval:
+    """libreco/algorithms/youtube_retrieval.py:169-260 (inference; SURVEY 8f-4 adjacent model) + the serving step of
+    ``DynEmbedBase.set_embeddings`` / ``dyn_user_embedding`` (``bases/dyn_embed_base.py:166-269``): the user vector is
+    ``dense_nn(concat(sqrtn-pooled behaviour sequence over seq_embeds_var, user sparse embeddings, user dense
+    value x embedding))`` (optionally L2-normalised) with a pseudo bias 1 appended, the item vector is
+    ``[item_embeds_var | item_bias_var]`` — the reference's own trick for folding the softmax bias into the dot
+    product — so all-items retrieval IS the embed scorer (K4) on d = H + 1.  The sequence of a user = its last
+    ``T`` consumed items (``_set_recent_seqs``; ``feat_models.recent_sequences``), pooled by ``b200_seq_pool``
+    (sum / sqrt(count) = ``safe_embedding_lookup_sparse(combiner="sqrtn")``, empty history -> zero vector)."""
+
+    def __init__(self, spec, weights, recent_seqs, recent_seq_lens, norm_embed=False, device=None):
+        import torch
+
+        self._torch = torch
+        K = int(np.asarray(weights["seq_embeds"]).shape[1])
+        self.base = FeatSpec(spec, K, device)
+        self.device, self.K, self.norm_embed = self.base.device, K, bool(norm_embed)
+        self.n_users, self.n_items = self.base.n_users, self.base.n_items
+        f32 = torch.float32
+        self.seq_embeds = _dev(weights["seq_embeds"], self.device, f32)              # [n_items, K]
+        self.item_embeds = _dev(weights["item_embeds"], self.device, f32)            # [n_items, H]
+        self.item_biases = _dev(np.asarray(weights["item_biases"]).reshape(-1), self.device, f32)
+        self.t = {k: _dev(weights.get(k), self.device, f32) for k in ("sparse_embeds", "dense_embeds")}
+        T = FeatTablesStruct()
+        for k, v in self.t.items():
+            setattr(T, k, v.data_ptr() if v is not None else None)
+        self.tables = T
+        L = FeatLayoutStruct.from_buffer_copy(self.base.layout)
+        L.id_mask = 0                                      # no id-embedding field: the pooled sequence takes its place
+        scols, dcols = self.base.user_sparse_cols, self.base.user_dense_cols
+        L.n_sparse, L.n_dense = len(scols), len(dcols)
+        for f in range(len(scols)):
+            L.sparse_side[f], L.sparse_col[f] = 0, f
+        for f in range(len(dcols)):
+            L.dense_side[f], L.dense_col[f] = 0, f
+            L.dense_embed_row[f] = dcols[f]
+        self.layout, self.n_feat = L, len(scols) + len(dcols)
+        self.seqs = _dev(recent_seqs, self.device, torch.int32)
+        self.lens = _dev(recent_seq_lens, self.device, torch.int32)
+        self.mlp = [(_dev(Wt, self.device, f32), _dev(b, self.device, f32), relu) for Wt, b, relu in fold_mlp(weights["mlp"])]
+
+    def user_vectors(self, ids):
+        """[n, H] user embeddings of the given (inner) user ids, before the pseudo bias."""
+        torch = self._torch
+        ids_d = torch.as_tensor(np.asarray(ids, dtype=np.int64)).to(self.device)
+        n, K = int(ids_d.numel()), self.K
+        x = torch.empty((n, (1 + self.n_feat) * K), dtype=torch.float32, device=self.device)
+        pooled = x[:, :K]
+        _lib.check(_lib.lib.b200_seq_pool(
+            _lib.ptr(self.seq_embeds), self.seq_embeds.stride(0), K, self.n_items, _lib.ptr(self.seqs),
+            self.seqs.stride(0), _lib.ptr(self.lens), self.seqs.shape[1], _lib.ptr(ids_d), n, 0, 0, _lib.ptr(pooled),
+            x.stride(0), _lib.current_stream()))
+        if self.n_feat:
+            feat = x[:, K:]
+            _lib.check(_lib.lib.b200_feat_forward(
+                ctypes.byref(self.layout), ctypes.byref(self.tables), _lib.ptr(ids_d), _lib.ptr(ids_d), n, 0, 0,
+                _lib.ptr(feat), x.stride(0), None, 0, None, None, None, 0.0, None, None, None, 0.0,
+                None, None, 0, _lib.current_stream()))
+        for Wt, b, relu in self.mlp:
+            x = linear(x, Wt, b, relu)
+        if self.norm_embed:
+            _lib.check(_lib.lib.b200_l2_normalize_rows(_lib.ptr(x), x.stride(0), n, x.shape[1], _lib.current_stream()))
+        return x
+
+    def set_embeddings(self, chunk=1 << 20):
+        """Device tensors ``U [n_users + 1, H + 1]`` (pseudo bias 1 in the last column, last row = mean OOV row) and
+        ``I [n_items + 1, H + 1]`` (``[item_embeds | item_biases]`` + the mean row) for :class:`engine.EmbedScorer`."""
+        torch = self._torch
+        rows = [self.user_vectors(np.arange(i, min(self.n_users, i + chunk))) for i in range(0, self.n_users, chunk)]
+        U = torch.cat(rows, dim=0)
+        if self.norm_embed:          # dyn_embed_base.py:264-265: the item side is normalised too (before the bias column)
+            I = self.item_embeds / self.item_embeds.norm(dim=1, keepdim=True)
+        else:
+            I = self.item_embeds
+        U = torch.cat([U, torch.ones((U.shape[0], 1), dtype=torch.float32, device=self.device)], dim=1)
+        I = torch.cat([I, self.item_biases[:, None]], dim=1)
+        return (torch.cat([U, U.mean(dim=0, keepdim=True)], dim=0).contiguous(),
+                torch.cat([I, I.mean(dim=0, keepdim=True)], dim=0).contiguous())

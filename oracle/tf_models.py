@@ -170,6 +170,29 @@ def deepfm_forward(w, users, items, sparse=None, dense=None, dtype=np.float32):
     return (cat @ w["out_kernel"].reshape(-1, 1) + w["out_bias"]).reshape(-1)
 
 
+def youtube_retrieval_user_vectors(w, spec, user_ids, seqs, lens, norm=False, dtype=np.float32):
+    """youtube_retrieval.py:169-260 + dyn_embed_base.py:281-313 — user embeddings (without the pseudo bias):
+    dense_nn(concat(sqrtn pooling of seq_embeds_var over the user's recent items, user sparse embeddings, user
+    dense value x embedding))."""
+    E = np.asarray(w["seq_embeds"], dtype=dtype)
+    n_items = E.shape[0]
+    Ez = np.concatenate([E, np.zeros((1, E.shape[1]), dtype=dtype)], axis=0)        # pad id n_items -> zero row
+    pooled = Ez[np.asarray(seqs)[user_ids]].sum(axis=1)
+    ln = np.sqrt(np.asarray(lens, dtype=dtype)[user_ids]).reshape(-1, 1)
+    pooled = np.divide(pooled, ln, out=np.zeros_like(pooled), where=ln != 0)
+    parts = [pooled]
+    if len(spec["user_sparse_col_index"]):
+        parts.append(np.asarray(w["sparse_embeds"], dtype=dtype)[spec["user_sparse_unique"][user_ids]].reshape(len(user_ids), -1))
+    if len(spec["user_dense_col_index"]):
+        cols = list(spec["user_dense_col_index"])
+        parts.append((spec["user_dense_unique"][user_ids][:, :, None].astype(dtype)
+                      * np.asarray(w["dense_embeds"], dtype=dtype)[cols][None]).reshape(len(user_ids), -1))
+    v = dense_nn(np.concatenate(parts, axis=1).astype(dtype), _cast(w["mlp"], dtype))
+    if norm:
+        v = v / np.linalg.norm(v, axis=1, keepdims=True)
+    return v
+
+
 def wide_deep_forward(wd, users, items, sparse=None, dense=None, dtype=np.float32):
     """wide_deep.py:150-176 — logits.  ``wd``: the reference's variables (user_wide [n+1], ..., wide_kernel [F],
     wide_bias, user_deep [n+1, K], ..., mlp, deep_kernel [H], deep_bias)."""

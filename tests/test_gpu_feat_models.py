@@ -390,3 +390,42 @@ def test_wide_deep_runs_on_the_deepfm_engine():
     full = tm.wide_deep_forward(wd, all_u, all_i, sp, dn, dtype=np.float64).reshape(len(uid), 260)
     ref_ids = orc.rank_recommendations("ranking", uid.tolist(), full.astype(np.float32).copy(), 10, 260, consumed, True)
     assert orc.near_tie_mask(ref_ids, got_ids, full.astype(np.float32), 1e-5).all()
+
+
+@pytest.mark.parametrize("norm,n_rows", [(False, 300), (True, 5000)])
+def test_youtube_retrieval_user_vectors_and_retrieval(norm, n_rows):
+    """SURVEY 8f-4 adjacent model: YouTubeRetrieval's user tower (sqrtn-pooled history + user features, K1 without an
+    id field, both the small-batch and the pipelined large-batch kernels) against the numpy restatement, then all-items
+    retrieval through the embed scorer with the reference's pseudo-bias column."""
+    from librecommender_b200.engine import EmbedScorer
+    from librecommender_b200.feat_models import YouTubeRetrieval, recent_sequences
+    from librecommender_b200.synthetic import _glorot, make_embeddings, make_mlp
+    from oracle import ranking as orc
+    from oracle import tf_models as tm
+
+    rng = np.random.default_rng(23 + n_rows)
+    n_users, n_items, K, H, T = n_rows, 900, 16, 32, 10
+    spec = tm.make_spec(rng, n_users, n_items, [8, 17], [5], 1, 0)
+    emb = make_embeddings(rng, spec, K, linear=False)
+    w = dict(seq_embeds=_glorot(rng, (n_items, K)), sparse_embeds=emb["sparse_embeds"], dense_embeds=emb["dense_embeds"],
+             mlp=make_mlp(rng, (1 + 2 + 1) * K, (64, H), True), item_embeds=_glorot(rng, (n_items, H)),
+             item_biases=(rng.standard_normal(n_items) * 0.1).astype(np.float32))
+    consumed = {u: rng.choice(n_items, size=int(rng.integers(1, 25)), replace=False).tolist() for u in range(n_users - 1)}
+    seqs, lens = recent_sequences(consumed, n_users, n_items, T)          # the last user has no history
+    model = YouTubeRetrieval(spec, w, seqs, lens, norm_embed=norm)
+    ids = np.arange(n_users)
+    got = model.user_vectors(ids).cpu().numpy()
+    ref = tm.youtube_retrieval_user_vectors(w, spec, ids, seqs, lens, norm, dtype=np.float64)
+    _close(got, ref, 3e-5)
+    U, I = model.set_embeddings()
+    assert U.shape == (n_users + 1, H + 1) and I.shape == (n_items + 1, H + 1)
+    assert float(U[:n_users, H].min()) == 1.0 and float(U[:n_users, H].max()) == 1.0
+    sc = EmbedScorer(U, I, n_items, consumed, n_users=n_users)
+    users = rng.integers(0, n_users, 64)
+    got_ids = sc.recommend(users, 10, True)
+    Ih = w["item_embeds"].astype(np.float64)
+    if norm:
+        Ih = Ih / np.linalg.norm(Ih, axis=1, keepdims=True)
+    full = ref[users] @ Ih.T + w["item_biases"].astype(np.float64)[None, :]
+    ref_ids = orc.rank_recommendations("ranking", users.tolist(), full.astype(np.float32).copy(), 10, n_items, consumed, True)
+    assert orc.near_tie_mask(ref_ids, got_ids, full.astype(np.float32), 2e-5).all()
