@@ -58,3 +58,23 @@ def test_load_reference_wide_deep_from_npz(tmp_path):
               deep_bias=np.float32(-0.01))
     np.testing.assert_allclose(tm.deepfm_forward(w, users, items, sparse, dense, dtype=np.float64),
                                tm.wide_deep_forward(wd, users, items, sparse, dense, dtype=np.float64), rtol=1e-12, atol=1e-12)
+
+
+def test_set_regularisation_validates_like_the_reference():
+    """training.set_regularisation mirrors tfops/configs.py:20-26 (reg must be a positive float) — host logic only."""
+    import types
+
+    import pytest
+
+    from librecommender_b200.training import set_regularisation
+
+    tr = types.SimpleNamespace()
+    set_regularisation(tr, reg=1e-3, lr_decay=True, decay_steps=50, decay_rate=0.9)
+    assert tr.reg == 1e-3 and tr.decay_steps == 50 and tr.decay_rate == 0.9
+    set_regularisation(tr, reg=None, lr_decay=False, decay_steps=50)
+    assert tr.reg == 0.0 and tr.decay_steps == 0
+    for bad in (-1.0, 0.0, 1):
+        if bad == 0.0:
+            continue                      # falsy reg = no regulariser (reg_config returns None)
+        with pytest.raises(ValueError, match="reg must be float and positive"):
+            set_regularisation(tr, reg=bad)
